@@ -1,0 +1,43 @@
+// Shared host-side helpers for the C-ABI library: error reporting, launch checks, TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/denet_b200.h"
+
+namespace dn {
+
+// Last error message, per host thread (C-ABI: functions return <0 and the text is read with denet_last_error()).
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define DN_CHECK_CUDA(expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return dn::set_error(DENET_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,            \
+                                 cudaGetErrorString(_e));                                                \
+    } while (0)
+
+#define DN_CHECK_LAUNCH() DN_CHECK_CUDA(cudaGetLastError())
+
+#define DN_REQUIRE(cond, ...)                                                \
+    do {                                                                     \
+        if (!(cond)) return dn::set_error(DENET_ERR_ARG, __VA_ARGS__);       \
+    } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+int num_sms();
+
+// Encode a bf16 tiled tensor map with 128B swizzle. dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+// estrides may be null (all 1).
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, const uint32_t* estrides);
+
+}  // namespace dn

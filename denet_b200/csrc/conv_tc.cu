@@ -1,0 +1,745 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (NHWC bf16 operands, fp32 accumulation in TMEM).
+//
+// Replaces the cuDNN calls behind the reference's ConvLayer (reference denet/layer/convolution.py:76-92,
+// tensor.nnet.conv2d + its autodiff dgrad/wgrad).
+//
+//  * conv_fprop_kernel : Y[pixel, co] = sum_{tap, ci} X[pixel + tap - pad, ci] * B[co, tap, ci]
+//      - stride-1 R x S correlation. The reference's *true* convolution (filter flip) and the dgrad
+//        (swap Cin/Cout, pad' = R-1-pad) are obtained purely by how denet_conv_weight_prep lays out B.
+//      - M tile = a TW x TH x TN patch of 128 output pixels, fetched per filter tap as ONE 4-D TMA box
+//        shifted by the tap offset; out-of-image rows/cols are zero-filled by TMA, which implements the
+//        'half'/'valid'/'full' borders without any im2col buffer.  With R=S=1 this is a plain GEMM.
+//      - K loop = terms x taps x 64-channel chunks.  terms=3 is the error-compensated bf16x3 split
+//        (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo) used by the fp32-parity mode; terms=1 is throughput mode.
+//  * conv_wgrad_kernel : dW[co, tap, ci] = sum_{pixel} dY[pixel, co] * X[pixel + tap - pad, ci]
+//      - both operands are MN-major (the contraction runs over pixels, channels are contiguous), split-K over
+//        pixel blocks into an fp32 workspace, reduced deterministically by wgrad_reduce_kernel.
+//
+// Structure (both kernels): persistent CTAs, 6 warps: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
+// warps2-5 = epilogue (TMEM -> registers -> global), mbarrier ring between producer and MMA, double-buffered
+// TMEM accumulator between MMA and epilogue.
+#include <string.h>
+#include <algorithm>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dn {
+
+constexpr int kBM = 128;      // UMMA M (TMEM lanes)
+constexpr int kBK = 64;       // K elements per pipeline stage (= 128 B of bf16 = one swizzle row)
+constexpr int kThreads = 192; // 6 warps
+
+struct ConvFpropParams {
+    CUtensorMap tmA[2];  // input  (C, W, H, N) bf16, [0] = hi, [1] = lo
+    CUtensorMap tmB[2];  // weight (KtotPad, Cout) bf16
+    int nterms;          // 1 or 3
+    int R, S, pad_h, pad_w;
+    int kchunks;         // ceil(Cin / 64)
+    int Wo, Ho, No;      // output extent
+    int TW, TH, TN;      // patch (TW*TH*TN == 128)
+    int tiles_w, tiles_h, tiles_n, tiles_co;
+    int num_tiles;
+    int Cout;
+    long long ldy;       // output pixel pitch (elements)
+    int y_fp32;
+    int relu;
+    void* y;
+    const float* bias;       // [Cout] or null
+    const void* residual;    // same layout/dtype as y, or null
+    float* stat_sum;         // optional per-channel sum / sum of squares accumulators (fp32 atomics), or null
+    float* stat_sqsum;
+};
+
+struct ConvWgradParams {
+    CUtensorMap tmDY[2];  // dY (Cout, Wo, Ho, N) bf16
+    CUtensorMap tmX[2];   // X  (Cin,  Wi, Hi, N) bf16
+    int nterms;
+    int R, S, pad_h, pad_w;
+    int TW, TH, TN;       // k-block patch (TW*TH*TN == 64)
+    int tiles_w, tiles_h, tiles_n;
+    int total_kblocks;
+    int splits;
+    int co_tiles, ci_tiles;
+    int num_tiles;
+    int Cout, Cin;
+    int ldws;             // workspace cin pitch (elements)
+    float* ws;            // [splits][Cout][taps][ldws]
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int kABytes = kBM * kBK * 2;
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+__device__ __forceinline__ void store_row_chunk(void* y, int y_fp32, long long elem_off, const float (&v)[32],
+                                                int ncols_valid) {
+    if (y_fp32) {
+        float* dst = reinterpret_cast<float*>(y) + elem_off;
+        if (ncols_valid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+            for (int i = 0; i < ncols_valid; ++i) dst[i] = v[i];
+        }
+    } else {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + elem_off;
+        if (ncols_valid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 u;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+                u.x = *reinterpret_cast<uint32_t*>(&p0);
+                u.y = *reinterpret_cast<uint32_t*>(&p1);
+                u.z = *reinterpret_cast<uint32_t*>(&p2);
+                u.w = *reinterpret_cast<uint32_t*>(&p3);
+                reinterpret_cast<uint4*>(dst)[i] = u;
+            }
+        } else {
+            for (int i = 0; i < ncols_valid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_row_chunk(const void* y, int y_fp32, long long elem_off, float (&v)[32],
+                                               int ncols_valid) {
+    if (y_fp32) {
+        const float* src = reinterpret_cast<const float*>(y) + elem_off;
+        for (int i = 0; i < 32; ++i) v[i] = (i < ncols_valid) ? src[i] : 0.f;
+    } else {
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(y) + elem_off;
+        for (int i = 0; i < 32; ++i) v[i] = (i < ncols_valid) ? __bfloat162float(src[i]) : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fprop / dgrad
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_constant__ ConvFpropParams p) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ntaps = p.R * p.S;
+    const int num_kb = p.nterms * ntaps * p.kchunks;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        if (lane == 0) {
+            ptx::tma_prefetch_desc(&p.tmA[0]);
+            ptx::tma_prefetch_desc(&p.tmB[0]);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int ct = tile % p.tiles_co;
+                int mt = tile / p.tiles_co;
+                const int tw = mt % p.tiles_w;
+                mt /= p.tiles_w;
+                const int th = mt % p.tiles_h;
+                const int tn = mt / p.tiles_h;
+                const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN, co0 = ct * BN;
+                for (int term = 0; term < p.nterms; ++term) {
+                    const int ai = (term == 1) ? 1 : 0;  // terms: (hi,hi) (lo,hi) (hi,lo)
+                    const int bi = (term == 2) ? 1 : 0;
+                    for (int tap = 0; tap < ntaps; ++tap) {
+                        const int dh = tap / p.S - p.pad_h;
+                        const int dw = tap % p.S - p.pad_w;
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                            uint8_t* sA = smem + stage * L::kStageBytes;
+                            uint8_t* sB = sA + L::kABytes;
+                            ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                            ptx::tma_load_4d(sA, &p.tmA[ai], &full_bar[stage], kc * kBK, w0 + dw, h0 + dh, n0);
+                            ptx::tma_load_2d(sB, &p.tmB[bi], &full_bar[stage], (tap * p.kchunks + kc) * kBK, co0);
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sA = ptx::smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sB = sA + L::kABytes;
+                    const uint64_t adesc = ptx::make_smem_desc(sA, 16, 1024);
+                    const uint64_t bdesc = ptx::make_smem_desc(sB, 16, 1024);
+#pragma unroll
+                    for (int j = 0; j < kBK / 16; ++j) {
+                        // advance 16 bf16 (32 B) along K inside the 128B-swizzled row
+                        ptx::umma_f16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | j) != 0);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarter warp%4)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int ct = tile % p.tiles_co;
+            int mt = tile / p.tiles_co;
+            const int tw = mt % p.tiles_w;
+            mt /= p.tiles_w;
+            const int th = mt % p.tiles_h;
+            const int tn = mt / p.tiles_h;
+            const int w = tw * p.TW + (row % p.TW);
+            const int h = th * p.TH + (row / p.TW) % p.TH;
+            const int n = tn * p.TN + row / (p.TW * p.TH);
+            const bool row_ok = (w < p.Wo) && (h < p.Ho) && (n < p.No);
+            const long long pix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;
+            const int co0 = ct * BN;
+
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0;
+                ptx::tmem_ld_32x32b_x32(taddr, r);
+                ptx::tmem_ld_wait();
+                const int co = co0 + c0;
+                int nvalid = p.Cout - co;
+                nvalid = nvalid > 32 ? 32 : nvalid;
+                if (nvalid > 0) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid) v[i] += __ldg(p.bias + co + i);
+                    }
+                    if (p.stat_sum) {
+                        // per-channel batch statistics of the (pre-activation) conv output: warp reduce, one atomic/warp
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float s = row_ok ? v[i] : 0.f;
+                            float s2 = s * s;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                s += __shfl_xor_sync(0xffffffffu, s, o);
+                                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                            }
+                            if (lane == 0 && i < nvalid) {
+                                atomicAdd(p.stat_sum + co + i, s);
+                                atomicAdd(p.stat_sqsum + co + i, s2);
+                            }
+                        }
+                    }
+                    if (row_ok) {
+                        const long long off = pix * p.ldy + co;
+                        if (p.residual) {
+                            float rres[32];
+                            load_row_chunk(p.residual, p.y_fp32, off, rres, nvalid);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += rres[i];
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        store_row_chunk(p.y, p.y_fp32, off, v, nvalid);
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_constant__ ConvWgradParams p) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+    constexpr int kBoxBytes = kBK * 128;  // one [64 pixels][64 channels] bf16 box
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ntaps = p.R * p.S;
+
+    // tile -> (co tile, ci tile, tap, split); split is the slowest index so that concurrently running CTAs
+    // share the same pixel range (L2 reuse of dY / X boxes).
+    auto decode = [&](int tile, int& cot, int& cit, int& tap, int& kb0, int& kb1) {
+        cot = tile % p.co_tiles;
+        int t = tile / p.co_tiles;
+        cit = t % p.ci_tiles;
+        t /= p.ci_tiles;
+        tap = t % ntaps;
+        const int split = t / ntaps;
+        kb0 = static_cast<int>(static_cast<long long>(p.total_kblocks) * split / p.splits);
+        kb1 = static_cast<int>(static_cast<long long>(p.total_kblocks) * (split + 1) / p.splits);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::tma_prefetch_desc(&p.tmDY[0]);
+            ptx::tma_prefetch_desc(&p.tmX[0]);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int cot, cit, tap, kb0, kb1;
+                decode(tile, cot, cit, tap, kb0, kb1);
+                const int dh = tap / p.S - p.pad_h;
+                const int dw = tap % p.S - p.pad_w;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int tw = kb % p.tiles_w;
+                    const int t2 = kb / p.tiles_w;
+                    const int th = t2 % p.tiles_h;
+                    const int tn = t2 / p.tiles_h;
+                    const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+                    for (int term = 0; term < p.nterms; ++term) {
+                        const int ai = (term == 1) ? 1 : 0;
+                        const int bi = (term == 2) ? 1 : 0;
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * L::kStageBytes;
+                        uint8_t* sB = sA + L::kABytes;
+                        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+#pragma unroll
+                        for (int i = 0; i < kBM / 64; ++i)
+                            ptx::tma_load_4d(sA + i * kBoxBytes, &p.tmDY[ai], &full_bar[stage], cot * kBM + i * 64, w0,
+                                             h0, n0);
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            ptx::tma_load_4d(sB + i * kBoxBytes, &p.tmX[bi], &full_bar[stage], cit * BN + i * 64,
+                                             w0 + dw, h0 + dh, n0);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                int cot, cit, tap, kb0, kb1;
+                decode(tile, cot, cit, tap, kb0, kb1);
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                const int nk = (kb1 - kb0) * p.nterms;
+                for (int kb = 0; kb < nk; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sA = ptx::smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sB = sA + L::kABytes;
+                    // MN-major: LBO = next 64-channel box, SBO = next group of 8 pixel rows
+                    const uint64_t adesc = ptx::make_smem_desc(sA, kBoxBytes, 1024);
+                    const uint64_t bdesc = ptx::make_smem_desc(sB, kBoxBytes, 1024);
+#pragma unroll
+                    for (int j = 0; j < kBK / 16; ++j) {
+                        // advance 16 pixel rows = 2048 B
+                        ptx::umma_f16(d_tmem, adesc + 128 * j, bdesc + 128 * j, idesc, (kb | j) != 0);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            int cot, cit, tap, kb0, kb1;
+            decode(tile, cot, cit, tap, kb0, kb1);
+            const int split = (tile / p.co_tiles / p.ci_tiles) / ntaps;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int co = cot * kBM + row;
+            const bool row_ok = co < p.Cout;
+            float* dst_row =
+                p.ws + ((static_cast<long long>(split) * p.Cout + co) * ntaps + tap) * static_cast<long long>(p.ldws);
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0;
+                ptx::tmem_ld_32x32b_x32(taddr, r);
+                ptx::tmem_ld_wait();
+                const int ci = cit * BN + c0;
+                int nvalid = p.Cin - ci;
+                nvalid = nvalid > 32 ? 32 : nvalid;
+                if (row_ok && nvalid > 0) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    store_row_chunk(dst_row, 1, ci, v, nvalid);
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// Sum the split-K partials and scatter into the reference filter layout (Cout, Cin, R, S) of the *true*
+// convolution (tap (r,s) of the correlation is element (R-1-r, S-1-s) of the reference filter).
+// accumulate != 0 adds into dw (used when a layer's weight receives gradient from two paths).
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cout, int Cin,
+                                    int R, int S, int ldws, int accumulate) {
+    const long long total = static_cast<long long>(Cout) * Cin * R * S;
+    const int ntaps = R * S;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        // idx enumerates (co, tap, ci) so that workspace reads are coalesced
+        const int ci = static_cast<int>(idx % Cin);
+        long long t = idx / Cin;
+        const int tap = static_cast<int>(t % ntaps);
+        const int co = static_cast<int>(t / ntaps);
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s)
+            acc += ws[((static_cast<long long>(s) * Cout + co) * ntaps + tap) * ldws + ci];
+        const int r = tap / S, sx = tap % S;
+        const long long o = ((static_cast<long long>(co) * Cin + ci) * R + (R - 1 - r)) * S + (S - 1 - sx);
+        dw[o] = accumulate ? dw[o] + acc : acc;
+    }
+}
+
+// Weight preparation: reference fp32 filters (Cout, Cin, R, S) [true convolution] -> GEMM B operand, bf16 hi (+lo).
+//   mode 0 (fprop): B[co][tap=(r,s)][ci] = W[co][ci][R-1-r][S-1-s]     rows = Cout, K = taps * CinP
+//   mode 1 (dgrad): B[ci][tap=(r,s)][co] = W[co][ci][r][s]             rows = Cin,  K = taps * CoutP
+__global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, int mode,
+                                   __nv_bfloat16* __restrict__ b_hi, __nv_bfloat16* __restrict__ b_lo) {
+    const int rows = mode == 0 ? Cout : Cin;
+    const int kin = mode == 0 ? Cin : Cout;
+    const int kp = (kin + 63) / 64 * 64;
+    const int ntaps = R * S;
+    const long long total = static_cast<long long>(rows) * ntaps * kp;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(idx % kp);
+        long long t = idx / kp;
+        const int tap = static_cast<int>(t % ntaps);
+        const int row = static_cast<int>(t / ntaps);
+        float v = 0.f;
+        if (k < kin) {
+            const int r = tap / S, s = tap % S;
+            if (mode == 0)
+                v = w[((static_cast<long long>(row) * Cin + k) * R + (R - 1 - r)) * S + (S - 1 - s)];
+            else
+                v = w[((static_cast<long long>(k) * Cin + row) * R + r) * S + s];
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        b_hi[idx] = hi;
+        if (b_lo) b_lo[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+// fp32 -> bf16 hi/lo split of an activation tensor (parity mode operand preparation).
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float v = x[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static void pick_patch(int W, int H, int N, int target, int& TW, int& TH, int& TN) {
+    // powers of two with TW*TH*TN == target, covering W first, then H, then batch
+    TW = 1;
+    while (TW < W && TW < target) TW <<= 1;
+    TH = 1;
+    while (TH < H && TW * TH < target) TH <<= 1;
+    TN = target / (TW * TH);
+    (void)N;
+}
+
+template <int BN, int STAGES>
+static int launch_fprop(const ConvFpropParams& p, cudaStream_t stream) {
+    using L = SmemLayout<BN, STAGES>;
+    auto kern = conv_fprop_kernel<BN, STAGES>;
+    DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    kern<<<grid, kThreads, L::kTotal, stream>>>(p);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const ConvWgradParams& p, cudaStream_t stream) {
+    using L = SmemLayout<BN, STAGES>;
+    auto kern = conv_wgrad_kernel<BN, STAGES>;
+    DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    kern<<<grid, kThreads, L::kTotal, stream>>>(p);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+static int make_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int N, long long ld, int TW, int TH,
+                        int TN) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * W, (uint64_t)ld * 2 * W * H};
+    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+    return encode_tmap_bf16(tm, base, 4, dims, strides, box, nullptr);
+}
+
+}  // namespace dn
+
+using namespace dn;
+
+extern "C" int denet_conv_weight_prep(const float* w, int Cout, int Cin, int R, int S, int mode, void* b_hi, void* b_lo,
+                                      cudaStream_t stream) {
+    DN_REQUIRE(w && b_hi, "weight_prep: null pointer");
+    DN_REQUIRE(mode == 0 || mode == 1, "weight_prep: mode must be 0 (fprop) or 1 (dgrad)");
+    const int rows = mode == 0 ? Cout : Cin;
+    const int kin = mode == 0 ? Cin : Cout;
+    const long long total = static_cast<long long>(rows) * R * S * ((kin + 63) / 64 * 64);
+    const int block = 256;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total, block), 148LL * 16);
+    weight_prep_kernel<<<grid, block, 0, stream>>>(w, Cout, Cin, R, S, mode, (__nv_bfloat16*)b_hi, (__nv_bfloat16*)b_lo);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_split_bf16(const float* x, void* hi, void* lo, long long n, cudaStream_t stream) {
+    DN_REQUIRE(x && hi, "split_bf16: null pointer");
+    if (n == 0) return 0;
+    const int block = 256;
+    const int grid = (int)std::min<long long>(ceil_div_ll(n, block), 148LL * 32);
+    split_bf16_kernel<<<grid, block, 0, stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin, long long ldx,
+                                  const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w,
+                                  void* y, int y_dtype, long long ldy, int Ho, int Wo, const float* bias,
+                                  const void* residual, int relu, float* stat_sum, float* stat_sqsum,
+                                  cudaStream_t stream) {
+    DN_REQUIRE(x_hi && b_hi && y, "conv2d_fprop: null pointer");
+    DN_REQUIRE((x_lo == nullptr) == (b_lo == nullptr), "conv2d_fprop: x_lo and b_lo must both be given or both null");
+    DN_REQUIRE(ldx % 8 == 0, "conv2d_fprop: input pixel pitch must be a multiple of 8 elements (16 B), got %lld", ldx);
+    DN_REQUIRE(y_dtype == DENET_F32 || y_dtype == DENET_BF16, "conv2d_fprop: bad y_dtype %d", y_dtype);
+    DN_REQUIRE(N > 0 && Hi > 0 && Wi > 0 && Cin > 0 && Cout > 0 && Ho > 0 && Wo > 0, "conv2d_fprop: empty tensor");
+    DN_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "conv2d_fprop: stat pointers must come in pairs");
+
+    ConvFpropParams p;
+    memset(&p, 0, sizeof(p));
+    p.nterms = x_lo ? 3 : 1;
+    p.R = R; p.S = S; p.pad_h = pad_h; p.pad_w = pad_w;
+    p.kchunks = ceil_div(Cin, 64);
+    p.Wo = Wo; p.Ho = Ho; p.No = N;
+    pick_patch(Wo, Ho, N, 128, p.TW, p.TH, p.TN);
+    p.tiles_w = ceil_div(Wo, p.TW);
+    p.tiles_h = ceil_div(Ho, p.TH);
+    p.tiles_n = ceil_div(N, p.TN);
+    const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    p.tiles_co = ceil_div(Cout, BN);
+    p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
+    p.Cout = Cout;
+    p.ldy = ldy;
+    p.y_fp32 = (y_dtype == DENET_F32);
+    p.relu = relu;
+    p.y = y;
+    p.bias = bias;
+    p.residual = residual;
+    p.stat_sum = stat_sum;
+    p.stat_sqsum = stat_sqsum;
+
+    int rc;
+    if ((rc = make_act_map(&p.tmA[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN))) return rc;
+    if (x_lo && (rc = make_act_map(&p.tmA[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN))) return rc;
+    {
+        const uint64_t ktot = (uint64_t)R * S * p.kchunks * 64;
+        uint64_t dims[2] = {ktot, (uint64_t)Cout};
+        uint64_t strides[1] = {ktot * 2};
+        uint32_t box[2] = {64, (uint32_t)BN};
+        if ((rc = encode_tmap_bf16(&p.tmB[0], b_hi, 2, dims, strides, box, nullptr))) return rc;
+        if (b_lo && (rc = encode_tmap_bf16(&p.tmB[1], b_lo, 2, dims, strides, box, nullptr))) return rc;
+    }
+    switch (BN) {
+        case 64: return launch_fprop<64, 8>(p, stream);
+        case 128: return launch_fprop<128, 6>(p, stream);
+        default: return launch_fprop<256, 4>(p, stream);
+    }
+}
+
+extern "C" size_t denet_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cout, int Cin, int R, int S) {
+    int TW, TH, TN;
+    pick_patch(Wo, Ho, N, 64, TW, TH, TN);
+    const int total_kb = ceil_div(Wo, TW) * ceil_div(Ho, TH) * ceil_div(N, TN);
+    const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
+    const int base_tiles = ceil_div(Cout, 128) * ceil_div(Cin, BN) * R * S;
+    int splits = ceil_div(2 * num_sms(), base_tiles);
+    if (splits > total_kb) splits = total_kb;
+    if (splits < 1) splits = 1;
+    const int ldws = (Cin + 3) / 4 * 4;
+    return (size_t)splits * Cout * R * S * ldws * sizeof(float);
+}
+
+extern "C" int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int Wo, int Cout, long long lddy,
+                                  const void* x_hi, const void* x_lo, int Hi, int Wi, int Cin, long long ldx, int R,
+                                  int S, int pad_h, int pad_w, float* dw, int accumulate, float* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
+    DN_REQUIRE(dy_hi && x_hi && dw && workspace, "conv2d_wgrad: null pointer");
+    DN_REQUIRE((dy_lo == nullptr) == (x_lo == nullptr), "conv2d_wgrad: dy_lo and x_lo must both be given or both null");
+    DN_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0, "conv2d_wgrad: pixel pitches must be multiples of 8 elements");
+    ConvWgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.nterms = dy_lo ? 3 : 1;
+    p.R = R; p.S = S; p.pad_h = pad_h; p.pad_w = pad_w;
+    pick_patch(Wo, Ho, N, 64, p.TW, p.TH, p.TN);
+    p.tiles_w = ceil_div(Wo, p.TW);
+    p.tiles_h = ceil_div(Ho, p.TH);
+    p.tiles_n = ceil_div(N, p.TN);
+    p.total_kblocks = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
+    p.co_tiles = ceil_div(Cout, 128);
+    p.ci_tiles = ceil_div(Cin, BN);
+    const int base_tiles = p.co_tiles * p.ci_tiles * R * S;
+    int splits = ceil_div(2 * num_sms(), base_tiles);
+    if (splits > p.total_kblocks) splits = p.total_kblocks;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    p.num_tiles = base_tiles * splits;
+    p.Cout = Cout; p.Cin = Cin;
+    p.ldws = (Cin + 3) / 4 * 4;
+    p.ws = workspace;
+    const size_t need = (size_t)splits * Cout * R * S * p.ldws * sizeof(float);
+    DN_REQUIRE(workspace_bytes >= need, "conv2d_wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+
+    int rc;
+    if ((rc = make_act_map(&p.tmDY[0], dy_hi, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
+    if (dy_lo && (rc = make_act_map(&p.tmDY[1], dy_lo, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
+    if ((rc = make_act_map(&p.tmX[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN))) return rc;
+    if (x_lo && (rc = make_act_map(&p.tmX[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN))) return rc;
+
+    switch (BN) {
+        case 64: rc = launch_wgrad<64, 8>(p, stream); break;
+        case 128: rc = launch_wgrad<128, 6>(p, stream); break;
+        default: rc = launch_wgrad<256, 4>(p, stream); break;
+    }
+    if (rc) return rc;
+    const long long total = (long long)Cout * Cin * R * S;
+    const int block = 256;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total, block), 148LL * 16);
+    wgrad_reduce_kernel<<<grid, block, 0, stream>>>(workspace, dw, splits, Cout, Cin, R, S, p.ldws, accumulate);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
