@@ -1,0 +1,791 @@
+// HBM-bound layers of the DeNet hot path on NHWC tensors: batch-norm (+ReLU, +residual) forward/backward, ReLU,
+// add, max / average pooling, pool-inv (nearest-neighbour upsampling) and NCHW<->NHWC layout conversion.
+//
+// Reference semantics followed (paths relative to the reference repository):
+//   batch-norm        denet/layer/batch_norm.py:47-53,75-76 (cuDNN spatial BN; EMA of mean and INVERSE STD)
+//   batch-norm + relu denet/layer/batch_norm_relu.py:31-57 (k_relu, grad masked by y > 0)
+//   pooling           denet/layer/pool.py:28-40 (cuDNN max / average_inc_pad)
+//   pool-inv          denet/layer/pool_inv_op.py:38-63 (fwd), :144-169 (bwd: fp32 running sum in (ry, rx) order)
+//   relu              denet/layer/activation.py:32-34
+// All kernels are grid-stride over 8-channel packs (16 B bf16 / 32 B fp32 per access, channels contiguous) and are
+// sized in multiples of the SM count; reductions are two-stage with a fixed order (deterministic).
+#include <algorithm>
+
+#include "common.cuh"
+#include "pack.cuh"
+
+namespace dn {
+
+static inline int ew_grid(long long work_items, int block) {
+    long long g = ceil_div_ll(work_items, block);
+    long long cap = (long long)num_sms() * 16;
+    return (int)std::max<long long>(1, std::min(g, cap));
+}
+
+// ------------------------------------------------------------------------------------------------ batch norm
+// stage 1: per row-slab partial sums of (x - K) and (x - K)^2 with K = x[row 0] (shifted sums: no cancellation)
+constexpr int kBnThreads = 256;
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_partial_kernel(const T* __restrict__ x, long long M, int C,
+                                                                        long long ld, int rows_per_block,
+                                                                        float* __restrict__ partial) {
+    // thread -> (channel pack cv, row lane rl); block covers rows [r0, r1) and channel packs [cv0, cv0 + cvt)
+    const int CV = C / VEC;
+    const int cvt = CV < kBnThreads ? CV : kBnThreads;
+    const int rlanes = kBnThreads / cvt;
+    const int cv = blockIdx.y * cvt + threadIdx.x % cvt;
+    const int rl = threadIdx.x / cvt;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    __shared__ float red[2 * kBnThreads * (VEC == 8 ? 8 : 1)];
+
+    float s[VEC], s2[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
+    const bool active = (cv < CV) && (rl < rlanes);
+    if (active) {
+        Pack<T, VEC> k;
+        k.load(x + (long long)cv * VEC);
+        for (long long r = r0 + rl; r < r1; r += rlanes) {
+            Pack<T, VEC> p;
+            p.load(x + r * ld + (long long)cv * VEC);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float d = p.v[i] - k.v[i];
+                s[i] += d;
+                s2[i] += d * d;
+            }
+        }
+    }
+    // reduce over row lanes (fixed order)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        red[(threadIdx.x * VEC + i) * 2 + 0] = s[i];
+        red[(threadIdx.x * VEC + i) * 2 + 1] = s2[i];
+    }
+    __syncthreads();
+    if (active && rl == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float a = 0.f, b = 0.f;
+            for (int l = 0; l < rlanes; ++l) {
+                const int t = l * cvt + threadIdx.x;
+                a += red[(t * VEC + i) * 2 + 0];
+                b += red[(t * VEC + i) * 2 + 1];
+            }
+            const int c = cv * VEC + i;
+            partial[((long long)blockIdx.x * 2 + 0) * C + c] = a;
+            partial[((long long)blockIdx.x * 2 + 1) * C + c] = b;
+        }
+    }
+}
+
+// stage 2: combine slabs in order, produce mean / inverse std and the running-statistics EMA
+template <typename T>
+__global__ void bn_stats_finalize_kernel(const T* __restrict__ x, const float* __restrict__ partial, int nslabs,
+                                         long long M, int C, float eps, float* __restrict__ mean,
+                                         float* __restrict__ invstd, float* __restrict__ run_mean,
+                                         float* __restrict__ run_stdinv, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < nslabs; ++s) {
+        a += partial[((long long)s * 2 + 0) * C + c];
+        b += partial[((long long)s * 2 + 1) * C + c];
+    }
+    const double k = to_f<T>(x[c]);
+    const double dm = a / (double)M;
+    double var = b / (double)M - dm * dm;
+    if (var < 0.0) var = 0.0;
+    const float m = (float)(k + dm);
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    mean[c] = m;
+    invstd[c] = is;
+    if (run_mean) run_mean[c] = momentum * run_mean[c] + (1.0f - momentum) * m;
+    if (run_stdinv) run_stdinv[c] = momentum * run_stdinv[c] + (1.0f - momentum) * is;
+}
+
+// y = [relu]( (x - mean) * (gamma * invstd) + beta [+ residual] )
+template <typename T, int VEC>
+__global__ void bn_apply_kernel(const T* __restrict__ x, long long M, int C, long long ld,
+                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const T* __restrict__ residual, int relu, T* __restrict__ y) {
+    const int CV = C / VEC;
+    const long long total = M * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        const long long r = idx / CV;
+        const long long off = r * ld + (long long)cv * VEC;
+        Pack<T, VEC> p, q;
+        p.load(x + off);
+        if (residual) q.load(residual + off);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int c = cv * VEC + i;
+            float v = (p.v[i] - __ldg(mean + c)) * (__ldg(gamma + c) * __ldg(invstd + c)) + __ldg(beta + c);
+            if (residual) v += q.v[i];
+            if (relu) v = fmaxf(v, 0.f);
+            p.v[i] = v;
+        }
+        p.store(y + off);
+    }
+}
+
+// backward stage 1: per-slab partial sums of dy' and dy' * xhat, dy' = dy * [y > 0] when relu
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const T* __restrict__ dy, const T* __restrict__ yout,
+                                                                      const T* __restrict__ x, long long M, int C,
+                                                                      long long ld, int rows_per_block,
+                                                                      const float* __restrict__ mean,
+                                                                      const float* __restrict__ invstd, int relu,
+                                                                      float* __restrict__ partial) {
+    const int CV = C / VEC;
+    const int cvt = CV < kBnThreads ? CV : kBnThreads;
+    const int rlanes = kBnThreads / cvt;
+    const int cv = blockIdx.y * cvt + threadIdx.x % cvt;
+    const int rl = threadIdx.x / cvt;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    __shared__ float red[2 * kBnThreads * (VEC == 8 ? 8 : 1)];
+    float s[VEC], s2[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
+    const bool active = (cv < CV) && (rl < rlanes);
+    if (active) {
+        float mu[VEC], is[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            mu[i] = mean[cv * VEC + i];
+            is[i] = invstd[cv * VEC + i];
+        }
+        for (long long r = r0 + rl; r < r1; r += rlanes) {
+            const long long off = r * ld + (long long)cv * VEC;
+            Pack<T, VEC> g, xv, yo;
+            g.load(dy + off);
+            xv.load(x + off);
+            if (relu) yo.load(yout + off);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float d = g.v[i];
+                if (relu && !(yo.v[i] > 0.f)) d = 0.f;
+                s[i] += d;
+                s2[i] += d * ((xv.v[i] - mu[i]) * is[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        red[(threadIdx.x * VEC + i) * 2 + 0] = s[i];
+        red[(threadIdx.x * VEC + i) * 2 + 1] = s2[i];
+    }
+    __syncthreads();
+    if (active && rl == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float a = 0.f, b = 0.f;
+            for (int l = 0; l < rlanes; ++l) {
+                const int t = l * cvt + threadIdx.x;
+                a += red[(t * VEC + i) * 2 + 0];
+                b += red[(t * VEC + i) * 2 + 1];
+            }
+            const int c = cv * VEC + i;
+            partial[((long long)blockIdx.x * 2 + 0) * C + c] = a;
+            partial[((long long)blockIdx.x * 2 + 1) * C + c] = b;
+        }
+    }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nslabs, int C,
+                                       float* __restrict__ sum_dy, float* __restrict__ sum_dy_xhat,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < nslabs; ++s) {
+        a += partial[((long long)s * 2 + 0) * C + c];
+        b += partial[((long long)s * 2 + 1) * C + c];
+    }
+    sum_dy[c] = (float)a;
+    sum_dy_xhat[c] = (float)b;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)a : (float)a;
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)b : (float)b;
+}
+
+// backward stage 2: dx = gamma*invstd * (dy' - sum_dy/M - xhat * sum_dy_xhat/M); optionally export dy' (residual grad)
+template <typename T, int VEC>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yout, const T* __restrict__ x,
+                                    long long M, int C, long long ld, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sum_dy, const float* __restrict__ sum_dy_xhat, int relu,
+                                    T* __restrict__ dx, T* __restrict__ dres) {
+    const int CV = C / VEC;
+    const long long total = M * CV;
+    const float inv_m = 1.0f / (float)M;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        const long long r = idx / CV;
+        const long long off = r * ld + (long long)cv * VEC;
+        Pack<T, VEC> g, xv, yo, o;
+        g.load(dy + off);
+        xv.load(x + off);
+        if (relu) yo.load(yout + off);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int c = cv * VEC + i;
+            float d = g.v[i];
+            if (relu && !(yo.v[i] > 0.f)) d = 0.f;
+            g.v[i] = d;
+            const float is = __ldg(invstd + c);
+            const float xh = (xv.v[i] - __ldg(mean + c)) * is;
+            o.v[i] = __ldg(gamma + c) * is * (d - __ldg(sum_dy + c) * inv_m - xh * __ldg(sum_dy_xhat + c) * inv_m);
+        }
+        o.store(dx + off);
+        if (dres) g.store(dres + off);
+    }
+}
+
+__global__ void bn_inference_invstd_kernel(const float* __restrict__ run_stdinv, float eps, float* __restrict__ out,
+                                           int C) {
+    // batch_norm.py:50-52: var = (1/stdinv)^2 is handed to cuDNN inference, which adds eps again
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sd = 1.0f / run_stdinv[c];
+    out[c] = 1.0f / sqrtf(sd * sd + eps);
+}
+
+// ------------------------------------------------------------------------------------------------ relu / add
+template <typename T, int VEC>
+__global__ void relu_fwd_kernel(const T* __restrict__ x, long long M, int C, long long ld, T* __restrict__ y) {
+    const int CV = C / VEC;
+    const long long total = M * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long off = (idx / CV) * ld + (idx % CV) * VEC;
+        Pack<T, VEC> p;
+        p.load(x + off);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) p.v[i] = fmaxf(p.v[i], 0.f);
+        p.store(y + off);
+    }
+}
+
+template <typename T, int VEC>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, long long M, int C, long long ld,
+                                T* __restrict__ dx) {
+    const int CV = C / VEC;
+    const long long total = M * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long off = (idx / CV) * ld + (idx % CV) * VEC;
+        Pack<T, VEC> g, o;
+        g.load(dy + off);
+        o.load(y + off);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) g.v[i] = o.v[i] > 0.f ? g.v[i] : 0.f;
+        g.store(dx + off);
+    }
+}
+
+template <typename T, int VEC>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, long long M, int C, long long ld, int relu,
+                           T* __restrict__ out) {
+    const int CV = C / VEC;
+    const long long total = M * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long off = (idx / CV) * ld + (idx % CV) * VEC;
+        Pack<T, VEC> p, q;
+        p.load(a + off);
+        q.load(b + off);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            p.v[i] += q.v[i];
+            if (relu) p.v[i] = fmaxf(p.v[i], 0.f);
+        }
+        p.store(out + off);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+// NCHW fp32 (host-facing layout of the reference) -> NHWC T with pitch ld; tiled transpose through shared memory
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long long HW, long long ld, T* __restrict__ y) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const float* xs = x + (long long)n * C * HW;
+    T* ys = y + (long long)n * HW * ld;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i;
+        const long long p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? xs[(long long)c * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long p = p0 + i;
+        const int c = c0 + threadIdx.x;
+        if (p < HW && c < C) ys[p * ld + c] = from_f<T>(tile[threadIdx.x][i]);
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int C, long long HW, long long ld, float* __restrict__ y) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const T* xs = x + (long long)n * HW * ld;
+    float* ys = y + (long long)n * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long p = p0 + i;
+        const int c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (p < HW && c < C) ? to_f<T>(xs[p * ld + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i;
+        const long long p = p0 + threadIdx.x;
+        if (c < C && p < HW) ys[(long long)c * HW + p] = tile[threadIdx.x][i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+template <typename T, int VEC>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, long long ldx, int kh, int kw,
+                                   int sh, int sw, int ph, int pw, int Ho, int Wo, long long ldy, T* __restrict__ y,
+                                   uint8_t* __restrict__ argmax) {
+    const int CV = C / VEC;
+    const long long total = (long long)N * Ho * Wo * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int wo = (int)(t % Wo);
+        t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        float best[VEC];
+        int bi[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            best[i] = -INFINITY;
+            bi[i] = 0;
+        }
+        for (int r = 0; r < kh; ++r) {
+            const int h = ho * sh - ph + r;
+            if (h < 0 || h >= H) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int w = wo * sw - pw + s;
+                if (w < 0 || w >= W) continue;
+                Pack<T, VEC> p;
+                p.load(x + (((long long)n * H + h) * W + w) * ldx + (long long)cv * VEC);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i)
+                    if (p.v[i] > best[i]) {
+                        best[i] = p.v[i];
+                        bi[i] = r * kw + s;
+                    }
+            }
+        }
+        const long long opix = ((long long)n * Ho + ho) * Wo + wo;
+        Pack<T, VEC> o;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            o.v[i] = best[i];
+            argmax[opix * C + cv * VEC + i] = (uint8_t)bi[i];
+        }
+        o.store(y + opix * ldy + (long long)cv * VEC);
+    }
+}
+
+// gather form (deterministic): every input pixel sums dy of the windows whose recorded argmax points at it
+template <typename T, int VEC>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ argmax, int N, int H, int W,
+                                   int C, long long ldx, int kh, int kw, int sh, int sw, int ph, int pw, int Ho, int Wo,
+                                   long long ldy, T* __restrict__ dx) {
+    const int CV = C / VEC;
+    const long long total = (long long)N * H * W * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int w = (int)(t % W);
+        t /= W;
+        const int h = (int)(t % H);
+        const int n = (int)(t / H);
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        // windows (ho, wo) with ho*sh - ph + r == h, 0 <= r < kh
+        for (int r = 0; r < kh; ++r) {
+            const int hn = h + ph - r;
+            if (hn < 0 || hn % sh != 0) continue;
+            const int ho = hn / sh;
+            if (ho >= Ho) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int wn = w + pw - s;
+                if (wn < 0 || wn % sw != 0) continue;
+                const int wo = wn / sw;
+                if (wo >= Wo) continue;
+                const long long opix = ((long long)n * Ho + ho) * Wo + wo;
+                Pack<T, VEC> g;
+                g.load(dy + opix * ldy + (long long)cv * VEC);
+                const int tap = r * kw + s;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i)
+                    if (argmax[opix * C + cv * VEC + i] == tap) acc[i] += g.v[i];
+            }
+        }
+        Pack<T, VEC> o;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+        o.store(dx + (((long long)n * H + h) * W + w) * ldx + (long long)cv * VEC);
+    }
+}
+
+// average_inc_pad: divisor is always kh*kw
+template <typename T, int VEC>
+__global__ void avgpool_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, long long ldx, int kh, int kw,
+                                   int sh, int sw, int ph, int pw, int Ho, int Wo, long long ldy, T* __restrict__ y) {
+    const int CV = C / VEC;
+    const long long total = (long long)N * Ho * Wo * CV;
+    const float inv = 1.0f / (float)(kh * kw);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int wo = (int)(t % Wo);
+        t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int r = 0; r < kh; ++r) {
+            const int h = ho * sh - ph + r;
+            if (h < 0 || h >= H) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int w = wo * sw - pw + s;
+                if (w < 0 || w >= W) continue;
+                Pack<T, VEC> p;
+                p.load(x + (((long long)n * H + h) * W + w) * ldx + (long long)cv * VEC);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += p.v[i];
+            }
+        }
+        Pack<T, VEC> o;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = acc[i] * inv;
+        o.store(y + (((long long)n * Ho + ho) * Wo + wo) * ldy + (long long)cv * VEC);
+    }
+}
+
+template <typename T, int VEC>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dy, int N, int H, int W, int C, long long ldx, int kh, int kw,
+                                   int sh, int sw, int ph, int pw, int Ho, int Wo, long long ldy, T* __restrict__ dx) {
+    const int CV = C / VEC;
+    const long long total = (long long)N * H * W * CV;
+    const float inv = 1.0f / (float)(kh * kw);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int w = (int)(t % W);
+        t /= W;
+        const int h = (int)(t % H);
+        const int n = (int)(t / H);
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int r = 0; r < kh; ++r) {
+            const int hn = h + ph - r;
+            if (hn < 0 || hn % sh != 0) continue;
+            const int ho = hn / sh;
+            if (ho >= Ho) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int wn = w + pw - s;
+                if (wn < 0 || wn % sw != 0) continue;
+                const int wo = wn / sw;
+                if (wo >= Wo) continue;
+                Pack<T, VEC> g;
+                g.load(dy + (((long long)n * Ho + ho) * Wo + wo) * ldy + (long long)cv * VEC);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += g.v[i];
+            }
+        }
+        Pack<T, VEC> o;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = acc[i] * inv;
+        o.store(dx + (((long long)n * H + h) * W + w) * ldx + (long long)cv * VEC);
+    }
+}
+
+// pool-inv forward: one thread per OUTPUT pixel pack (coalesced writes; the 4 reads of an input pack hit L1/L2)
+template <typename T, int VEC>
+__global__ void pool_inv_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, long long ldx, int sw, int sh,
+                                    long long ldy, T* __restrict__ y) {
+    const int CV = C / VEC;
+    const int RH = H * sh, RW = W * sw;
+    const long long total = (long long)N * RH * RW * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int rx = (int)(t % RW);
+        t /= RW;
+        const int ry = (int)(t % RH);
+        const int n = (int)(t / RH);
+        Pack<T, VEC> p;
+        p.load(x + (((long long)n * H + ry / sh) * W + rx / sw) * ldx + (long long)cv * VEC);
+        p.store(y + (((long long)n * RH + ry) * RW + rx) * ldy + (long long)cv * VEC);
+    }
+}
+
+// pool-inv backward: fp32 running sum over the sh x sw window in (ry, rx) order starting from 0 (reference order)
+template <typename T, int VEC>
+__global__ void pool_inv_bwd_kernel(const T* __restrict__ dy, int N, int H, int W, int C, long long ldx, int sw, int sh,
+                                    long long ldy, T* __restrict__ dx) {
+    const int CV = C / VEC;
+    const int RH = H * sh, RW = W * sw;
+    const long long total = (long long)N * H * W * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int w = (int)(t % W);
+        t /= W;
+        const int h = (int)(t % H);
+        const int n = (int)(t / H);
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int ry = h * sh; ry < h * sh + sh; ++ry)
+            for (int rx = w * sw; rx < w * sw + sw; ++rx) {
+                Pack<T, VEC> g;
+                g.load(dy + (((long long)n * RH + ry) * RW + rx) * ldy + (long long)cv * VEC);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += g.v[i];
+            }
+        Pack<T, VEC> o;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+        o.store(dx + (((long long)n * H + h) * W + w) * ldx + (long long)cv * VEC);
+    }
+}
+
+static int bn_slabs(long long M, int C, int vec, int* rows_per_block, int* ychunks) {
+    const int CV = C / vec;
+    const int cvt = CV < kBnThreads ? CV : kBnThreads;
+    *ychunks = ceil_div(CV, cvt);
+    long long target = (long long)num_sms() * 4;
+    long long rpb = ceil_div_ll(M, target);
+    const int rlanes = kBnThreads / cvt;
+    if (rpb < rlanes * 4) rpb = rlanes * 4;
+    *rows_per_block = (int)std::min<long long>(rpb, 1 << 30);
+    return (int)ceil_div_ll(M, *rows_per_block);
+}
+
+}  // namespace dn
+
+using namespace dn;
+
+extern "C" size_t denet_bn_workspace_bytes(long long M, int C) {
+    int rpb, yc;
+    // worst case is the scalar variant (more slabs never happen: slabs depend on M only through rows_per_block)
+    const int n1 = bn_slabs(M, C, 1, &rpb, &yc);
+    const int n8 = (C % 8 == 0) ? bn_slabs(M, C, 8, &rpb, &yc) : 0;
+    const int n = n1 > n8 ? n1 : n8;
+    return ((size_t)n * 2 * C + 2 * (size_t)C) * sizeof(float);
+}
+
+extern "C" int denet_bn_stats(const void* x, int dtype, long long M, int C, long long ld, float eps, float* mean,
+                              float* invstd, float* run_mean, float* run_stdinv, float momentum, float* workspace,
+                              size_t workspace_bytes, cudaStream_t stream) {
+    DN_REQUIRE(x && mean && invstd && workspace, "bn_stats: null pointer");
+    DN_REQUIRE(M > 0 && C > 0, "bn_stats: empty tensor");
+    DN_REQUIRE(workspace_bytes >= denet_bn_workspace_bytes(M, C), "bn_stats: workspace too small");
+    const bool v = vec8_ok(C, ld, x);
+    int rpb, yc;
+    const int nslabs = bn_slabs(M, C, v ? 8 : 1, &rpb, &yc);
+    DN_DISPATCH(dtype, v, {
+        bn_stats_partial_kernel<T, VEC><<<dim3(nslabs, yc), kBnThreads, 0, stream>>>((const T*)x, M, C, ld, rpb, workspace);
+        bn_stats_finalize_kernel<T><<<ceil_div(C, 128), 128, 0, stream>>>((const T*)x, workspace, nslabs, M, C, eps, mean,
+                                                                            invstd, run_mean, run_stdinv, momentum);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_bn_apply(const void* x, int dtype, long long M, int C, long long ld, const float* mean,
+                              const float* invstd, const float* gamma, const float* beta, const void* residual,
+                              int relu, void* y, cudaStream_t stream) {
+    DN_REQUIRE(x && y && mean && invstd && gamma && beta, "bn_apply: null pointer");
+    const bool v = vec8_ok(C, ld, x, y, residual);
+    DN_DISPATCH(dtype, v, {
+        bn_apply_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>(
+            (const T*)x, M, C, ld, mean, invstd, gamma, beta, (const T*)residual, relu, (T*)y);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_bn_inference_invstd(const float* run_stdinv, float eps, float* out, int C, cudaStream_t stream) {
+    DN_REQUIRE(run_stdinv && out, "bn_inference_invstd: null pointer");
+    bn_inference_invstd_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(run_stdinv, eps, out, C);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x, int dtype, long long M, int C,
+                                 long long ld, const float* mean, const float* invstd, const float* gamma, int relu,
+                                 void* dx, void* dres, float* dgamma, float* dbeta, int accumulate, float* workspace,
+                                 size_t workspace_bytes, cudaStream_t stream) {
+    DN_REQUIRE(dy && x && dx && mean && invstd && gamma && workspace, "bn_backward: null pointer");
+    DN_REQUIRE(!relu || yout, "bn_backward: relu mask needs the forward output");
+    DN_REQUIRE(workspace_bytes >= denet_bn_workspace_bytes(M, C), "bn_backward: workspace too small");
+    const bool v = vec8_ok(C, ld, dy, x, dx, yout) && vec8_ok(C, ld, dres);
+    int rpb, yc;
+    const int nslabs = bn_slabs(M, C, v ? 8 : 1, &rpb, &yc);
+    float* sums = workspace + (size_t)nslabs * 2 * C;
+    DN_DISPATCH(dtype, v, {
+        bn_bwd_partial_kernel<T, VEC><<<dim3(nslabs, yc), kBnThreads, 0, stream>>>(
+            (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb, mean, invstd, relu, workspace);
+        bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(workspace, nslabs, C, sums, sums + C, dgamma, dbeta,
+                                                                     accumulate);
+        bn_bwd_apply_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>(
+            (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, mean, invstd, gamma, sums, sums + C, relu, (T*)dx,
+            (T*)dres);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_relu_fwd(const void* x, int dtype, long long M, int C, long long ld, void* y, cudaStream_t stream) {
+    DN_REQUIRE(x && y, "relu_fwd: null pointer");
+    const bool v = vec8_ok(C, ld, x, y);
+    DN_DISPATCH(dtype, v, {
+        relu_fwd_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>((const T*)x, M, C, ld, (T*)y);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_relu_bwd(const void* dy, const void* y, int dtype, long long M, int C, long long ld, void* dx,
+                              cudaStream_t stream) {
+    DN_REQUIRE(dy && y && dx, "relu_bwd: null pointer");
+    const bool v = vec8_ok(C, ld, dy, y, dx);
+    DN_DISPATCH(dtype, v, {
+        relu_bwd_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>((const T*)dy, (const T*)y, M, C, ld,
+                                                                                   (T*)dx);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_add(const void* a, const void* b, int dtype, long long M, int C, long long ld, int relu, void* out,
+                         cudaStream_t stream) {
+    DN_REQUIRE(a && b && out, "add: null pointer");
+    const bool v = vec8_ok(C, ld, a, b, out);
+    DN_DISPATCH(dtype, v, {
+        add_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>((const T*)a, (const T*)b, M, C, ld, relu,
+                                                                              (T*)out);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_nchw_to_nhwc(const float* x, int N, int C, int H, int W, void* y, int dtype, long long ld,
+                                  cudaStream_t stream) {
+    DN_REQUIRE(x && y, "nchw_to_nhwc: null pointer");
+    const long long HW = (long long)H * W;
+    dim3 grid((unsigned)ceil_div_ll(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N), block(32, 8);
+    if (dtype == DENET_F32)
+        nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(x, C, HW, ld, (float*)y);
+    else
+        nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(x, C, HW, ld, (__nv_bfloat16*)y);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_nhwc_to_nchw(const void* x, int dtype, long long ld, int N, int C, int H, int W, float* y,
+                                  cudaStream_t stream) {
+    DN_REQUIRE(x && y, "nhwc_to_nchw: null pointer");
+    const long long HW = (long long)H * W;
+    dim3 grid((unsigned)ceil_div_ll(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N), block(32, 8);
+    if (dtype == DENET_F32)
+        nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>((const float*)x, C, HW, ld, y);
+    else
+        nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, C, HW, ld, y);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_pool_fwd(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int mode, int kh,
+                              int kw, int sh, int sw, int ph, int pw, void* y, int Ho, int Wo, long long ldy,
+                              uint8_t* argmax, cudaStream_t stream) {
+    DN_REQUIRE(x && y, "pool_fwd: null pointer");
+    DN_REQUIRE(mode == 0 || mode == 1, "pool_fwd: mode must be 0 (max) or 1 (average_inc_pad)");
+    DN_REQUIRE(mode == 1 || argmax, "pool_fwd: max pooling needs an argmax buffer (N*Ho*Wo*C bytes)");
+    DN_REQUIRE(kh * kw <= 255, "pool_fwd: window too large");
+    const bool v = vec8_ok(C, ldx, x) && vec8_ok(C, ldy, y);
+    DN_DISPATCH(dtype, v, {
+        const int grid = ew_grid((long long)N * Ho * Wo * (C / VEC), 256);
+        if (mode == 0)
+            maxpool_fwd_kernel<T, VEC><<<grid, 256, 0, stream>>>((const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, ph, pw, Ho,
+                                                                  Wo, ldy, (T*)y, argmax);
+        else
+            avgpool_fwd_kernel<T, VEC><<<grid, 256, 0, stream>>>((const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, ph, pw, Ho,
+                                                                  Wo, ldy, (T*)y);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_pool_bwd(const void* dy, int dtype, int N, int H, int W, int C, long long ldx, int mode, int kh,
+                              int kw, int sh, int sw, int ph, int pw, int Ho, int Wo, long long ldy,
+                              const uint8_t* argmax, void* dx, cudaStream_t stream) {
+    DN_REQUIRE(dy && dx, "pool_bwd: null pointer");
+    DN_REQUIRE(mode == 1 || argmax, "pool_bwd: max pooling needs the argmax buffer of the forward pass");
+    const bool v = vec8_ok(C, ldx, dx) && vec8_ok(C, ldy, dy);
+    DN_DISPATCH(dtype, v, {
+        const int grid = ew_grid((long long)N * H * W * (C / VEC), 256);
+        if (mode == 0)
+            maxpool_bwd_kernel<T, VEC><<<grid, 256, 0, stream>>>((const T*)dy, argmax, N, H, W, C, ldx, kh, kw, sh, sw, ph,
+                                                                  pw, Ho, Wo, ldy, (T*)dx);
+        else
+            avgpool_bwd_kernel<T, VEC><<<grid, 256, 0, stream>>>((const T*)dy, N, H, W, C, ldx, kh, kw, sh, sw, ph, pw, Ho,
+                                                                  Wo, ldy, (T*)dx);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_pool_inv_fwd(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sw, int sh,
+                                  void* y, long long ldy, cudaStream_t stream) {
+    DN_REQUIRE(x && y, "pool_inv_fwd: null pointer");
+    DN_REQUIRE(sw > 0 && sh > 0, "pool_inv_fwd: bad size");
+    const bool v = vec8_ok(C, ldx, x) && vec8_ok(C, ldy, y);
+    DN_DISPATCH(dtype, v, {
+        pool_inv_fwd_kernel<T, VEC><<<ew_grid((long long)N * H * sh * W * sw * (C / VEC), 256), 256, 0, stream>>>(
+            (const T*)x, N, H, W, C, ldx, sw, sh, ldy, (T*)y);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_pool_inv_bwd(const void* dy, int dtype, int N, int H, int W, int C, long long ldx, int sw, int sh,
+                                  void* dx, long long ldy, cudaStream_t stream) {
+    DN_REQUIRE(dy && dx, "pool_inv_bwd: null pointer");
+    const bool v = vec8_ok(C, ldx, dx) && vec8_ok(C, ldy, dy);
+    DN_DISPATCH(dtype, v, {
+        pool_inv_bwd_kernel<T, VEC><<<ew_grid((long long)N * H * W * (C / VEC), 256), 256, 0, stream>>>(
+            (const T*)dy, N, H, W, C, ldx, sw, sh, ldy, (T*)dx);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,292 @@
+// Cost layers of the DeNet hot path: forward value and gradient w.r.t. the producing conv output in one pass.
+//
+// Reference semantics (paths relative to the reference repository):
+//   corner map     denet/layer/denet_corner.py:50-53 (logits [+z,-z] -> 2-way log-softmax, theano_util.py:27-29),
+//                  cost :126-131   -sum(t*logp) per image, mean over batch, / ln 2, * cost_factor
+//   detection      denet/layer/denet_detect.py:76-78 (log-softmax over classNum+1), :257 (-sum(t*logp)/ln(s0)),
+//                  :289-295 (Fast R-CNN smooth-L1 box loss), :304-313 (sums / batch, factors)
+//   classification denet/layer/regression.py:41,65-68,97-98 (log-softmax, -mean(logp[target]))
+// Costs are reduced in two stages with a fixed order (deterministic).  Gradients are written in the activation
+// dtype directly into the buffer that becomes the dY operand of the layer's 1x1 convolution.
+#include <algorithm>
+
+#include "common.cuh"
+#include "pack.cuh"
+
+namespace dn {
+
+constexpr int kLossThreads = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += sh[w];
+    __syncthreads();
+    return r;  // valid in thread 0
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int n, int ncols, float scale,
+                                    float* __restrict__ out) {
+    // out[col] = scale * sum_i partial[i*ncols + col], summed in order (double accumulator)
+    const int col = threadIdx.x;
+    if (col >= ncols) return;
+    double a = 0.0;
+    for (int i = 0; i < n; ++i) a += partial[(long long)i * ncols + col];
+    out[col] = (float)(a * scale);
+}
+
+__global__ void sum_partials2_kernel(const float* __restrict__ partial, int n, float scale0, float scale1,
+                                     float* __restrict__ out) {
+    if (threadIdx.x >= 2) return;
+    double a = 0.0;
+    for (int i = 0; i < n; ++i) a += partial[(long long)i * 2 + threadIdx.x];
+    out[threadIdx.x] = (float)(a * (threadIdx.x == 0 ? scale0 : scale1));
+}
+
+// z: conv output rows = B*H*W pixels (NHWC), corner channels [0, cn).  corner_pr: (B, 2, cn, H, W) fp32.
+template <typename T>
+__global__ void corner_logprob_kernel(const T* __restrict__ z, long long ldz, int B, int cn, int H, int W,
+                                      float* __restrict__ corner_pr) {
+    const long long HW = (long long)H * W;
+    const long long total = (long long)B * cn * HW;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long pix = idx % HW;
+        long long t = idx / HW;
+        const int c = (int)(t % cn);
+        const int b = (int)(t / cn);
+        const float v = to_f<T>(z[((long long)b * HW + pix) * ldz + c]);
+        // log_softmax([v, -v]) exactly as theano_util.log_softmax: xdev = x - max; xdev - log(sum(exp(xdev)))
+        const float m = fabsf(v);
+        const float d0 = v - m, d1 = -v - m;
+        const float lse = logf(expf(d0) + expf(d1));
+        corner_pr[(((long long)b * 2 + 0) * cn + c) * HW + pix] = d0 - lse;
+        corner_pr[(((long long)b * 2 + 1) * cn + c) * HW + pix] = d1 - lse;
+    }
+}
+
+// cost partial sums + gradient w.r.t. z.  target: (B,2,cn,H,W) fp32.  grad_scale = total factor / (B * ln 2).
+template <typename T>
+__global__ void __launch_bounds__(kLossThreads) corner_cost_kernel(const T* __restrict__ z, long long ldz, int B, int cn,
+                                                                    int H, int W, const float* __restrict__ target,
+                                                                    float grad_scale, T* __restrict__ dz,
+                                                                    float* __restrict__ partial) {
+    __shared__ float sh[kLossThreads / 32];
+    const long long HW = (long long)H * W;
+    const long long total = (long long)B * cn * HW;
+    float acc = 0.f;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long pix = idx % HW;
+        long long t = idx / HW;
+        const int c = (int)(t % cn);
+        const int b = (int)(t / cn);
+        const long long zoff = ((long long)b * HW + pix) * ldz + c;
+        const float v = to_f<T>(z[zoff]);
+        const float m = fabsf(v);
+        const float d0 = v - m, d1 = -v - m;
+        const float e0 = expf(d0), e1 = expf(d1);
+        const float lse = logf(e0 + e1);
+        const float t0 = target[(((long long)b * 2 + 0) * cn + c) * HW + pix];
+        const float t1 = target[(((long long)b * 2 + 1) * cn + c) * HW + pix];
+        acc += t0 * (d0 - lse) + t1 * (d1 - lse);
+        // d/dv [t0*lp0 + t1*lp1] with lp0 = v - lse(v,-v), lp1 = -v - lse(v,-v), dlse/dv = (e0 - e1)/(e0 + e1)
+        const float th = (e0 - e1) / (e0 + e1);
+        const float g = t0 * (1.0f - th) + t1 * (-1.0f - th);
+        dz[zoff] = from_f<T>(-g * grad_scale);
+    }
+    const float s = block_sum(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// One warp per RoI row. o: conv output rows (R, ld) with [0,s0) class logits and [s0,s0+4) box regression.
+// target_det (B,s0,sn,sn), target_valid (B,sn,sn), target_reg (B,8,sn,sn) in the reference's NCHW packing.
+// partial[blk] = {sum t*logp, sum smoothL1 term}; gradients written for channels [0, s0+4), zero for the padding.
+template <typename T>
+__global__ void __launch_bounds__(kLossThreads) detect_cost_kernel(const T* __restrict__ o, long long ld, int R, int s0,
+                                                                    int sn2, int use_bbox,
+                                                                    const float* __restrict__ target_det,
+                                                                    const float* __restrict__ target_valid,
+                                                                    const float* __restrict__ target_reg,
+                                                                    float det_grad_scale, float bbox_factor,
+                                                                    float bbox_grad_scale, T* __restrict__ dout,
+                                                                    int ncols_grad, float* __restrict__ partial) {
+    __shared__ float sh[kLossThreads / 32];
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    float acc_det = 0.f, acc_box = 0.f;
+    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < R;
+         row += (long long)gridDim.x * warps_per_block) {
+        const int b = (int)(row / sn2);
+        const int ji = (int)(row % sn2);
+        const T* orow = o + row * ld;
+        T* grow = dout + row * ld;
+        float mx = -INFINITY;
+        for (int k = lane; k < s0; k += 32) mx = fmaxf(mx, to_f<T>(orow[k]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        float se = 0.f, st = 0.f;
+        for (int k = lane; k < s0; k += 32) {
+            se += expf(to_f<T>(orow[k]) - mx);
+            st += target_det[((long long)b * s0 + k) * sn2 + ji];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, off);
+            st += __shfl_xor_sync(0xffffffffu, st, off);
+        }
+        const float lse = logf(se);
+        for (int k = lane; k < s0; k += 32) {
+            const float xd = to_f<T>(orow[k]) - mx;
+            const float lp = xd - lse;
+            const float t = target_det[((long long)b * s0 + k) * sn2 + ji];
+            acc_det += t * lp;
+            const float p = expf(lp);
+            grow[k] = from_f<T>(-(t - p * st) * det_grad_scale);
+        }
+        if (use_bbox) {
+            if (lane < 4) {
+                const float valid = target_valid[(long long)b * sn2 + ji];
+                const float tg_c = target_reg[((long long)b * 8 + (lane & 1)) * sn2 + ji];          // target centre x|y
+                const float tg_s = target_reg[((long long)b * 8 + 2 + (lane & 1)) * sn2 + ji];      // target w|h
+                const float sm_c = target_reg[((long long)b * 8 + 4 + (lane & 1)) * sn2 + ji];      // sample centre
+                const float sm_s = target_reg[((long long)b * 8 + 6 + (lane & 1)) * sn2 + ji];      // sample w|h
+                const float t = lane < 2 ? (tg_c - sm_c) / sm_s : logf(tg_s / sm_s);
+                const float d = t - to_f<T>(orow[s0 + lane]);
+                const float ad = fabsf(d);
+                const float l = ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+                acc_box += bbox_factor * valid * l;
+                const float dl = ad < 1.0f ? d : (d > 0.f ? 1.0f : -1.0f);
+                grow[s0 + lane] = from_f<T>(-bbox_factor * valid * dl * bbox_grad_scale);
+            }
+        }
+        for (int k = s0 + (use_bbox ? 4 : 0) + lane; k < ncols_grad; k += 32) grow[k] = from_f<T>(0.f);
+    }
+    const float s_det = block_sum(acc_det, sh);
+    const float s_box = block_sum(acc_box, sh);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x * 2 + 0] = s_det;
+        partial[blockIdx.x * 2 + 1] = s_box;
+    }
+}
+
+// classification head: rows (B, ld) logits over `classes`; label[b] int32.  cost = -mean(logp[label]).
+template <typename T>
+__global__ void __launch_bounds__(kLossThreads) softmax_nll_kernel(const T* __restrict__ o, long long ld, int B,
+                                                                    int classes, const int* __restrict__ label,
+                                                                    float grad_scale, T* __restrict__ dout,
+                                                                    float* __restrict__ logp_out,
+                                                                    float* __restrict__ partial) {
+    __shared__ float sh[kLossThreads / 32];
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    float acc = 0.f;
+    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < B;
+         row += (long long)gridDim.x * warps_per_block) {
+        const T* orow = o + row * ld;
+        float mx = -INFINITY;
+        for (int k = lane; k < classes; k += 32) mx = fmaxf(mx, to_f<T>(orow[k]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        float se = 0.f;
+        for (int k = lane; k < classes; k += 32) se += expf(to_f<T>(orow[k]) - mx);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) se += __shfl_xor_sync(0xffffffffu, se, off);
+        const float lse = logf(se);
+        const int lab = label[row];
+        for (int k = lane; k < classes; k += 32) {
+            const float lp = to_f<T>(orow[k]) - mx - lse;
+            if (logp_out) logp_out[row * classes + k] = lp;
+            if (k == lab) acc += lp;
+            if (dout) dout[row * ld + k] = from_f<T>((expf(lp) - (k == lab ? 1.0f : 0.0f)) * grad_scale);
+        }
+    }
+    const float s = block_sum(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+}  // namespace dn
+
+using namespace dn;
+
+static const int kLossBlocks = 148;
+
+extern "C" size_t denet_loss_workspace_bytes(void) { return sizeof(float) * 2 * kLossBlocks; }
+
+extern "C" int denet_corner_logprob(const void* z, int dtype, long long ldz, int B, int cn, int H, int W,
+                                    float* corner_pr, cudaStream_t stream) {
+    DN_REQUIRE(z && corner_pr, "corner_logprob: null pointer");
+    const long long total = (long long)B * cn * H * W;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 8);
+    if (dtype == DENET_F32)
+        corner_logprob_kernel<float><<<grid, 256, 0, stream>>>((const float*)z, ldz, B, cn, H, W, corner_pr);
+    else
+        corner_logprob_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)z, ldz, B, cn, H, W,
+                                                                        corner_pr);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_corner_cost(const void* z, int dtype, long long ldz, int B, int cn, int H, int W,
+                                 const float* target, float cost_factor, float grad_factor, void* dz, float* cost,
+                                 float* workspace, cudaStream_t stream) {
+    DN_REQUIRE(z && target && dz && cost && workspace, "corner_cost: null pointer");
+    const float inv = 1.0f / ((float)B * 0.6931471805599453f);
+    if (dtype == DENET_F32)
+        corner_cost_kernel<float><<<kLossBlocks, kLossThreads, 0, stream>>>(
+            (const float*)z, ldz, B, cn, H, W, target, cost_factor * grad_factor * inv, (float*)dz, workspace);
+    else
+        corner_cost_kernel<__nv_bfloat16><<<kLossBlocks, kLossThreads, 0, stream>>>(
+            (const __nv_bfloat16*)z, ldz, B, cn, H, W, target, cost_factor * grad_factor * inv, (__nv_bfloat16*)dz,
+            workspace);
+    sum_partials_kernel<<<1, 32, 0, stream>>>(workspace, kLossBlocks, 1, -cost_factor * inv, cost);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_detect_cost(const void* o, int dtype, long long ld, int B, int sn, int s0, int use_bbox,
+                                 const float* target_det, const float* target_valid, const float* target_reg,
+                                 float cost_factor, float bbox_factor, float grad_factor, void* dout, int ncols_grad,
+                                 float* cost2, float* workspace, cudaStream_t stream) {
+    DN_REQUIRE(o && target_det && dout && cost2 && workspace, "detect_cost: null pointer");
+    DN_REQUIRE(!use_bbox || (target_valid && target_reg), "detect_cost: bbox targets missing");
+    const int sn2 = sn * sn;
+    const int R = B * sn2;
+    const float det_scale = cost_factor / ((float)B * logf((float)s0));
+    const float box_scale = bbox_factor / (float)B;
+    if (dtype == DENET_F32)
+        detect_cost_kernel<float><<<kLossBlocks, kLossThreads, 0, stream>>>(
+            (const float*)o, ld, R, s0, sn2, use_bbox, target_det, target_valid, target_reg, det_scale * grad_factor,
+            bbox_factor, box_scale * grad_factor, (float*)dout, ncols_grad, workspace);
+    else
+        detect_cost_kernel<__nv_bfloat16><<<kLossBlocks, kLossThreads, 0, stream>>>(
+            (const __nv_bfloat16*)o, ld, R, s0, sn2, use_bbox, target_det, target_valid, target_reg,
+            det_scale * grad_factor, bbox_factor, box_scale * grad_factor, (__nv_bfloat16*)dout, ncols_grad, workspace);
+    // cost2[0] = detection cost, cost2[1] = box cost, each including its factors (reference :308-310)
+    sum_partials2_kernel<<<1, 32, 0, stream>>>(workspace, kLossBlocks, -det_scale, box_scale, cost2);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_softmax_nll(const void* o, int dtype, long long ld, int B, int classes, const int* label,
+                                 float grad_factor, void* dout, float* logp_out, float* cost, float* workspace,
+                                 cudaStream_t stream) {
+    DN_REQUIRE(o && label && cost && workspace, "softmax_nll: null pointer");
+    const int grid = std::min(kLossBlocks, ceil_div(B, kLossThreads / 32));
+    if (dtype == DENET_F32)
+        softmax_nll_kernel<float><<<grid, kLossThreads, 0, stream>>>((const float*)o, ld, B, classes, label,
+                                                                     grad_factor / (float)B, (float*)dout, logp_out,
+                                                                     workspace);
+    else
+        softmax_nll_kernel<__nv_bfloat16><<<grid, kLossThreads, 0, stream>>>(
+            (const __nv_bfloat16*)o, ld, B, classes, label, grad_factor / (float)B, (__nv_bfloat16*)dout, logp_out,
+            workspace);
+    sum_partials_kernel<<<1, 32, 0, stream>>>(workspace, grid, 1, -1.0f / (float)B, cost);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
