@@ -1,0 +1,426 @@
+// Directed sparse sampling: corner log-probability maps -> ranked RoI set, on the device.
+//
+// Replaces the reference's C++ CPython extension entry point build_samples (denet/layer/denet_sparse.cc:559-668):
+// run_build_samples :489-557 (threshold scan, optional local-max test, top-max_corners per corner type),
+// search_corners :321-374 (TL x BR and TR x BL pairing with bbox-hash dedupe), get_sample :271-308 (score) and the
+// final top sample_num^2 by score (:547-549).  SURVEY.md §8 row a10.  The reference runs one std::thread per image
+// on the host after a device->host copy of corner_pr; here the maps never leave HBM.
+//
+// Kernel 1 (corner_select_kernel, one CTA per image x corner type): ordered (row-major) stream compaction of the
+//   positions with logp > ln(threshold); if more than max_corners survive, a 4-pass radix select on the
+//   order-preserving bit pattern keeps the max_corners most probable (ties at the cut: lowest position first).
+// Kernel 2 (pair_select_kernel, one CTA per image): enumerates corner pairs warp-strided, scores them with the
+//   reference's exact fp32 sequence, and selects the sample_num^2 best with an MSB-first radix select over a unique
+//   64-bit key (score distance bits : box), then sorts the survivors in shared memory (bitonic) - fully
+//   deterministic, no hash table: a TR x BL box duplicates a TL x BR box iff its (x0,y0) is a TL corner and its
+//   (x1,y1) a BR corner, which two position bitmaps in shared memory answer.
+//
+// Ranking: the reference sorts by pr = 1/(1+exp(d)), d = |pr_f - pr_t|, descending, with an unstable sort; ranking
+// by d ascending is the same order wherever the reference's order is defined, and breaks its ties by box.
+#include "common.cuh"
+
+namespace dn {
+
+constexpr int kBsThreads = 1024;
+constexpr int kRadixBits = 11;
+constexpr int kRadixBins = 1 << kRadixBits;
+constexpr int kSortCap = 4096;  // survivors sorted in shared memory (>= sample_num^2)
+
+// block-wide exclusive scan of one int per thread (kBsThreads threads); returns the exclusive prefix, total in *total
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_sums[lane] = winc - w;  // exclusive
+        if (lane == 31) warp_sums[32] = winc;
+    }
+    __syncthreads();
+    const int r = warp_sums[warp] + inc - v;
+    *total = warp_sums[32];
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+    // ascending unsigned order == ascending float order
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// reference get_local_max (:474-487), including its exclusive upper loop bounds
+__device__ __forceinline__ float local_max_at(const float* __restrict__ map, int H, int W, int y, int x, int lm) {
+    const int x0 = max(0, x - lm), y0 = max(0, y - lm);
+    const int x1 = min(W - 1, x + lm), y1 = min(H - 1, y + lm);
+    float m = -100000.f;
+    for (int yy = y0; yy < y1; ++yy)
+        for (int xx = x0; xx < x1; ++xx) m = fmaxf(m, map[yy * W + xx]);
+    return m;
+}
+
+__device__ __forceinline__ bool is_corner(const float* __restrict__ map, int H, int W, int pos, float thr, int lm,
+                                          float* lp_out) {
+    const float lp = map[pos];
+    *lp_out = lp;
+    if (!(lp > thr)) return false;
+    if (lm > 0 && lp < local_max_at(map, H, W, pos / W, pos % W, lm)) return false;
+    return true;
+}
+
+// corners: [B][4][max_corners] packed (y << 16 | x); counts: [B][4]
+__global__ void __launch_bounds__(kBsThreads) corner_select_kernel(const float* __restrict__ corner_pr, int H, int W,
+                                                                    float thr, int max_corners, int local_max,
+                                                                    uint32_t* __restrict__ corners,
+                                                                    int* __restrict__ counts) {
+    __shared__ int warp_sums[33];
+    __shared__ int hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_need;
+    const int b = blockIdx.x >> 2, ci = blockIdx.x & 3;
+    const int HW = H * W;
+    const float* map = corner_pr + (((long long)b * 2 + 1) * 4 + ci) * HW;
+    uint32_t* out = corners + ((long long)b * 4 + ci) * max_corners;
+
+    // pass 0: count
+    int mine = 0;
+    for (int pos = threadIdx.x; pos < HW; pos += kBsThreads) {
+        float lp;
+        mine += is_corner(map, H, W, pos, thr, local_max, &lp) ? 1 : 0;
+    }
+    int total;
+    block_excl_scan(mine, warp_sums, &total);
+
+    uint32_t cut_key = 0;  // keep keys > cut_key, plus the first `need_ties` positions with key == cut_key
+    int need_ties = 0;
+    const bool select = total > max_corners;
+    if (select) {
+        // radix select (MSB first, 8 bits per pass) of the max_corners-th LARGEST key
+        if (threadIdx.x == 0) {
+            s_prefix = 0;
+            s_need = max_corners;
+        }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            for (int pos = threadIdx.x; pos < HW; pos += kBsThreads) {
+                float lp;
+                if (is_corner(map, H, W, pos, thr, local_max, &lp)) {
+                    const uint32_t k = float_order_key(lp);
+                    if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int need = s_need, bin = 255;
+                for (; bin > 0; --bin) {
+                    if (hist[bin] >= need) break;
+                    need -= hist[bin];
+                }
+                s_prefix = prefix | ((uint32_t)bin << shift);
+                s_need = need;
+            }
+            __syncthreads();
+        }
+        cut_key = s_prefix;
+        need_ties = s_need;
+    }
+
+    // ordered compaction, 1024 positions per round (row-major order == the reference's scan order)
+    int base = 0, tie_base = 0;
+    for (int p0 = 0; p0 < HW; p0 += kBsThreads) {
+        const int pos = p0 + threadIdx.x;
+        float lp = 0.f;
+        bool ok = pos < HW && is_corner(map, H, W, pos, thr, local_max, &lp);
+        bool tie = false;
+        if (ok && select) {
+            const uint32_t k = float_order_key(lp);
+            tie = (k == cut_key);
+            ok = k > cut_key;
+        }
+        int ntie;
+        const int tie_rank = block_excl_scan(tie ? 1 : 0, warp_sums, &ntie);
+        if (tie && tie_base + tie_rank < need_ties) ok = true;
+        int n;
+        const int rank = block_excl_scan(ok ? 1 : 0, warp_sums, &n);
+        if (ok) out[base + rank] = ((uint32_t)(pos / W) << 16) | (uint32_t)(pos % W);
+        base += n;
+        tie_base += ntie;
+    }
+    if (threadIdx.x == 0) counts[b * 4 + ci] = base;
+}
+
+struct PairCtx {
+    const float* cp;  // corner_pr[b] = (2,4,H,W)
+    int H, W, HW;
+    const uint32_t* c0;  // TL
+    const uint32_t* c1;  // TR
+    const uint32_t* c2;  // BL
+    const uint32_t* c3;  // BR
+    int n0, n1, n2, n3;
+    const uint32_t* bm_tl;
+    const uint32_t* bm_br;
+};
+
+// candidate idx -> unique 64-bit rank key (d bits << 32 | box); false if the pair is not a sample
+__device__ __forceinline__ bool pair_key(const PairCtx& c, long long idx, long long nA, uint64_t* key) {
+    int x0, y0, x1, y1;
+    if (idx < nA) {  // top-left x bottom-right (:337-353)
+        const uint32_t tl = c.c0[idx / c.n3], br = c.c3[idx % c.n3];
+        x0 = tl & 0xffff; y0 = tl >> 16; x1 = br & 0xffff; y1 = br >> 16;
+        if (x1 <= x0 || y1 <= y0) return false;
+    } else {  // top-right x bottom-left (:357-373); skipped when the TL x BR search already produced the box
+        const long long j = idx - nA;
+        const uint32_t tr = c.c1[j / c.n2], bl = c.c2[j % c.n2];
+        x1 = tr & 0xffff; y0 = tr >> 16; x0 = bl & 0xffff; y1 = bl >> 16;
+        if (x1 <= x0 || y1 <= y0) return false;
+        const int p00 = y0 * c.W + x0, p11 = y1 * c.W + x1;
+        if (((c.bm_tl[p00 >> 5] >> (p00 & 31)) & 1u) && ((c.bm_br[p11 >> 5] >> (p11 & 31)) & 1u)) return false;
+    }
+    // get_sample (:280-294): fp32 sums in the reference's order, starting from 0
+    const float* f = c.cp;
+    const float* t = c.cp + 4 * c.HW;
+    const int p00 = y0 * c.W + x0, p01 = y0 * c.W + x1, p10 = y1 * c.W + x0, p11 = y1 * c.W + x1;
+    float pr_f = __fadd_rn(0.f, f[p00]);
+    pr_f = __fadd_rn(pr_f, f[c.HW + p01]);
+    pr_f = __fadd_rn(pr_f, f[2 * c.HW + p10]);
+    pr_f = __fadd_rn(pr_f, f[3 * c.HW + p11]);
+    float pr_t = __fadd_rn(0.f, t[p00]);
+    pr_t = __fadd_rn(pr_t, t[c.HW + p01]);
+    pr_t = __fadd_rn(pr_t, t[2 * c.HW + p10]);
+    pr_t = __fadd_rn(pr_t, t[3 * c.HW + p11]);
+    const float d = fabsf(__fsub_rn(pr_f, pr_t));
+    const uint32_t box = ((uint32_t)x0 << 24) | ((uint32_t)y0 << 16) | ((uint32_t)x1 << 8) | (uint32_t)y1;
+    *key = ((uint64_t)__float_as_uint(d) << 32) | box;  // d >= 0 (or NaN, which sorts last like the reference's pr=NaN)
+    return true;
+}
+
+__global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __restrict__ corner_pr, int H, int W,
+                                                                  int max_corners, int K,
+                                                                  const uint32_t* __restrict__ corners,
+                                                                  const int* __restrict__ counts,
+                                                                  float* __restrict__ out_pr,
+                                                                  float* __restrict__ out_bbox,
+                                                                  int* __restrict__ out_ibox,
+                                                                  int* __restrict__ out_count,
+                                                                  int* __restrict__ out_ncand) {
+    extern __shared__ __align__(16) uint8_t bs_smem[];
+    const int b = blockIdx.x;
+    const int HW = H * W;
+    const int bm_words = (HW + 31) / 32;
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(bs_smem);                   // kSortCap
+    uint32_t* s_c = reinterpret_cast<uint32_t*>(s_keys + kSortCap);            // 4 * max_corners
+    uint32_t* s_bm_tl = s_c + 4 * max_corners;                                 // bm_words
+    uint32_t* s_bm_br = s_bm_tl + bm_words;                                    // bm_words
+    int* s_hist = reinterpret_cast<int*>(s_bm_br + bm_words);                  // kRadixBins
+    __shared__ int s_cnt;
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need, s_below, s_done;
+
+    PairCtx c;
+    c.cp = corner_pr + (long long)b * 8 * HW;
+    c.H = H; c.W = W; c.HW = HW;
+    c.n0 = counts[b * 4 + 0]; c.n1 = counts[b * 4 + 1]; c.n2 = counts[b * 4 + 2]; c.n3 = counts[b * 4 + 3];
+    c.c0 = s_c; c.c1 = s_c + max_corners; c.c2 = s_c + 2 * max_corners; c.c3 = s_c + 3 * max_corners;
+    c.bm_tl = s_bm_tl; c.bm_br = s_bm_br;
+
+    const uint32_t* gc = corners + (long long)b * 4 * max_corners;
+    for (int i = threadIdx.x; i < 4 * max_corners; i += kBsThreads) {
+        const int ci = i / max_corners, j = i % max_corners;
+        const int n = ci == 0 ? c.n0 : (ci == 1 ? c.n1 : (ci == 2 ? c.n2 : c.n3));
+        s_c[i] = j < n ? gc[i] : 0u;
+    }
+    for (int i = threadIdx.x; i < 2 * bm_words; i += kBsThreads) s_bm_tl[i] = 0u;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < c.n0; i += kBsThreads) {
+        const int p = (int)(s_c[i] >> 16) * W + (int)(s_c[i] & 0xffff);
+        atomicOr(&s_bm_tl[p >> 5], 1u << (p & 31));
+    }
+    for (int i = threadIdx.x; i < c.n3; i += kBsThreads) {
+        const uint32_t v = s_c[3 * max_corners + i];
+        const int p = (int)(v >> 16) * W + (int)(v & 0xffff);
+        atomicOr(&s_bm_br[p >> 5], 1u << (p & 31));
+    }
+    __syncthreads();
+
+    const long long nA = (long long)c.n0 * c.n3;
+    const long long nP = nA + (long long)c.n1 * c.n2;
+
+    // total number of samples (unique valid boxes)
+    {
+        int mine = 0;
+        for (long long idx = threadIdx.x; idx < nP; idx += kBsThreads) {
+            uint64_t key;
+            mine += pair_key(c, idx, nA, &key) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+        __syncthreads();
+    }
+    const int total = s_cnt;
+    __syncthreads();
+
+    // MSB-first radix select of the K-th smallest key; stop as soon as everything up to the selected bin fits in
+    // the shared-memory sort buffer.  prefix/shift describe the accepted key range: (key >> shift) <= prefix.
+    int shift = 64;
+    unsigned long long prefix = 0;
+    if (total > kSortCap) {
+        if (threadIdx.x == 0) {
+            s_prefix = 0;
+            s_need = K;
+            s_below = 0;
+            s_done = 0;
+        }
+        __syncthreads();
+        while (true) {
+            const int bits = shift > 32 ? ((shift - 32) >= kRadixBits ? kRadixBits : shift - 32)
+                                        : (shift >= kRadixBits ? kRadixBits : shift);
+            const int nshift = shift - bits;
+            for (int i = threadIdx.x; i < kRadixBins; i += kBsThreads) s_hist[i] = 0;
+            __syncthreads();
+            const unsigned long long pfx = s_prefix;
+            for (long long idx = threadIdx.x; idx < nP; idx += kBsThreads) {
+                uint64_t key;
+                if (pair_key(c, idx, nA, &key)) {
+                    if (shift == 64 || (key >> shift) == pfx) atomicAdd(&s_hist[(key >> nshift) & ((1u << bits) - 1)], 1);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int need = s_need, bin = 0;
+                const int nb = 1 << bits;
+                for (; bin < nb - 1; ++bin) {
+                    if (s_hist[bin] >= need) break;
+                    need -= s_hist[bin];
+                    s_below += s_hist[bin];
+                }
+                s_prefix = (pfx << bits) | (unsigned long long)bin;
+                s_need = need;
+                s_done = (s_below + s_hist[bin] <= kSortCap) || nshift == 0;
+            }
+            __syncthreads();
+            shift = nshift;
+            if (s_done) break;
+        }
+        prefix = s_prefix;
+    }
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+
+    // collect survivors
+    for (long long idx = threadIdx.x; idx < nP; idx += kBsThreads) {
+        uint64_t key;
+        if (pair_key(c, idx, nA, &key)) {
+            if (shift == 64 || (key >> shift) <= prefix) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot < kSortCap) s_keys[slot] = key;
+            }
+        }
+    }
+    __syncthreads();
+    const int nsurv = s_cnt < kSortCap ? s_cnt : kSortCap;
+    int npow = 1;
+    while (npow < nsurv) npow <<= 1;
+    for (int i = nsurv + threadIdx.x; i < npow; i += kBsThreads) s_keys[i] = ~0ull;
+    __syncthreads();
+    // bitonic sort ascending
+    for (int k = 2; k <= npow; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow; i += kBsThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a = s_keys[i], bb = s_keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > bb) == up) {
+                        s_keys[i] = bb;
+                        s_keys[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int nout = nsurv < K ? nsurv : K;
+    for (int i = threadIdx.x; i < K; i += kBsThreads) {
+        const long long o = (long long)b * K + i;
+        if (i < nout) {
+            const uint64_t key = s_keys[i];
+            const float d = __uint_as_float((uint32_t)(key >> 32));
+            const uint32_t box = (uint32_t)key;
+            const int x0 = box >> 24, y0 = (box >> 16) & 255, x1 = (box >> 8) & 255, y1 = box & 255;
+            // :306  float pr = 1.0 / (1.0 + std::exp(fabs(pr_f - pr_t)))  - float exp, double division, rounded to float
+            const float e = (float)exp((double)d);
+            out_pr[o] = (float)(1.0 / (1.0 + (double)e));
+            // :307  (double)x0 / width ... rounded to float by the SampleType constructor
+            out_bbox[o * 4 + 0] = (float)((double)x0 / (double)W);
+            out_bbox[o * 4 + 1] = (float)((double)y0 / (double)H);
+            out_bbox[o * 4 + 2] = (float)((double)(x1 + 1) / (double)W);
+            out_bbox[o * 4 + 3] = (float)((double)(y1 + 1) / (double)H);
+            out_ibox[o * 4 + 0] = x0; out_ibox[o * 4 + 1] = y0; out_ibox[o * 4 + 2] = x1; out_ibox[o * 4 + 3] = y1;
+        } else {
+            out_pr[o] = 0.f;
+            out_bbox[o * 4 + 0] = out_bbox[o * 4 + 1] = out_bbox[o * 4 + 2] = out_bbox[o * 4 + 3] = 0.f;
+            out_ibox[o * 4 + 0] = out_ibox[o * 4 + 1] = out_ibox[o * 4 + 2] = out_ibox[o * 4 + 3] = 0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        out_count[b] = nout;
+        if (out_ncand) out_ncand[b] = total;
+    }
+}
+
+static size_t pair_smem_bytes(int H, int W, int max_corners) {
+    const size_t bm_words = ((size_t)H * W + 31) / 32;
+    return sizeof(uint64_t) * kSortCap + sizeof(uint32_t) * 4 * max_corners + sizeof(uint32_t) * 2 * bm_words +
+           sizeof(int) * kRadixBins;
+}
+
+}  // namespace dn
+
+using namespace dn;
+
+extern "C" size_t denet_build_samples_workspace(int B, int H, int W, int max_corners) {
+    (void)H; (void)W;
+    return (size_t)B * 4 * max_corners * sizeof(uint32_t) + (size_t)B * 4 * sizeof(int);
+}
+
+extern "C" int denet_build_samples(const float* corner_pr, int B, int H, int W, float corner_threshold, int sample_num,
+                                   int max_corners, int local_max, float* out_pr, float* out_bbox, int* out_ibox,
+                                   int* out_count, int* out_ncand, void* workspace, size_t workspace_bytes,
+                                   cudaStream_t stream) {
+    DN_REQUIRE(corner_pr && out_pr && out_bbox && out_ibox && out_count && workspace, "build_samples: null pointer");
+    DN_REQUIRE(B > 0 && H > 0 && W > 0 && H <= 256 && W <= 256, "build_samples: map size must be in [1,256]");
+    DN_REQUIRE(sample_num > 0 && sample_num * sample_num <= kSortCap, "build_samples: sample_num^2 must be <= %d",
+               kSortCap);
+    DN_REQUIRE(max_corners > 0 && max_corners <= 4096, "build_samples: max_corners must be in [1,4096]");
+    DN_REQUIRE(workspace_bytes >= denet_build_samples_workspace(B, H, W, max_corners),
+               "build_samples: workspace too small");
+    uint32_t* corners = reinterpret_cast<uint32_t*>(workspace);
+    int* counts = reinterpret_cast<int*>(corners + (size_t)B * 4 * max_corners);
+    const float thr = logf(corner_threshold);  // std::log(float), denet_sparse.cc:504
+    corner_select_kernel<<<B * 4, kBsThreads, 0, stream>>>(corner_pr, H, W, thr, max_corners, local_max, corners, counts);
+    DN_CHECK_LAUNCH();
+    const size_t smem = pair_smem_bytes(H, W, max_corners);
+    DN_REQUIRE(smem <= 200 * 1024, "build_samples: shared memory budget exceeded");
+    DN_CHECK_CUDA(cudaFuncSetAttribute(pair_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pair_select_kernel<<<B, kBsThreads, smem, stream>>>(corner_pr, H, W, max_corners, sample_num * sample_num, corners,
+                                                        counts, out_pr, out_bbox, out_ibox, out_count, out_ncand);
+    DN_CHECK_LAUNCH();
+    return 0;
+}

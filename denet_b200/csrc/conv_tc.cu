@@ -35,6 +35,7 @@ struct ConvFpropParams {
     CUtensorMap tmB[2];  // weight (KtotPad, Cout) bf16
     int nterms;          // 1 or 3
     int R, S, pad_h, pad_w;
+    int stride_h, stride_w;
     int kchunks;         // ceil(Cin / 64)
     int Wo, Ho, No;      // output extent
     int TW, TH, TN;      // patch (TW*TH*TN == 128)
@@ -56,6 +57,7 @@ struct ConvWgradParams {
     CUtensorMap tmX[2];   // X  (Cin,  Wi, Hi, N) bf16
     int nterms;
     int R, S, pad_h, pad_w;
+    int stride_h, stride_w;
     int TW, TH, TN;       // k-block patch (TW*TH*TN == 64)
     int tiles_w, tiles_h, tiles_n;
     int total_kblocks;
@@ -173,7 +175,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                 mt /= p.tiles_w;
                 const int th = mt % p.tiles_h;
                 const int tn = mt / p.tiles_h;
-                const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN, co0 = ct * BN;
+                // input-space origin of the patch: the tensor map walks the image with element strides (stride_w,
+                // stride_h), so a strided convolution is the same box fetch started at (w0*stride + tap offset)
+                const int w0 = tw * p.TW * p.stride_w, h0 = th * p.TH * p.stride_h, n0 = tn * p.TN, co0 = ct * BN;
                 for (int term = 0; term < p.nterms; ++term) {
                     const int ai = (term == 1) ? 1 : 0;  // terms: (hi,hi) (lo,hi) (hi,lo)
                     const int bi = (term == 2) ? 1 : 0;
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
 #pragma unroll
                         for (int i = 0; i < BN / 64; ++i)
                             ptx::tma_load_4d(sB + i * kBoxBytes, &p.tmX[bi], &full_bar[stage], cit * BN + i * 64,
-                                             w0 + dw, h0 + dh, n0);
+                                             w0 * p.stride_w + dw, h0 * p.stride_h + dh, n0);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -591,12 +595,16 @@ static int launch_wgrad(const ConvWgradParams& p, cudaStream_t stream) {
     return 0;
 }
 
+// sw/sh: traversal (element) strides along W/H.  With a stride s the box must span TW*s input columns to deliver
+// TW elements (cuTensorMapEncodeTiled loads ceil(box/stride) elements per dimension).
 static int make_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int N, long long ld, int TW, int TH,
-                        int TN) {
+                        int TN, int sw = 1, int sh = 1) {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * W, (uint64_t)ld * 2 * W * H};
-    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
-    return encode_tmap_bf16(tm, base, 4, dims, strides, box, nullptr);
+    uint32_t box[4] = {64, (uint32_t)(TW * sw), (uint32_t)(TH * sh), (uint32_t)TN};
+    uint32_t estr[4] = {1, (uint32_t)sw, (uint32_t)sh, 1};
+    if (box[1] > 256 || box[2] > 256) return set_error(DENET_ERR_ARG, "conv: strided patch exceeds the TMA box limit");
+    return encode_tmap_bf16(tm, base, 4, dims, strides, box, estr);
 }
 
 }  // namespace dn
@@ -629,7 +637,8 @@ extern "C" int denet_split_bf16(const float* x, void* hi, void* lo, long long n,
 
 extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin, long long ldx,
                                   const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w,
-                                  void* y, int y_dtype, long long ldy, int Ho, int Wo, const float* bias,
+                                  int stride_h, int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo,
+                                  const float* bias,
                                   const void* residual, int relu, float* stat_sum, float* stat_sqsum,
                                   cudaStream_t stream) {
     DN_REQUIRE(x_hi && b_hi && y, "conv2d_fprop: null pointer");
@@ -638,11 +647,13 @@ extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int
     DN_REQUIRE(y_dtype == DENET_F32 || y_dtype == DENET_BF16, "conv2d_fprop: bad y_dtype %d", y_dtype);
     DN_REQUIRE(N > 0 && Hi > 0 && Wi > 0 && Cin > 0 && Cout > 0 && Ho > 0 && Wo > 0, "conv2d_fprop: empty tensor");
     DN_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "conv2d_fprop: stat pointers must come in pairs");
+    DN_REQUIRE(stride_h >= 1 && stride_h <= 8 && stride_w >= 1 && stride_w <= 8, "conv2d_fprop: stride must be in [1,8]");
 
     ConvFpropParams p;
     memset(&p, 0, sizeof(p));
     p.nterms = x_lo ? 3 : 1;
     p.R = R; p.S = S; p.pad_h = pad_h; p.pad_w = pad_w;
+    p.stride_h = stride_h; p.stride_w = stride_w;
     p.kchunks = ceil_div(Cin, 64);
     p.Wo = Wo; p.Ho = Ho; p.No = N;
     pick_patch(Wo, Ho, N, 128, p.TW, p.TH, p.TN);
@@ -663,8 +674,9 @@ extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int
     p.stat_sqsum = stat_sqsum;
 
     int rc;
-    if ((rc = make_act_map(&p.tmA[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN))) return rc;
-    if (x_lo && (rc = make_act_map(&p.tmA[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN))) return rc;
+    if ((rc = make_act_map(&p.tmA[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h))) return rc;
+    if (x_lo && (rc = make_act_map(&p.tmA[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h)))
+        return rc;
     {
         const uint64_t ktot = (uint64_t)R * S * p.kchunks * 64;
         uint64_t dims[2] = {ktot, (uint64_t)Cout};
@@ -695,15 +707,17 @@ extern "C" size_t denet_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cout, 
 
 extern "C" int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int Wo, int Cout, long long lddy,
                                   const void* x_hi, const void* x_lo, int Hi, int Wi, int Cin, long long ldx, int R,
-                                  int S, int pad_h, int pad_w, float* dw, int accumulate, float* workspace,
-                                  size_t workspace_bytes, cudaStream_t stream) {
+                                  int S, int pad_h, int pad_w, int stride_h, int stride_w, float* dw, int accumulate,
+                                  float* workspace, size_t workspace_bytes, cudaStream_t stream) {
     DN_REQUIRE(dy_hi && x_hi && dw && workspace, "conv2d_wgrad: null pointer");
     DN_REQUIRE((dy_lo == nullptr) == (x_lo == nullptr), "conv2d_wgrad: dy_lo and x_lo must both be given or both null");
     DN_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0, "conv2d_wgrad: pixel pitches must be multiples of 8 elements");
     ConvWgradParams p;
     memset(&p, 0, sizeof(p));
+    DN_REQUIRE(stride_h >= 1 && stride_h <= 8 && stride_w >= 1 && stride_w <= 8, "conv2d_wgrad: stride must be in [1,8]");
     p.nterms = dy_lo ? 3 : 1;
     p.R = R; p.S = S; p.pad_h = pad_h; p.pad_w = pad_w;
+    p.stride_h = stride_h; p.stride_w = stride_w;
     pick_patch(Wo, Ho, N, 64, p.TW, p.TH, p.TN);
     p.tiles_w = ceil_div(Wo, p.TW);
     p.tiles_h = ceil_div(Ho, p.TH);
@@ -727,8 +741,9 @@ extern "C" int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, i
     int rc;
     if ((rc = make_act_map(&p.tmDY[0], dy_hi, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
     if (dy_lo && (rc = make_act_map(&p.tmDY[1], dy_lo, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
-    if ((rc = make_act_map(&p.tmX[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN))) return rc;
-    if (x_lo && (rc = make_act_map(&p.tmX[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN))) return rc;
+    if ((rc = make_act_map(&p.tmX[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h))) return rc;
+    if (x_lo && (rc = make_act_map(&p.tmX[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h)))
+        return rc;
 
     switch (BN) {
         case 64: rc = launch_wgrad<64, 8>(p, stream); break;

@@ -578,6 +578,116 @@ __global__ void pool_inv_bwd_kernel(const T* __restrict__ dy, int N, int H, int 
     }
 }
 
+// zero-insertion upsampling used by the strided dgrad: out[n, h*sh, w*sw, :] = x[n, h, w, :], zero elsewhere.
+// One thread per OUTPUT pack so every byte of `out` is written exactly once (no separate memset pass).
+template <typename T, int VEC>
+__global__ void dilate_kernel(const T* __restrict__ x, int N, int H, int W, int C, long long ldx, int sh, int sw, int Hd,
+                              int Wd, long long ldy, T* __restrict__ y) {
+    const int CV = C / VEC;
+    const long long total = (long long)N * Hd * Wd * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int wd = (int)(t % Wd);
+        t /= Wd;
+        const int hd = (int)(t % Hd);
+        const int n = (int)(t / Hd);
+        Pack<T, VEC> p;
+        const int h = hd / sh, w = wd / sw;
+        if (hd % sh == 0 && wd % sw == 0 && h < H && w < W) {
+            p.load(x + (((long long)n * H + h) * W + w) * ldx + (long long)cv * VEC);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) p.v[i] = 0.f;
+        }
+        p.store(y + (((long long)n * Hd + hd) * Wd + wd) * ldy + (long long)cv * VEC);
+    }
+}
+
+// batch statistics from the per-channel sum / sum-of-squares accumulated by the conv epilogue (throughput mode)
+__global__ void bn_finalize_sums_kernel(const float* __restrict__ sum, const float* __restrict__ sqsum, long long M,
+                                        int C, float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                        float* __restrict__ run_mean, float* __restrict__ run_stdinv, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = (double)sum[c] / (double)M;
+    double var = (double)sqsum[c] / (double)M - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mf = (float)m;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    mean[c] = mf;
+    invstd[c] = is;
+    if (run_mean) run_mean[c] = momentum * run_mean[c] + (1.0f - momentum) * mf;
+    if (run_stdinv) run_stdinv[c] = momentum * run_stdinv[c] + (1.0f - momentum) * is;
+}
+
+// dtype conversion of a pitched NHWC tensor (fp32 <-> bf16), e.g. fp32 master gradient -> bf16 dY operand
+template <typename TI, typename TO, int VEC>
+__global__ void convert_kernel(const TI* __restrict__ x, long long M, int C, long long ldx, long long ldy,
+                               TO* __restrict__ y) {
+    const int CV = C / VEC;
+    const long long total = M * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / CV;
+        const int cv = (int)(idx % CV);
+        Pack<TI, VEC> p;
+        p.load(x + r * ldx + (long long)cv * VEC);
+        Pack<TO, VEC> q;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) q.v[i] = p.v[i];
+        q.store(y + r * ldy + (long long)cv * VEC);
+    }
+}
+
+// per-channel sum over rows (bias gradient of a convolution: sum over pixels of dy), two-stage, fixed order
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBnThreads) colsum_partial_kernel(const T* __restrict__ x, long long M, int C,
+                                                                      long long ld, int rows_per_block,
+                                                                      float* __restrict__ partial) {
+    const int CV = C / VEC;
+    const int cvt = CV < kBnThreads ? CV : kBnThreads;
+    const int rlanes = kBnThreads / cvt;
+    const int cv = blockIdx.y * cvt + threadIdx.x % cvt;
+    const int rl = threadIdx.x / cvt;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    __shared__ float red[kBnThreads * (VEC == 8 ? 8 : 1)];
+    float s[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = 0.f;
+    const bool active = (cv < CV) && (rl < rlanes);
+    if (active) {
+        for (long long r = r0 + rl; r < r1; r += rlanes) {
+            Pack<T, VEC> p;
+            p.load(x + r * ld + (long long)cv * VEC);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) s[i] += p.v[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) red[threadIdx.x * VEC + i] = s[i];
+    __syncthreads();
+    if (active && rl == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float a = 0.f;
+            for (int l = 0; l < rlanes; ++l) a += red[(l * cvt + threadIdx.x) * VEC + i];
+            partial[(long long)blockIdx.x * C + cv * VEC + i] = a;
+        }
+    }
+}
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nslabs, int C, float* __restrict__ out,
+                                       int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double a = 0.0;
+    for (int s = 0; s < nslabs; ++s) a += partial[(long long)s * C + c];
+    out[c] = accumulate ? out[c] + (float)a : (float)a;
+}
+
 static int bn_slabs(long long M, int C, int vec, int* rows_per_block, int* ychunks) {
     const int CV = C / vec;
     const int cvt = CV < kBnThreads ? CV : kBnThreads;
@@ -786,6 +896,65 @@ extern "C" int denet_pool_inv_bwd(const void* dy, int dtype, int N, int H, int W
         pool_inv_bwd_kernel<T, VEC><<<ew_grid((long long)N * H * W * (C / VEC), 256), 256, 0, stream>>>(
             (const T*)dy, N, H, W, C, ldx, sw, sh, ldy, (T*)dx);
     });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_dilate(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sh, int sw, void* y,
+                            int Hd, int Wd, long long ldy, cudaStream_t stream) {
+    DN_REQUIRE(x && y, "dilate: null pointer");
+    DN_REQUIRE(sh >= 1 && sw >= 1, "dilate: bad stride");
+    const bool v = vec8_ok(C, ldx, x) && vec8_ok(C, ldy, y);
+    DN_DISPATCH(dtype, v, {
+        dilate_kernel<T, VEC><<<ew_grid((long long)N * Hd * Wd * (C / VEC), 256), 256, 0, stream>>>(
+            (const T*)x, N, H, W, C, ldx, sh, sw, Hd, Wd, ldy, (T*)y);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_bn_finalize_sums(const float* sum, const float* sqsum, long long M, int C, float eps, float* mean,
+                                      float* invstd, float* run_mean, float* run_stdinv, float momentum,
+                                      cudaStream_t stream) {
+    DN_REQUIRE(sum && sqsum && mean && invstd, "bn_finalize_sums: null pointer");
+    bn_finalize_sums_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(sum, sqsum, M, C, eps, mean, invstd, run_mean,
+                                                                  run_stdinv, momentum);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_convert(const void* x, int src_dtype, long long M, int C, long long ldx, void* y, int dst_dtype,
+                             long long ldy, cudaStream_t stream) {
+    DN_REQUIRE(x && y, "convert: null pointer");
+    if (M == 0) return 0;
+    const bool v = vec8_ok(C, ldx, x) && vec8_ok(C, ldy, y);
+    const int grid = ew_grid(M * (C / (v ? 8 : 1)), 256);
+#define DN_CONVERT(TI, TO)                                                                                     \
+    do {                                                                                                       \
+        if (v) convert_kernel<TI, TO, 8><<<grid, 256, 0, stream>>>((const TI*)x, M, C, ldx, ldy, (TO*)y);      \
+        else convert_kernel<TI, TO, 1><<<grid, 256, 0, stream>>>((const TI*)x, M, C, ldx, ldy, (TO*)y);        \
+    } while (0)
+    if (src_dtype == DENET_F32 && dst_dtype == DENET_BF16) DN_CONVERT(float, __nv_bfloat16);
+    else if (src_dtype == DENET_BF16 && dst_dtype == DENET_F32) DN_CONVERT(__nv_bfloat16, float);
+    else if (src_dtype == DENET_F32 && dst_dtype == DENET_F32) DN_CONVERT(float, float);
+    else DN_CONVERT(__nv_bfloat16, __nv_bfloat16);
+#undef DN_CONVERT
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_colsum(const void* x, int dtype, long long M, int C, long long ld, float* out, int accumulate,
+                            float* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    DN_REQUIRE(x && out && workspace, "colsum: null pointer");
+    DN_REQUIRE(M > 0 && C > 0, "colsum: empty tensor");
+    DN_REQUIRE(workspace_bytes >= denet_bn_workspace_bytes(M, C), "colsum: workspace too small");
+    const bool v = vec8_ok(C, ld, x);
+    int rpb, yc;
+    const int nslabs = bn_slabs(M, C, v ? 8 : 1, &rpb, &yc);
+    DN_DISPATCH(dtype, v, {
+        colsum_partial_kernel<T, VEC><<<dim3(nslabs, yc), kBnThreads, 0, stream>>>((const T*)x, M, C, ld, rpb, workspace);
+    });
+    colsum_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(workspace, nslabs, C, out, accumulate);
     DN_CHECK_LAUNCH();
     return 0;
 }

@@ -72,6 +72,33 @@ struct Pack<__nv_bfloat16, 8> {
     }
 };
 
+template <>
+struct Pack<float, 4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+template <>
+struct Pack<__nv_bfloat16, 4> {
+    float v[4];
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+        v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    }
+    __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+};
+
 // dispatch on dtype code and on whether 8-wide vector access is legal (C % 8 == 0, pitch % 8 == 0, 16B base)
 #define DN_DISPATCH(dtype, vec_ok, ...)                                    \
     do {                                                                   \

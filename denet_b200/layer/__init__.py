@@ -1,0 +1,240 @@
+"""Layer plugin API of the reference (denet/layer/__init__.py:64-143), re-hosted on PyTorch nn.Modules.
+
+What stays identical for callers (ModelCNN / bin/model-train): the `layer_types` registry, per-class static
+`parse_desc(layers, name, tags, params) -> bool`, `type_name`, `layer_index`, `layers` (sub-layers), `has_split`,
+`input_shape` / `output_shape` as (B, C, H, W) tuples, `weights() / biases() / params() / updates(cost)`,
+`cost(yt_index, yt_value)`, `get_target(model, data_x, metas)`, `export_json() / import_json()`.
+
+What changes underneath: the reference extends a symbolic Theano graph in every constructor and lets Theano
+differentiate it; here every layer is an nn.Module with an explicit `forward(x)` and `backward(dy)` that enqueue
+hand-written sm_100a kernels (denet_b200.ops -> C-ABI) on the current CUDA stream.  Activations travel as NHWC device
+tensors (bf16 in throughput mode, fp32 in parity mode); `output` holds the tensor of the last forward pass instead of
+a symbolic variable.  There is no autograd graph and no CPU fallback.
+"""
+import numpy
+import torch
+from torch import nn
+
+# ---------------------------------------------------------------------------------------------------------------
+# global switches (the reference keeps train flag / epoch / iteration as module-level Theano symbols,
+# denet/layer/__init__.py:5-28)
+_state = {"train": False, "epoch": 0, "iteration": 0, "precision": "bf16", "device": "cuda", "param_version": 0,
+          "fuse_bn_stats": True}
+
+
+def get_train():
+    return _state["train"]
+
+
+def set_train(v):
+    _state["train"] = bool(v)
+
+
+def get_epoch():
+    return _state["epoch"]
+
+
+def set_epoch(v):
+    _state["epoch"] = int(v)
+
+
+def get_iteration():
+    return _state["iteration"]
+
+
+def set_iteration(v):
+    _state["iteration"] = int(v)
+
+
+def get_precision():
+    """'bf16' (throughput: bf16 activations, bf16 x bf16 -> fp32 MMA) or 'fp32' (parity: fp32 activations,
+    error-compensated bf16x3 MMA)"""
+    return _state["precision"]
+
+
+def set_precision(p):
+    assert p in ("bf16", "fp32"), p
+    _state["precision"] = p
+
+
+def act_dtype():
+    return torch.bfloat16 if _state["precision"] == "bf16" else torch.float32
+
+
+def get_device():
+    return _state["device"]
+
+
+def set_device(d):
+    _state["device"] = d
+
+
+def param_version():
+    return _state["param_version"]
+
+
+def bump_param_version():
+    """parameters changed (solver step / import_json): cached GEMM operands of the conv layers are stale"""
+    _state["param_version"] += 1
+
+
+def fuse_bn_stats():
+    return _state["fuse_bn_stats"] and _state["precision"] == "bf16"
+
+
+def set_fuse_bn_stats(v):
+    _state["fuse_bn_stats"] = bool(v)
+
+
+def set_rng_seed(v):
+    torch.manual_seed(v)
+
+
+def import_json(json_layers, x, x_shape, layer_range=None):
+    """rebuild a layer list from exported JSON (reference denet/layer/__init__.py:31-60)"""
+    if layer_range is None:
+        layer_start, layer_end = 0, len(json_layers)
+    elif type(layer_range) is tuple:
+        layer_start, layer_end = layer_range[0], min(len(json_layers), layer_range[1])
+    elif type(layer_range) is int:
+        layer_start, layer_end = 0, min(len(json_layers), layer_range)
+    else:
+        raise Exception("Unknown layer range format:", layer_range)
+
+    from .layer_types import layer_types
+    layers = [InitialLayer(x, x_shape)]
+    for layer_json in json_layers[layer_start:layer_end]:
+        layer = None
+        for layer_type in layer_types:
+            if layer_json["type"] == layer_type.type_name:
+                layer = layer_type(layers, json_param=layer_json)
+                break
+        assert layer is not None, "ERROR Unknown layer type: " + layer_json["type"]
+        layer.import_json(layer_json)
+        layers.append(layer)
+    return layers
+
+
+def new_param(array):
+    """fp32 master parameter in the reference's layout; gradients are managed by the layers, not autograd"""
+    t = torch.as_tensor(numpy.ascontiguousarray(numpy.asarray(array, dtype=numpy.float32)))
+    return nn.Parameter(t.clone(), requires_grad=False)
+
+
+def set_param(p, array):
+    with torch.no_grad():
+        p.copy_(torch.as_tensor(numpy.asarray(array, dtype=numpy.float32)).reshape(p.shape))
+    bump_param_version()
+
+
+def get_param(p):
+    return p.detach().cpu().numpy()
+
+
+class AbstractLayer(nn.Module):
+    """reference AbstractLayer (denet/layer/__init__.py:64-143) + explicit forward / backward"""
+    type_name = "abstract"
+    has_cost = False
+
+    def __init__(self, layer_index, has_split=False):
+        super().__init__()
+        self.output = self.input = None
+        self.output_shape = self.input_shape = None
+        self.has_split = has_split
+        self.layers = nn.ModuleList()
+        self.layer_index = layer_index
+
+    def __str__(self):
+        groups = {"int": [], "str": [], "float": [], "bool": [], "tuple": []}
+        for k, v in self.__dict__.items():
+            if k in ("has_split", "layer_index", "output_shape", "training") or k.startswith("_"):
+                continue
+            if type(v) is int:
+                groups["int"].append(k + ": %i" % v)
+            elif type(v) is str:
+                groups["str"].append(k + ": " + v)
+            elif type(v) is float:
+                groups["float"].append(k + ": %.3f" % v)
+            elif type(v) is bool:
+                groups["bool"].append(k + ": %s" % v)
+            elif type(v) is tuple:
+                groups["tuple"].append(k + ": " + str(v))
+        text = ""
+        for name in ("tuple", "str", "int", "float", "bool"):
+            if groups[name]:
+                text += " " + " ".join(sorted(groups[name]))
+        return "%i:" % self.layer_index + self.type_name + " - " + text
+
+    __repr__ = __str__
+
+    # ---- parameter bookkeeping (same meaning as the reference)
+    def weights(self):
+        return sum([x.weights() for x in self.layers], [])
+
+    def biases(self):
+        return sum([x.biases() for x in self.layers], [])
+
+    def params(self):
+        return self.weights() + self.biases()
+
+    def updates(self, cost=None):
+        """[(state tensor, description)] updated as a side effect of a training forward pass (BN running stats)"""
+        return sum([x.updates(cost) for x in self.layers], [])
+
+    def split_forward(self):
+        return []
+
+    def split_backward(self, cost, known_grads):
+        return []
+
+    def split_known_grads(self):
+        return {}
+
+    # ---- costs / targets
+    def cost(self, yt_index, yt_value):
+        return None
+
+    def get_target(self, model, samples, metas):
+        return None
+
+    def set_target(self, yt_index, yt_value):
+        pass
+
+    # ---- execution
+    def forward(self, x):
+        self.output = x
+        return x
+
+    def backward(self, dy):
+        return dy
+
+    # ---- load / save
+    def export_json(self):
+        return {"type": type(self).type_name, "layers": [layer.export_json() for layer in self.layers]}
+
+    def import_json(self, json_param):
+        if "layers" in json_param:
+            for i, json_layer in enumerate(json_param["layers"]):
+                self.layers[i].import_json(json_layer)
+
+
+class InitialLayer(AbstractLayer):
+    type_name = "initial"
+
+    def __init__(self, x, x_shape, json_param={}):
+        super().__init__(layer_index=0)
+        self.output = self.input = x
+        self.output_shape = self.input_shape = tuple(x_shape)
+
+
+class IdentityLayer(AbstractLayer):
+    type_name = "identity"
+
+    def __init__(self, layers, json_param={}):
+        super().__init__(layer_index=len(layers))
+        self.output = self.input = layers[-1].output
+        self.output_shape = self.input_shape = layers[-1].output_shape
+
+    @staticmethod
+    def parse_desc(layers, name, tags, params):
+        return False

@@ -1,0 +1,226 @@
+"""Convolution layer: same constructor / parse_desc / JSON contract as the reference ConvLayer
+(denet/layer/convolution.py:10-136); fprop / dgrad / wgrad run as tcgen05 implicit GEMMs (csrc/conv_tc.cu).
+
+Theano's conv2d flips the filter (true convolution, convolution.py:83).  The fp32 master weight `omega` keeps the
+reference layout (Cout, Cin, R, S) of that true convolution, so checkpoints are interchangeable; the flip is folded
+into the bf16 GEMM operands that denet_conv_weight_prep derives from it after every solver step.
+"""
+import math
+
+import numpy
+import torch
+
+from .. import ops
+from . import (AbstractLayer, act_dtype, get_param, get_precision, new_param, param_version, set_param)
+
+
+def conv_output_hw(in_hw, size, stride, border_mode):
+    """output extent exactly as convolution.py:55-74 computes it, plus the zero padding that implements the border"""
+    out, pad = [], []
+    for i in range(2):
+        n, k, s = in_hw[i], size[i], stride[i]
+        if border_mode == "valid":
+            p, o = 0, math.ceil((n - k + 1) / s)
+        elif border_mode == "full":
+            p, o = k - 1, math.ceil((n + k - 1) / s)
+        elif border_mode == "half":
+            p = k // 2
+            o = math.ceil((n + 2 * p - k + 1) / s)
+        elif border_mode == "same":
+            assert tuple(stride) == (1, 1)
+            # full convolution cropped at (k-1)//2  ==  correlation with leading pad (k-1) - (k-1)//2
+            p, o = (k - 1) - (k - 1) // 2, n
+        elif isinstance(border_mode, (int, bool)):
+            p = int(border_mode)
+            o = math.ceil((n + 2 * p - k + 1) / s)
+        elif isinstance(border_mode, (tuple, list)):
+            p = int(border_mode[i])
+            o = math.ceil((n + 2 * p - k + 1) / s)
+        else:
+            raise Exception("Unknown border mode: " + str(border_mode))
+        out.append(int(o))
+        pad.append(p)
+    return tuple(out), tuple(pad)
+
+
+class ConvLayer(AbstractLayer):
+    type_name = "conv"
+    IM2COL_MAX_CIN = 16   # below this the 64-channel K chunks of the TMA path would be mostly zero padding
+
+    def __init__(self, layers, filter_shape=None, filter_stride=(1, 1), use_bias=False, border_mode="half",
+                 wb="he-backward", json_param={}):
+        super().__init__(layer_index=len(layers))
+        self.input = layers[-1].output
+        self.input_shape = tuple(layers[-1].output_shape)
+        self.is_first = getattr(layers[-1], "is_model_input", False)   # no data gradient needed for the images
+
+        self.border_mode = json_param.get("border", border_mode)
+        if isinstance(self.border_mode, list):
+            self.border_mode = tuple(self.border_mode)
+        self.filter_shape = tuple(int(v) for v in json_param.get("shape", filter_shape))
+        self.stride = tuple(int(v) for v in json_param.get("stride", filter_stride))
+        self.use_bias = bool(json_param.get("useBias", use_bias))
+        self.size = (self.filter_shape[2], self.filter_shape[3])
+        self.enabled = json_param.get("enabled", True)
+
+        # weight initialisation, same numpy.random call sequence as convolution.py:28-46
+        fs = self.filter_shape
+        if type(wb) is float or type(wb) is int:
+            self.w_bound = float(wb)
+        elif "he-forward" in wb:
+            self.w_bound = math.sqrt(2.0 / (fs[2] * fs[3] * fs[1]))
+        elif "he-backward" in wb:
+            self.w_bound = math.sqrt(2.0 / (fs[2] * fs[3] * fs[0]))
+        elif "xavier-forward" in wb:
+            self.w_bound = math.sqrt(1.0 / (fs[2] * fs[3] * fs[1]))
+        elif "xavier-backward" in wb:
+            self.w_bound = math.sqrt(1.0 / (fs[2] * fs[3] * fs[0]))
+        else:
+            raise Exception("Unknown weight initialisation: " + str(wb))
+        if self.w_bound > 0:
+            if type(wb) is str and "uniform" in wb:
+                w = numpy.random.uniform(-self.w_bound, self.w_bound, size=fs)
+            else:
+                w = numpy.random.normal(0.0, self.w_bound, size=fs)
+        else:
+            w = numpy.zeros(shape=fs)
+        self.omega = new_param(w)
+        if self.use_bias:
+            self.beta = new_param(numpy.zeros((fs[0],)))
+
+        (oh, ow), self.pad = conv_output_hw(self.input_shape[2:], self.size, self.stride, self.border_mode)
+        self.output_shape = (self.input_shape[0], fs[0], oh, ow)
+        self.output = None
+        self.out_fp32 = False          # logits layers (DNC / DND / R) keep an fp32 output in bf16 mode
+        self.stat_consumer = None      # BatchNorm layer fed by this conv's epilogue statistics (set by link pass)
+        self._wver = -1
+        self._wop_f = self._wop_d = self._w2 = None
+
+    @staticmethod
+    def parse_desc(layers, name, tags, params):
+        if name != "C":
+            return False
+        use_bias = bool("B" in tags)
+        cin = layers[-1].output_shape[1]
+        if bool("X" in tags):
+            filter_shape = (params.get(0), cin, params.get(1), params.get(2))
+            filter_stride = (params.get(3, 1), params.get(4, 1))
+        else:
+            filter_shape = (params.get(0), cin, params.get(1, 1), params.get(1, 1))
+            filter_stride = (params.get(2, 1), params.get(2, 1))
+        layers.append(ConvLayer(layers, filter_shape, filter_stride, use_bias, params["borderMode"], params["wb"]))
+        return True
+
+    def weights(self):
+        return super().weights() + ([self.omega] if self.enabled else [])
+
+    def biases(self):
+        return super().biases() + ([self.beta] if self.use_bias and self.enabled else [])
+
+    def import_json(self, json_param):
+        super().import_json(json_param)
+        if self.use_bias:
+            set_param(self.beta, json_param["bias"])
+        set_param(self.omega, json_param["weight"])
+
+    def export_json(self):
+        json = super().export_json()
+        json.update({"shape": self.filter_shape, "stride": self.stride, "border": self.border_mode,
+                     "enabled": self.enabled, "useBias": self.use_bias,
+                     "bias": get_param(self.beta) if self.use_bias else None, "weight": get_param(self.omega)})
+        return json
+
+    # ---------------------------------------------------------------------------------------------- execution
+    @property
+    def use_im2col(self):
+        return self.filter_shape[1] <= self.IM2COL_MAX_CIN and self.size != (1, 1)
+
+    def _operands(self):
+        """bf16 GEMM operands derived from omega; refreshed when the parameters changed"""
+        if self._wver != param_version():
+            split = get_precision() == "fp32"
+            if self._wop_f is not None and (self._wop_f.lo is not None) != split:
+                self._wop_f = self._wop_d = None
+            w = self.omega
+            if self.use_im2col:
+                self._w2 = ops.weight_to_im2col(w, self._w2)
+                w = self._w2
+            self._wop_f = ops.conv_weight_prep(w, 0, split, self._wop_f)
+            if not self.is_first:
+                self._wop_d = ops.conv_weight_prep(w, 1, split, self._wop_d)
+            self._wver = param_version()
+        return self._wop_f, self._wop_d
+
+    def _as_operand(self, t):
+        """activation / gradient tensor -> MMA operand of the current precision mode"""
+        if get_precision() == "bf16" and t.dtype == torch.float32:
+            t = ops.convert(t, torch.bfloat16)
+        return ops.act_operand(t)
+
+    def forward(self, x, residual=None, relu=False):
+        self.input = x
+        if not self.enabled:
+            self.output = x
+            return x
+        wop_f, _ = self._operands()
+        n, ci, h, w = self.input_shape
+        _, co, oh, ow = self.output_shape
+        out_dtype = torch.float32 if self.out_fp32 else act_dtype()
+        stats = None
+        if self.stat_consumer is not None and self.stat_consumer.wants_fused_stats():
+            stats = self.stat_consumer.fused_stat_buffers()
+        bias = self.beta if self.use_bias else None
+        if self.use_im2col:
+            col = ops.im2col(x, self.size[0], self.size[1], self.stride, self.pad, (oh, ow))
+            self._xop = self._as_operand(col)
+            y = ops.conv2d_fprop(self._xop, wop_f, (0, 0), (oh, ow), out_dtype, bias=bias, residual=residual,
+                                 relu=relu, stats=stats)
+        else:
+            self._xop = self._as_operand(x)
+            y = ops.conv2d_fprop(self._xop, wop_f, self.pad, (oh, ow), out_dtype, stride=self.stride, bias=bias,
+                                 residual=residual, relu=relu, stats=stats)
+        self.output = y
+        return y
+
+    def backward(self, dy, add_to=None):
+        """dy: gradient wrt the conv output (before any fused residual / relu).  Writes omega.grad (and beta.grad),
+        returns the gradient wrt the input (+ add_to, fused into the dgrad epilogue where possible)."""
+        if not self.enabled:
+            return dy if add_to is None else ops.add(dy, add_to)
+        _, wop_d = self._operands()
+        n, ci, h, w = self.input_shape
+        R, S = self.size
+        dyop = self._as_operand(dy)
+        if self.use_bias and self.beta.grad is not None:
+            ops.colsum(dy, self.beta.grad)
+        gdt = act_dtype()
+        dx = None
+        if self.use_im2col:
+            dw2 = ops.conv2d_wgrad(dyop, self._xop, 1, 1, (0, 0))
+            ops.weight_grad_from_im2col(dw2, self.omega.grad)
+            if not self.is_first:
+                dcol = ops.conv2d_fprop(dyop, wop_d, (0, 0), dy.shape[1:3], gdt)
+                dx = ops.col2im(dcol, (n, h, w, ci), R, S, self.stride, self.pad)
+                if add_to is not None:
+                    dx = ops.add(dx, add_to, out=dx)
+        else:
+            ops.conv2d_wgrad(dyop, self._xop, R, S, self.pad, self.stride, dw=self.omega.grad)
+            if not self.is_first:
+                if self.stride == (1, 1):
+                    dx = ops.conv2d_fprop(dyop, wop_d, (R - 1 - self.pad[0], S - 1 - self.pad[1]), (h, w), gdt,
+                                          residual=add_to)
+                elif (R, S) == (1, 1) and self.pad == (0, 0):
+                    # a 1x1 convolution commutes with the zero insertion: GEMM at the small resolution, then scatter
+                    dxc = ops.conv2d_fprop(dyop, wop_d, (0, 0), dy.shape[1:3], gdt)
+                    dx = ops.dilate(dxc, self.stride, (h, w))
+                    if add_to is not None:
+                        dx = ops.add(dx, add_to, out=dx)
+                else:
+                    oh, ow = dy.shape[1:3]
+                    hd, wd = (oh - 1) * self.stride[0] + 1, (ow - 1) * self.stride[1] + 1
+                    dyd = ops.ActOperand(ops.dilate(dyop.hi, self.stride, (hd, wd)),
+                                         None if dyop.lo is None else ops.dilate(dyop.lo, self.stride, (hd, wd)))
+                    dx = ops.conv2d_fprop(dyd, wop_d, (R - 1 - self.pad[0], S - 1 - self.pad[1]), (h, w), gdt,
+                                          residual=add_to)
+        self._xop = None
+        return dx

@@ -1,0 +1,181 @@
+"""DeNet detect layer 'DND[overlap_thr,cost_factor,bbox_factor,fitness_factor]'
+(reference denet/layer/denet_detect.py:24-313; training path only).
+
+A zero-initialised 1x1 convolution with bias classifies every RoI into classNum+1 classes (+4 box regression
+outputs when bbox_factor > 0).  get_target assigns classes / box targets by IoU against the ground truth
+(:147-235); the cost is -sum(t*logp)/ln(s0) per RoI summed / batch * cost_factor, plus the Fast R-CNN smooth-L1 box
+loss (:238-313, bbox_factor applied in :295 and again in :310).  Joint / independent fitness, bounded IoU and the
+predict-time get_detections + NMS are outside the hot path.
+"""
+import numpy
+import torch
+
+from .. import common, ops
+from . import AbstractLayer, InitialLayer, get_train
+from .convolution import ConvLayer
+
+
+def overlap_iou_matrix(obj_bboxs, sample_bboxs):
+    """IoU matrix in float32 with the operation order of the reference's compiled Theano function
+    (common/theano_util.py:38-59)"""
+    x = numpy.asarray(obj_bboxs, dtype=numpy.float32)
+    y = numpy.asarray(sample_bboxs, dtype=numpy.float32)
+    x_area = (x[:, 2] - x[:, 0]) * (x[:, 3] - x[:, 1])
+    y_area = (y[:, 2] - y[:, 0]) * (y[:, 3] - y[:, 1])
+    dx = numpy.maximum(numpy.minimum(x[:, None, 2], y[None, :, 2]) - numpy.maximum(x[:, None, 0], y[None, :, 0]), 0)
+    dy = numpy.maximum(numpy.minimum(x[:, None, 3], y[None, :, 3]) - numpy.maximum(x[:, None, 1], y[None, :, 1]), 0)
+    inter = dx * dy
+    union = x_area[:, None] + y_area[None, :] - inter
+    with numpy.errstate(divide="ignore", invalid="ignore"):
+        return inter / union
+
+
+class DeNetDetectLayer(AbstractLayer):
+    type_name = "denet-detect"
+    has_cost = True
+
+    def __init__(self, layers, class_num=10, overlap_threshold=0.5, cost_factor=1.0, bbox_factor=0.0, indfit_factor=0.0,
+                 use_jointfit=False, use_bounded_iou=False, json_param={}):
+        super().__init__(layer_index=len(layers))
+        self.input = layers[-1].output
+        self.input_shape = self.output_shape = tuple(layers[-1].output_shape)
+
+        self.cost_factor = json_param.get("costFactor", cost_factor)
+        self.bbox_factor = json_param.get("bboxFactor", bbox_factor)
+        self.class_num = json_param.get("classNum", class_num)
+        self.overlap_threshold = json_param.get("overlapThreshold", overlap_threshold)
+        self.use_jointfit = json_param.get("useJointFitness", use_jointfit)
+        self.use_bounded_iou = json_param.get("useBoundedIoU", use_bounded_iou)
+        self.indfit_factor = json_param.get("fitnessFactor", indfit_factor)
+        self.use_indfit = self.indfit_factor > 0.0
+        if self.use_jointfit or self.use_indfit or self.use_bounded_iou:
+            raise Exception("denet-detect: joint / independent fitness and bounded IoU are not on the B200 hot path")
+
+        sparse_layer = common.find_layers(layers, "denet-sparse", False)
+        assert sparse_layer is not None, "Error: Requires denet-sparse layer to be specified before denet-detect layer!"
+        object.__setattr__(self, "sparse_layer", sparse_layer)
+
+        self.use_bbox_reg = self.bbox_factor > 0.0
+        self.batch_size = sparse_layer.batch_size
+        self.sample_num = sparse_layer.sample_num
+        self.null_class = self.class_num
+        s0 = self.class_num + 1
+        s1 = 4 if self.use_bbox_reg else 0
+        conv = ConvLayer([InitialLayer(None, self.input_shape)], (s0 + s1, self.input_shape[1], 1, 1), (1, 1), True,
+                         "valid", 0.0)
+        conv.out_fp32 = True
+        self.layers.append(conv)
+        self.det_shape = (self.batch_size, s0, self.sample_num, self.sample_num)
+        if self.use_bbox_reg:
+            self.bbox_shape = (self.batch_size, s1, self.sample_num, self.sample_num)
+        self.grad_factor = 1.0
+        self.cost_value = None     # device tensor [detection cost, box cost] of the last training forward
+        self._targets = None
+        self._dout = None
+        self.logits = None
+
+    @staticmethod
+    def parse_desc(layers, name, tags, params):
+        if name != "DND":
+            return False
+        layers.append(DeNetDetectLayer(layers, params.get("classNum"), params.get(0, 0.5), params.get(1, 1.0),
+                                       params.get(2, 0.0), params.get(3, 0.0), "J" in tags, "B" in tags))
+        return True
+
+    def import_json(self, json_param):
+        super().import_json(json_param)
+        if "conv" in json_param:   # backward compatibility (denet_detect.py:127-129)
+            self.layers[0].import_json(json_param["conv"])
+
+    def export_json(self):
+        json = super().export_json()
+        json.update({"costFactor": self.cost_factor, "bboxFactor": self.bbox_factor,
+                     "fitnessFactor": self.indfit_factor, "useJointFitness": self.use_jointfit,
+                     "useBoundedIoU": self.use_bounded_iou, "classNum": self.class_num,
+                     "overlapThreshold": self.overlap_threshold})
+        return json
+
+    def _thresholds(self):
+        # the reference indexes overlap_threshold[0] / [1] although parse_desc passes a scalar: accept both
+        t = self.overlap_threshold
+        return (t[0], t[1]) if isinstance(t, (tuple, list)) else (t, t)
+
+    def get_target(self, model, samples, metas):
+        """denet_detect.py:147-235 on the host arrays of the sparse layer (no per-RoI python tuples)"""
+        thr0, thr1 = self._thresholds()
+        sn = self.sample_num
+        det_pr = numpy.zeros(self.det_shape, dtype=numpy.float32)
+        det_pr[:, self.null_class] = 1.0
+        if self.use_bbox_reg:
+            bbox_valid = numpy.zeros((self.batch_size, sn, sn), dtype=numpy.float32)
+            bbox_reg = numpy.zeros((self.batch_size, 8, sn, sn), dtype=numpy.float32)
+            bbox_reg[:, [2, 3, 6, 7]] = 1.0
+        all_samples = self.sparse_layer.sample_bbox_host            # (B,K,4) float64
+        for b, meta in enumerate(metas):
+            samples = all_samples[b]
+            if len(meta["bbox"]) == 0 or len(samples) == 0:
+                continue
+            overlap = overlap_iou_matrix(meta["bbox"], samples)
+            bbox_indexs, sample_indexs = numpy.where(overlap > thr0)
+            if len(bbox_indexs) > 0:
+                cls = numpy.asarray(meta["class"], dtype=numpy.int64)[bbox_indexs]
+                det_pr[b, cls, sample_indexs // sn, sample_indexs % sn] = 1.0
+                det_pr[b, self.null_class, sample_indexs // sn, sample_indexs % sn] = 0.0
+            if self.use_bbox_reg:
+                overlap_max = overlap.argmax(axis=0)
+                index = numpy.arange(len(samples))
+                sel = index[overlap[overlap_max, index] > thr1]
+                if len(sel) > 0:
+                    target = numpy.asarray(meta["bbox"], dtype=numpy.float64)[overlap_max[sel]]
+                    sample = samples[sel]
+                    sj, si = sel // sn, sel % sn
+                    bbox_valid[b, sj, si] = 1.0
+                    bbox_reg[b, 0, sj, si] = 0.5 * (target[:, 0] + target[:, 2])
+                    bbox_reg[b, 1, sj, si] = 0.5 * (target[:, 1] + target[:, 3])
+                    bbox_reg[b, 2, sj, si] = target[:, 2] - target[:, 0]
+                    bbox_reg[b, 3, sj, si] = target[:, 3] - target[:, 1]
+                    bbox_reg[b, 4, sj, si] = 0.5 * (sample[:, 0] + sample[:, 2])
+                    bbox_reg[b, 5, sj, si] = 0.5 * (sample[:, 1] + sample[:, 3])
+                    bbox_reg[b, 6, sj, si] = sample[:, 2] - sample[:, 0]
+                    bbox_reg[b, 7, sj, si] = sample[:, 3] - sample[:, 1]
+        det_pr /= det_pr.sum(axis=1)[:, None]
+        nfactor = sn * sn
+        det_pr /= nfactor
+        yt_value = det_pr.flatten()
+        if self.use_bbox_reg:
+            bbox_valid /= nfactor
+            yt_value = numpy.concatenate((yt_value, bbox_valid.flatten(), bbox_reg.flatten()))
+        return numpy.array([], dtype=numpy.int64), yt_value
+
+    def set_target(self, yt_index, yt_value):
+        v = torch.from_numpy(numpy.ascontiguousarray(yt_value, dtype=numpy.float32)).pin_memory().cuda(
+            non_blocking=True)
+        n0 = int(numpy.prod(self.det_shape))
+        n1 = self.batch_size * self.sample_num * self.sample_num
+        if self.use_bbox_reg:
+            self._targets = (v[:n0], v[n0:n0 + n1], v[n0 + n1:n0 + 9 * n1])
+        else:
+            self._targets = (v[:n0], None, None)
+
+    def forward(self, x):
+        self.input = self.output = x
+        o = self.layers[0].forward(x)            # (B,sn,sn,s0+s1) fp32
+        self.logits = o
+        if self.cost_value is None:
+            self.cost_value = torch.zeros((2,), dtype=torch.float32, device=x.device)
+        if get_train():
+            assert self._targets is not None, "denet-detect: get_target/set_target must precede a training forward"
+            self._dout = ops.alloc_like(o)
+            t_det, t_valid, t_reg = self._targets
+            ops.detect_cost(o, self.sample_num, self.det_shape[1], self.use_bbox_reg, t_det, t_valid, t_reg,
+                            float(self.cost_factor), float(self.bbox_factor), self.grad_factor, self._dout,
+                            self.cost_value)
+        return x
+
+    def cost(self, yt_index=None, yt_value=None):
+        return None if self.cost_value is None else self.cost_value.sum()
+
+    def backward(self, dy):
+        dx = self.layers[0].backward(self._dout)
+        self._dout = None
+        return dx if dy is None else ops.add(dx, dy)

@@ -1,0 +1,187 @@
+"""DeNet sparse layer 'DNS[grid,sample_num,corner_thr,random_sample,local_max,nms_thr]'
+(reference denet/layer/denet_sparse.py:26-219).
+
+get_target() turns the corner maps of THIS forward pass into the RoI set: the reference re-runs the whole backbone in a
+second compiled function, copies corner_pr to the host and calls the C++ extension build_samples (:117-145); here
+the maps stay in HBM and denet_build_samples ranks the boxes on the device (csrc/build_samples.cu).  Only the ranked
+RoIs (a few hundred KB) visit the host, where the reference's python `random` post-processing runs unchanged in
+meaning AND in random-stream consumption (:184-201): sub-sample to make room for random boxes, pad with random boxes,
+overwrite the tail with the ground truth.  forward() is the sparse RoI feature gather (DeNetSparseOp,
+denet_sparse_op.py:42-85), backward() its scatter-add (:171-212).
+"""
+import math
+import random
+
+import numpy
+import torch
+
+from .. import common, ops
+from . import AbstractLayer, act_dtype, get_train
+
+
+def py_random_doubles(k):
+    """the next k values of python's random.random(), advanced exactly as k calls would (vectorised through numpy's
+    MT19937, which shares CPython's generator and its 53-bit double construction)"""
+    if k <= 0:
+        return numpy.empty((0,), dtype=numpy.float64)
+    if k < 32:
+        return numpy.array([random.random() for _ in range(k)], dtype=numpy.float64)
+    version, internal, gauss = random.getstate()
+    rs = numpy.random.RandomState()
+    rs.set_state(("MT19937", numpy.array(internal[:-1], dtype=numpy.uint32), int(internal[-1])))
+    out = rs.random_sample(k)
+    st = rs.get_state()
+    random.setstate((version, tuple(int(v) for v in st[1]) + (int(st[2]),), gauss))
+    return out
+
+
+class DeNetSparseLayer(AbstractLayer):
+    type_name = "denet-sparse"
+
+    def __init__(self, layers, grid_size=3, sample_num=16, corner_threshold=0.01, random_sample=0.0, local_max=0,
+                 nms_threshold=0.7, sample_gt=True, version="v2", json_param={}):
+        super().__init__(layer_index=len(layers))
+        self.input = layers[-1].output
+        self.input_shape = tuple(layers[-1].output_shape)
+        self.batch_size = self.input_shape[0]
+
+        self.grid_size = json_param.get("gridSize", grid_size)
+        self.sample_num = json_param.get("sampleNum", sample_num)
+        self.sample_gt = json_param.get("sampleGT", sample_gt)
+        self.corner_threshold = json_param.get("cornerThreshold", corner_threshold)
+        self.nms_threshold = json_param.get("nmsThreshold", nms_threshold)
+        self.random_sample = json_param.get("randomSample", random_sample)
+        self.local_max = json_param.get("localMax", local_max)
+        self.version = json_param.get("version", version)
+        if self.nms_threshold < 1.0:
+            raise Exception("denet-sparse: corner clustering (nmsThreshold < 1) is not on the B200 hot path")
+
+        self.corner_max = 1024
+        self.thread_num = self.batch_size
+        self.sample_count = self.sample_num * self.sample_num
+
+        corner_layer = common.find_layers(layers, "denet-corner", True)
+        if corner_layer.corner_num != 4:
+            raise Exception("denet-sparse: centre corners (DNC.C) are not on the B200 hot path")
+        object.__setattr__(self, "corner_layer", corner_layer)
+
+        self.sample_bbox = None           # (B,sn,sn,4) fp32 device tensor consumed by the gather kernel
+        self.sample_bbox_host = None      # (B,sn*sn,4) float64: what the reference keeps as python floats
+        self.sample_pr_host = None        # (B,sn*sn)   float64
+        self._sample_bbox_list = None
+        self.output_feat = self.grid_size * self.grid_size * corner_layer.sample_shape[1] + 2
+        self.output_shape = (self.batch_size, self.output_feat, self.sample_num, self.sample_num)
+
+    @staticmethod
+    def parse_desc(layers, name, tags, params):
+        if name != "DNS":
+            return False
+        layers.append(DeNetSparseLayer(layers, params.get(0, 3), params.get(1, 4), params.get(2, 0.01),
+                                       params.get(3, 0.1), params.get(4, 0), params.get(5, 1.0), "G" not in tags))
+        return True
+
+    def export_json(self):
+        json = super().export_json()
+        json.update({"gridSize": self.grid_size, "sampleNum": self.sample_num, "sampleGT": self.sample_gt,
+                     "localMax": self.local_max, "cornerThreshold": self.corner_threshold,
+                     "randomSample": self.random_sample, "nmsThreshold": self.nms_threshold,
+                     "version": self.version})
+        return json
+
+    # ---------------------------------------------------------------------------------------------- sampling
+    def get_samples_arrays(self, corner_pr=None):
+        """device sampler -> host arrays: pr (B,K) f32, bbox (B,K,4) f32, count (B) (one small device->host copy)"""
+        if corner_pr is None:
+            corner_pr = self.corner_layer.corner_pr
+        assert corner_pr is not None, "denet-sparse: the corner layer has not run a forward pass yet"
+        pr, bbox, _, count, _ = ops.build_samples(corner_pr, self.corner_threshold, self.sample_num, self.corner_max,
+                                                  self.local_max)
+        k = self.sample_count
+        packed = torch.cat([pr.reshape(-1), bbox.reshape(-1), count.to(torch.float32)]).cpu().numpy()
+        b = self.batch_size
+        return (packed[:b * k].reshape(b, k), packed[b * k:5 * b * k].reshape(b, k, 4),
+                packed[5 * b * k:].astype(numpy.int64))
+
+    def get_samples(self, data_x=None, train=False, store_shared=False):
+        """reference return format (denet_sparse.py:117-145): per image a list of (pr, (x0,y0,x1,y1))"""
+        pr, bbox, count = self.get_samples_arrays()
+        return [[(float(pr[b, i]), tuple(float(v) for v in bbox[b, i])) for i in range(int(count[b]))]
+                for b in range(self.batch_size)]
+
+    @property
+    def sample_bbox_list(self):
+        if self._sample_bbox_list is None and self.sample_bbox_host is not None:
+            self._sample_bbox_list = [[(float(self.sample_pr_host[b, i]), tuple(float(v) for v in
+                                                                           self.sample_bbox_host[b, i]))
+                                       for i in range(self.sample_count)] for b in range(self.batch_size)]
+        return self._sample_bbox_list
+
+    def set_samples_arrays(self, pr, bbox):
+        """pr (B,K) / bbox (B,K,4) float64 host arrays; row i of image b lands at (i // sn, i % sn)
+        (build_bbox_array, denet_sparse.cc:670-699)"""
+        self.sample_pr_host, self.sample_bbox_host = pr, bbox
+        self._sample_bbox_list = None
+        arr = numpy.ascontiguousarray(bbox.astype(numpy.float32).reshape(self.batch_size, self.sample_num,
+                                                                         self.sample_num, 4))
+        self.sample_bbox = torch.from_numpy(arr).pin_memory().cuda(non_blocking=True)
+        return arr
+
+    def set_samples(self, sample_bboxs):
+        """reference entry point: list (per image) of lists of (pr, bbox)"""
+        k = self.sample_count
+        pr = numpy.zeros((self.batch_size, k), dtype=numpy.float64)
+        bbox = numpy.zeros((self.batch_size, k, 4), dtype=numpy.float64)
+        for b, samples in enumerate(sample_bboxs):
+            for i, (p, bb) in enumerate(samples[:k]):
+                pr[b, i] = p
+                bbox[b, i] = bb
+        return self.set_samples_arrays(pr, bbox)
+
+    def get_target(self, model, data_x, metas):
+        """denet_sparse.py:164-206, vectorised; consumes python's `random` stream exactly like the reference loops"""
+        pr32, bbox32, count = self.get_samples_arrays()
+        k = self.sample_count
+        n_keep = k - math.floor(self.random_sample * k)
+        pr = numpy.zeros((self.batch_size, k), dtype=numpy.float64)
+        bbox = numpy.zeros((self.batch_size, k, 4), dtype=numpy.float64)
+        for b, meta in enumerate(metas):
+            cnt = int(count[b])
+            if cnt > n_keep:
+                keep = random.sample(range(cnt), n_keep)     # same draws as random.sample(list_of_cnt_items, n_keep)
+                pr[b, :n_keep] = pr32[b, keep]
+                bbox[b, :n_keep] = bbox32[b, keep]
+                cnt = n_keep
+            else:
+                pr[b, :cnt] = pr32[b, :cnt]
+                bbox[b, :cnt] = bbox32[b, :cnt]
+            m = k - cnt
+            if m > 0:
+                # random.uniform(a, b) = a + (b-a)*random():  x0,y0 ~ U(0,1), x1 ~ U(x0,1), y1 ~ U(y0,1)
+                u = py_random_doubles(4 * m).reshape(m, 4)
+                x0 = 0.0 + (1.0 - 0.0) * u[:, 0]
+                y0 = 0.0 + (1.0 - 0.0) * u[:, 1]
+                bbox[b, cnt:, 0] = x0
+                bbox[b, cnt:, 1] = y0
+                bbox[b, cnt:, 2] = x0 + (1.0 - x0) * u[:, 2]
+                bbox[b, cnt:, 3] = y0 + (1.0 - y0) * u[:, 3]
+                pr[b, cnt:] = 0.0
+            if self.sample_gt:
+                for index, gt in enumerate(meta["bbox"]):
+                    pr[b, k - (index + 1)] = 1.0
+                    bbox[b, k - (index + 1)] = gt
+        self.set_samples_arrays(pr, bbox)
+        return None
+
+    # ---------------------------------------------------------------------------------------------- execution
+    def forward(self, x):
+        self.input = x
+        assert self.sample_bbox is not None, "denet-sparse: get_target()/set_samples() must precede forward()"
+        fmap = self.corner_layer.sample
+        self._fmap_shape = tuple(fmap.shape)
+        self.output = ops.sparse_sample_fwd(fmap, self.sample_bbox, self.grid_size, out_dtype=act_dtype())
+        return self.output
+
+    def backward(self, dy):
+        dfmap = ops.sparse_sample_bwd(dy, self.sample_bbox, self.grid_size, self._fmap_shape)
+        self.corner_layer.set_sample_grad(dfmap)
+        return None   # the reference op has no gradient wrt the boxes, and the layer input is not used (:38)

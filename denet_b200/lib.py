@@ -1,37 +1,48 @@
 """ctypes binding of the C-ABI library (include/denet_b200.h).
 
-The product path has NO CPU fallback: if libdenet_b200.so is missing or a call fails, this raises.
+The prototypes are read from the header itself, so the binding mirrors it one to one.  The product path has NO CPU
+fallback: if libdenet_b200.so is missing or a call fails, this raises.
 """
 import ctypes
 import os
+import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdenet_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "denet_b200.h")
 
 DENET_F32 = 0
 DENET_BF16 = 1
 
-c_void_p = ctypes.c_void_p
-c_int = ctypes.c_int
-c_ll = ctypes.c_longlong
-c_size_t = ctypes.c_size_t
-c_float = ctypes.c_float
+_SCALARS = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "size_t": ctypes.c_size_t,
+            "cudaStream_t": ctypes.c_void_p}
 
-# name -> (restype, argtypes); mirrors include/denet_b200.h one to one.
-SIGNATURES = {
-    "denet_last_error": (ctypes.c_char_p, []),
-    "denet_abi_version": (c_int, []),
-    "denet_conv_weight_prep": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "denet_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
-    "denet_conv2d_fprop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ll,
-                                   c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                   c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_int,
-                                   c_void_p, c_void_p, c_void_p]),
-    "denet_conv2d_wgrad_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
-    "denet_conv2d_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ll,
-                                   c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_int, c_int, c_int, c_int,
-                                   c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
-}
+
+def _ctype(decl):
+    decl = decl.strip()
+    if "*" in decl:
+        return ctypes.c_char_p if decl.replace(" ", "") == "constchar*" else ctypes.c_void_p
+    decl = re.sub(r"\bconst\b", "", decl).strip()
+    return _SCALARS[decl]
+
+
+def parse_header(path=HEADER_PATH):
+    """{name: (restype, [argtypes])} for every function declared in the C header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][\w \*]*?)\b(denet_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        argtypes = []
+        if args.strip() not in ("", "void"):
+            for a in args.split(","):
+                a = a.strip()
+                # drop the parameter name (last identifier), keep the type
+                t = re.sub(r"\s*\b\w+$", "", a) if not a.endswith("*") else a
+                argtypes.append(_ctype(t))
+        out[name] = (_ctype(ret), argtypes)
+    return out
 
 
 class DenetError(RuntimeError):
@@ -39,11 +50,12 @@ class DenetError(RuntimeError):
 
 
 _lib = None
+SIGNATURES = None
 
 
 def load():
     """Load the shared library (once) and attach the prototypes. Raises if it is not built."""
-    global _lib
+    global _lib, SIGNATURES
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
@@ -51,10 +63,13 @@ def load():
             "denet_b200: %s not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback)" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
+    SIGNATURES = parse_header()
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
+    if lib.denet_abi_version() != 2:
+        raise DenetError("denet_b200: ABI version mismatch (library %d, binding 2) - rebuild" % lib.denet_abi_version())
     _lib = lib
     return lib
 
@@ -65,7 +80,17 @@ def check(rc, what=""):
         raise DenetError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 
+_launches = 0
+
+
+def launch_count():
+    """number of C-ABI calls issued so far by this process (bench.py reports the per-step delta)"""
+    return _launches
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise DenetError on a non-zero status."""
+    global _launches
+    _launches += 1
     fn = getattr(load(), name)
     check(fn(*args), name)

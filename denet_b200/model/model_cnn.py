@@ -1,0 +1,464 @@
+"""ModelCNN: the reference's model container and training step (denet/model/model_cnn.py:86-571) on the B200 kernels.
+
+Same driver-facing surface: initialize(args, ...), ModelCNN.build / build_layer (model-desc grammar TYPE.TAGS[ARGS],
+model_cnn.py:122-157), export_json / import_json (+ load_from_file / save_to_file, gz-JSON checkpoints),
+build_train_func(solver_mode, cost_factors), train_step(data_x, data_m, epoch, it, lr, momentum, decay) ->
+(cost, [costs]), train_epoch, predict_output_step / predict_output / predict_label.
+
+What replaces theano.function + tensor.grad: ONE eager forward pass over the layer list (the reference runs the
+backbone twice per iteration, once in DeNetSparseLayer.corner_func and once in train_step; both in train mode with
+identical batch statistics, so one pass that pauses at the sparse layer for sampling is result-equivalent), an
+explicit reverse pass calling each layer's backward(), and one multi-tensor solver kernel
+(model_cnn.py:282-305: sgd / torch|nesterov / adam; L2 decay on weights only, :320-324).  With torch.distributed
+initialised the gradients are all-reduced over NCCL in buckets that overlap the remaining backward pass
+(denet_b200/multi), replacing denet/multi's host-side parameter averaging.
+"""
+import ctypes
+import getpass
+import math
+import random
+import time
+
+import numpy
+import torch
+
+from .. import common, layer as layer_mod, lib, ops
+from ..common import json_util
+from ..layer import InitialLayer
+from ..layer.layer_types import layer_types
+
+SOLVER_CODES = {"sgd": 0, "torch": 1, "nesterov": 1, "adam": 2}
+
+
+def load_from_json(json_obj, batch_size=32, layer_range=None):
+    model = ModelCNN()
+    model.batch_size = batch_size
+    model.import_json(json_obj, layer_range)
+    return model
+
+
+def load_from_file(fname, batch_size=32, layer_range=None):
+    model = load_from_json(json_util.json_from_gz(fname), batch_size, layer_range)
+    model.fname = fname
+    return model
+
+
+def save_to_file(model, fname, compresslevel=9):
+    json_util.json_to_gz(fname, model.export_json(), compresslevel)
+
+
+def initialize(args, data_shape, class_labels, class_num):
+    """reference model_cnn.initialize (:46-83)"""
+    if args.model is None:
+        model = ModelCNN()
+        model.batch_size = args.batch_size
+        model.class_labels = class_labels
+        model.class_num = class_num
+        try:
+            n = int(args.border_mode)
+            border_mode = (n, n)
+        except ValueError:
+            border_mode = args.border_mode
+        model.build(args.model_desc, data_shape, args.activation, border_mode, list(args.weight_init))
+    else:
+        model = load_from_file(args.model, args.batch_size)
+        model.class_labels = class_labels
+        model.class_num = class_num
+        assert tuple(data_shape) == tuple(model.data_shape), "Mismatching data shapes in .mdl and data: " + \
+            str(data_shape) + "!=" + str(model.data_shape)
+    model.skip_layer_updates = getattr(args, "skip_layer_updates", [])
+    return model
+
+
+def _walk(layers):
+    """depth-first over a layer list and its sub-layers"""
+    for l in layers:
+        yield l
+        yield from _walk(l.layers)
+
+
+def link_fusions(layers):
+    """conv -> batch-norm pairs: the conv epilogue accumulates the statistics its batch-norm consumes"""
+    from ..layer.batch_norm import BatchNormLayer
+    from ..layer.convolution import ConvLayer
+    bns = []
+    for seq in [layers] + [l.layers for l in _walk(layers)]:
+        seq = list(seq)
+        for a, b in zip(seq[:-1], seq[1:]):
+            if isinstance(a, ConvLayer) and isinstance(b, BatchNormLayer) and b.enabled and a.enabled \
+                    and not a.out_fp32:
+                object.__setattr__(a, "stat_consumer", b)
+                bns.append(b)
+    return bns
+
+
+class ModelCNN:
+
+    def __init__(self):
+        self.batch_size = 0
+        self.iteration = 0
+        self.class_labels = None
+        self.data_shape = None
+        self.class_num = 0
+        self.rng_seed = random.randint(1, 9999)
+        layer_mod.set_rng_seed(self.rng_seed)
+
+        self.gradient_clip = 0.0
+        self.skip_layer_updates = []
+        self.bias_decay = False
+        self.layers = []
+        self.distort_mode = []
+        self.func = {}
+        self.input = None
+        self.device = None
+        self.ddp = None             # denet_b200.multi.GradientAllReduce when running data parallel
+        self._ready = False
+        self.last_costs_device = None
+
+    # ---------------------------------------------------------------------------------------------- shapes
+    def get_input_shape(self):
+        assert self.data_shape is not None, "Data shape hasn't been set!"
+        return tuple([self.batch_size] + list(self.data_shape))
+
+    def get_output_shape(self):
+        return self.layers[-1].output_shape
+
+    def get_parameter_num(self):
+        n = 0
+        for layer in self.layers:
+            for param in layer.params():
+                n += param.numel()
+        return n
+
+    # ---------------------------------------------------------------------------------------------- building
+    def _initial_layer(self):
+        init = InitialLayer(None, self.get_input_shape())
+        init.is_model_input = True
+        return init
+
+    def build_layer(self, layer_desc, layers, activation, border_mode, wb):
+        """TYPE.TAGS[a,b,...] -> parse_desc of every registered layer type (model_cnn.py:122-145)"""
+        p_start = layer_desc.find("[")
+        p_end = layer_desc.find("]")
+        layer_params = {"classNum": self.class_num, "activation": activation, "borderMode": border_mode, "wb": wb}
+        if p_start > 0 and p_end > p_start:
+            layer_type = layer_desc[:p_start]
+            for i, p in enumerate(layer_desc[(p_start + 1):p_end].split(",")):
+                layer_params[i] = common.convert_num(p)
+        else:
+            layer_type = layer_desc
+        t_index = layer_type.find(".")
+        if t_index > 0:
+            layer_tags = layer_type[(t_index + 1):]
+            layer_type = layer_type[:t_index]
+        else:
+            layer_tags = ""
+        for layer in layer_types:
+            if layer.parse_desc(layers, layer_type, layer_tags, layer_params):
+                return
+        raise Exception("Invalid layer - type: ", layer_type, "tags:", layer_tags, "params:", layer_params)
+
+    def build(self, model_desc, data_shape, activation="relu", border_mode="valid", weight_init="he-forward"):
+        if isinstance(model_desc, str):
+            model_desc = model_desc.split()
+        if isinstance(weight_init, str):
+            weight_init = [weight_init]
+        self.model_desc = " ".join(model_desc)
+        self.data_shape = tuple(data_shape)
+        self.layers = [self._initial_layer()]
+        for i, layer_desc in enumerate(model_desc):
+            wb = weight_init[min(len(weight_init) - 1, i)]
+            self.build_layer(layer_desc, self.layers, activation, border_mode, wb)
+        self._ready = False
+
+    def export_json(self):
+        self._sync_params_to_host()
+        json_layers = [self.layers[index].export_json() for index in range(1, len(self.layers))]
+        from time import gmtime, strftime
+        json_obj = {"classifierType": "CNN", "classLabels": self.class_labels, "classNum": self.class_num,
+                    "dataShape": self.data_shape, "date": strftime("%Y-%m-%d %H:%M:%S", gmtime()),
+                    "user": getpass.getuser()}
+        json_obj.update({"version": 3, "layers": json_layers})
+        return json_obj
+
+    def import_json(self, json_obj, layer_range=None):
+        self.func = {}
+        if json_obj.get("version", 0) == 0:
+            raise Exception("Old format model file detected, no compatibility!")
+        self.class_labels = json_obj["classLabels"]
+        if "imageSize" in json_obj and "imageMode" in json_obj:
+            width, height = json_obj["imageSize"][0], json_obj["imageSize"][1]
+            self.data_shape = ({"RGB": 3, "L": 1}[json_obj.get("imageMode", "RGB")], width, height)
+        elif "dataShape" in json_obj:
+            self.data_shape = tuple(json_obj["dataShape"])
+        else:
+            assert False, "Bad mdl file, Cannot determine input data shape!"
+        assert json_obj.get("imageBorder", 0) == 0
+        self.class_num = json_obj.get("classNum", len(self.class_labels) if self.class_labels else 0)
+        layers = layer_mod.import_json(json_obj["layers"], None, self.get_input_shape(), layer_range)
+        layers[0].is_model_input = True
+        # the first real layer was built before the flag existed: refresh it
+        for l in layers[1:2]:
+            if hasattr(l, "is_first"):
+                l.is_first = True
+        self.layers = layers
+        self._ready = False
+
+    def convert_bn_relu(self):
+        """merge batchnorm + relu pairs into batchnorm-relu layers, at the top level and inside 'original' ResNet
+        blocks - what `model-modify --convert-bn-relu` does to build the DeNet stacks (reference model/modify.py:70-110)"""
+        js = self.export_json()
+
+        def as_bnrelu(j):
+            j = dict(j)
+            j["type"] = "batchnorm-relu"
+            return j
+
+        def is_bn_relu_pair(a, b):
+            return a["type"] == "batchnorm" and b is not None and b["type"] == "activation" and \
+                b.get("activation") == "relu"
+
+        src, out, i = js["layers"], [], 0
+        while i < len(src):
+            cur = src[i]
+            nxt = src[i + 1] if i + 1 < len(src) else None
+            if is_bn_relu_pair(cur, nxt):
+                out.append(as_bnrelu(cur))
+                i += 2
+                continue
+            if cur["type"] == "resnet" and "bnrelu" not in cur["version"] and "pre-activation" not in cur["version"]:
+                cur = dict(cur)
+                sub = [l for l in cur["layers"] if l["type"] != "identity"]
+                sub[2] = as_bnrelu(sub[2])
+                del sub[3]
+                if cur["bottleneck"] > 0:
+                    sub[4] = as_bnrelu(sub[4])
+                    del sub[5]
+                cur["layers"] = sub
+                cur["version"] = cur["version"] + ",bnrelu"
+            out.append(cur)
+            i += 1
+        js["layers"] = out
+        batch_size = self.batch_size
+        self.import_json(js)
+        self.batch_size = batch_size
+        return self
+
+    def _sync_params_to_host(self):
+        if self.device is not None:
+            torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------------------------------------- device setup
+    def to_device(self, device=None, precision=None):
+        """move parameters to the GPU, allocate one flat fp32 gradient buffer and the solver tables"""
+        if not torch.cuda.is_available():
+            raise lib.DenetError("denet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        lib.load()
+        if precision is not None:
+            layer_mod.set_precision(precision)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        layer_mod.set_device(self.device)
+        for l in _walk(self.layers):
+            l.to(self.device)
+        # trainable parameters in the reference's order: per layer weights() then biases() (model_cnn.py:308-316)
+        self.train_params = []
+        owners = []
+        for index, l in enumerate(self.layers):
+            if index in self.skip_layer_updates:
+                continue
+            mine = [(p, True) for p in l.weights()] + [(p, False) for p in l.biases()]
+            self.train_params += mine
+            owners += [index] * len(mine)
+        total = sum(p.numel() for p, _ in self.train_params)
+        # every tensor starts on a 16-byte boundary inside the flat buffer
+        offsets, off = [], 0
+        self.layer_grad_ranges = {}     # top-level layer index -> [start, end) of its gradients in flat_grad
+        for (p, _), owner in zip(self.train_params, owners):
+            offsets.append(off)
+            start = self.layer_grad_ranges.get(owner, (off, off))[0]
+            off += (p.numel() + 3) // 4 * 4
+            self.layer_grad_ranges[owner] = (start, off)
+        self.flat_grad = torch.zeros((max(off, 4),), dtype=torch.float32, device=self.device)
+        self.grad_offsets = offsets
+        for (p, _), o in zip(self.train_params, offsets):
+            p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+        self.num_trainable = total
+        # per-step batch-norm statistics buffer (conv epilogue -> bn finalize), zeroed once per step
+        bns = link_fusions(self.layers)
+        csum = sum(2 * b.input_shape[1] for b in bns)
+        self.bn_stat_buffer = torch.zeros((max(csum, 2),), dtype=torch.float32, device=self.device)
+        o = 0
+        for b in bns:
+            c = b.input_shape[1]
+            b._fused = (self.bn_stat_buffer[o:o + c], self.bn_stat_buffer[o + c:o + 2 * c])
+            o += 2 * c
+        layer_mod.bump_param_version()
+        self._ready = True
+        return self
+
+    def enable_data_parallel(self, bucket_bytes=32 << 20, average_bn_stats=True, group=None):
+        """gradient all-reduce across the ranks of torch.distributed (NCCL on GPUs), overlapped with backward"""
+        from ..multi import GradientAllReduce
+        if not self._ready:
+            self.to_device()
+        ranges = [(index, r[0], r[1]) for index, r in sorted(self.layer_grad_ranges.items())]
+        extra = []
+        if average_bn_stats:
+            for l in _walk(self.layers):
+                extra += [t for t, _ in l.updates()] if not len(l.layers) else []
+        self.ddp = GradientAllReduce(self.flat_grad, ranges, bucket_bytes, extra, group)
+        return self.ddp
+
+    def _build_solver_tables(self):
+        chunk = lib.load().denet_solver_chunk()
+        entry_bytes = lib.load().denet_solver_entry_bytes()
+        assert entry_bytes == 48, entry_bytes
+        n = len(self.train_params)
+        self.momenta = [torch.zeros_like(p) for p, _ in self.train_params]
+        self.momenta2 = [torch.zeros_like(p) for p, _ in self.train_params] if self.solver_mode == "adam" else None
+        table = numpy.zeros((n, 6), dtype=numpy.int64)   # p, g, m, v, n, (is_weight | pad<<32)
+        block_tensor, block_offset = [], []
+        for i, (p, is_weight) in enumerate(self.train_params):
+            table[i, 0] = p.data_ptr()
+            table[i, 1] = p.grad.data_ptr()
+            table[i, 2] = self.momenta[i].data_ptr()
+            table[i, 3] = self.momenta2[i].data_ptr() if self.momenta2 is not None else 0
+            table[i, 4] = p.numel()
+            table[i, 5] = 1 if is_weight else 0
+            for o in range(0, p.numel(), chunk):
+                block_tensor.append(i)
+                block_offset.append(o)
+        self._solver_entries = torch.from_numpy(table).to(self.device)
+        self._solver_block_tensor = torch.tensor(block_tensor, dtype=torch.int32, device=self.device)
+        self._solver_block_offset = torch.tensor(block_offset, dtype=torch.int64, device=self.device)
+        self._solver_nblocks = len(block_tensor)
+
+    def build_train_func(self, solver_mode="sgd", cost_factors=[], use_acc_mode=False, skip_build=False):
+        """collect the cost layers and prepare the solver (model_cnn.py:205-405)"""
+        if solver_mode not in SOLVER_CODES:
+            solver_mode = "sgd"   # the reference falls through to sgd for unknown names (:301-305)
+        self.solver_mode = solver_mode
+        self.cost_layers = [l for l in self.layers if l.has_cost]
+        self.cost_layer_names = [l.type_name for l in self.cost_layers]
+        self.cost_factors = [1.0] * len(self.cost_layers) if len(cost_factors) == 0 else [float(c) for c in
+                                                                                            cost_factors]
+        assert len(self.cost_factors) == len(self.cost_layers), \
+            "Different number of cost factors (%i) and cost layers (%i)" % (len(self.cost_factors),
+                                                                            len(self.cost_layers))
+        for l, f in zip(self.cost_layers, self.cost_factors):
+            l.grad_factor = f
+        self.use_split_mode = False
+        self.use_acc_mode = use_acc_mode
+        self._cost_factor_t = None
+        if skip_build:
+            return
+        if not self._ready:
+            self.to_device()
+        self._build_solver_tables()
+        self.func["train_step"] = self._train_step_device
+
+    # ---------------------------------------------------------------------------------------------- execution
+    def upload(self, data_x):
+        """host NCHW fp32 batch (numpy or pinned tensor) -> NHWC device activation"""
+        if isinstance(data_x, numpy.ndarray):
+            t = torch.from_numpy(numpy.ascontiguousarray(data_x, dtype=numpy.float32))
+        else:
+            t = data_x
+        if not t.is_cuda:
+            t = t.to(self.device, non_blocking=True)
+        return ops.nchw_to_nhwc(t.contiguous(), layer_mod.act_dtype())
+
+    def forward(self, data_x, data_m=None, train=False):
+        """one pass over the layer list; in train mode every layer's get_target runs right before its forward so
+        that the sparse layer can sample from the corner maps of this very pass"""
+        layer_mod.set_train(train)
+        x = self.upload(data_x)
+        self.layers[0].output = x
+        for l in self.layers[1:]:
+            if train:
+                target = l.get_target(self, data_x, data_m)
+                if target is not None:
+                    l.set_target(*target)
+            x = l.forward(x)
+        return x
+
+    def backward(self):
+        dy = None
+        hook = self.ddp.layer_done if self.ddp is not None else None
+        for index in range(len(self.layers) - 1, 0, -1):
+            dy = self.layers[index].backward(dy)
+            if hook is not None:
+                hook(index)
+        return dy
+
+    def solver_step(self, learning_rate, momentum, decay, iteration, grad_scale=1.0):
+        mom = list(momentum) + [0.0, 0.0]
+        lib.call("denet_solver_update", self._solver_entries.data_ptr(), self._solver_block_tensor.data_ptr(),
+                 self._solver_block_offset.data_ptr(), self._solver_nblocks, SOLVER_CODES[self.solver_mode],
+                 float(learning_rate), float(mom[0]), float(mom[1]), float(decay), int(iteration),
+                 int(self.bias_decay), float(grad_scale), torch.cuda.current_stream().cuda_stream)
+        layer_mod.bump_param_version()
+
+    def _train_step_device(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):
+        """forward + backward + update on the device; returns the device tensor [total, cost_0, cost_1, ...]"""
+        layer_mod.set_epoch(epoch)
+        layer_mod.set_iteration(it)
+        self.bn_stat_buffer.zero_()
+        with torch.no_grad():
+            self.forward(data_x, data_m, train=True)
+            if self.ddp is not None:
+                self.ddp.begin_step()
+            self.backward()
+            grad_scale = 1.0
+            if self.ddp is not None:
+                grad_scale = self.ddp.finish_step()
+            self.solver_step(learning_rate, momentum, decay, it, grad_scale)
+            costs = torch.stack([l.cost().reshape(()) for l in self.cost_layers])
+            if self._cost_factor_t is None:
+                self._cost_factor_t = torch.tensor(self.cost_factors, dtype=torch.float32).to(costs.device)
+            total = (costs * self._cost_factor_t).sum().reshape(1)
+            self.last_costs_device = torch.cat([total, costs])
+        layer_mod.set_train(False)
+        return self.last_costs_device
+
+    def train_step(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):
+        """reference contract (model_cnn.py:407-445): returns (cost, [layer costs]) as python floats"""
+        assert "train_step" in self.func, "Call build_train_func() before calling train_step()"
+        costs = self._train_step_device(data_x, data_m, epoch, it, learning_rate, momentum, decay).cpu().numpy()
+        return float(costs[0]), [float(c) for c in costs[1:]]
+
+    def train_epoch(self, dataset, epoch, learning_rate, momentum=[0, 1, 0], decay=0.0, solver_mode="sgd"):
+        dataset_x, dataset_m, dataset_size = dataset.export(self.batch_size)
+        index_num = math.ceil(dataset_size / self.batch_size)
+        total_cost = 0
+        for index in range(index_num):
+            data_x = dataset_x[index * self.batch_size:(index + 1) * self.batch_size]
+            data_m = dataset_m[index * self.batch_size:(index + 1) * self.batch_size]
+            cost, _ = self.train_step(data_x, data_m, epoch, self.iteration, learning_rate, momentum, decay)
+            if math.isnan(cost):   # watch out for GPUs randomly producing NaN (model_cnn.py:463)
+                raise Exception("ERROR: Cost is NaN")
+            total_cost += cost
+            self.iteration += 1
+        return total_cost
+
+    # ---------------------------------------------------------------------------------------------- prediction
+    def predict_output_step(self, data_x):
+        if not self._ready:
+            self.to_device()
+        with torch.no_grad():
+            out = self.forward(data_x, None, train=False)
+        if out.dim() == 4:
+            out = ops.nhwc_to_nchw(out)
+        return out.float().cpu().numpy()
+
+    def predict_output(self, dataset):
+        dataset_x, dataset_y, dataset_size = dataset.export(self.batch_size)
+        n = math.ceil(dataset_size / self.batch_size)
+        pr = [self.predict_output_step(dataset_x[i * self.batch_size:(i + 1) * self.batch_size]) for i in range(n)]
+        pr = numpy.concatenate(pr, axis=0)
+        return pr[:dataset_size]
+
+    def predict_label(self, dataset):
+        pr = self.predict_output(dataset)
+        assert pr.ndim == 2
+        return [int(numpy.argmax(pr[i])) for i in range(pr.shape[0])]

@@ -1,7 +1,8 @@
 """Tensor-level wrappers over the C-ABI (include/denet_b200.h).
 
 torch is used for device memory and streams only; every op here is one or more calls into libdenet_b200.so
-on the current CUDA stream.  Activations are NHWC tensors (N, H, W, C) whose last-dim pitch may be padded.
+on the current CUDA stream.  Activations are NHWC tensors (N, H, W, C) whose last-dim pitch may be padded to a
+multiple of 8 elements (TMA needs 16-byte strides).  Nothing here falls back to torch arithmetic.
 """
 import torch
 
@@ -36,8 +37,46 @@ def _pitch(t):
     assert t.stride(-1) == 1, "channel dimension must be contiguous"
     ld = t.stride(-2)
     n, h, w, _ = t.shape
-    assert t.stride(1) == ld * w and (n == 1 or t.stride(0) == ld * w * h), "tensor is not pixel-contiguous NHWC"
+    assert (w == 1 or t.stride(2) == ld) and (h == 1 or t.stride(1) == ld * w) and \
+        (n == 1 or t.stride(0) == ld * w * h), "tensor is not pixel-contiguous NHWC"
     return ld
+
+
+def _rows(t):
+    n, h, w, _ = t.shape
+    return n * h * w
+
+
+def alloc_nhwc(n, h, w, c, dtype, device="cuda", zero=False):
+    """NHWC tensor whose pixel pitch is padded to a multiple of 8 elements."""
+    ld = (c + 7) // 8 * 8
+    buf = (torch.zeros if zero or ld != c else torch.empty)((n, h, w, ld), dtype=dtype, device=device)
+    return buf[..., :c] if ld != c else buf
+
+
+def alloc_like(x, dtype=None):
+    n, h, w, c = x.shape
+    return alloc_nhwc(n, h, w, c, dtype or x.dtype, x.device)
+
+
+def _padded_base(x):
+    """the (N, H, W, ld) buffer behind a channel-sliced NHWC view made by alloc_nhwc"""
+    n, h, w, _ = x.shape
+    ld = _pitch(x)
+    return torch.as_strided(x, (n, h, w, ld), (h * w * ld, w * ld, ld, 1), x.storage_offset())
+
+
+# ---------------------------------------------------------------------------------------------- workspaces
+_ws = {}
+
+
+def workspace(nbytes, device, tag="ws"):
+    key = (tag, str(device))
+    ws = _ws.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty((max(1024, (nbytes + 3) // 4),), dtype=torch.float32, device=device)
+        _ws[key] = ws
+    return ws
 
 
 # ---------------------------------------------------------------------------------------------- conv operands
@@ -48,17 +87,19 @@ class ConvOperand:
         self.hi, self.lo, self.rows, self.kin, self.R, self.S = hi, lo, rows, kin, R, S
 
 
-def conv_weight_prep(w, mode, split):
+def conv_weight_prep(w, mode, split, out=None):
     """w: (Cout, Cin, R, S) fp32 reference filters. mode 0 = fprop operand, 1 = dgrad operand."""
     _require_cuda(w)
     assert w.dtype == torch.float32 and w.is_contiguous()
     cout, cin, R, S = w.shape
     rows, kin = (cout, cin) if mode == 0 else (cin, cout)
     kp = (kin + 63) // 64 * 64
-    hi = torch.empty((rows, R * S, kp), dtype=torch.bfloat16, device=w.device)
-    lo = torch.empty_like(hi) if split else None
-    call("denet_conv_weight_prep", w.data_ptr(), cout, cin, R, S, mode, hi.data_ptr(), _ptr(lo), _stream())
-    return ConvOperand(hi, lo, rows, kin, R, S)
+    if out is None:
+        hi = torch.empty((rows, R * S, kp), dtype=torch.bfloat16, device=w.device)
+        lo = torch.empty_like(hi) if split else None
+        out = ConvOperand(hi, lo, rows, kin, R, S)
+    call("denet_conv_weight_prep", w.data_ptr(), cout, cin, R, S, mode, out.hi.data_ptr(), _ptr(out.lo), _stream())
+    return out
 
 
 class ActOperand:
@@ -72,23 +113,11 @@ class ActOperand:
         return self.hi.shape
 
 
-def alloc_nhwc(n, h, w, c, dtype, device="cuda", zero=False):
-    """NHWC tensor whose pixel pitch is padded to a multiple of 8 elements (TMA needs 16-byte strides)."""
-    ld = (c + 7) // 8 * 8
-    buf = (torch.zeros if zero or ld != c else torch.empty)((n, h, w, ld), dtype=dtype, device=device)
-    return buf[..., :c] if ld != c else buf
-
-
-def _padded_base(x):
-    """the (N, H, W, ld) buffer behind a channel-sliced NHWC view made by alloc_nhwc"""
-    n, h, w, _ = x.shape
-    ld = _pitch(x)
-    return torch.as_strided(x, (n, h, w, ld), (h * w * ld, w * ld, ld, 1))
-
-
 def act_operand(x):
     """NHWC activation -> ActOperand. bf16 tensors are used as-is; fp32 tensors are split into hi/lo."""
     _require_cuda(x)
+    if isinstance(x, ActOperand):
+        return x
     if x.dtype == torch.bfloat16:
         return ActOperand(x)
     assert x.dtype == torch.float32
@@ -100,9 +129,9 @@ def act_operand(x):
     return ActOperand(hi[..., :c], lo[..., :c])
 
 
-def conv2d_fprop(xop, wop, pad_h, pad_w, out_hw, out_dtype, bias=None, residual=None, relu=False, stats=None,
+def conv2d_fprop(xop, wop, pad, out_hw, out_dtype, stride=(1, 1), bias=None, residual=None, relu=False, stats=None,
                  out=None):
-    """Stride-1 correlation with a prepared operand (see denet_conv2d_fprop). Returns NHWC (N, Ho, Wo, rows)."""
+    """Correlation with a prepared operand (see denet_conv2d_fprop). Returns NHWC (N, Ho, Wo, rows)."""
     x = xop.hi
     n, hi_, wi_, cin = x.shape
     assert cin == wop.kin, (cin, wop.kin)
@@ -110,13 +139,13 @@ def conv2d_fprop(xop, wop, pad_h, pad_w, out_hw, out_dtype, bias=None, residual=
     ho, wo = out_hw
     cout = wop.rows
     if out is None:
-        out = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
+        out = alloc_nhwc(n, ho, wo, cout, out_dtype, x.device)
     ldx = _pitch(x)
     ldy = _pitch(out)
     if residual is not None:
         assert residual.shape == out.shape and residual.dtype == out.dtype and _pitch(residual) == ldy
-    # 1x1 convolutions are plain GEMMs over all pixels: flatten so that M tiles are 128 consecutive pixels
-    if wop.R == 1 and wop.S == 1 and pad_h == 0 and pad_w == 0 and (ho, wo) == (hi_, wi_):
+    # 1x1 stride-1 convolutions are plain GEMMs over all pixels: flatten so that M tiles are 128 consecutive pixels
+    if wop.R == 1 and wop.S == 1 and tuple(pad) == (0, 0) and tuple(stride) == (1, 1) and (ho, wo) == (hi_, wi_):
         n_, h_, w_ = 1, 1, n * hi_ * wi_
         ho_, wo_ = 1, w_
     else:
@@ -124,24 +153,13 @@ def conv2d_fprop(xop, wop, pad_h, pad_w, out_hw, out_dtype, bias=None, residual=
         ho_, wo_ = ho, wo
     s0, s1 = (stats if stats is not None else (None, None))
     call("denet_conv2d_fprop", x.data_ptr(), _ptr(xop.lo), n_, h_, w_, cin, ldx,
-         wop.hi.data_ptr(), _ptr(wop.lo), cout, wop.R, wop.S, pad_h, pad_w,
+         wop.hi.data_ptr(), _ptr(wop.lo), cout, wop.R, wop.S, pad[0], pad[1], stride[0], stride[1],
          out.data_ptr(), _dtype_code(out), ldy, ho_, wo_, _ptr(bias), _ptr(residual), int(relu),
          _ptr(s0), _ptr(s1), _stream())
     return out
 
 
-_wgrad_ws = {}
-
-
-def _workspace(nbytes, device):
-    ws = _wgrad_ws.get(device)
-    if ws is None or ws.numel() * 4 < nbytes:
-        ws = torch.empty(((nbytes + 3) // 4,), dtype=torch.float32, device=device)
-        _wgrad_ws[device] = ws
-    return ws
-
-
-def conv2d_wgrad(dyop, xop, R, S, pad_h, pad_w, dw=None, accumulate=False):
+def conv2d_wgrad(dyop, xop, R, S, pad, stride=(1, 1), dw=None, accumulate=False):
     """Filter gradient in the reference layout (Cout, Cin, R, S). dy: (N,Ho,Wo,Cout), x: (N,Hi,Wi,Cin)."""
     dy, x = dyop.hi, xop.hi
     n, ho, wo, cout = dy.shape
@@ -151,13 +169,289 @@ def conv2d_wgrad(dyop, xop, R, S, pad_h, pad_w, dw=None, accumulate=False):
     if dw is None:
         dw = torch.empty((cout, cin, R, S), dtype=torch.float32, device=x.device)
         accumulate = False
-    if R == 1 and S == 1 and pad_h == 0 and pad_w == 0 and (ho, wo) == (hi_, wi_):
+    if R == 1 and S == 1 and tuple(pad) == (0, 0) and tuple(stride) == (1, 1) and (ho, wo) == (hi_, wi_):
         n_, ho_, wo_, hi2, wi2 = 1, 1, n * ho * wo, 1, n * ho * wo
     else:
         n_, ho_, wo_, hi2, wi2 = n, ho, wo, hi_, wi_
     nbytes = lib.load().denet_conv2d_wgrad_workspace(n_, ho_, wo_, cout, cin, R, S)
-    ws = _workspace(nbytes, x.device)
+    ws = workspace(nbytes, x.device, "wgrad")
     call("denet_conv2d_wgrad", dy.data_ptr(), _ptr(dyop.lo), n_, ho_, wo_, cout, _pitch(dy),
-         x.data_ptr(), _ptr(xop.lo), hi2, wi2, cin, _pitch(x), R, S, pad_h, pad_w,
+         x.data_ptr(), _ptr(xop.lo), hi2, wi2, cin, _pitch(x), R, S, pad[0], pad[1], stride[0], stride[1],
          dw.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel() * 4, _stream())
     return dw
+
+
+def dilate(x, stride, out_hw):
+    """zero-insertion upsampling (strided dgrad helper): y[:, h*sh, w*sw] = x[:, h, w]"""
+    n, h, w, c = x.shape
+    y = alloc_nhwc(n, out_hw[0], out_hw[1], c, x.dtype, x.device)
+    call("denet_dilate", x.data_ptr(), _dtype_code(x), n, h, w, c, _pitch(x), stride[0], stride[1], y.data_ptr(),
+         out_hw[0], out_hw[1], _pitch(y), _stream())
+    return y
+
+
+def im2col(x, R, S, stride, pad, out_hw):
+    """NHWC -> column matrix (N, Ho, Wo, R*S*C) (pitch padded to 8, tail zeroed)"""
+    n, h, w, c = x.shape
+    ho, wo = out_hw
+    k = R * S * c
+    col = alloc_nhwc(n, ho, wo, k, x.dtype, x.device)
+    call("denet_im2col", x.data_ptr(), _dtype_code(x), n, h, w, c, _pitch(x), R, S, stride[0], stride[1], pad[0],
+         pad[1], ho, wo, col.data_ptr(), _pitch(col), _stream())
+    return col
+
+
+def col2im(dcol, x_shape, R, S, stride, pad):
+    n, h, w, c = x_shape
+    _, ho, wo, _ = dcol.shape
+    dx = alloc_nhwc(n, h, w, c, dcol.dtype, dcol.device)
+    call("denet_col2im", dcol.data_ptr(), _dtype_code(dcol), _pitch(dcol), n, h, w, c, _pitch(dx), R, S, stride[0],
+         stride[1], pad[0], pad[1], ho, wo, dx.data_ptr(), _stream())
+    return dx
+
+
+def weight_to_im2col(w, out=None):
+    cout, cin, R, S = w.shape
+    if out is None:
+        out = torch.empty((cout, R * S * cin, 1, 1), dtype=torch.float32, device=w.device)
+    call("denet_weight_to_im2col", w.data_ptr(), cout, cin, R, S, out.data_ptr(), _stream())
+    return out
+
+
+def weight_grad_from_im2col(dw2, dw, accumulate=False):
+    cout, cin, R, S = dw.shape
+    call("denet_weight_grad_from_im2col", dw2.data_ptr(), cout, cin, R, S, dw.data_ptr(), int(accumulate), _stream())
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------- batch norm
+def _bn_ws(M, C, device):
+    nbytes = lib.load().denet_bn_workspace_bytes(M, C)
+    return workspace(nbytes, device, "bn")
+
+
+def bn_stats(x, eps, mean, invstd, run_mean=None, run_stdinv=None, momentum=0.9):
+    M, C = _rows(x), x.shape[-1]
+    ws = _bn_ws(M, C, x.device)
+    call("denet_bn_stats", x.data_ptr(), _dtype_code(x), M, C, _pitch(x), eps, mean.data_ptr(), invstd.data_ptr(),
+         _ptr(run_mean), _ptr(run_stdinv), momentum, ws.data_ptr(), ws.numel() * 4, _stream())
+
+
+def bn_finalize_sums(sums, sqsums, M, eps, mean, invstd, run_mean=None, run_stdinv=None, momentum=0.9):
+    call("denet_bn_finalize_sums", sums.data_ptr(), sqsums.data_ptr(), M, sums.numel(), eps, mean.data_ptr(),
+         invstd.data_ptr(), _ptr(run_mean), _ptr(run_stdinv), momentum, _stream())
+
+
+def bn_apply(x, mean, invstd, gamma, beta, residual=None, relu=False, out=None):
+    if out is None:
+        out = alloc_like(x)
+    assert _pitch(out) == _pitch(x) and (residual is None or _pitch(residual) == _pitch(x))
+    call("denet_bn_apply", x.data_ptr(), _dtype_code(x), _rows(x), x.shape[-1], _pitch(x), mean.data_ptr(),
+         invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(residual), int(relu), out.data_ptr(), _stream())
+    return out
+
+
+def bn_inference_invstd(run_stdinv, eps):
+    out = torch.empty_like(run_stdinv)
+    call("denet_bn_inference_invstd", run_stdinv.data_ptr(), eps, out.data_ptr(), run_stdinv.numel(), _stream())
+    return out
+
+
+def bn_backward(dy, yout, x, mean, invstd, gamma, relu, dgamma, dbeta, accumulate=False, want_dres=False, dx=None):
+    M, C = _rows(x), x.shape[-1]
+    ws = _bn_ws(M, C, x.device)
+    if dx is None:
+        dx = alloc_like(x)
+    dres = alloc_like(x) if want_dres else None
+    ld = _pitch(x)
+    assert _pitch(dy) == ld and _pitch(dx) == ld and (yout is None or _pitch(yout) == ld)
+    call("denet_bn_backward", dy.data_ptr(), _ptr(yout), x.data_ptr(), _dtype_code(x), M, C, ld, mean.data_ptr(),
+         invstd.data_ptr(), gamma.data_ptr(), int(relu), dx.data_ptr(), _ptr(dres), _ptr(dgamma), _ptr(dbeta),
+         int(accumulate), ws.data_ptr(), ws.numel() * 4, _stream())
+    return dx, dres
+
+
+# ---------------------------------------------------------------------------------------------- elementwise
+def relu_fwd(x, out=None):
+    if out is None:
+        out = alloc_like(x)
+    call("denet_relu_fwd", x.data_ptr(), _dtype_code(x), _rows(x), x.shape[-1], _pitch(x), out.data_ptr(), _stream())
+    return out
+
+
+def relu_bwd(dy, y, out=None):
+    if out is None:
+        out = alloc_like(dy)
+    assert _pitch(dy) == _pitch(y) == _pitch(out)
+    call("denet_relu_bwd", dy.data_ptr(), y.data_ptr(), _dtype_code(dy), _rows(dy), dy.shape[-1], _pitch(dy),
+         out.data_ptr(), _stream())
+    return out
+
+
+def add(a, b, relu=False, out=None):
+    if out is None:
+        out = alloc_like(a)
+    assert a.shape == b.shape and _pitch(a) == _pitch(b) == _pitch(out) and a.dtype == b.dtype
+    call("denet_add", a.data_ptr(), b.data_ptr(), _dtype_code(a), _rows(a), a.shape[-1], _pitch(a), int(relu),
+         out.data_ptr(), _stream())
+    return out
+
+
+def colsum(x, out, accumulate=False):
+    M, C = _rows(x), x.shape[-1]
+    ws = _bn_ws(M, C, x.device)
+    call("denet_colsum", x.data_ptr(), _dtype_code(x), M, C, _pitch(x), out.data_ptr(), int(accumulate),
+         ws.data_ptr(), ws.numel() * 4, _stream())
+    return out
+
+
+def convert(x, dtype, out=None):
+    if out is None:
+        out = alloc_like(x, dtype)
+    call("denet_convert", x.data_ptr(), _dtype_code(x), _rows(x), x.shape[-1], _pitch(x), out.data_ptr(),
+         _dtype_code(out), _pitch(out), _stream())
+    return out
+
+
+def nchw_to_nhwc(x, dtype):
+    """x: (N,C,H,W) fp32 contiguous device tensor -> NHWC activation"""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, c, h, w = x.shape
+    y = alloc_nhwc(n, h, w, c, dtype, x.device, zero=True)
+    call("denet_nchw_to_nhwc", x.data_ptr(), n, c, h, w, y.data_ptr(), _dtype_code(y), _pitch(y), _stream())
+    return y
+
+
+def nhwc_to_nchw(x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    call("denet_nhwc_to_nchw", x.data_ptr(), _dtype_code(x), _pitch(x), n, c, h, w, y.data_ptr(), _stream())
+    return y
+
+
+# ---------------------------------------------------------------------------------------------- pooling
+def pool_fwd(x, mode, size, stride, pad, out_hw):
+    n, h, w, c = x.shape
+    ho, wo = out_hw
+    y = alloc_nhwc(n, ho, wo, c, x.dtype, x.device)
+    argmax = torch.empty((n * ho * wo * c,), dtype=torch.uint8, device=x.device) if mode == 0 else None
+    call("denet_pool_fwd", x.data_ptr(), _dtype_code(x), n, h, w, c, _pitch(x), mode, size[0], size[1], stride[0],
+         stride[1], pad[0], pad[1], y.data_ptr(), ho, wo, _pitch(y), _ptr(argmax), _stream())
+    return y, argmax
+
+
+def pool_bwd(dy, mode, size, stride, pad, x_shape, argmax):
+    n, h, w, c = x_shape
+    _, ho, wo, _ = dy.shape
+    dx = alloc_nhwc(n, h, w, c, dy.dtype, dy.device)
+    call("denet_pool_bwd", dy.data_ptr(), _dtype_code(dy), n, h, w, c, _pitch(dx), mode, size[0], size[1], stride[0],
+         stride[1], pad[0], pad[1], ho, wo, _pitch(dy), _ptr(argmax), dx.data_ptr(), _stream())
+    return dx
+
+
+def pool_inv_fwd(x, size):
+    """size = (size_w, size_h) as in the reference PoolInvLayer"""
+    n, h, w, c = x.shape
+    y = alloc_nhwc(n, h * size[1], w * size[0], c, x.dtype, x.device)
+    call("denet_pool_inv_fwd", x.data_ptr(), _dtype_code(x), n, h, w, c, _pitch(x), size[0], size[1], y.data_ptr(),
+         _pitch(y), _stream())
+    return y
+
+
+def pool_inv_bwd(dy, size):
+    n, rh, rw, c = dy.shape
+    h, w = rh // size[1], rw // size[0]
+    dx = alloc_nhwc(n, h, w, c, dy.dtype, dy.device)
+    call("denet_pool_inv_bwd", dy.data_ptr(), _dtype_code(dy), n, h, w, c, _pitch(dx), size[0], size[1],
+         dx.data_ptr(), _pitch(dy), _stream())
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------- DSS head
+def sparse_sample_fwd(fmap, bbox, gs, out=None, out_dtype=None):
+    """fmap (B,H,W,F), bbox (B,sn,sn,4) fp32 device -> (B, sn, sn, gs*gs*F+2)"""
+    b, h, w, f = fmap.shape
+    sn = bbox.shape[1]
+    assert bbox.dtype == torch.float32 and bbox.is_contiguous()
+    oc = gs * gs * f + 2
+    if out is None:
+        out = alloc_nhwc(b, sn, sn, oc, out_dtype or fmap.dtype, fmap.device)
+    call("denet_sparse_sample_fwd", fmap.data_ptr(), _dtype_code(fmap), b, h, w, f, _pitch(fmap), bbox.data_ptr(),
+         sn * sn, gs, out.data_ptr(), _dtype_code(out), _pitch(out), _stream())
+    return out
+
+
+def sparse_sample_bwd(dy, bbox, gs, fmap_shape):
+    """dy (B,sn,sn,gs*gs*F+2) -> dfmap (B,H,W,F) fp32 (dense)"""
+    b, h, w, f = fmap_shape
+    sn = bbox.shape[1]
+    dfmap = torch.empty((b, h, w, f), dtype=torch.float32, device=dy.device)
+    call("denet_sparse_sample_bwd", dy.data_ptr(), _dtype_code(dy), _pitch(dy), bbox.data_ptr(), b, h, w, f, sn * sn,
+         gs, dfmap.data_ptr(), _stream())
+    return dfmap
+
+
+def sparse_sample_index(bbox, gs, H, W):
+    nroi = bbox.numel() // 4
+    ys = torch.empty((nroi, gs), dtype=torch.int32, device=bbox.device)
+    xs = torch.empty_like(ys)
+    call("denet_sparse_sample_index", bbox.data_ptr(), nroi, gs, H, W, ys.data_ptr(), xs.data_ptr(), _stream())
+    return ys, xs
+
+
+def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, local_max=0):
+    """corner_pr (B,2,4,H,W) fp32 device.  Returns (pr (B,K), bbox (B,K,4), ibox (B,K,4) int32, count (B), ncand (B))"""
+    assert corner_pr.dtype == torch.float32 and corner_pr.is_contiguous() and corner_pr.shape[1:3] == (2, 4)
+    b, _, _, h, w = corner_pr.shape
+    k = sample_num * sample_num
+    dev = corner_pr.device
+    pr = torch.empty((b, k), dtype=torch.float32, device=dev)
+    bbox = torch.empty((b, k, 4), dtype=torch.float32, device=dev)
+    ibox = torch.empty((b, k, 4), dtype=torch.int32, device=dev)
+    count = torch.empty((b,), dtype=torch.int32, device=dev)
+    ncand = torch.empty((b,), dtype=torch.int32, device=dev)
+    nbytes = lib.load().denet_build_samples_workspace(b, h, w, max_corners)
+    ws = workspace(nbytes, dev, "samples")
+    call("denet_build_samples", corner_pr.data_ptr(), b, h, w, corner_threshold, sample_num, max_corners, local_max,
+         pr.data_ptr(), bbox.data_ptr(), ibox.data_ptr(), count.data_ptr(), ncand.data_ptr(), ws.data_ptr(),
+         ws.numel() * 4, _stream())
+    return pr, bbox, ibox, count, ncand
+
+
+# ---------------------------------------------------------------------------------------------- costs
+def _loss_ws(device):
+    return workspace(lib.load().denet_loss_workspace_bytes(), device, "loss")
+
+
+def corner_logprob(z, cn):
+    """z (B,H,W,>=cn) -> (B,2,cn,H,W) fp32"""
+    b, h, w, _ = z.shape
+    out = torch.empty((b, 2, cn, h, w), dtype=torch.float32, device=z.device)
+    call("denet_corner_logprob", z.data_ptr(), _dtype_code(z), _pitch(z), b, cn, h, w, out.data_ptr(), _stream())
+    return out
+
+
+def corner_cost(z, cn, target, cost_factor, grad_factor, dz, cost):
+    b, h, w, _ = z.shape
+    assert _pitch(dz) == _pitch(z) and dz.dtype == z.dtype
+    ws = _loss_ws(z.device)
+    call("denet_corner_cost", z.data_ptr(), _dtype_code(z), _pitch(z), b, cn, h, w, target.data_ptr(), cost_factor,
+         grad_factor, dz.data_ptr(), cost.data_ptr(), ws.data_ptr(), _stream())
+
+
+def detect_cost(o, sn, s0, use_bbox, target_det, target_valid, target_reg, cost_factor, bbox_factor, grad_factor, dout,
+                cost2):
+    b = o.shape[0]
+    assert _pitch(dout) == _pitch(o) and dout.dtype == o.dtype
+    ws = _loss_ws(o.device)
+    call("denet_detect_cost", o.data_ptr(), _dtype_code(o), _pitch(o), b, sn, s0, int(use_bbox), target_det.data_ptr(),
+         _ptr(target_valid), _ptr(target_reg), cost_factor, bbox_factor, grad_factor, dout.data_ptr(), dout.shape[-1],
+         cost2.data_ptr(), ws.data_ptr(), _stream())
+
+
+def softmax_nll(o, classes, label, grad_factor, dout, logp, cost):
+    """o: (B, 1, 1, classes) logits; label int32 (B)"""
+    b = o.shape[0]
+    ws = _loss_ws(o.device)
+    call("denet_softmax_nll", o.data_ptr(), _dtype_code(o), _pitch(o), b, classes, label.data_ptr(), grad_factor,
+         _ptr(dout), _ptr(logp), cost.data_ptr(), ws.data_ptr(), _stream())

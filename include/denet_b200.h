@@ -4,12 +4,13 @@
  * cudaStream_t, enqueues work on that stream and returns without synchronising.  Nothing here allocates:
  * outputs and workspaces are owned by the caller.  Return value: 0 on success, <0 on error; the message of
  * the last error on the calling host thread is returned by denet_last_error().  Calls on distinct streams
- * are thread-safe.
+ * are thread-safe.  No entry point has a CPU fallback.
  *
  * Layout convention: activations are NHWC ("pixel-major"): element (n, h, w, c) of a tensor with pixel pitch
  * `ld` lives at ((n*H + h)*W + w)*ld + c.  Dtypes are DENET_F32 or DENET_BF16.  Filters keep the reference's
  * layout (Cout, Cin, R, S) fp32 *for the true (flipped) convolution* that Theano's conv2d computes
- * (reference denet/layer/convolution.py:83), so reference checkpoints load unchanged.
+ * (reference denet/layer/convolution.py:83), so reference checkpoints load unchanged.  Host-facing tensors
+ * that the reference exposes in NCHW (corner_pr, targets, images) keep that layout here.
  *
  * Each function names the reference interface it replaces (paths relative to the reference repository).
  */
@@ -27,7 +28,7 @@ typedef struct CUstream_st* cudaStream_t;
 extern "C" {
 #endif
 
-#define DENET_ABI_VERSION 1
+#define DENET_ABI_VERSION 2
 
 #define DENET_F32 0
 #define DENET_BF16 1
@@ -53,25 +54,160 @@ int denet_conv_weight_prep(const float* w, int Cout, int Cin, int R, int S, int 
 /* fp32 -> bf16 hi (+ lo = bf16(x - hi)) operand split.  lo may be NULL. */
 int denet_split_bf16(const float* x, void* hi, void* lo, long long n, cudaStream_t stream);
 
-/* Stride-1 R x S correlation of an NHWC bf16 tensor with a prepared operand:
- *   y[n,h,w,co] = sum_{r,s,ci} x[n, h+r-pad_h, w+s-pad_w, ci] * B[co][r*S+s][ci]   (zero outside the image)
+/* R x S correlation (stride stride_h x stride_w) of an NHWC bf16 tensor with a prepared operand:
+ *   y[n,h,w,co] = sum_{r,s,ci} x[n, h*stride_h+r-pad_h, w*stride_w+s-pad_w, ci] * B[co][r*S+s][ci]  (zero outside)
  * followed by the fused epilogue  (+bias[co]) (+residual) (relu)  and optional per-channel sum / sum-of-squares
  * accumulation of the conv output (before residual/relu) for batch-norm statistics.
- * With mode-0 operands this is the reference fprop; with mode-1 operands, Cin/Cout swapped and
- * pad = R-1-pad it is the reference dgrad. */
+ * With mode-0 operands this is the reference fprop; with mode-1 operands, Cin/Cout swapped, stride 1 and
+ * pad = R-1-pad it is the reference dgrad (of a stride-1 convolution, or of a strided one after denet_dilate). */
 int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin, long long ldx,
-                       const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w, void* y,
-                       int y_dtype, long long ldy, int Ho, int Wo, const float* bias, const void* residual, int relu,
-                       float* stat_sum, float* stat_sqsum, cudaStream_t stream);
+                       const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w, int stride_h,
+                       int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo, const float* bias,
+                       const void* residual, int relu, float* stat_sum, float* stat_sqsum, cudaStream_t stream);
 
-/* Filter gradient in the reference layout: dw[co][ci][R-1-r][S-1-s] (+)= sum_pixels dy[p,co] * x[p+(r,s)-pad, ci].
+/* Filter gradient in the reference layout:
+ *   dw[co][ci][R-1-r][S-1-s] (+)= sum_pixels dy[p,co] * x[p*stride+(r,s)-pad, ci].
  * Split-K partial sums go through `workspace` (size from denet_conv2d_wgrad_workspace) and are reduced in a
  * fixed order (deterministic). */
 size_t denet_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cout, int Cin, int R, int S);
 int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int Wo, int Cout, long long lddy,
                        const void* x_hi, const void* x_lo, int Hi, int Wi, int Cin, long long ldx, int R, int S,
-                       int pad_h, int pad_w, float* dw, int accumulate, float* workspace, size_t workspace_bytes,
+                       int pad_h, int pad_w, int stride_h, int stride_w, float* dw, int accumulate, float* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
+
+/* Zero-insertion upsampling y[n, h*sh, w*sw, :] = x[n,h,w,:] (zero elsewhere), (Hd, Wd) = extent of y: turns the
+ * data gradient of a strided convolution into a stride-1 correlation (cuDNN bwd-data of convolution.py:83). */
+int denet_dilate(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sh, int sw, void* y, int Hd,
+                 int Wd, long long ldy, cudaStream_t stream);
+
+/* Explicit im2col / col2im (column order k = (r*S+s)*C + c) for the 3-channel stem, whose 147-element patch rows
+ * are too ragged for the TMA implicit-GEMM path; the GEMM then runs as a 1x1 convolution over the column matrix.
+ * weight_to_im2col / weight_grad_from_im2col permute between (Cout,Cin,R,S) [true convolution] and (Cout, R*S*Cin). */
+int denet_im2col(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int R, int S, int sh, int sw,
+                 int ph, int pw, int Ho, int Wo, void* col, long long ldc, cudaStream_t stream);
+int denet_col2im(const void* dcol, int dtype, long long ldc, int N, int H, int W, int C, long long ldx, int R, int S,
+                 int sh, int sw, int ph, int pw, int Ho, int Wo, void* dx, cudaStream_t stream);
+int denet_weight_to_im2col(const float* w, int Cout, int Cin, int R, int S, float* w2, cudaStream_t stream);
+int denet_weight_grad_from_im2col(const float* dw2, int Cout, int Cin, int R, int S, float* dw, int accumulate,
+                                  cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ batch norm
+ * Replaces dnn_batch_normalization_train / _test and BatchNormReluOp + k_relu (denet/layer/batch_norm.py:47-53,
+ * 75-76; denet/layer/batch_norm_relu.py:31-57).  x is (M = N*H*W, C) with pitch ld.
+ * bn_stats: batch mean / inverse std (biased variance, 1/sqrt(var+eps)) by a deterministic two-stage shifted
+ * reduction, plus the reference's EMA of mean and INVERSE STD (run_* may be NULL).
+ * bn_finalize_sums: same outputs from the sum / sum-of-squares accumulated by denet_conv2d_fprop's epilogue.
+ * bn_apply: y = [relu]((x-mean)*gamma*invstd + beta [+ residual]).
+ * bn_inference_invstd: the reference's test-time quirk var = (1/stdinv)^2, eps added again (batch_norm.py:50-52).
+ * bn_backward: dy' = dy*[y>0] if relu; dx = gamma*invstd*(dy' - mean(dy') - xhat*mean(dy'*xhat));
+ *   dgamma/dbeta (+)=; dres (optional) receives dy' (gradient of the residual input). */
+size_t denet_bn_workspace_bytes(long long M, int C);
+int denet_bn_stats(const void* x, int dtype, long long M, int C, long long ld, float eps, float* mean, float* invstd,
+                   float* run_mean, float* run_stdinv, float momentum, float* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
+int denet_bn_finalize_sums(const float* sum, const float* sqsum, long long M, int C, float eps, float* mean,
+                           float* invstd, float* run_mean, float* run_stdinv, float momentum, cudaStream_t stream);
+int denet_bn_apply(const void* x, int dtype, long long M, int C, long long ld, const float* mean, const float* invstd,
+                   const float* gamma, const float* beta, const void* residual, int relu, void* y,
+                   cudaStream_t stream);
+int denet_bn_inference_invstd(const float* run_stdinv, float eps, float* out, int C, cudaStream_t stream);
+int denet_bn_backward(const void* dy, const void* yout, const void* x, int dtype, long long M, int C, long long ld,
+                      const float* mean, const float* invstd, const float* gamma, int relu, void* dx, void* dres,
+                      float* dgamma, float* dbeta, int accumulate, float* workspace, size_t workspace_bytes,
+                      cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ elementwise
+ * relu: tensor.nnet.relu (denet/layer/activation.py:32-34).  add: skip / residual sums (denet/layer/skip.py:78-86,
+ * denet/layer/resnet.py:113).  convert: dtype / pitch conversion.  nchw<->nhwc: host-facing layout conversion. */
+int denet_relu_fwd(const void* x, int dtype, long long M, int C, long long ld, void* y, cudaStream_t stream);
+int denet_relu_bwd(const void* dy, const void* y, int dtype, long long M, int C, long long ld, void* dx,
+                   cudaStream_t stream);
+int denet_add(const void* a, const void* b, int dtype, long long M, int C, long long ld, int relu, void* out,
+              cudaStream_t stream);
+/* colsum: out[c] (+)= sum over rows of x[:, c] - the bias gradient of a convolution (autodiff of
+ * `y += beta[None,:,None,None]`, denet/layer/convolution.py:88-89); workspace as for denet_bn_stats. */
+int denet_colsum(const void* x, int dtype, long long M, int C, long long ld, float* out, int accumulate,
+                 float* workspace, size_t workspace_bytes, cudaStream_t stream);
+int denet_convert(const void* x, int src_dtype, long long M, int C, long long ldx, void* y, int dst_dtype,
+                  long long ldy, cudaStream_t stream);
+int denet_nchw_to_nhwc(const float* x, int N, int C, int H, int W, void* y, int dtype, long long ld,
                        cudaStream_t stream);
+int denet_nhwc_to_nchw(const void* x, int dtype, long long ld, int N, int C, int H, int W, float* y,
+                       cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ pooling
+ * pool: dnn_pool max / average_inc_pad (denet/layer/pool.py:36-38); mode 0 = max (argmax buffer
+ * N*Ho*Wo*C bytes), 1 = average_inc_pad.  pool_inv: PoolInvOp / PoolInvGradOp, kernels k_pool_inv_WxH and
+ * k_pool_inv_grad_WxH (denet/layer/pool_inv_op.py:38-63, 144-169); x is the small (H, W) tensor. */
+int denet_pool_fwd(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int mode, int kh, int kw,
+                   int sh, int sw, int ph, int pw, void* y, int Ho, int Wo, long long ldy, uint8_t* argmax,
+                   cudaStream_t stream);
+int denet_pool_bwd(const void* dy, int dtype, int N, int H, int W, int C, long long ldx, int mode, int kh, int kw,
+                   int sh, int sw, int ph, int pw, int Ho, int Wo, long long ldy, const uint8_t* argmax, void* dx,
+                   cudaStream_t stream);
+int denet_pool_inv_fwd(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sw, int sh, void* y,
+                       long long ldy, cudaStream_t stream);
+int denet_pool_inv_bwd(const void* dy, int dtype, int N, int H, int W, int C, long long ldx, int sw, int sh, void* dx,
+                       long long ldy, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ DSS head
+ * sparse_sample_fwd/bwd: DeNetSparseOp / DeNetSparseGradOp, kernels k_sparse_sample<gs> / k_sparse_sample_grad<gs>
+ * (denet/layer/denet_sparse_op.py:42-85, 171-212).  fmap (B,H,W,F) pitch ldf; bbox
+ * (B*rois_per_image, 4) fp32 (x0,y0,x1,y1); out rows (B*rois_per_image, gs*gs*F+2) pitch ldo in the reference's
+ * channel order (yi*gs+xi)*F+f, then (box height, box width).  bwd zeroes dfmap (B,H,W,F fp32) and scatter-adds.
+ * sparse_sample_index: the integer grid coordinates alone (ys, xs: (nroi, gs) int32), for parity tests. */
+int denet_sparse_sample_fwd(const void* fmap, int dtype, int B, int H, int W, int F, long long ldf, const float* bbox,
+                            int rois_per_image, int gs, void* out, int out_dtype, long long ldo, cudaStream_t stream);
+int denet_sparse_sample_bwd(const void* dy, int dtype, long long ldo, const float* bbox, int B, int H, int W, int F,
+                            int rois_per_image, int gs, float* dfmap, cudaStream_t stream);
+int denet_sparse_sample_index(const float* bbox, long long nroi, int gs, int H, int W, int* ys, int* xs,
+                              cudaStream_t stream);
+
+/* build_samples: the reference's C++ extension entry point build_samples(thread_num, corner_pr, corner_threshold,
+ * sample_num, max_corners, local_max, cluster_threshold) (denet/layer/denet_sparse.cc:559-668, run_build_samples
+ * :489-557, search_corners :321-374, get_sample :271-308) for 4 corner types without clustering
+ * (cluster_threshold >= 1, the DNS default).  corner_pr: (B,2,4,H,W) fp32 log-probabilities on the device.
+ * Outputs per image, sorted by probability descending: out_pr (B,K) fp32, out_bbox (B,K,4) fp32 normalised
+ * (x0/W, y0/H, (x1+1)/W, (y1+1)/H), out_ibox (B,K,4) int32 corner positions, out_count (B) int32 (<= K = sample_num^2),
+ * out_ncand (B) int32 number of unique candidate boxes before the top-K (may be NULL).
+ * workspace: denet_build_samples_workspace(B, H, W, max_corners) bytes. */
+size_t denet_build_samples_workspace(int B, int H, int W, int max_corners);
+int denet_build_samples(const float* corner_pr, int B, int H, int W, float corner_threshold, int sample_num,
+                        int max_corners, int local_max, float* out_pr, float* out_bbox, int* out_ibox, int* out_count,
+                        int* out_ncand, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ costs
+ * corner_logprob: DeNetCornerLayer.corner_pr (denet/layer/denet_corner.py:50-53 + common/theano_util.py:27-29):
+ *   z (B*H*W rows, channels [0,cn)) -> (B,2,cn,H,W) fp32 log_softmax([z,-z]).
+ * corner_cost: DeNetCornerLayer.cost (:126-134) value + gradient wrt z (written over channels [0,cn) of dz).
+ * detect_cost: DeNetDetectLayer.get_errors/.cost (denet/layer/denet_detect.py:238-313), Fast R-CNN box loss variant;
+ *   cost2[0] = detection cost, cost2[1] = box cost (factors included); gradient over [0, ncols_grad) of dout rows.
+ * softmax_nll: RegressionLayer log-softmax + cost (denet/layer/regression.py:65-68, 97-98).
+ * grad_factor multiplies the gradient only (ModelCNN cost_factors, model/model_cnn.py:229-235). */
+size_t denet_loss_workspace_bytes(void);
+int denet_corner_logprob(const void* z, int dtype, long long ldz, int B, int cn, int H, int W, float* corner_pr,
+                         cudaStream_t stream);
+int denet_corner_cost(const void* z, int dtype, long long ldz, int B, int cn, int H, int W, const float* target,
+                      float cost_factor, float grad_factor, void* dz, float* cost, float* workspace,
+                      cudaStream_t stream);
+int denet_detect_cost(const void* o, int dtype, long long ld, int B, int sn, int s0, int use_bbox,
+                      const float* target_det, const float* target_valid, const float* target_reg, float cost_factor,
+                      float bbox_factor, float grad_factor, void* dout, int ncols_grad, float* cost2, float* workspace,
+                      cudaStream_t stream);
+int denet_softmax_nll(const void* o, int dtype, long long ld, int B, int classes, const int* label, float grad_factor,
+                      void* dout, float* logp_out, float* cost, float* workspace, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ solver
+ * ModelCNN.build_train_func update rules (model/model_cnn.py:282-305, 320-324) for ALL parameter
+ * tensors in one launch.  `entries` is a device array of denet_solver_entry_bytes()-sized records
+ * {float* p; const float* g; float* m; float* v; long long n; int is_weight; int pad}; block i updates elements
+ * [block_offset[i], +denet_solver_chunk()) of tensor block_tensor[i].  solver: 0 sgd, 1 nesterov/"torch", 2 adam.
+ * grad_scale multiplies g first (1/world_size after a gradient all-reduce-sum). */
+int denet_solver_entry_bytes(void);
+int denet_solver_chunk(void);
+int denet_solver_update(const void* entries, const int* block_tensor, const long long* block_offset, int nblocks,
+                        int solver, float lr, float momentum0, float momentum1, float decay, int iteration,
+                        int bias_decay, float grad_scale, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,208 @@
+"""Whole-model parity: a training step through the Layer API on the CUDA path vs the oracle's RefModel (torch-CPU
+fp64 restatement of the Theano graph + autograd), on the same weights (exchanged through the reference's JSON layer
+schema), inputs, RoIs and targets.  fp32-parity mode is held to north_star's 1e-4 relative per tensor for the shallow
+configs; for the deeper stacks the measured error is asserted against the stated looser bound."""
+import random
+
+import numpy
+import pytest
+import torch
+
+from oracle import ref_ops as R
+from oracle.ref_model import RefModel
+from util import relerr, synthetic_metas
+
+pytestmark = pytest.mark.gpu
+
+CFG1 = "C[128,3] BN A P[2] C[256,3] BN A P[2] C[512,3] BN A P.A R"                      # BASELINE.json configs[0]
+RESNET_SMALL = "C.B[16,7,2] BN A P[3,2,1] nRSN.O[2,16,3] nRSN.O[2,32,3,2] nRSN.O[1,64,3,2,16] P.A[2] R.TB"
+DENET_SMALL = ("C.B[32,7,2] BN A P[3,2,1] nRSN.O[1,32,3] nRSN.O[1,64,3,2] SKIPSRC[0] nRSN.O[1,128,3,2] SKIPSRC[1] "
+               "nRSN.O[1,256,3,2] PI[2] C[64,3] SKIP[1] BNA PI[2] C[32,3] SKIP[0] BNA DNC[32,100] "
+               "DNS[7,8,0.01,0.1] C[128,1] BNA C.B[64,1] BNA DND[0.5,1,1]")
+
+
+def build(desc, data_shape, batch, classes, precision, convert=False, seed=1):
+    from denet_b200.model import model_cnn
+    numpy.random.seed(seed)
+    model = model_cnn.ModelCNN()
+    model.batch_size, model.class_num = batch, classes
+    model.build(desc.split(), data_shape, "relu", "half", ["he-backward"])
+    if convert:
+        model.convert_bn_relu()
+    return model
+
+
+def named_params(model):
+    """{RefModel path.name: (param, is_weight)} by the same depth-first walk over the exported layer lists"""
+    out = {}
+
+    def walk(layer, path):
+        t = layer.type_name
+        if t == "conv":
+            out[path + ".weight"] = layer.omega
+            if layer.use_bias:
+                out[path + ".bias"] = layer.beta
+        elif t in ("batchnorm", "batchnorm-relu") and layer.enabled:
+            out[path + ".gamma"] = layer.omega
+            out[path + ".bias"] = layer.beta
+            out[path + ".mean"] = layer.mean
+            out[path + ".std"] = layer.stdinv
+        for i, sub in enumerate(layer.layers):
+            walk(sub, path + "/" + str(i))
+    for i, l in enumerate(model.layers[1:]):
+        walk(l, str(i))
+    return out
+
+
+def run_step(model, x, metas, solver="nesterov", lr=0.05, mom=(0.9, 0.9), decay=1e-4, it=1, seed=5):
+    """GPU train step; returns what is needed to replay it on the oracle"""
+    js = model.export_json()["layers"]
+    before = {k: p.detach().cpu().double().clone() for k, p in named_params(model).items()}
+    random.seed(seed)
+    numpy.random.seed(seed)
+    captured = []
+    for l in model.layers:
+        if l.has_cost or l.type_name == "denet-sparse":
+            orig = l.get_target
+
+            def wrapped(m, dx, dm, _orig=orig, _l=l):
+                t = _orig(m, dx, dm)
+                if t is not None:
+                    captured.append((_l.type_name, t))
+                return t
+            l.get_target = wrapped
+    cost, costs = model.train_step(x, metas, 0, it, lr, list(mom), decay)
+    for l in model.layers:
+        if "get_target" in l.__dict__:
+            del l.__dict__["get_target"]
+    return js, before, captured, cost, costs
+
+
+def compare(model, js, before, captured, x, cost, costs, solver, lr, mom, decay, it, tol, sample_bbox=None):
+    ref = RefModel(js, x.shape, model.class_num, dtype=torch.float64)
+    targets = [t for _, t in captured]
+    total, ref_costs, grads, out = ref.train_gradients(x, targets, sample_bbox=sample_bbox)
+    assert abs(cost - total) <= tol * abs(total), (cost, total)
+    for c, rc in zip(costs, ref_costs):
+        assert abs(c - rc) <= tol * max(abs(rc), 1e-6), (costs, ref_costs)
+    mine = named_params(model)
+    worst = 0.0
+    ref_named = {n: (p, w) for n, p, w in ref.named_params()}
+    for name, g in grads.items():
+        p = mine[name]
+        scale = g.norm().item()
+        if scale < 1e-12:
+            assert p.grad.norm().item() < 1e-8, name
+            continue
+        e = relerr(p.grad, g)
+        worst = max(worst, e)
+        assert e < tol, "gradient of %s: rel err %.3e" % (name, e)
+        # solver step replayed on the oracle's gradient (momentum buffers start at zero)
+        p_new = R.solver_update(before[name], g, torch.zeros_like(g), solver, it, lr, list(mom), decay,
+                                ref_named[name][1])[0]
+        assert relerr(p, p_new) < 1e-5, name
+    for path, (m_new, s_new) in ref.bn_updates.items():
+        assert relerr(mine[path + ".mean"], m_new) < tol
+        assert relerr(mine[path + ".std"], s_new) < tol
+    return worst
+
+
+def test_cfg1_cifar_cnn_train_step_fp32(cuda):
+    """BASELINE.json configs[0]: 3-layer CIFAR10 CNN, batch 32, synthetic 3x32x32, 10 classes"""
+    model = build(CFG1, (3, 32, 32), 32, 10, "fp32")
+    model.to_device(precision="fp32")
+    model.build_train_func("sgd", [])
+    numpy.random.seed(1)
+    x = numpy.random.uniform(0, 1, (32, 3, 32, 32)).astype(numpy.float32)
+    metas = [{"image_class": int(c), "bbox": [], "class": []} for c in numpy.random.randint(0, 10, 32)]
+    js, before, cap, cost, costs = run_step(model, x, metas, "sgd", 0.1, (0.9, 0.9), 1e-4, 0)
+    worst = compare(model, js, before, cap, x, cost, costs, "sgd", 0.1, (0.9, 0.9), 1e-4, 0, tol=1e-4)
+    print("cfg1 worst gradient rel err %.2e" % worst)
+
+
+@pytest.mark.parametrize("convert", [False, True])
+def test_resnet_classifier_train_step_fp32(cuda, convert):
+    model = build(RESNET_SMALL, (3, 64, 64), 8, 10, "fp32", convert)
+    model.to_device(precision="fp32")
+    model.build_train_func("nesterov", [])
+    numpy.random.seed(2)
+    x = numpy.random.uniform(0, 1, (8, 3, 64, 64)).astype(numpy.float32)
+    metas = [{"image_class": int(c), "bbox": [], "class": []} for c in numpy.random.randint(0, 10, 8)]
+    js, before, cap, cost, costs = run_step(model, x, metas, "nesterov", 0.05, (0.9, 0.9), 1e-4, 1)
+    worst = compare(model, js, before, cap, x, cost, costs, "nesterov", 0.05, (0.9, 0.9), 1e-4, 1, tol=3e-4)
+    print("resnet worst gradient rel err %.2e" % worst)
+
+
+def _denet_step(cuda, precision, tol):
+    from denet_b200.layer import set_param, get_param
+    model = build(DENET_SMALL, (3, 128, 128), 4, 20, precision, convert=True)
+    # a corner detector that fires: random corner rows, bias near the decision boundary
+    dnc = [l for l in model.layers if l.type_name == "denet-corner"][0]
+    conv = dnc.layers[1]
+    rng = numpy.random.RandomState(4)
+    w = get_param(conv.omega).copy()
+    w[:4] = rng.randn(*w[:4].shape) * 0.3
+    set_param(conv.omega, w)
+    b = get_param(conv.beta).copy()
+    b[:4] = 2.0
+    set_param(conv.beta, b)
+    model.to_device(precision=precision)
+    model.build_train_func("nesterov", [1.0, 0.5])
+    numpy.random.seed(3)
+    x = numpy.random.uniform(0, 1, (4, 3, 128, 128)).astype(numpy.float32)
+    metas = synthetic_metas(4, 20, seed=3, max_boxes=4)
+    js, before, cap, cost, costs = run_step(model, x, metas, "nesterov", 0.02, (0.9, 0.9), 1e-4, 1)
+    dns = [l for l in model.layers if l.type_name == "denet-sparse"][0]
+    bbox = dns.sample_bbox_host.astype(numpy.float32).reshape(4, 8, 8, 4)
+    return model, js, before, cap, x, cost, costs, bbox
+
+
+def test_denet_train_step_fp32(cuda):
+    """conv stack + skip + pool-inv + DNC/DNS/DND head, forward/backward/update vs the oracle on the same RoIs"""
+    model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "fp32", 5e-4)
+    ref = RefModel(js, x.shape, 20, dtype=torch.float64)
+    targets = [t for _, t in cap]
+    total, ref_costs, grads, out = ref.train_gradients(x, targets, sample_bbox=bbox, cost_factors=[1.0, 0.5])
+    assert abs(cost - total) < 5e-4 * abs(total), (cost, total, costs, ref_costs)
+    mine = named_params(model)
+    worst = 0.0
+    for name, g in grads.items():
+        if g.norm().item() < 1e-12:
+            continue
+        e = relerr(mine[name].grad, g)
+        worst = max(worst, e)
+        assert e < 5e-4, "gradient of %s: rel err %.3e" % (name, e)
+    print("denet worst gradient rel err %.2e" % worst)
+
+
+def test_denet_train_step_bf16_tracks_oracle(cuda):
+    """throughput mode (bf16 activations / MMA): costs within 2 %, gradients well aligned with the fp64 oracle"""
+    model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "bf16", None)
+    ref = RefModel(js, x.shape, 20, dtype=torch.float64)
+    targets = [t for _, t in cap]
+    total, ref_costs, grads, out = ref.train_gradients(x, targets, sample_bbox=bbox, cost_factors=[1.0, 0.5])
+    assert abs(cost - total) < 2e-2 * abs(total), (cost, total)
+    mine = named_params(model)
+    cos = []
+    for name, g in grads.items():
+        if g.norm().item() < 1e-12 or g.numel() < 64:
+            continue
+        a = mine[name].grad.detach().cpu().double().flatten()
+        cos.append(torch.dot(a, g.flatten()).item() / (a.norm().item() * g.norm().item() + 1e-30))
+    assert min(cos) > 0.95 and sum(cos) / len(cos) > 0.99, (min(cos), sum(cos) / len(cos))
+
+
+def test_json_roundtrip_and_predict(cuda):
+    from denet_b200.model import model_cnn
+    model = build(CFG1, (3, 32, 32), 4, 10, "fp32")
+    model.to_device(precision="fp32")
+    x = numpy.random.RandomState(0).uniform(0, 1, (4, 3, 32, 32)).astype(numpy.float32)
+    p0 = model.predict_output_step(x)
+    assert p0.shape == (4, 10) and numpy.allclose(p0.sum(axis=1), 1.0, atol=1e-5)
+    js = model.export_json()
+    m2 = model_cnn.load_from_json(js, batch_size=4)
+    m2.to_device(precision="fp32")
+    assert numpy.array_equal(m2.predict_output_step(x), p0)
+    ref = RefModel(js["layers"], x.shape, 10, dtype=torch.float64)
+    out = ref.forward(x, train=False)
+    assert relerr(p0, out["output"].detach()) < 1e-4
