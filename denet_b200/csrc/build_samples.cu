@@ -18,6 +18,7 @@
 // Ranking: the reference sorts by pr = 1/(1+exp(d)), d = |pr_f - pr_t|, descending, with an unstable sort; ranking
 // by d ascending is the same order wherever the reference's order is defined, and breaks its ties by box.
 #include "common.cuh"
+#include "expf_glibc.cuh"
 
 namespace dn {
 
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __
             const uint32_t box = (uint32_t)key;
             const int x0 = box >> 24, y0 = (box >> 16) & 255, x1 = (box >> 8) & 255, y1 = box & 255;
             // :306  float pr = 1.0 / (1.0 + std::exp(fabs(pr_f - pr_t)))  - float exp, double division, rounded to float
-            const float e = (float)exp((double)d);
+            const float e = expf_glibc(d);  // libm expf bit for bit (expf_glibc.cuh)
             out_pr[o] = (float)(1.0 / (1.0 + (double)e));
             // :307  (double)x0 / width ... rounded to float by the SampleType constructor
             out_bbox[o * 4 + 0] = (float)((double)x0 / (double)W);
@@ -414,12 +415,12 @@ extern "C" int denet_build_samples(const float* corner_pr, int B, int H, int W, 
     uint32_t* corners = reinterpret_cast<uint32_t*>(workspace);
     int* counts = reinterpret_cast<int*>(corners + (size_t)B * 4 * max_corners);
     const float thr = logf(corner_threshold);  // std::log(float), denet_sparse.cc:504
-    corner_select_kernel<<<B * 4, kBsThreads, 0, stream>>>(corner_pr, H, W, thr, max_corners, local_max, corners, counts);
+    corner_select_kernel<<<DN_G(B * 4), kBsThreads, 0, stream>>>(corner_pr, H, W, thr, max_corners, local_max, corners, counts);
     DN_CHECK_LAUNCH();
     const size_t smem = pair_smem_bytes(H, W, max_corners);
     DN_REQUIRE(smem <= 200 * 1024, "build_samples: shared memory budget exceeded");
     DN_CHECK_CUDA(cudaFuncSetAttribute(pair_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pair_select_kernel<<<B, kBsThreads, smem, stream>>>(corner_pr, H, W, max_corners, sample_num * sample_num, corners,
+    pair_select_kernel<<<DN_G(B), kBsThreads, smem, stream>>>(corner_pr, H, W, max_corners, sample_num * sample_num, corners,
                                                         counts, out_pr, out_bbox, out_ibox, out_count, out_ncand);
     DN_CHECK_LAUNCH();
     return 0;

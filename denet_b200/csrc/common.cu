@@ -1,5 +1,6 @@
 // Error reporting, device queries and TMA descriptor encoding shared by all C-ABI entry points.
 #include <string.h>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -16,6 +17,10 @@ int set_error(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
     static int cached = 0;
@@ -85,3 +90,6 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 extern "C" const char* denet_last_error(void) { return dn::last_error_buf(); }
 
 extern "C" int denet_abi_version(void) { return DENET_ABI_VERSION; }
+
+namespace dn { long long launch_count(); }
+extern "C" long long denet_launch_count(void) { return dn::launch_count(); }

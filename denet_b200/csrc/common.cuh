@@ -30,6 +30,11 @@ int set_error(int code, const char* fmt, ...);
         if (!(cond)) return dn::set_error(DENET_ERR_ARG, __VA_ARGS__);       \
     } while (0)
 
+// Every kernel launch site wraps its grid argument in DN_G(): counts the kernels this process has enqueued
+// (denet_launch_count(); bench.py reports the per-step figure as gpu_launches).
+void note_launch();
+#define DN_G(grid) (dn::note_launch(), (grid))
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

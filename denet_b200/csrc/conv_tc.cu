@@ -579,7 +579,7 @@ static int launch_fprop(const ConvFpropParams& p, cudaStream_t stream) {
     auto kern = conv_fprop_kernel<BN, STAGES>;
     DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    kern<<<grid, kThreads, L::kTotal, stream>>>(p);
+    kern<<<DN_G(grid), kThreads, L::kTotal, stream>>>(p);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -590,7 +590,7 @@ static int launch_wgrad(const ConvWgradParams& p, cudaStream_t stream) {
     auto kern = conv_wgrad_kernel<BN, STAGES>;
     DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    kern<<<grid, kThreads, L::kTotal, stream>>>(p);
+    kern<<<DN_G(grid), kThreads, L::kTotal, stream>>>(p);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -620,7 +620,7 @@ extern "C" int denet_conv_weight_prep(const float* w, int Cout, int Cin, int R, 
     const long long total = static_cast<long long>(rows) * R * S * ((kin + 63) / 64 * 64);
     const int block = 256;
     const int grid = (int)std::min<long long>(ceil_div_ll(total, block), 148LL * 16);
-    weight_prep_kernel<<<grid, block, 0, stream>>>(w, Cout, Cin, R, S, mode, (__nv_bfloat16*)b_hi, (__nv_bfloat16*)b_lo);
+    weight_prep_kernel<<<DN_G(grid), block, 0, stream>>>(w, Cout, Cin, R, S, mode, (__nv_bfloat16*)b_hi, (__nv_bfloat16*)b_lo);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -630,7 +630,7 @@ extern "C" int denet_split_bf16(const float* x, void* hi, void* lo, long long n,
     if (n == 0) return 0;
     const int block = 256;
     const int grid = (int)std::min<long long>(ceil_div_ll(n, block), 148LL * 32);
-    split_bf16_kernel<<<grid, block, 0, stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+    split_bf16_kernel<<<DN_G(grid), block, 0, stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -754,7 +754,7 @@ extern "C" int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, i
     const long long total = (long long)Cout * Cin * R * S;
     const int block = 256;
     const int grid = (int)std::min<long long>(ceil_div_ll(total, block), 148LL * 16);
-    wgrad_reduce_kernel<<<grid, block, 0, stream>>>(workspace, dw, splits, Cout, Cin, R, S, p.ldws, accumulate);
+    wgrad_reduce_kernel<<<DN_G(grid), block, 0, stream>>>(workspace, dw, splits, Cout, Cin, R, S, p.ldws, accumulate);
     DN_CHECK_LAUNCH();
     return 0;
 }

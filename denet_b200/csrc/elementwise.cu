@@ -723,8 +723,8 @@ extern "C" int denet_bn_stats(const void* x, int dtype, long long M, int C, long
     int rpb, yc;
     const int nslabs = bn_slabs(M, C, v ? 8 : 1, &rpb, &yc);
     DN_DISPATCH(dtype, v, {
-        bn_stats_partial_kernel<T, VEC><<<dim3(nslabs, yc), kBnThreads, 0, stream>>>((const T*)x, M, C, ld, rpb, workspace);
-        bn_stats_finalize_kernel<T><<<ceil_div(C, 128), 128, 0, stream>>>((const T*)x, workspace, nslabs, M, C, eps, mean,
+        bn_stats_partial_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>((const T*)x, M, C, ld, rpb, workspace);
+        bn_stats_finalize_kernel<T><<<DN_G(ceil_div(C, 128)), 128, 0, stream>>>((const T*)x, workspace, nslabs, M, C, eps, mean,
                                                                             invstd, run_mean, run_stdinv, momentum);
     });
     DN_CHECK_LAUNCH();
@@ -737,7 +737,7 @@ extern "C" int denet_bn_apply(const void* x, int dtype, long long M, int C, long
     DN_REQUIRE(x && y && mean && invstd && gamma && beta, "bn_apply: null pointer");
     const bool v = vec8_ok(C, ld, x, y, residual);
     DN_DISPATCH(dtype, v, {
-        bn_apply_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>(
+        bn_apply_kernel<T, VEC><<<DN_G(ew_grid(M * (C / VEC), 256)), 256, 0, stream>>>(
             (const T*)x, M, C, ld, mean, invstd, gamma, beta, (const T*)residual, relu, (T*)y);
     });
     DN_CHECK_LAUNCH();
@@ -746,7 +746,7 @@ extern "C" int denet_bn_apply(const void* x, int dtype, long long M, int C, long
 
 extern "C" int denet_bn_inference_invstd(const float* run_stdinv, float eps, float* out, int C, cudaStream_t stream) {
     DN_REQUIRE(run_stdinv && out, "bn_inference_invstd: null pointer");
-    bn_inference_invstd_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(run_stdinv, eps, out, C);
+    bn_inference_invstd_kernel<<<DN_G(ceil_div(C, 128)), 128, 0, stream>>>(run_stdinv, eps, out, C);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -763,11 +763,11 @@ extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x
     const int nslabs = bn_slabs(M, C, v ? 8 : 1, &rpb, &yc);
     float* sums = workspace + (size_t)nslabs * 2 * C;
     DN_DISPATCH(dtype, v, {
-        bn_bwd_partial_kernel<T, VEC><<<dim3(nslabs, yc), kBnThreads, 0, stream>>>(
+        bn_bwd_partial_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>(
             (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb, mean, invstd, relu, workspace);
-        bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(workspace, nslabs, C, sums, sums + C, dgamma, dbeta,
+        bn_bwd_finalize_kernel<<<DN_G(ceil_div(C, 128)), 128, 0, stream>>>(workspace, nslabs, C, sums, sums + C, dgamma, dbeta,
                                                                      accumulate);
-        bn_bwd_apply_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>(
+        bn_bwd_apply_kernel<T, VEC><<<DN_G(ew_grid(M * (C / VEC), 256)), 256, 0, stream>>>(
             (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, mean, invstd, gamma, sums, sums + C, relu, (T*)dx,
             (T*)dres);
     });
@@ -779,7 +779,7 @@ extern "C" int denet_relu_fwd(const void* x, int dtype, long long M, int C, long
     DN_REQUIRE(x && y, "relu_fwd: null pointer");
     const bool v = vec8_ok(C, ld, x, y);
     DN_DISPATCH(dtype, v, {
-        relu_fwd_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>((const T*)x, M, C, ld, (T*)y);
+        relu_fwd_kernel<T, VEC><<<DN_G(ew_grid(M * (C / VEC), 256)), 256, 0, stream>>>((const T*)x, M, C, ld, (T*)y);
     });
     DN_CHECK_LAUNCH();
     return 0;
@@ -790,7 +790,7 @@ extern "C" int denet_relu_bwd(const void* dy, const void* y, int dtype, long lon
     DN_REQUIRE(dy && y && dx, "relu_bwd: null pointer");
     const bool v = vec8_ok(C, ld, dy, y, dx);
     DN_DISPATCH(dtype, v, {
-        relu_bwd_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>((const T*)dy, (const T*)y, M, C, ld,
+        relu_bwd_kernel<T, VEC><<<DN_G(ew_grid(M * (C / VEC), 256)), 256, 0, stream>>>((const T*)dy, (const T*)y, M, C, ld,
                                                                                    (T*)dx);
     });
     DN_CHECK_LAUNCH();
@@ -802,7 +802,7 @@ extern "C" int denet_add(const void* a, const void* b, int dtype, long long M, i
     DN_REQUIRE(a && b && out, "add: null pointer");
     const bool v = vec8_ok(C, ld, a, b, out);
     DN_DISPATCH(dtype, v, {
-        add_kernel<T, VEC><<<ew_grid(M * (C / VEC), 256), 256, 0, stream>>>((const T*)a, (const T*)b, M, C, ld, relu,
+        add_kernel<T, VEC><<<DN_G(ew_grid(M * (C / VEC), 256)), 256, 0, stream>>>((const T*)a, (const T*)b, M, C, ld, relu,
                                                                               (T*)out);
     });
     DN_CHECK_LAUNCH();
@@ -815,9 +815,9 @@ extern "C" int denet_nchw_to_nhwc(const float* x, int N, int C, int H, int W, vo
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)ceil_div_ll(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N), block(32, 8);
     if (dtype == DENET_F32)
-        nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(x, C, HW, ld, (float*)y);
+        nchw_to_nhwc_kernel<float><<<DN_G(grid), block, 0, stream>>>(x, C, HW, ld, (float*)y);
     else
-        nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(x, C, HW, ld, (__nv_bfloat16*)y);
+        nchw_to_nhwc_kernel<__nv_bfloat16><<<DN_G(grid), block, 0, stream>>>(x, C, HW, ld, (__nv_bfloat16*)y);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -828,9 +828,9 @@ extern "C" int denet_nhwc_to_nchw(const void* x, int dtype, long long ld, int N,
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)ceil_div_ll(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N), block(32, 8);
     if (dtype == DENET_F32)
-        nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>((const float*)x, C, HW, ld, y);
+        nhwc_to_nchw_kernel<float><<<DN_G(grid), block, 0, stream>>>((const float*)x, C, HW, ld, y);
     else
-        nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, C, HW, ld, y);
+        nhwc_to_nchw_kernel<__nv_bfloat16><<<DN_G(grid), block, 0, stream>>>((const __nv_bfloat16*)x, C, HW, ld, y);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -846,10 +846,10 @@ extern "C" int denet_pool_fwd(const void* x, int dtype, int N, int H, int W, int
     DN_DISPATCH(dtype, v, {
         const int grid = ew_grid((long long)N * Ho * Wo * (C / VEC), 256);
         if (mode == 0)
-            maxpool_fwd_kernel<T, VEC><<<grid, 256, 0, stream>>>((const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, ph, pw, Ho,
+            maxpool_fwd_kernel<T, VEC><<<DN_G(grid), 256, 0, stream>>>((const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, ph, pw, Ho,
                                                                   Wo, ldy, (T*)y, argmax);
         else
-            avgpool_fwd_kernel<T, VEC><<<grid, 256, 0, stream>>>((const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, ph, pw, Ho,
+            avgpool_fwd_kernel<T, VEC><<<DN_G(grid), 256, 0, stream>>>((const T*)x, N, H, W, C, ldx, kh, kw, sh, sw, ph, pw, Ho,
                                                                   Wo, ldy, (T*)y);
     });
     DN_CHECK_LAUNCH();
@@ -865,10 +865,10 @@ extern "C" int denet_pool_bwd(const void* dy, int dtype, int N, int H, int W, in
     DN_DISPATCH(dtype, v, {
         const int grid = ew_grid((long long)N * H * W * (C / VEC), 256);
         if (mode == 0)
-            maxpool_bwd_kernel<T, VEC><<<grid, 256, 0, stream>>>((const T*)dy, argmax, N, H, W, C, ldx, kh, kw, sh, sw, ph,
+            maxpool_bwd_kernel<T, VEC><<<DN_G(grid), 256, 0, stream>>>((const T*)dy, argmax, N, H, W, C, ldx, kh, kw, sh, sw, ph,
                                                                   pw, Ho, Wo, ldy, (T*)dx);
         else
-            avgpool_bwd_kernel<T, VEC><<<grid, 256, 0, stream>>>((const T*)dy, N, H, W, C, ldx, kh, kw, sh, sw, ph, pw, Ho,
+            avgpool_bwd_kernel<T, VEC><<<DN_G(grid), 256, 0, stream>>>((const T*)dy, N, H, W, C, ldx, kh, kw, sh, sw, ph, pw, Ho,
                                                                   Wo, ldy, (T*)dx);
     });
     DN_CHECK_LAUNCH();
@@ -881,7 +881,7 @@ extern "C" int denet_pool_inv_fwd(const void* x, int dtype, int N, int H, int W,
     DN_REQUIRE(sw > 0 && sh > 0, "pool_inv_fwd: bad size");
     const bool v = vec8_ok(C, ldx, x) && vec8_ok(C, ldy, y);
     DN_DISPATCH(dtype, v, {
-        pool_inv_fwd_kernel<T, VEC><<<ew_grid((long long)N * H * sh * W * sw * (C / VEC), 256), 256, 0, stream>>>(
+        pool_inv_fwd_kernel<T, VEC><<<DN_G(ew_grid((long long)N * H * sh * W * sw * (C / VEC), 256)), 256, 0, stream>>>(
             (const T*)x, N, H, W, C, ldx, sw, sh, ldy, (T*)y);
     });
     DN_CHECK_LAUNCH();
@@ -893,7 +893,7 @@ extern "C" int denet_pool_inv_bwd(const void* dy, int dtype, int N, int H, int W
     DN_REQUIRE(dy && dx, "pool_inv_bwd: null pointer");
     const bool v = vec8_ok(C, ldx, dx) && vec8_ok(C, ldy, dy);
     DN_DISPATCH(dtype, v, {
-        pool_inv_bwd_kernel<T, VEC><<<ew_grid((long long)N * H * W * (C / VEC), 256), 256, 0, stream>>>(
+        pool_inv_bwd_kernel<T, VEC><<<DN_G(ew_grid((long long)N * H * W * (C / VEC), 256)), 256, 0, stream>>>(
             (const T*)dy, N, H, W, C, ldx, sw, sh, ldy, (T*)dx);
     });
     DN_CHECK_LAUNCH();
@@ -906,7 +906,7 @@ extern "C" int denet_dilate(const void* x, int dtype, int N, int H, int W, int C
     DN_REQUIRE(sh >= 1 && sw >= 1, "dilate: bad stride");
     const bool v = vec8_ok(C, ldx, x) && vec8_ok(C, ldy, y);
     DN_DISPATCH(dtype, v, {
-        dilate_kernel<T, VEC><<<ew_grid((long long)N * Hd * Wd * (C / VEC), 256), 256, 0, stream>>>(
+        dilate_kernel<T, VEC><<<DN_G(ew_grid((long long)N * Hd * Wd * (C / VEC), 256)), 256, 0, stream>>>(
             (const T*)x, N, H, W, C, ldx, sh, sw, Hd, Wd, ldy, (T*)y);
     });
     DN_CHECK_LAUNCH();
@@ -917,7 +917,7 @@ extern "C" int denet_bn_finalize_sums(const float* sum, const float* sqsum, long
                                       float* invstd, float* run_mean, float* run_stdinv, float momentum,
                                       cudaStream_t stream) {
     DN_REQUIRE(sum && sqsum && mean && invstd, "bn_finalize_sums: null pointer");
-    bn_finalize_sums_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(sum, sqsum, M, C, eps, mean, invstd, run_mean,
+    bn_finalize_sums_kernel<<<DN_G(ceil_div(C, 128)), 128, 0, stream>>>(sum, sqsum, M, C, eps, mean, invstd, run_mean,
                                                                   run_stdinv, momentum);
     DN_CHECK_LAUNCH();
     return 0;
@@ -931,8 +931,8 @@ extern "C" int denet_convert(const void* x, int src_dtype, long long M, int C, l
     const int grid = ew_grid(M * (C / (v ? 8 : 1)), 256);
 #define DN_CONVERT(TI, TO)                                                                                     \
     do {                                                                                                       \
-        if (v) convert_kernel<TI, TO, 8><<<grid, 256, 0, stream>>>((const TI*)x, M, C, ldx, ldy, (TO*)y);      \
-        else convert_kernel<TI, TO, 1><<<grid, 256, 0, stream>>>((const TI*)x, M, C, ldx, ldy, (TO*)y);        \
+        if (v) convert_kernel<TI, TO, 8><<<DN_G(grid), 256, 0, stream>>>((const TI*)x, M, C, ldx, ldy, (TO*)y);      \
+        else convert_kernel<TI, TO, 1><<<DN_G(grid), 256, 0, stream>>>((const TI*)x, M, C, ldx, ldy, (TO*)y);        \
     } while (0)
     if (src_dtype == DENET_F32 && dst_dtype == DENET_BF16) DN_CONVERT(float, __nv_bfloat16);
     else if (src_dtype == DENET_BF16 && dst_dtype == DENET_F32) DN_CONVERT(__nv_bfloat16, float);
@@ -952,9 +952,9 @@ extern "C" int denet_colsum(const void* x, int dtype, long long M, int C, long l
     int rpb, yc;
     const int nslabs = bn_slabs(M, C, v ? 8 : 1, &rpb, &yc);
     DN_DISPATCH(dtype, v, {
-        colsum_partial_kernel<T, VEC><<<dim3(nslabs, yc), kBnThreads, 0, stream>>>((const T*)x, M, C, ld, rpb, workspace);
+        colsum_partial_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>((const T*)x, M, C, ld, rpb, workspace);
     });
-    colsum_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(workspace, nslabs, C, out, accumulate);
+    colsum_finalize_kernel<<<DN_G(ceil_div(C, 128)), 128, 0, stream>>>(workspace, nslabs, C, out, accumulate);
     DN_CHECK_LAUNCH();
     return 0;
 }

@@ -121,10 +121,10 @@ extern "C" int denet_im2col(const void* x, int dtype, int N, int H, int W, int C
     const bool v = vec8_ok(C, ldx, x) && vec8_ok(C, ldc, col);
     const long long rows = (long long)N * Ho * Wo;
     DN_DISPATCH(dtype, v, {
-        im2col_kernel<T, VEC><<<grid_for(rows * R * S * (C / VEC)), 256, 0, stream>>>(
+        im2col_kernel<T, VEC><<<DN_G(grid_for(rows * R * S * (C / VEC))), 256, 0, stream>>>(
             (const T*)x, N, H, W, C, ldx, R, S, sh, sw, ph, pw, Ho, Wo, (T*)col, ldc);
         if (ldc > (long long)R * S * C)
-            zero_tail_kernel<T><<<grid_for(rows * (ldc - (long long)R * S * C)), 256, 0, stream>>>((T*)col, rows,
+            zero_tail_kernel<T><<<DN_G(grid_for(rows * (ldc - (long long)R * S * C))), 256, 0, stream>>>((T*)col, rows,
                                                                                                     R * S * C, ldc);
     });
     DN_CHECK_LAUNCH();
@@ -136,7 +136,7 @@ extern "C" int denet_col2im(const void* dcol, int dtype, long long ldc, int N, i
     DN_REQUIRE(dcol && dx, "col2im: null pointer");
     const bool v = vec8_ok(C, ldx, dx) && vec8_ok(C, ldc, dcol);
     DN_DISPATCH(dtype, v, {
-        col2im_kernel<T, VEC><<<grid_for((long long)N * H * W * (C / VEC)), 256, 0, stream>>>(
+        col2im_kernel<T, VEC><<<DN_G(grid_for((long long)N * H * W * (C / VEC))), 256, 0, stream>>>(
             (const T*)dcol, ldc, N, H, W, C, ldx, R, S, sh, sw, ph, pw, Ho, Wo, (T*)dx);
     });
     DN_CHECK_LAUNCH();
@@ -145,7 +145,7 @@ extern "C" int denet_col2im(const void* dcol, int dtype, long long ldc, int N, i
 
 extern "C" int denet_weight_to_im2col(const float* w, int Cout, int Cin, int R, int S, float* w2, cudaStream_t stream) {
     DN_REQUIRE(w && w2, "weight_to_im2col: null pointer");
-    weight_im2col_perm_kernel<<<grid_for((long long)Cout * Cin * R * S), 256, 0, stream>>>(w, w2, Cout, Cin, R, S, 0, 0);
+    weight_im2col_perm_kernel<<<DN_G(grid_for((long long)Cout * Cin * R * S)), 256, 0, stream>>>(w, w2, Cout, Cin, R, S, 0, 0);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -153,7 +153,7 @@ extern "C" int denet_weight_to_im2col(const float* w, int Cout, int Cin, int R, 
 extern "C" int denet_weight_grad_from_im2col(const float* dw2, int Cout, int Cin, int R, int S, float* dw,
                                              int accumulate, cudaStream_t stream) {
     DN_REQUIRE(dw2 && dw, "weight_grad_from_im2col: null pointer");
-    weight_im2col_perm_kernel<<<grid_for((long long)Cout * Cin * R * S), 256, 0, stream>>>(dw2, dw, Cout, Cin, R, S, 1,
+    weight_im2col_perm_kernel<<<DN_G(grid_for((long long)Cout * Cin * R * S)), 256, 0, stream>>>(dw2, dw, Cout, Cin, R, S, 1,
                                                                                           accumulate);
     DN_CHECK_LAUNCH();
     return 0;

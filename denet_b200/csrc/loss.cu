@@ -224,9 +224,9 @@ extern "C" int denet_corner_logprob(const void* z, int dtype, long long ldz, int
     const long long total = (long long)B * cn * H * W;
     const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 8);
     if (dtype == DENET_F32)
-        corner_logprob_kernel<float><<<grid, 256, 0, stream>>>((const float*)z, ldz, B, cn, H, W, corner_pr);
+        corner_logprob_kernel<float><<<DN_G(grid), 256, 0, stream>>>((const float*)z, ldz, B, cn, H, W, corner_pr);
     else
-        corner_logprob_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)z, ldz, B, cn, H, W,
+        corner_logprob_kernel<__nv_bfloat16><<<DN_G(grid), 256, 0, stream>>>((const __nv_bfloat16*)z, ldz, B, cn, H, W,
                                                                         corner_pr);
     DN_CHECK_LAUNCH();
     return 0;
@@ -238,13 +238,13 @@ extern "C" int denet_corner_cost(const void* z, int dtype, long long ldz, int B,
     DN_REQUIRE(z && target && dz && cost && workspace, "corner_cost: null pointer");
     const float inv = 1.0f / ((float)B * 0.6931471805599453f);
     if (dtype == DENET_F32)
-        corner_cost_kernel<float><<<kLossBlocks, kLossThreads, 0, stream>>>(
+        corner_cost_kernel<float><<<DN_G(kLossBlocks), kLossThreads, 0, stream>>>(
             (const float*)z, ldz, B, cn, H, W, target, cost_factor * grad_factor * inv, (float*)dz, workspace);
     else
-        corner_cost_kernel<__nv_bfloat16><<<kLossBlocks, kLossThreads, 0, stream>>>(
+        corner_cost_kernel<__nv_bfloat16><<<DN_G(kLossBlocks), kLossThreads, 0, stream>>>(
             (const __nv_bfloat16*)z, ldz, B, cn, H, W, target, cost_factor * grad_factor * inv, (__nv_bfloat16*)dz,
             workspace);
-    sum_partials_kernel<<<1, 32, 0, stream>>>(workspace, kLossBlocks, 1, -cost_factor * inv, cost);
+    sum_partials_kernel<<<DN_G(1), 32, 0, stream>>>(workspace, kLossBlocks, 1, -cost_factor * inv, cost);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -260,15 +260,15 @@ extern "C" int denet_detect_cost(const void* o, int dtype, long long ld, int B, 
     const float det_scale = cost_factor / ((float)B * logf((float)s0));
     const float box_scale = bbox_factor / (float)B;
     if (dtype == DENET_F32)
-        detect_cost_kernel<float><<<kLossBlocks, kLossThreads, 0, stream>>>(
+        detect_cost_kernel<float><<<DN_G(kLossBlocks), kLossThreads, 0, stream>>>(
             (const float*)o, ld, R, s0, sn2, use_bbox, target_det, target_valid, target_reg, det_scale * grad_factor,
             bbox_factor, box_scale * grad_factor, (float*)dout, ncols_grad, workspace);
     else
-        detect_cost_kernel<__nv_bfloat16><<<kLossBlocks, kLossThreads, 0, stream>>>(
+        detect_cost_kernel<__nv_bfloat16><<<DN_G(kLossBlocks), kLossThreads, 0, stream>>>(
             (const __nv_bfloat16*)o, ld, R, s0, sn2, use_bbox, target_det, target_valid, target_reg,
             det_scale * grad_factor, bbox_factor, box_scale * grad_factor, (__nv_bfloat16*)dout, ncols_grad, workspace);
     // cost2[0] = detection cost, cost2[1] = box cost, each including its factors (reference :308-310)
-    sum_partials2_kernel<<<1, 32, 0, stream>>>(workspace, kLossBlocks, -det_scale, box_scale, cost2);
+    sum_partials2_kernel<<<DN_G(1), 32, 0, stream>>>(workspace, kLossBlocks, -det_scale, box_scale, cost2);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -279,14 +279,14 @@ extern "C" int denet_softmax_nll(const void* o, int dtype, long long ld, int B, 
     DN_REQUIRE(o && label && cost && workspace, "softmax_nll: null pointer");
     const int grid = std::min(kLossBlocks, ceil_div(B, kLossThreads / 32));
     if (dtype == DENET_F32)
-        softmax_nll_kernel<float><<<grid, kLossThreads, 0, stream>>>((const float*)o, ld, B, classes, label,
+        softmax_nll_kernel<float><<<DN_G(grid), kLossThreads, 0, stream>>>((const float*)o, ld, B, classes, label,
                                                                      grad_factor / (float)B, (float*)dout, logp_out,
                                                                      workspace);
     else
-        softmax_nll_kernel<__nv_bfloat16><<<grid, kLossThreads, 0, stream>>>(
+        softmax_nll_kernel<__nv_bfloat16><<<DN_G(grid), kLossThreads, 0, stream>>>(
             (const __nv_bfloat16*)o, ld, B, classes, label, grad_factor / (float)B, (__nv_bfloat16*)dout, logp_out,
             workspace);
-    sum_partials_kernel<<<1, 32, 0, stream>>>(workspace, grid, 1, -1.0f / (float)B, cost);
+    sum_partials_kernel<<<DN_G(1), 32, 0, stream>>>(workspace, grid, 1, -1.0f / (float)B, cost);
     DN_CHECK_LAUNCH();
     return 0;
 }

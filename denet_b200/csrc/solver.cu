@@ -70,7 +70,7 @@ extern "C" int denet_solver_update(const void* entries, const int* block_tensor,
     DN_REQUIRE(solver >= 0 && solver <= 2, "solver_update: solver must be 0 (sgd), 1 (nesterov/torch) or 2 (adam)");
     if (nblocks == 0) return 0;
     const float rho = iteration > 0 ? momentum0 : 0.0f;
-    solver_update_kernel<<<nblocks, 256, 0, stream>>>((const SolverEntry*)entries, block_tensor, block_offset, solver, lr,
+    solver_update_kernel<<<DN_G(nblocks), 256, 0, stream>>>((const SolverEntry*)entries, block_tensor, block_offset, solver, lr,
                                                       momentum0, momentum1, rho, decay, iteration, bias_decay,
                                                       grad_scale);
     DN_CHECK_LAUNCH();

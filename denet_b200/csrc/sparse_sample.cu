@@ -133,13 +133,13 @@ static void launch_fwd(int vec, const void* fmap, long long ldf, const float* bb
                        int gs, void* out, long long ldo, cudaStream_t stream) {
     const int grid = B * rpi;
     if (vec == 8)
-        sparse_sample_fwd_kernel<TI, TO, 8><<<grid, kSsThreads, 0, stream>>>((const TI*)fmap, ldf, bbox, B, F, H, W, rpi,
+        sparse_sample_fwd_kernel<TI, TO, 8><<<DN_G(grid), kSsThreads, 0, stream>>>((const TI*)fmap, ldf, bbox, B, F, H, W, rpi,
                                                                              gs, (TO*)out, ldo);
     else if (vec == 4)
-        sparse_sample_fwd_kernel<TI, TO, 4><<<grid, kSsThreads, 0, stream>>>((const TI*)fmap, ldf, bbox, B, F, H, W, rpi,
+        sparse_sample_fwd_kernel<TI, TO, 4><<<DN_G(grid), kSsThreads, 0, stream>>>((const TI*)fmap, ldf, bbox, B, F, H, W, rpi,
                                                                              gs, (TO*)out, ldo);
     else
-        sparse_sample_fwd_kernel<TI, TO, 1><<<grid, kSsThreads, 0, stream>>>((const TI*)fmap, ldf, bbox, B, F, H, W, rpi,
+        sparse_sample_fwd_kernel<TI, TO, 1><<<DN_G(grid), kSsThreads, 0, stream>>>((const TI*)fmap, ldf, bbox, B, F, H, W, rpi,
                                                                              gs, (TO*)out, ldo);
 }
 
@@ -178,7 +178,7 @@ extern "C" int denet_sparse_sample_bwd(const void* dy, int dtype, long long ldo,
     const int vec = pick_vec(F, ldo, dy, es, F, dfmap, 4);
     const int grid = B * rois_per_image;
 #define DN_SS_BWD(T, V)                                                                                              \
-    sparse_sample_bwd_kernel<T, V><<<grid, kSsThreads, 0, stream>>>((const T*)dy, ldo, bbox, B, F, H, W,             \
+    sparse_sample_bwd_kernel<T, V><<<DN_G(grid), kSsThreads, 0, stream>>>((const T*)dy, ldo, bbox, B, F, H, W,             \
                                                                     rois_per_image, gs, dfmap)
     if (dtype == DENET_F32) {
         if (vec == 8) DN_SS_BWD(float, 8); else if (vec == 4) DN_SS_BWD(float, 4); else DN_SS_BWD(float, 1);
@@ -196,7 +196,7 @@ extern "C" int denet_sparse_sample_index(const float* bbox, long long nroi, int 
     DN_REQUIRE(bbox && ys && xs, "sparse_sample_index: null pointer");
     if (nroi == 0) return 0;
     const long long total = nroi * gs;
-    sparse_sample_index_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(bbox, nroi, gs, H, W, ys, xs);
+    sparse_sample_index_kernel<<<DN_G((unsigned)ceil_div_ll(total, 256)), 256, 0, stream>>>(bbox, nroi, gs, H, W, ys, xs);
     DN_CHECK_LAUNCH();
     return 0;
 }

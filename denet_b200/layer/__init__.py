@@ -115,6 +115,27 @@ def import_json(json_layers, x, x_shape, layer_range=None):
     return layers
 
 
+# host <-> device traffic of the training step, counted so that bench.py can report it (e2e.h2d/d2h_bytes_per_step)
+transfer_bytes = {"h2d": 0, "d2h": 0}
+
+
+def h2d(array, device=None):
+    """host numpy array / CPU tensor -> device tensor through pinned memory, asynchronous on the current stream"""
+    t = array if torch.is_tensor(array) else torch.from_numpy(numpy.ascontiguousarray(array))
+    if t.is_cuda:
+        return t
+    transfer_bytes["h2d"] += t.numel() * t.element_size()
+    if not t.is_pinned():
+        t = t.pin_memory()
+    return t.to(device if device is not None else (_state["device"] or "cuda"), non_blocking=True)
+
+
+def d2h(tensor):
+    """device tensor -> numpy (synchronises the current stream)"""
+    transfer_bytes["d2h"] += tensor.numel() * tensor.element_size()
+    return tensor.cpu().numpy()
+
+
 def new_param(array):
     """fp32 master parameter in the reference's layout; gradients are managed by the layers, not autograd"""
     t = torch.as_tensor(numpy.ascontiguousarray(numpy.asarray(array, dtype=numpy.float32)))

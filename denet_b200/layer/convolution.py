@@ -10,7 +10,7 @@ import math
 import numpy
 import torch
 
-from .. import ops
+from .. import lib, ops
 from . import (AbstractLayer, act_dtype, get_param, get_precision, new_param, param_version, set_param)
 
 
@@ -111,6 +111,11 @@ class ConvLayer(AbstractLayer):
         layers.append(ConvLayer(layers, filter_shape, filter_stride, use_bias, params["borderMode"], params["wb"]))
         return True
 
+    def fprop_flops(self):
+        """algorithmic FLOPs of one forward pass: 2 * N * Cout * Ho * Wo * Cin * R * S"""
+        n, co, oh, ow = self.output_shape
+        return 2.0 * n * co * oh * ow * self.filter_shape[1] * self.size[0] * self.size[1]
+
     def weights(self):
         return super().weights() + ([self.omega] if self.enabled else [])
 
@@ -163,6 +168,7 @@ class ConvLayer(AbstractLayer):
             self.output = x
             return x
         wop_f, _ = self._operands()
+        lib.set_tag(("fprop", self))
         n, ci, h, w = self.input_shape
         _, co, oh, ow = self.output_shape
         out_dtype = torch.float32 if self.out_fp32 else act_dtype()
@@ -188,6 +194,7 @@ class ConvLayer(AbstractLayer):
         if not self.enabled:
             return dy if add_to is None else ops.add(dy, add_to)
         _, wop_d = self._operands()
+        lib.set_tag(("bwd", self))
         n, ci, h, w = self.input_shape
         R, S = self.size
         dyop = self._as_operand(dy)

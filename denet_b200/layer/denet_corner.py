@@ -11,7 +11,7 @@ import numpy
 import torch
 
 from .. import ops
-from . import AbstractLayer, InitialLayer, get_train, set_param, get_param
+from . import AbstractLayer, InitialLayer, get_train, h2d, set_param, get_param
 from .convolution import ConvLayer
 
 
@@ -100,8 +100,7 @@ class DeNetCornerLayer(AbstractLayer):
         return numpy.array([], dtype=numpy.int64), corner_pr.flatten()
 
     def set_target(self, yt_index, yt_value):
-        t = torch.from_numpy(numpy.ascontiguousarray(yt_value, dtype=numpy.float32))
-        self._target = t.pin_memory().cuda(non_blocking=True)
+        self._target = h2d(numpy.ascontiguousarray(yt_value, dtype=numpy.float32))
 
     def forward(self, x):
         self.input = self.output = x

@@ -11,7 +11,7 @@ import numpy
 import torch
 
 from .. import common, ops
-from . import AbstractLayer, InitialLayer, get_train
+from . import AbstractLayer, InitialLayer, get_train, h2d
 from .convolution import ConvLayer
 
 
@@ -148,8 +148,7 @@ class DeNetDetectLayer(AbstractLayer):
         return numpy.array([], dtype=numpy.int64), yt_value
 
     def set_target(self, yt_index, yt_value):
-        v = torch.from_numpy(numpy.ascontiguousarray(yt_value, dtype=numpy.float32)).pin_memory().cuda(
-            non_blocking=True)
+        v = h2d(numpy.ascontiguousarray(yt_value, dtype=numpy.float32))
         n0 = int(numpy.prod(self.det_shape))
         n1 = self.batch_size * self.sample_num * self.sample_num
         if self.use_bbox_reg:

@@ -16,7 +16,7 @@ import numpy
 import torch
 
 from .. import common, ops
-from . import AbstractLayer, act_dtype, get_train
+from . import AbstractLayer, act_dtype, d2h, get_train, h2d
 
 
 def py_random_doubles(k):
@@ -97,7 +97,7 @@ class DeNetSparseLayer(AbstractLayer):
         pr, bbox, _, count, _ = ops.build_samples(corner_pr, self.corner_threshold, self.sample_num, self.corner_max,
                                                   self.local_max)
         k = self.sample_count
-        packed = torch.cat([pr.reshape(-1), bbox.reshape(-1), count.to(torch.float32)]).cpu().numpy()
+        packed = d2h(torch.cat([pr.reshape(-1), bbox.reshape(-1), count.to(torch.float32)]))
         b = self.batch_size
         return (packed[:b * k].reshape(b, k), packed[b * k:5 * b * k].reshape(b, k, 4),
                 packed[5 * b * k:].astype(numpy.int64))
@@ -123,7 +123,7 @@ class DeNetSparseLayer(AbstractLayer):
         self._sample_bbox_list = None
         arr = numpy.ascontiguousarray(bbox.astype(numpy.float32).reshape(self.batch_size, self.sample_num,
                                                                          self.sample_num, 4))
-        self.sample_bbox = torch.from_numpy(arr).pin_memory().cuda(non_blocking=True)
+        self.sample_bbox = h2d(arr)
         return arr
 
     def set_samples(self, sample_bboxs):

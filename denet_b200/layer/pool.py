@@ -33,6 +33,7 @@ class PoolLayer(AbstractLayer):
             w = int(math.ceil((self.input_shape[3] + 2 * self.pad[1]) / self.stride[1]))
         self.output_shape = (self.input_shape[0], self.input_shape[1], h, w)
         self._argmax = None
+        self.last_argmax = None
 
     @staticmethod
     def parse_desc(layers, name, tags, params):
@@ -57,6 +58,7 @@ class PoolLayer(AbstractLayer):
         mode = 0 if self.mode == "max" else 1
         y, self._argmax = ops.pool_fwd(x, mode, self.size, self.stride, self.pad, self.output_shape[2:])
         self._in_shape = tuple(x.shape)
+        self.last_argmax = self._argmax    # (N,Ho,Wo,C) uint8 window tap of the maximum; kept for inspection / tests
         self.output = y
         return y
 

@@ -5,7 +5,7 @@ import numpy
 import torch
 
 from .. import ops
-from . import AbstractLayer, get_train
+from . import AbstractLayer, get_train, h2d
 from .convolution import ConvLayer
 
 
@@ -61,7 +61,7 @@ class RegressionLayer(AbstractLayer):
     def set_target(self, yt_index, yt_value):
         classes = self.output_shape[1]
         label = (numpy.asarray(yt_index, dtype=numpy.int64) % classes).astype(numpy.int32)
-        self._label = torch.from_numpy(label).cuda(non_blocking=True)
+        self._label = h2d(label)
 
     def forward(self, x):
         self.input = x

@@ -88,9 +88,48 @@ def launch_count():
     return _launches
 
 
+# ---------------------------------------------------------------------------------------------- per-entry timing
+# bench.py brackets selected entry points with CUDA events on the stream they are enqueued on (the roofline figure
+# needs the device duration of the conv kernels measured live inside the timed region).
+_timed = None     # {entry point name: [(start_event, end_event, tag)]} while timing is on
+
+
+def start_timing(names):
+    global _timed
+    _timed = {n: [] for n in names}
+
+
+def stop_timing():
+    """-> {name: [(milliseconds, tag)]}; synchronises the device"""
+    global _timed
+    import torch
+    torch.cuda.synchronize()
+    out = {n: [(a.elapsed_time(b), tag) for a, b, tag in evs] for n, evs in (_timed or {}).items()}
+    _timed = None
+    return out
+
+
+_tag = None
+
+
+def set_tag(tag):
+    """label attached to the timed calls that follow (bench.py: which layer / pass issued the kernel)"""
+    global _tag
+    _tag = tag
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise DenetError on a non-zero status."""
     global _launches
     _launches += 1
     fn = getattr(load(), name)
+    if _timed is not None and name in _timed:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        _timed[name].append((a, b, _tag))
+        check(rc, name)
+        return
     check(fn(*args), name)

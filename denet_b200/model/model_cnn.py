@@ -361,11 +361,8 @@ class ModelCNN:
     def upload(self, data_x):
         """host NCHW fp32 batch (numpy or pinned tensor) -> NHWC device activation"""
         if isinstance(data_x, numpy.ndarray):
-            t = torch.from_numpy(numpy.ascontiguousarray(data_x, dtype=numpy.float32))
-        else:
-            t = data_x
-        if not t.is_cuda:
-            t = t.to(self.device, non_blocking=True)
+            data_x = numpy.ascontiguousarray(data_x, dtype=numpy.float32)
+        t = layer_mod.h2d(data_x, self.device)
         return ops.nchw_to_nhwc(t.contiguous(), layer_mod.act_dtype())
 
     def forward(self, data_x, data_m=None, train=False):
@@ -424,7 +421,7 @@ class ModelCNN:
     def train_step(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):
         """reference contract (model_cnn.py:407-445): returns (cost, [layer costs]) as python floats"""
         assert "train_step" in self.func, "Call build_train_func() before calling train_step()"
-        costs = self._train_step_device(data_x, data_m, epoch, it, learning_rate, momentum, decay).cpu().numpy()
+        costs = layer_mod.d2h(self._train_step_device(data_x, data_m, epoch, it, learning_rate, momentum, decay))
         return float(costs[0]), [float(c) for c in costs[1:]]
 
     def train_epoch(self, dataset, epoch, learning_rate, momentum=[0, 1, 0], decay=0.0, solver_mode="sgd"):

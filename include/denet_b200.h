@@ -38,6 +38,8 @@ extern "C" {
 
 const char* denet_last_error(void);
 int denet_abi_version(void);
+/* number of CUDA kernels this library has enqueued in this process so far (all streams, all threads) */
+long long denet_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------ convolution
  * Replaces tensor.nnet.conv2d / its autodiff gradients, i.e. the cuDNN fprop / bwd-data / bwd-filter calls

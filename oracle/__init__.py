@@ -149,5 +149,16 @@ def reference_cuda():
         path = os.path.join(REF_DIR, "libref_cuda_kernels.so")
         if not os.path.exists(path):
             return None
-        _ref_cuda = ctypes.CDLL(path)
+        lib = ctypes.CDLL(path)
+        # the launchers take size_t dims: without argtypes ctypes passes 32-bit ints and stack-passed ones are garbage
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        for gs in (3, 7, 10):
+            for d in ("fwd", "bwd"):
+                fn = getattr(lib, "refcuda_sparse_sample_%s_%d" % (d, gs))
+                fn.argtypes, fn.restype = [vp, vp, vp, sz, sz, sz, sz, sz], ctypes.c_int
+        for d in ("fwd", "bwd"):
+            fn = getattr(lib, "refcuda_pool_inv_%s_2x2" % d)
+            fn.argtypes, fn.restype = [vp, vp, sz, sz, sz, sz], ctypes.c_int
+        lib.refcuda_relu.argtypes, lib.refcuda_relu.restype = [vp, sz], ctypes.c_int
+        _ref_cuda = lib
     return _ref_cuda

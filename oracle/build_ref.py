@@ -90,6 +90,11 @@ LAUNCHERS = r"""
 #include <cmath>
 // launch geometry = the reference c_code blocks: 1024 threads, ceil(total/1024) blocks, contiguous NCHW strides
 static inline dim3 ref_grid(size_t total) { return dim3((unsigned)((total + 1023) / 1024), 1, 1); }
+static inline int ref_finish() {
+    cudaError_t e = cudaGetLastError();   // launch failures (e.g. too many registers for 1024 threads) must surface
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaDeviceSynchronize();
+}
 
 #define SPARSE_LAUNCHER(GS)                                                                                       \
 extern "C" int refcuda_sparse_sample_fwd_##GS(float* fmap, float* bbox, float* r, size_t bs, size_t fn, size_t h,  \
@@ -97,7 +102,7 @@ extern "C" int refcuda_sparse_sample_fwd_##GS(float* fmap, float* bbox, float* r
     size_t oc = fn * GS * GS + 2;                                                                                  \
     k_sparse_sample##GS<<<ref_grid(bs * sn * sn), 1024>>>(fmap, fn * h * w, h * w, w, 1, bbox, sn * sn * 4, sn * 4, \
                                                           4, 1, r, oc * sn * sn, sn * sn, sn, 1, fn, h, w, sn, bs); \
-    return (int)cudaDeviceSynchronize();                                                                           \
+    return ref_finish();                                                                           \
 }                                                                                                                  \
 extern "C" int refcuda_sparse_sample_bwd_##GS(float* dy, float* bbox, float* r, size_t bs, size_t fn, size_t h,    \
                                               size_t w, size_t sn) {                                               \
@@ -106,24 +111,24 @@ extern "C" int refcuda_sparse_sample_bwd_##GS(float* dy, float* bbox, float* r, 
     k_sparse_sample_grad##GS<<<ref_grid(bs * sn * sn), 1024>>>(dy, oc * sn * sn, sn * sn, sn, 1, bbox, sn * sn * 4, \
                                                                sn * 4, 4, 1, r, fn * h * w, h * w, w, 1, fn, h, w, \
                                                                sn, bs);                                            \
-    return (int)cudaDeviceSynchronize();                                                                           \
+    return ref_finish();                                                                           \
 }
 
 #define POOLINV_LAUNCHER(SW, SH)                                                                                   \
 extern "C" int refcuda_pool_inv_fwd_##SW##x##SH(float* x, float* r, size_t bs, size_t fn, size_t h, size_t w) {     \
     k_pool_inv_##SW##x##SH<<<ref_grid(bs * h * w), 1024>>>(x, fn * h * w, h * w, w, 1, r, fn * h * SH * w * SW,     \
                                                            h * SH * w * SW, w * SW, 1, bs, fn, h, w);              \
-    return (int)cudaDeviceSynchronize();                                                                           \
+    return ref_finish();                                                                           \
 }                                                                                                                  \
 extern "C" int refcuda_pool_inv_bwd_##SW##x##SH(float* dy, float* r, size_t bs, size_t fn, size_t h, size_t w) {    \
     k_pool_inv_grad_##SW##x##SH<<<ref_grid(bs * h * w), 1024>>>(dy, fn * h * SH * w * SW, h * SH * w * SW, w * SW,  \
                                                                 1, r, fn * h * w, h * w, w, 1, bs, fn, h, w);      \
-    return (int)cudaDeviceSynchronize();                                                                           \
+    return ref_finish();                                                                           \
 }
 
 extern "C" int refcuda_relu(float* x, size_t n) {
     k_relu<<<ref_grid(n), 1024>>>(x, n);
-    return (int)cudaDeviceSynchronize();
+    return ref_finish();
 }
 """
 
@@ -164,8 +169,9 @@ def build_reference_cuda():
     with open(gen, "w") as f:
         f.write("\n".join(parts))
     # default nvcc flags (fmad on), like Theano's nvcc invocation (SURVEY.md §2a "Build flags")
-    run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-shared", "-Xcompiler", "-fPIC", "-w", gen,
-         "-o", out])
+    # -maxrregcount 64: the reference launches 1024 threads per block, which needs <= 64 registers per thread
+    run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-maxrregcount", "64", "-shared", "-Xcompiler",
+         "-fPIC", "-w", gen, "-o", out])
     return out
 
 

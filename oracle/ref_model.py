@@ -33,6 +33,14 @@ class RefModel:
         self.input_shape = tuple(input_shape)
         self.class_num = class_num
         self.nodes = [self._build(js, str(i)) for i, js in enumerate(json_layers)]
+        # ReLU is discontinuous in its gradient: an fp32 run and this fp64 run disagree on the sign of the few
+        # pre-activations that are ~1e-6 from zero, and one flipped mask element moves a gradient by far more than
+        # the arithmetic error being tested.  relu_masks {node path: bool (B,C,H,W)} lets a test hand over the masks
+        # of the run under test; they are used ONLY where |pre-activation| < relu_mask_tol * max|pre-activation|.
+        self.relu_masks = None
+        self.relu_mask_tol = 1e-4
+        self.relu_overrides = 0
+        self.pool_argmax = None      # same idea for max-pool gradient routing: {node path: tap index (B,C,oh,ow)}
 
     # ------------------------------------------------------------------ construction
     def _build(self, js, path):
@@ -70,6 +78,17 @@ class RefModel:
         return out
 
     # ------------------------------------------------------------------ layer semantics
+    def _relu(self, y, path):
+        if not self.relu_masks or path not in self.relu_masks:
+            return R.relu(y)
+        with torch.no_grad():
+            given = torch.as_tensor(np.asarray(self.relu_masks[path])).reshape(y.shape).bool()
+            own = y > 0
+            ambiguous = y.abs() < self.relu_mask_tol * y.abs().max()
+            mask = torch.where(ambiguous, given, own)
+            self.relu_overrides += int((mask != own).sum())
+        return y * mask.to(y.dtype)
+
     def _conv(self, node, x):
         js = node.js
         return R.conv2d(x, node.params["weight"], tuple(js.get("stride", (1, 1))), _border(js.get("border", "half")),
@@ -87,7 +106,7 @@ class RefModel:
                                           R.bn_running_update(p["std"], invstd.detach(), mom))
         else:
             y = R.batchnorm_test(x, p["gamma"], p["bias"], p["mean"], p["std"], js.get("eps", 1e-5))
-        return R.relu(y) if apply_relu else y
+        return self._relu(y, node.path) if apply_relu else y
 
     def _resnet(self, node, x, train):
         """resnet.py:52-113, 'original' (post-activation) versions incl. the bnrelu-converted form"""
@@ -115,7 +134,7 @@ class RefModel:
                 y = self._bn(b, y, train, False)
                 a = next(it)
                 assert a.kind == "activation"
-                y = R.relu(y)
+                y = self._relu(y, a.path)
         rest = list(it)
         if rest:  # projection shortcut: 1x1 conv (+BN for 'original') on the block input
             s = self._conv(rest[0], x)
@@ -123,7 +142,7 @@ class RefModel:
                 s = self._bn(rest[1], s, train, False)
         else:
             s = x
-        return R.relu(s + y)
+        return self._relu(s + y, node.path)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, sample_bbox=None, train=True, stop_at_corner=False):
@@ -143,9 +162,15 @@ class RefModel:
                 h = self._bn(node, h, train, True)
             elif k == "activation":
                 assert js.get("activation", "relu") == "relu"
-                h = R.relu(h)
+                h = self._relu(h, node.path)
             elif k == "pool":
-                h = R.pool2d(h, js["size"], js["stride"] or js["size"], js.get("pad", (0, 0)), js.get("mode", "max"))
+                stride = js["stride"] or js["size"]
+                if js.get("mode", "max") == "max" and self.pool_argmax and node.path in self.pool_argmax:
+                    h, moved = R.max_pool2d_routed(h, js["size"], stride, js.get("pad", (0, 0)),
+                                                   self.pool_argmax[node.path], self.relu_mask_tol)
+                    self.relu_overrides += moved
+                else:
+                    h = R.pool2d(h, js["size"], stride, js.get("pad", (0, 0)), js.get("mode", "max"))
             elif k == "pool-inv":
                 h = R.pool_inv(h, js["size"])
             elif k == "resnet":
@@ -253,7 +278,7 @@ class RefModel:
         total.backward()
         grads = {name: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p))
                  for name, p, _ in self.named_params()}
-        return float(total), [float(c) for c in costs], grads, out
+        return float(total.detach()), [float(c.detach()) for c in costs], grads, out
 
 
 def _border(b):

@@ -53,10 +53,10 @@ def conv_pad(k_hw, border_mode):
         return (k_hw[0] - 1, k_hw[1] - 1)
     if border_mode == "half":
         return (k_hw[0] // 2, k_hw[1] // 2)
-    if isinstance(border_mode, int):
-        return (border_mode, border_mode)
+    if isinstance(border_mode, (int, bool)):   # denet_corner.py:39 passes border_mode=False (== pad 0)
+        return (int(border_mode), int(border_mode))
     if isinstance(border_mode, (tuple, list)):
-        return tuple(border_mode)
+        return tuple(int(v) for v in border_mode)
     raise Exception("Unknown border mode: " + str(border_mode))
 
 
@@ -141,6 +141,27 @@ def pool2d(x, size, stride, pad, mode):
         return F.avg_pool2d(x, kernel_size=tuple(size), stride=tuple(stride), padding=tuple(pad),
                             count_include_pad=True)
     raise Exception("unsupported pool mode " + mode)
+
+
+def max_pool2d_routed(x, size, stride, pad, given, tol):
+    """max pooling whose gradient routing follows `given` (window tap index r*kw+s, (B,C,oh,ow)) wherever the two
+    largest values of a window are closer than tol * max|x| - there an fp32 run and an fp64 run may pick different
+    taps, which re-routes a gradient element although both forward values agree.  Returns (y, number of re-routes)."""
+    kh, kw = size
+    B, C, H, W = x.shape
+    oh, ow = pool_out_hw((H, W), size, stride, pad)
+    xp = F.pad(x, (pad[1], pad[1], pad[0], pad[0]), value=float("-inf"))
+    win = xp.unfold(2, kh, stride[0]).unfold(3, kw, stride[1])[:, :, :oh, :ow].reshape(B, C, oh, ow, kh * kw)
+    with torch.no_grad():
+        top = win.topk(2, dim=-1)
+        own = top.indices[..., 0]
+        given = torch.as_tensor(given).reshape(own.shape).long().clamp(0, kh * kw - 1)
+        eps = tol * x.abs().max()
+        near = (top.values[..., 0] - top.values[..., 1]) < eps
+        ok = (top.values[..., 0] - win.gather(-1, given.unsqueeze(-1)).squeeze(-1)) < eps
+        idx = torch.where(near & ok, given, own)
+        moved = int((idx != own).sum())
+    return win.gather(-1, idx.unsqueeze(-1)).squeeze(-1), moved
 
 
 def pool_inv(x, size):

@@ -363,8 +363,9 @@ def test_build_samples_vs_oracle(cuda, k, H, sn):
 
 
 def test_build_samples_edge_cases(cuda):
-    # untrained net: bias 5 everywhere -> no corner passes the threshold -> zero samples
-    cp = busy_corner_map(2, 32, 32, 0, seed=1)
+    # untrained net: bias 5 everywhere (denet_corner.py:42-47) -> no corner passes the threshold -> zero samples
+    from util import log_softmax_corner
+    cp = log_softmax_corner(numpy.full((2, 4, 32, 32), 5.0, numpy.float32))
     count, ncand = _check_samples(cp, 8)
     assert count.sum() == 0 and ncand.sum() == 0
     # more than max_corners candidates per type (radix-select path) and > sort-buffer candidates (multi-pass select)

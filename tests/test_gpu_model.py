@@ -54,6 +54,32 @@ def named_params(model):
     return out
 
 
+def relu_masks(model):
+    """{RefModel node path: (B,C,H,W) bool} sign of every ReLU input as THIS run saw it - the oracle uses them only for
+    pre-activations within 1e-4 of zero (see RefModel.relu_masks), where fp32 and fp64 legitimately disagree"""
+    out = {}
+
+    def walk(layer, path):
+        if layer.type_name in ("activation", "batchnorm-relu", "resnet") and torch.is_tensor(layer.output) \
+                and layer.output.dim() == 4:
+            out[path] = (layer.output.float().permute(0, 3, 1, 2) > 0).cpu().numpy()
+        for i, sub in enumerate(layer.layers):
+            walk(sub, path + "/" + str(i))
+    for i, l in enumerate(model.layers[1:]):
+        walk(l, str(i))
+    return out
+
+
+def pool_argmax(model):
+    """{RefModel node path: (B,C,oh,ow) window tap of each maximum} as THIS run picked them (near-ties only matter)"""
+    out = {}
+    for i, l in enumerate(model.layers[1:]):
+        if l.type_name == "pool" and getattr(l, "last_argmax", None) is not None:
+            b, c, oh, ow = l.output_shape
+            out[str(i)] = l.last_argmax.reshape(b, oh, ow, c).permute(0, 3, 1, 2).cpu().numpy()
+    return out
+
+
 def run_step(model, x, metas, solver="nesterov", lr=0.05, mom=(0.9, 0.9), decay=1e-4, it=1, seed=5):
     """GPU train step; returns what is needed to replay it on the oracle"""
     js = model.export_json()["layers"]
@@ -80,6 +106,8 @@ def run_step(model, x, metas, solver="nesterov", lr=0.05, mom=(0.9, 0.9), decay=
 
 def compare(model, js, before, captured, x, cost, costs, solver, lr, mom, decay, it, tol, sample_bbox=None):
     ref = RefModel(js, x.shape, model.class_num, dtype=torch.float64)
+    ref.relu_masks = relu_masks(model)
+    ref.pool_argmax = pool_argmax(model)
     targets = [t for _, t in captured]
     total, ref_costs, grads, out = ref.train_gradients(x, targets, sample_bbox=sample_bbox)
     assert abs(cost - total) <= tol * abs(total), (cost, total)
@@ -88,19 +116,26 @@ def compare(model, js, before, captured, x, cost, costs, solver, lr, mom, decay,
     mine = named_params(model)
     worst = 0.0
     ref_named = {n: (p, w) for n, p, w in ref.named_params()}
+    gmax = max(g.norm().item() for g in grads.values())
     for name, g in grads.items():
         p = mine[name]
         scale = g.norm().item()
         if scale < 1e-12:
-            assert p.grad.norm().item() < 1e-8, name
+            # analytically zero (e.g. a conv bias feeding a batch norm): fp32 leaves cancellation noise only
+            assert p.grad.norm().item() < 1e-6 * gmax, name
             continue
         e = relerr(p.grad, g)
         worst = max(worst, e)
         assert e < tol, "gradient of %s: rel err %.3e" % (name, e)
-        # solver step replayed on the oracle's gradient (momentum buffers start at zero)
+        # solver step (momentum buffers start at zero) replayed on the oracle's gradient, and - to pin the update
+        # rule itself independently of the gradient error - on the gradient the CUDA path produced
         p_new = R.solver_update(before[name], g, torch.zeros_like(g), solver, it, lr, list(mom), decay,
                                 ref_named[name][1])[0]
-        assert relerr(p, p_new) < 1e-5, name
+        assert relerr(p, p_new) < tol, name
+        g_mine = p.grad.detach().cpu().double()
+        p_own = R.solver_update(before[name], g_mine, torch.zeros_like(g), solver, it, lr, list(mom), decay,
+                                ref_named[name][1])[0]
+        assert relerr(p, p_own) < 1e-6, name
     for path, (m_new, s_new) in ref.bn_updates.items():
         assert relerr(mine[path + ".mean"], m_new) < tol
         assert relerr(mine[path + ".std"], s_new) < tol
@@ -161,6 +196,8 @@ def test_denet_train_step_fp32(cuda):
     """conv stack + skip + pool-inv + DNC/DNS/DND head, forward/backward/update vs the oracle on the same RoIs"""
     model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "fp32", 5e-4)
     ref = RefModel(js, x.shape, 20, dtype=torch.float64)
+    ref.relu_masks = relu_masks(model)
+    ref.pool_argmax = pool_argmax(model)
     targets = [t for _, t in cap]
     total, ref_costs, grads, out = ref.train_gradients(x, targets, sample_bbox=bbox, cost_factors=[1.0, 0.5])
     assert abs(cost - total) < 5e-4 * abs(total), (cost, total, costs, ref_costs)
@@ -179,6 +216,9 @@ def test_denet_train_step_bf16_tracks_oracle(cuda):
     """throughput mode (bf16 activations / MMA): costs within 2 %, gradients well aligned with the fp64 oracle"""
     model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "bf16", None)
     ref = RefModel(js, x.shape, 20, dtype=torch.float64)
+    ref.relu_masks = relu_masks(model)
+    ref.pool_argmax = pool_argmax(model)
+    ref.relu_mask_tol = 2e-2     # bf16 activations: 8 mantissa bits
     targets = [t for _, t in cap]
     total, ref_costs, grads, out = ref.train_gradients(x, targets, sample_bbox=bbox, cost_factors=[1.0, 0.5])
     assert abs(cost - total) < 2e-2 * abs(total), (cost, total)
