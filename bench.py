@@ -242,7 +242,8 @@ def run_b200(args):
         sampler.start()
 
     # ---- region A: inputs resident in HBM (value), conv entry points bracketed by CUDA events (roofline)
-    timed_names = ["denet_conv2d_fprop", "denet_conv2d_wgrad"]
+    timed_names = ["denet_conv2d_fprop", "denet_conv2d_wgrad", "denet_conv2d_rowfold_fprop",
+                   "denet_conv2d_rowfold_wgrad"]
     barrier()
     lib.start_timing(timed_names)
     l0 = clib.denet_launch_count()

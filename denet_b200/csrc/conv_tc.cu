@@ -75,7 +75,8 @@ struct SmemLayout {
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
-    static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+    static constexpr int kStatOffset = kBarOffset + 256;     // fprop: per-warp running batch-norm sums [4][BN][2] fp32
+    static constexpr int kTotal = kStatOffset + 4 * BN * 8 + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ void store_row_chunk(void* y, int y_fp32, long long elem_off, const float (&v)[32],
@@ -87,7 +88,9 @@ __device__ __forceinline__ void store_row_chunk(void* y, int y_fp32, long long e
             for (int i = 0; i < 8; ++i)
                 reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         } else {
-            for (int i = 0; i < ncols_valid; ++i) dst[i] = v[i];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < ncols_valid) dst[i] = v[i];
         }
     } else {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + elem_off;
@@ -106,7 +109,9 @@ __device__ __forceinline__ void store_row_chunk(void* y, int y_fp32, long long e
                 reinterpret_cast<uint4*>(dst)[i] = u;
             }
         } else {
-            for (int i = 0; i < ncols_valid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < ncols_valid) dst[i] = __float2bfloat16_rn(v[i]);
         }
     }
 }
@@ -115,10 +120,28 @@ __device__ __forceinline__ void load_row_chunk(const void* y, int y_fp32, long l
                                                int ncols_valid) {
     if (y_fp32) {
         const float* src = reinterpret_cast<const float*>(y) + elem_off;
+#pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = (i < ncols_valid) ? src[i] : 0.f;
     } else {
         const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(y) + elem_off;
+#pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = (i < ncols_valid) ? __bfloat162float(src[i]) : 0.f;
+    }
+}
+
+// Column sums across the 32 lanes of a warp: lane r holds v[0..31] (row r, 32 columns); on return v[0] of lane l is
+// sum over rows of column l.  Each round halves the live values: a lane keeps the half of the columns selected by
+// one bit of its lane index and trades the other half with its partner.
+__device__ __forceinline__ void butterfly_colsum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float keep = upper ? v[i + o] : v[i];
+            const float send = upper ? v[i] : v[i + o];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
     }
 }
 
@@ -239,10 +262,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int it = 0;
+        // running per-channel sums of this warp (warp-private shared memory: entry [c][0] = sum, [c][1] = sum of squares)
+        float2* sacc = reinterpret_cast<float2*>(smem + L::kStatOffset) + q * BN;
+        if (p.stat_sum)
+            for (int c = lane; c < BN; c += 32) sacc[c] = make_float2(0.f, 0.f);
+        int acc_ct = -1;
+        auto flush_stats = [&]() {
+            if (p.stat_sum && acc_ct >= 0) {
+                for (int i = lane; i < BN; i += 32) {
+                    const int c = acc_ct * BN + i;
+                    const float2 a = sacc[i];
+                    if (c < p.Cout) {
+                        atomicAdd(p.stat_sum + c, a.x);
+                        atomicAdd(p.stat_sqsum + c, a.y);
+                    }
+                    sacc[i] = make_float2(0.f, 0.f);
+                }
+            }
+        };
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int ct = tile % p.tiles_co;
+            if (ct != acc_ct) {
+                flush_stats();
+                acc_ct = ct;
+            }
             int mt = tile / p.tiles_co;
             const int tw = mt % p.tiles_w;
             mt /= p.tiles_w;
@@ -276,21 +321,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                             if (i < nvalid) v[i] += __ldg(p.bias + co + i);
                     }
                     if (p.stat_sum) {
-                        // per-channel batch statistics of the (pre-activation) conv output: warp reduce, one atomic/warp
+                        // per-channel batch statistics of the (pre-activation) conv output.  Lane = pixel row, v[] = 32
+                        // channels: a halving butterfly (16+8+4+2+1 exchanges per quantity instead of 32 x 5) leaves
+                        // lane l with the 32-row sum of channel co + l; it is accumulated in registers across the
+                        // tiles of this CTA and flushed with one atomic per lane when the channel tile changes.
+                        float s[32], sq[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            float s = row_ok ? v[i] : 0.f;
-                            float s2 = s * s;
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                s += __shfl_xor_sync(0xffffffffu, s, o);
-                                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                            }
-                            if (lane == 0 && i < nvalid) {
-                                atomicAdd(p.stat_sum + co + i, s);
-                                atomicAdd(p.stat_sqsum + co + i, s2);
-                            }
+                            s[i] = row_ok ? v[i] : 0.f;
+                            sq[i] = s[i] * s[i];
                         }
+                        butterfly_colsum(s, lane);
+                        butterfly_colsum(sq, lane);
+                        float2 a = sacc[c0 + lane];
+                        a.x += s[0];
+                        a.y += sq[0];
+                        sacc[c0 + lane] = a;
                     }
                     if (row_ok) {
                         const long long off = pix * p.ldy + co;
@@ -312,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
         }
+        flush_stats();
     }
 
     ptx::tc_fence_before();
@@ -607,6 +654,44 @@ static int make_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, 
     return encode_tmap_bf16(tm, base, 4, dims, strides, box, estr);
 }
 
+
+// weight tensor map(s) + kernel dispatch, shared by the generic and the row-folded entry points.  p must hold the
+// A map(s), the tiling and the epilogue fields; p.tiles_co / p.num_tiles are filled here.
+int fprop_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStream_t stream) {
+    const int Cout = p.Cout;
+    const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    p.tiles_co = ceil_div(Cout, BN);
+    p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
+    int rc;
+    const uint64_t ktot = (uint64_t)p.R * p.S * p.kchunks * 64;
+    uint64_t dims[2] = {ktot, (uint64_t)Cout};
+    uint64_t strides[1] = {ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    if ((rc = encode_tmap_bf16(&p.tmB[0], b_hi, 2, dims, strides, box, nullptr))) return rc;
+    if (b_lo && (rc = encode_tmap_bf16(&p.tmB[1], b_lo, 2, dims, strides, box, nullptr))) return rc;
+    switch (BN) {
+        case 64: return launch_fprop<64, 8>(p, stream);
+        case 128: return launch_fprop<128, 6>(p, stream);
+        default: return launch_fprop<256, 4>(p, stream);
+    }
+}
+
+int wgrad_splits(int total_kblocks, int base_tiles) {
+    int splits = ceil_div(2 * num_sms(), base_tiles);
+    if (splits > total_kblocks) splits = total_kblocks;
+    return splits < 1 ? 1 : splits;
+}
+
+// dispatch of the wgrad GEMM; p holds the maps, the k-block tiling, Cout/Cin (GEMM N extent), R, S and the workspace
+int wgrad_launch(ConvWgradParams& p, cudaStream_t stream) {
+    const int BN = p.Cin <= 64 ? 64 : (p.Cin <= 128 ? 128 : 256);
+    switch (BN) {
+        case 64: return launch_wgrad<64, 8>(p, stream);
+        case 128: return launch_wgrad<128, 6>(p, stream);
+        default: return launch_wgrad<256, 4>(p, stream);
+    }
+}
+
 }  // namespace dn
 
 using namespace dn;
@@ -660,9 +745,6 @@ extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int
     p.tiles_w = ceil_div(Wo, p.TW);
     p.tiles_h = ceil_div(Ho, p.TH);
     p.tiles_n = ceil_div(N, p.TN);
-    const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
-    p.tiles_co = ceil_div(Cout, BN);
-    p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
     p.Cout = Cout;
     p.ldy = ldy;
     p.y_fp32 = (y_dtype == DENET_F32);
@@ -677,19 +759,7 @@ extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int
     if ((rc = make_act_map(&p.tmA[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h))) return rc;
     if (x_lo && (rc = make_act_map(&p.tmA[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h)))
         return rc;
-    {
-        const uint64_t ktot = (uint64_t)R * S * p.kchunks * 64;
-        uint64_t dims[2] = {ktot, (uint64_t)Cout};
-        uint64_t strides[1] = {ktot * 2};
-        uint32_t box[2] = {64, (uint32_t)BN};
-        if ((rc = encode_tmap_bf16(&p.tmB[0], b_hi, 2, dims, strides, box, nullptr))) return rc;
-        if (b_lo && (rc = encode_tmap_bf16(&p.tmB[1], b_lo, 2, dims, strides, box, nullptr))) return rc;
-    }
-    switch (BN) {
-        case 64: return launch_fprop<64, 8>(p, stream);
-        case 128: return launch_fprop<128, 6>(p, stream);
-        default: return launch_fprop<256, 4>(p, stream);
-    }
+    return fprop_finish(p, b_hi, b_lo, stream);
 }
 
 extern "C" size_t denet_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cout, int Cin, int R, int S) {
@@ -755,6 +825,212 @@ extern "C" int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, i
     const int block = 256;
     const int grid = (int)std::min<long long>(ceil_div_ll(total, block), 148LL * 16);
     wgrad_reduce_kernel<<<DN_G(grid), block, 0, stream>>>(workspace, dw, splits, Cout, Cin, R, S, p.ldws, accumulate);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ row-folded conv
+// Convolutions with very few input channels (the 3-channel image stem, reference ConvLayer C.B[64,7,2] of
+// examples/resnet34-imagenet.sh:7): a 64-channel K chunk per filter tap would be >90 % zero padding and an explicit
+// im2col matrix costs ~0.6 GB of HBM traffic per pass.  Instead the image is kept zero-PADDED in NHWC with Cp (4 or 8)
+// channels, and the A operand is described to TMA as an OVERLAPPING-window tensor:
+//     dim0 = the S*Cp contiguous elements of one filter row under an output pixel   (K of one "tap" = filter row r)
+//     dim1 = output column wo, stride = stride_w * Cp elements (16 B)               (windows overlap)
+//     dim2 = padded input row, walked with element stride stride_h;  dim3 = image
+// so the same fprop / wgrad kernels run an R-tap "1-D" convolution with K = 64 per filter row (columns >= S*Cp are
+// TMA zero fill or multiply zero weights).  No im2col buffer exists in either direction.
+namespace dn {
+
+static int rowfold_k(int S, int Cp) { return (S * Cp + 7) / 8 * 8; }   // dim0 extent (elements), <= 64
+
+static int make_rowfold_map(CUtensorMap* tm, const void* base, int Cp, int S, int Wo, int Hp, int Wp, int N,
+                            int stride_w, int stride_h, int TW, int TH, int TN) {
+    const int kf = rowfold_k(S, Cp);
+    uint64_t dims[4] = {(uint64_t)kf, (uint64_t)Wo, (uint64_t)Hp, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)stride_w * Cp * 2, (uint64_t)Wp * Cp * 2, (uint64_t)Hp * Wp * Cp * 2};
+    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)(TH * stride_h), (uint32_t)TN};
+    uint32_t estr[4] = {1, 1, (uint32_t)stride_h, 1};
+    if (box[2] > 256) return set_error(DENET_ERR_ARG, "rowfold conv: strided patch exceeds the TMA box limit");
+    return encode_tmap_bf16(tm, base, 4, dims, strides, box, estr);
+}
+
+static int rowfold_check(const char* what, int Cin, int Cp, int R, int S, int stride_h, int stride_w, int Ho, int Wo,
+                         int Hp, int Wp) {
+    if (!(Cp == 4 || Cp == 8) || Cin > Cp) return set_error(DENET_ERR_ARG, "%s: Cp must be 4 or 8 and >= Cin", what);
+    if ((stride_w * Cp) % 8 != 0) return set_error(DENET_ERR_ARG, "%s: stride_w*Cp must be a multiple of 8", what);
+    if ((Wp * Cp) % 8 != 0) return set_error(DENET_ERR_ARG, "%s: Wp*Cp must be a multiple of 8", what);
+    if (rowfold_k(S, Cp) > 64) return set_error(DENET_ERR_ARG, "%s: S*Cp must be <= 64", what);
+    if (stride_h < 1 || stride_h > 8 || stride_w < 1) return set_error(DENET_ERR_ARG, "%s: bad stride", what);
+    if ((Ho - 1) * stride_h + R > Hp) return set_error(DENET_ERR_ARG, "%s: padded height %d too small", what, Hp);
+    if ((long long)(Wo - 1) * stride_w * Cp + rowfold_k(S, Cp) > (long long)Wp * Cp)
+        return set_error(DENET_ERR_ARG, "%s: padded width %d too small", what, Wp);
+    return 0;
+}
+
+// B[co][r][k], k = s*Cp + c  <-  W[co][c][R-1-r][S-1-s]  (true convolution -> correlation taps), 64 columns per row r
+__global__ void weight_prep_rowfold_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, int Cp,
+                                           __nv_bfloat16* __restrict__ b_hi, __nv_bfloat16* __restrict__ b_lo) {
+    const long long total = (long long)Cout * R * 64;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % 64);
+        const int r = (int)((idx / 64) % R);
+        const int co = (int)(idx / (64LL * R));
+        const int s = k / Cp, c = k % Cp;
+        float v = 0.f;
+        if (s < S && c < Cin) v = w[(((long long)co * Cin + c) * R + (R - 1 - r)) * S + (S - 1 - s)];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        b_hi[idx] = hi;
+        if (b_lo) b_lo[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+// split-K partials [split][Cout][R][ldws] (column k = s*Cp + c) -> reference filter gradient (Cout, Cin, R, S)
+__global__ void wgrad_reduce_rowfold_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cout,
+                                            int Cin, int R, int S, int Cp, int ldws, int accumulate) {
+    const long long total = (long long)Cout * Cin * R * S;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int sf = (int)(idx % S);
+        const int rf = (int)((idx / S) % R);
+        const int c = (int)((idx / ((long long)S * R)) % Cin);
+        const int co = (int)(idx / ((long long)S * R * Cin));
+        const int r = R - 1 - rf, s = S - 1 - sf;
+        float acc = 0.f;
+        for (int sp = 0; sp < splits; ++sp)
+            acc += ws[(((long long)sp * Cout + co) * R + r) * ldws + s * Cp + c];
+        dw[idx] = accumulate ? dw[idx] + acc : acc;
+    }
+}
+
+// NCHW fp32 image -> interior of a zero-padded NHWC-Cp bf16 buffer (hi [+ lo]); borders and pad channels untouched
+__global__ void nchw_to_padded_kernel(const float* __restrict__ x, int N, int C, int H, int W, int Cp, int ph, int pw,
+                                      int Hp, int Wp, __nv_bfloat16* __restrict__ y_hi,
+                                      __nv_bfloat16* __restrict__ y_lo) {
+    const long long total = (long long)N * H * W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(idx % W);
+        const int h = (int)((idx / W) % H);
+        const int n = (int)(idx / ((long long)W * H));
+        const long long o = (((long long)n * Hp + h + ph) * Wp + w + pw) * Cp;
+        for (int c = 0; c < Cp; ++c) {
+            const float v = c < C ? x[(((long long)n * C + c) * H + h) * W + w] : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            y_hi[o + c] = hi;
+            if (y_lo) y_lo[o + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
+    }
+}
+
+}  // namespace dn
+
+extern "C" int denet_nchw_to_padded_nhwc(const float* x, int N, int C, int H, int W, int Cp, int pad_h, int pad_w,
+                                         int Hp, int Wp, void* y_hi, void* y_lo, cudaStream_t stream) {
+    DN_REQUIRE(x && y_hi, "nchw_to_padded_nhwc: null pointer");
+    DN_REQUIRE(C <= Cp && H + pad_h <= Hp && W + pad_w <= Wp, "nchw_to_padded_nhwc: image does not fit the buffer");
+    const long long total = (long long)N * H * W;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 32);
+    nchw_to_padded_kernel<<<DN_G(grid), 256, 0, stream>>>(x, N, C, H, W, Cp, pad_h, pad_w, Hp, Wp, (__nv_bfloat16*)y_hi,
+                                                          (__nv_bfloat16*)y_lo);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_conv_weight_prep_rowfold(const float* w, int Cout, int Cin, int R, int S, int Cp, void* b_hi,
+                                              void* b_lo, cudaStream_t stream) {
+    DN_REQUIRE(w && b_hi, "weight_prep_rowfold: null pointer");
+    DN_REQUIRE(Cin <= Cp && rowfold_k(S, Cp) <= 64, "weight_prep_rowfold: S*Cp must be <= 64 and Cp >= Cin");
+    const long long total = (long long)Cout * R * 64;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 16);
+    weight_prep_rowfold_kernel<<<DN_G(grid), 256, 0, stream>>>(w, Cout, Cin, R, S, Cp, (__nv_bfloat16*)b_hi,
+                                                               (__nv_bfloat16*)b_lo);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_conv2d_rowfold_fprop(const void* x_hi, const void* x_lo, int N, int Hp, int Wp, int Cp, int Cin,
+                                          const void* b_hi, const void* b_lo, int Cout, int R, int S, int stride_h,
+                                          int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo,
+                                          const float* bias, int relu, float* stat_sum, float* stat_sqsum,
+                                          cudaStream_t stream) {
+    DN_REQUIRE(x_hi && b_hi && y, "conv2d_rowfold_fprop: null pointer");
+    DN_REQUIRE((x_lo == nullptr) == (b_lo == nullptr), "conv2d_rowfold_fprop: x_lo and b_lo must come together");
+    DN_REQUIRE(y_dtype == DENET_F32 || y_dtype == DENET_BF16, "conv2d_rowfold_fprop: bad y_dtype %d", y_dtype);
+    DN_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "conv2d_rowfold_fprop: stat pointers come in pairs");
+    int rc;
+    if ((rc = rowfold_check("conv2d_rowfold_fprop", Cin, Cp, R, S, stride_h, stride_w, Ho, Wo, Hp, Wp))) return rc;
+    ConvFpropParams p;
+    memset(&p, 0, sizeof(p));
+    p.nterms = x_lo ? 3 : 1;
+    p.R = R; p.S = 1; p.pad_h = 0; p.pad_w = 0;       // taps = filter rows; the padding lives in the buffer
+    p.stride_h = stride_h; p.stride_w = 1;             // the column stride lives in the tensor map
+    p.kchunks = 1;
+    p.Wo = Wo; p.Ho = Ho; p.No = N;
+    pick_patch(Wo, Ho, N, 128, p.TW, p.TH, p.TN);
+    p.tiles_w = ceil_div(Wo, p.TW);
+    p.tiles_h = ceil_div(Ho, p.TH);
+    p.tiles_n = ceil_div(N, p.TN);
+    p.Cout = Cout;
+    p.ldy = ldy;
+    p.y_fp32 = (y_dtype == DENET_F32);
+    p.relu = relu;
+    p.y = y;
+    p.bias = bias;
+    p.stat_sum = stat_sum;
+    p.stat_sqsum = stat_sqsum;
+    if ((rc = make_rowfold_map(&p.tmA[0], x_hi, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, p.TH, p.TN))) return rc;
+    if (x_lo && (rc = make_rowfold_map(&p.tmA[1], x_lo, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, p.TH, p.TN)))
+        return rc;
+    return fprop_finish(p, b_hi, b_lo, stream);
+}
+
+extern "C" size_t denet_conv2d_rowfold_wgrad_workspace(int N, int Ho, int Wo, int Cout, int R) {
+    int TW, TH, TN;
+    pick_patch(Wo, Ho, N, 64, TW, TH, TN);
+    const int total_kb = ceil_div(Wo, TW) * ceil_div(Ho, TH) * ceil_div(N, TN);
+    const int splits = wgrad_splits(total_kb, ceil_div(Cout, 128) * R);
+    return (size_t)splits * Cout * R * 64 * sizeof(float);
+}
+
+extern "C" int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int Wo, int Cout,
+                                          long long lddy, const void* x_hi, const void* x_lo, int Hp, int Wp, int Cp,
+                                          int Cin, int R, int S, int stride_h, int stride_w, float* dw, int accumulate,
+                                          float* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    DN_REQUIRE(dy_hi && x_hi && dw && workspace, "conv2d_rowfold_wgrad: null pointer");
+    DN_REQUIRE((dy_lo == nullptr) == (x_lo == nullptr), "conv2d_rowfold_wgrad: dy_lo and x_lo must come together");
+    DN_REQUIRE(lddy % 8 == 0, "conv2d_rowfold_wgrad: dy pitch must be a multiple of 8 elements");
+    int rc;
+    if ((rc = rowfold_check("conv2d_rowfold_wgrad", Cin, Cp, R, S, stride_h, stride_w, Ho, Wo, Hp, Wp))) return rc;
+    ConvWgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.nterms = dy_lo ? 3 : 1;
+    p.R = R; p.S = 1; p.pad_h = 0; p.pad_w = 0;
+    p.stride_h = stride_h; p.stride_w = 1;
+    pick_patch(Wo, Ho, N, 64, p.TW, p.TH, p.TN);
+    p.tiles_w = ceil_div(Wo, p.TW);
+    p.tiles_h = ceil_div(Ho, p.TH);
+    p.tiles_n = ceil_div(N, p.TN);
+    p.total_kblocks = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.co_tiles = ceil_div(Cout, 128);
+    p.ci_tiles = 1;
+    p.splits = wgrad_splits(p.total_kblocks, p.co_tiles * R);
+    p.num_tiles = p.co_tiles * R * p.splits;
+    p.Cout = Cout; p.Cin = 64;             // GEMM N extent: the 64 folded columns of a filter row
+    p.ldws = 64;
+    p.ws = workspace;
+    const size_t need = (size_t)p.splits * Cout * R * 64 * sizeof(float);
+    DN_REQUIRE(workspace_bytes >= need, "conv2d_rowfold_wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+    if ((rc = make_act_map(&p.tmDY[0], dy_hi, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
+    if (dy_lo && (rc = make_act_map(&p.tmDY[1], dy_lo, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
+    if ((rc = make_rowfold_map(&p.tmX[0], x_hi, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, p.TH, p.TN))) return rc;
+    if (x_lo && (rc = make_rowfold_map(&p.tmX[1], x_lo, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, p.TH, p.TN)))
+        return rc;
+    if ((rc = wgrad_launch(p, stream))) return rc;
+    const long long total = (long long)Cout * Cin * R * S;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 16);
+    wgrad_reduce_rowfold_kernel<<<DN_G(grid), 256, 0, stream>>>(workspace, dw, p.splits, Cout, Cin, R, S, Cp, p.ldws,
+                                                                accumulate);
     DN_CHECK_LAUNCH();
     return 0;
 }

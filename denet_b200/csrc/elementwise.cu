@@ -81,19 +81,47 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_partial_kernel(const T* _
     }
 }
 
+// Second stage of the two-stage reductions: partial[(slab*NQ + q)*C + c] summed over slabs in a FIXED order
+// (deterministic).  Block = 32 channels x 32 slab lanes: lane j adds slabs j, j+32, ... in double, then the 32 lane
+// sums are combined in lane order by the thread with slab lane 0, which returns true and holds the totals.
+constexpr int kFinThreads = 1024;
+template <int NQ>
+__device__ __forceinline__ bool reduce_slabs(const float* __restrict__ partial, int nslabs, int C, int* c_out,
+                                             double (&tot)[NQ]) {
+    __shared__ double red[NQ][32][33];
+    const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    double acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+    if (c < C)
+        for (int s = sl; s < nslabs; s += 32)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[q] += (double)partial[((long long)s * NQ + q) * C + c];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) red[q][sl][cl] = acc[q];
+    __syncthreads();
+    *c_out = c;
+    if (sl != 0 || c >= C) return false;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        double t = 0.0;
+        for (int j = 0; j < 32; ++j) t += red[q][j][cl];
+        tot[q] = t;
+    }
+    return true;
+}
+
 // stage 2: combine slabs in order, produce mean / inverse std and the running-statistics EMA
 template <typename T>
 __global__ void bn_stats_finalize_kernel(const T* __restrict__ x, const float* __restrict__ partial, int nslabs,
                                          long long M, int C, float eps, float* __restrict__ mean,
                                          float* __restrict__ invstd, float* __restrict__ run_mean,
                                          float* __restrict__ run_stdinv, float momentum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double a = 0.0, b = 0.0;
-    for (int s = 0; s < nslabs; ++s) {
-        a += partial[((long long)s * 2 + 0) * C + c];
-        b += partial[((long long)s * 2 + 1) * C + c];
-    }
+    int c;
+    double tot[2];
+    if (!reduce_slabs<2>(partial, nslabs, C, &c, tot)) return;
+    const double a = tot[0], b = tot[1];
     const double k = to_f<T>(x[c]);
     const double dm = a / (double)M;
     double var = b / (double)M - dm * dm;
@@ -201,13 +229,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const T* __r
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nslabs, int C,
                                        float* __restrict__ sum_dy, float* __restrict__ sum_dy_xhat,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double a = 0.0, b = 0.0;
-    for (int s = 0; s < nslabs; ++s) {
-        a += partial[((long long)s * 2 + 0) * C + c];
-        b += partial[((long long)s * 2 + 1) * C + c];
-    }
+    int c;
+    double tot[2];
+    if (!reduce_slabs<2>(partial, nslabs, C, &c, tot)) return;
+    const double a = tot[0], b = tot[1];
     sum_dy[c] = (float)a;
     sum_dy_xhat[c] = (float)b;
     if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)a : (float)a;
@@ -681,10 +706,10 @@ __global__ void __launch_bounds__(kBnThreads) colsum_partial_kernel(const T* __r
 
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nslabs, int C, float* __restrict__ out,
                                        int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double a = 0.0;
-    for (int s = 0; s < nslabs; ++s) a += partial[(long long)s * C + c];
+    int c;
+    double tot[1];
+    if (!reduce_slabs<1>(partial, nslabs, C, &c, tot)) return;
+    const double a = tot[0];
     out[c] = accumulate ? out[c] + (float)a : (float)a;
 }
 
@@ -724,7 +749,7 @@ extern "C" int denet_bn_stats(const void* x, int dtype, long long M, int C, long
     const int nslabs = bn_slabs(M, C, v ? 8 : 1, &rpb, &yc);
     DN_DISPATCH(dtype, v, {
         bn_stats_partial_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>((const T*)x, M, C, ld, rpb, workspace);
-        bn_stats_finalize_kernel<T><<<DN_G(ceil_div(C, 128)), 128, 0, stream>>>((const T*)x, workspace, nslabs, M, C, eps, mean,
+        bn_stats_finalize_kernel<T><<<DN_G(ceil_div(C, 32)), kFinThreads, 0, stream>>>((const T*)x, workspace, nslabs, M, C, eps, mean,
                                                                             invstd, run_mean, run_stdinv, momentum);
     });
     DN_CHECK_LAUNCH();
@@ -765,7 +790,7 @@ extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x
     DN_DISPATCH(dtype, v, {
         bn_bwd_partial_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>(
             (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb, mean, invstd, relu, workspace);
-        bn_bwd_finalize_kernel<<<DN_G(ceil_div(C, 128)), 128, 0, stream>>>(workspace, nslabs, C, sums, sums + C, dgamma, dbeta,
+        bn_bwd_finalize_kernel<<<DN_G(ceil_div(C, 32)), kFinThreads, 0, stream>>>(workspace, nslabs, C, sums, sums + C, dgamma, dbeta,
                                                                      accumulate);
         bn_bwd_apply_kernel<T, VEC><<<DN_G(ew_grid(M * (C / VEC), 256)), 256, 0, stream>>>(
             (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, mean, invstd, gamma, sums, sums + C, relu, (T*)dx,
@@ -954,7 +979,7 @@ extern "C" int denet_colsum(const void* x, int dtype, long long M, int C, long l
     DN_DISPATCH(dtype, v, {
         colsum_partial_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>((const T*)x, M, C, ld, rpb, workspace);
     });
-    colsum_finalize_kernel<<<DN_G(ceil_div(C, 128)), 128, 0, stream>>>(workspace, nslabs, C, out, accumulate);
+    colsum_finalize_kernel<<<DN_G(ceil_div(C, 32)), kFinThreads, 0, stream>>>(workspace, nslabs, C, out, accumulate);
     DN_CHECK_LAUNCH();
     return 0;
 }

@@ -137,8 +137,17 @@ class ConvLayer(AbstractLayer):
 
     # ---------------------------------------------------------------------------------------------- execution
     @property
+    def rowfold(self):
+        """(Cp, Hp, Wp) when this is the image stem and runs as a row-folded conv over a zero-padded NHWC-Cp image
+        (no im2col matrix, see csrc/conv_tc.cu), else None"""
+        if not (self.is_first and self.enabled and self.size != (1, 1)) or not isinstance(self.pad[0], int):
+            return None
+        return ops.rowfold_geometry(self.input_shape[2:], self.filter_shape[1], self.size, self.stride, self.pad,
+                                    self.output_shape[2:])
+
+    @property
     def use_im2col(self):
-        return self.filter_shape[1] <= self.IM2COL_MAX_CIN and self.size != (1, 1)
+        return self.filter_shape[1] <= self.IM2COL_MAX_CIN and self.size != (1, 1) and self.rowfold is None
 
     def _operands(self):
         """bf16 GEMM operands derived from omega; refreshed when the parameters changed"""
@@ -147,6 +156,10 @@ class ConvLayer(AbstractLayer):
             if self._wop_f is not None and (self._wop_f.lo is not None) != split:
                 self._wop_f = self._wop_d = None
             w = self.omega
+            if self.rowfold is not None:
+                self._wop_f = ops.conv_weight_prep_rowfold(w, self.rowfold[0], split, self._wop_f)
+                self._wver = param_version()
+                return self._wop_f, None
             if self.use_im2col:
                 self._w2 = ops.weight_to_im2col(w, self._w2)
                 w = self._w2
@@ -176,7 +189,11 @@ class ConvLayer(AbstractLayer):
         if self.stat_consumer is not None and self.stat_consumer.wants_fused_stats():
             stats = self.stat_consumer.fused_stat_buffers()
         bias = self.beta if self.use_bias else None
-        if self.use_im2col:
+        if self.rowfold is not None:
+            assert isinstance(x, ops.PaddedImage) and residual is None, "the stem conv reads the padded model input"
+            self._xop = x
+            y = ops.conv2d_rowfold_fprop(x, wop_f, self.stride, (oh, ow), out_dtype, bias=bias, relu=relu, stats=stats)
+        elif self.use_im2col:
             col = ops.im2col(x, self.size[0], self.size[1], self.stride, self.pad, (oh, ow))
             self._xop = self._as_operand(col)
             y = ops.conv2d_fprop(self._xop, wop_f, (0, 0), (oh, ow), out_dtype, bias=bias, residual=residual,
@@ -202,7 +219,9 @@ class ConvLayer(AbstractLayer):
             ops.colsum(dy, self.beta.grad)
         gdt = act_dtype()
         dx = None
-        if self.use_im2col:
+        if self.rowfold is not None:
+            ops.conv2d_rowfold_wgrad(dyop, self._xop, R, S, self.stride, self.omega.grad)
+        elif self.use_im2col:
             dw2 = ops.conv2d_wgrad(dyop, self._xop, 1, 1, (0, 0))
             ops.weight_grad_from_im2col(dw2, self.omega.grad)
             if not self.is_first:

@@ -114,6 +114,7 @@ class ModelCNN:
         self.ddp = None             # denet_b200.multi.GradientAllReduce when running data parallel
         self._ready = False
         self.last_costs_device = None
+        self._image = None          # padded input buffer of a row-folded stem conv
 
     # ---------------------------------------------------------------------------------------------- shapes
     def get_input_shape(self):
@@ -362,8 +363,18 @@ class ModelCNN:
         """host NCHW fp32 batch (numpy or pinned tensor) -> NHWC device activation"""
         if isinstance(data_x, numpy.ndarray):
             data_x = numpy.ascontiguousarray(data_x, dtype=numpy.float32)
-        t = layer_mod.h2d(data_x, self.device)
-        return ops.nchw_to_nhwc(t.contiguous(), layer_mod.act_dtype())
+        t = layer_mod.h2d(data_x, self.device).contiguous()
+        first = self.layers[1] if len(self.layers) > 1 else None
+        geom = getattr(first, "rowfold", None)
+        if geom is not None:
+            # image stem: keep the batch zero-padded in NHWC-Cp, the layout the row-folded conv's TMA windows read
+            n, c, h, w = t.shape
+            split = layer_mod.get_precision() == "fp32"
+            img = self._image
+            if img is None or (img.n, img.c, img.h, img.w, (img.lo is not None)) != (n, c, h, w, split):
+                img = self._image = ops.PaddedImage(n, c, h, w, geom[0], first.pad, geom[1], geom[2], split, t.device)
+            return img.fill(t)
+        return ops.nchw_to_nhwc(t, layer_mod.act_dtype())
 
     def forward(self, data_x, data_m=None, train=False):
         """one pass over the layer list; in train mode every layer's get_target runs right before its forward so
@@ -393,7 +404,7 @@ class ModelCNN:
         lib.call("denet_solver_update", self._solver_entries.data_ptr(), self._solver_block_tensor.data_ptr(),
                  self._solver_block_offset.data_ptr(), self._solver_nblocks, SOLVER_CODES[self.solver_mode],
                  float(learning_rate), float(mom[0]), float(mom[1]), float(decay), int(iteration),
-                 int(self.bias_decay), float(grad_scale), torch.cuda.current_stream().cuda_stream)
+                 int(self.bias_decay), float(grad_scale), ops._stream())
         layer_mod.bump_param_version()
 
     def _train_step_device(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):
@@ -401,6 +412,14 @@ class ModelCNN:
         layer_mod.set_epoch(epoch)
         layer_mod.set_iteration(it)
         self.bn_stat_buffer.zero_()
+        ops.pin_stream(True)
+        try:
+            return self._train_step_pinned(data_x, data_m, it, learning_rate, momentum, decay)
+        finally:
+            ops.pin_stream(False)
+            layer_mod.set_train(False)
+
+    def _train_step_pinned(self, data_x, data_m, it, learning_rate, momentum, decay):
         with torch.no_grad():
             self.forward(data_x, data_m, train=True)
             if self.ddp is not None:
@@ -415,7 +434,6 @@ class ModelCNN:
                 self._cost_factor_t = torch.tensor(self.cost_factors, dtype=torch.float32).to(costs.device)
             total = (costs * self._cost_factor_t).sum().reshape(1)
             self.last_costs_device = torch.cat([total, costs])
-        layer_mod.set_train(False)
         return self.last_costs_device
 
     def train_step(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):

@@ -10,8 +10,21 @@ from . import lib
 from .lib import DENET_BF16, DENET_F32, call
 
 
+_stream_handle = None
+
+
 def _stream():
+    """raw handle of the stream the kernels are enqueued on.  torch.cuda.current_stream() costs ~15 us of host time
+    per call, so ModelCNN pins it once per step with pin_stream(); unpinned callers pay the lookup."""
+    if _stream_handle is not None:
+        return _stream_handle
     return torch.cuda.current_stream().cuda_stream
+
+
+def pin_stream(on=True):
+    """cache (or release) the current stream handle for subsequent ops"""
+    global _stream_handle
+    _stream_handle = torch.cuda.current_stream().cuda_stream if on else None
 
 
 def _ptr(t):
@@ -178,6 +191,74 @@ def conv2d_wgrad(dyop, xop, R, S, pad, stride=(1, 1), dw=None, accumulate=False)
     call("denet_conv2d_wgrad", dy.data_ptr(), _ptr(dyop.lo), n_, ho_, wo_, cout, _pitch(dy),
          x.data_ptr(), _ptr(xop.lo), hi2, wi2, cin, _pitch(x), R, S, pad[0], pad[1], stride[0], stride[1],
          dw.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel() * 4, _stream())
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------- row-folded stem conv
+class PaddedImage:
+    """zero-padded NHWC-Cp bf16 image batch (hi [+ lo]) read by the row-folded convolution through overlapping TMA
+    windows; `shape` is the logical NCHW-style (N, H, W, C) of the unpadded image"""
+
+    def __init__(self, n, c, h, w, cp, pad, hp, wp, split, device):
+        self.n, self.c, self.h, self.w, self.cp, self.pad, self.hp, self.wp = n, c, h, w, cp, pad, hp, wp
+        self.hi = torch.zeros((n, hp, wp, cp), dtype=torch.bfloat16, device=device)
+        self.lo = torch.zeros_like(self.hi) if split else None
+        self.shape = (n, h, w, c)
+        self.device = device
+
+    def fill(self, x_nchw):
+        """x_nchw: (N,C,H,W) fp32 contiguous device tensor; only the interior is written, the border stays zero"""
+        assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and tuple(x_nchw.shape) == \
+            (self.n, self.c, self.h, self.w)
+        call("denet_nchw_to_padded_nhwc", x_nchw.data_ptr(), self.n, self.c, self.h, self.w, self.cp, self.pad[0],
+             self.pad[1], self.hp, self.wp, self.hi.data_ptr(), _ptr(self.lo), _stream())
+        return self
+
+
+def rowfold_geometry(in_hw, cin, size, stride, pad, out_hw):
+    """(Cp, Hp, Wp) of the padded buffer a row-folded conv needs, or None when the shape does not qualify"""
+    R, S = size
+    for cp in (4, 8):
+        if cin <= cp and (stride[1] * cp) % 8 == 0 and (S * cp + 7) // 8 * 8 <= 64:
+            kf = (S * cp + 7) // 8 * 8
+            hp = max(in_hw[0] + 2 * pad[0], (out_hw[0] - 1) * stride[0] + R)
+            wp = max(in_hw[1] + 2 * pad[1], -(-((out_hw[1] - 1) * stride[1] * cp + kf) // cp))
+            while (wp * cp) % 8:
+                wp += 1
+            return cp, hp, wp
+    return None
+
+
+def conv_weight_prep_rowfold(w, cp, split, out=None):
+    cout, cin, R, S = w.shape
+    if out is None:
+        hi = torch.empty((cout, R, 64), dtype=torch.bfloat16, device=w.device)
+        out = ConvOperand(hi, torch.empty_like(hi) if split else None, cout, cin, R, S)
+    call("denet_conv_weight_prep_rowfold", w.data_ptr(), cout, cin, R, S, cp, out.hi.data_ptr(), _ptr(out.lo),
+         _stream())
+    return out
+
+
+def conv2d_rowfold_fprop(img, wop, stride, out_hw, out_dtype, bias=None, relu=False, stats=None):
+    assert (img.lo is None) == (wop.lo is None), "operand split modes differ"
+    ho, wo = out_hw
+    out = alloc_nhwc(img.n, ho, wo, wop.rows, out_dtype, img.device)
+    s0, s1 = (stats if stats is not None else (None, None))
+    call("denet_conv2d_rowfold_fprop", img.hi.data_ptr(), _ptr(img.lo), img.n, img.hp, img.wp, img.cp, img.c,
+         wop.hi.data_ptr(), _ptr(wop.lo), wop.rows, wop.R, wop.S, stride[0], stride[1], out.data_ptr(),
+         _dtype_code(out), _pitch(out), ho, wo, _ptr(bias), int(relu), _ptr(s0), _ptr(s1), _stream())
+    return out
+
+
+def conv2d_rowfold_wgrad(dyop, img, R, S, stride, dw, accumulate=False):
+    dy = dyop.hi
+    n, ho, wo, cout = dy.shape
+    assert (dyop.lo is None) == (img.lo is None)
+    nbytes = lib.load().denet_conv2d_rowfold_wgrad_workspace(n, ho, wo, cout, R)
+    ws = workspace(nbytes, dy.device, "wgrad")
+    call("denet_conv2d_rowfold_wgrad", dy.data_ptr(), _ptr(dyop.lo), n, ho, wo, cout, _pitch(dy), img.hi.data_ptr(),
+         _ptr(img.lo), img.hp, img.wp, img.cp, img.c, R, S, stride[0], stride[1], dw.data_ptr(), int(accumulate),
+         ws.data_ptr(), ws.numel() * 4, _stream())
     return dw
 
 

@@ -28,7 +28,7 @@ typedef struct CUstream_st* cudaStream_t;
 extern "C" {
 #endif
 
-#define DENET_ABI_VERSION 2
+#define DENET_ABI_VERSION 3
 
 #define DENET_F32 0
 #define DENET_BF16 1
@@ -92,6 +92,26 @@ int denet_col2im(const void* dcol, int dtype, long long ldc, int N, int H, int W
 int denet_weight_to_im2col(const float* w, int Cout, int Cin, int R, int S, float* w2, cudaStream_t stream);
 int denet_weight_grad_from_im2col(const float* dw2, int Cout, int Cin, int R, int S, float* dw, int accumulate,
                                   cudaStream_t stream);
+
+/* Row-folded convolution for inputs with very few channels (the 3-channel image stem C.B[64,7,2] of
+ * examples/resnet34-imagenet.sh:7; same reference op as above, denet/layer/convolution.py:76-92).  The image lives
+ * zero-padded in an NHWC buffer (N, Hp, Wp, Cp) bf16 with Cp = 4 or 8 channels (stride_w*Cp and Wp*Cp multiples of 8,
+ * S*Cp <= 64), image pixel (h, w) at (h + pad_h, w + pad_w); TMA reads overlapping windows of it, one filter row per
+ * K chunk, so no im2col matrix is ever materialised.  nchw_to_padded_nhwc fills the interior (borders must already be
+ * zero); weight_prep_rowfold lays the filters out as [Cout][R][64]; rowfold_wgrad returns dw in the reference layout. */
+int denet_nchw_to_padded_nhwc(const float* x, int N, int C, int H, int W, int Cp, int pad_h, int pad_w, int Hp, int Wp,
+                              void* y_hi, void* y_lo, cudaStream_t stream);
+int denet_conv_weight_prep_rowfold(const float* w, int Cout, int Cin, int R, int S, int Cp, void* b_hi, void* b_lo,
+                                   cudaStream_t stream);
+int denet_conv2d_rowfold_fprop(const void* x_hi, const void* x_lo, int N, int Hp, int Wp, int Cp, int Cin,
+                               const void* b_hi, const void* b_lo, int Cout, int R, int S, int stride_h, int stride_w,
+                               void* y, int y_dtype, long long ldy, int Ho, int Wo, const float* bias, int relu,
+                               float* stat_sum, float* stat_sqsum, cudaStream_t stream);
+size_t denet_conv2d_rowfold_wgrad_workspace(int N, int Ho, int Wo, int Cout, int R);
+int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int Wo, int Cout, long long lddy,
+                               const void* x_hi, const void* x_lo, int Hp, int Wp, int Cp, int Cin, int R, int S,
+                               int stride_h, int stride_w, float* dw, int accumulate, float* workspace,
+                               size_t workspace_bytes, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ batch norm
  * Replaces dnn_batch_normalization_train / _test and BatchNormReluOp + k_relu (denet/layer/batch_norm.py:47-53,

@@ -9,7 +9,9 @@ from denet_b200 import lib
 def test_library_present_and_loads():
     assert os.path.exists(lib.LIB_PATH), "build it first: python -c 'import __graft_entry__ as g; g.build()'"
     l = lib.load()
-    assert l.denet_abi_version() == 2
+    import re
+    header = open(lib.HEADER_PATH).read()
+    assert l.denet_abi_version() == int(re.search(r"#define DENET_ABI_VERSION (\d+)", header).group(1))
     assert l.denet_last_error() is not None
 
 

@@ -86,6 +86,52 @@ def test_conv_fprop_dgrad_wgrad(cuda, case, split):
     assert relerr(nchw(dx), dxref) < tol
 
 
+ROWFOLD_CASES = [
+    # n, cin, h, w, cout, k, stride, pad
+    (2, 3, 32, 32, 16, 7, 2, 3),      # the ResNet stem shape (C.B[64,7,2]) in small
+    (3, 3, 16, 16, 128, 3, 1, 1),     # cfg1's first layer C[128,3]: stride 1 -> 8-channel padding
+    (2, 1, 20, 28, 40, 5, 2, 2),      # one input channel, non-square image
+    (2, 4, 64, 64, 64, 7, 2, 3),
+]
+
+
+@pytest.mark.parametrize("case", ROWFOLD_CASES)
+@pytest.mark.parametrize("split", [False, True])
+def test_conv_rowfold_stem(cuda, case, split):
+    """row-folded stem convolution (overlapping TMA windows over the zero-padded image) vs the oracle conv"""
+    ops = _ops()
+    n, cin, h, w, cout, k, s, pad = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.rand(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    bias = torch.randn(cout, generator=g)
+    oh = math.ceil((h + 2 * pad - k + 1) / s)
+    ow = math.ceil((w + 2 * pad - k + 1) / s)
+    dy = torch.randn(n, cout, oh, ow, generator=g)
+    geom = ops.rowfold_geometry((h, w), cin, (k, k), (s, s), (pad, pad), (oh, ow))
+    assert geom is not None
+    img = ops.PaddedImage(n, cin, h, w, geom[0], (pad, pad), geom[1], geom[2], split, cuda).fill(x.to(cuda))
+    if split:
+        xr, wr, dyr, tol = x, wt, dy, TOL_FP32
+        dyd = ops.act_operand(nhwc(dy, torch.float32, cuda))
+    else:
+        xr, wr, dyr, tol = x.bfloat16().float(), wt.bfloat16().float(), dy.bfloat16().float(), TOL_BF16
+        dyd = ops.ActOperand(nhwc(dy, torch.bfloat16, cuda))
+    wdev = wt.to(cuda)
+    wop = ops.conv_weight_prep_rowfold(wdev, geom[0], split)
+    ssum, ssq = torch.zeros(cout, device=cuda), torch.zeros(cout, device=cuda)
+    y = ops.conv2d_rowfold_fprop(img, wop, (s, s), (oh, ow), torch.float32, bias=bias.to(cuda), stats=(ssum, ssq))
+    xg, wg = xr.double().requires_grad_(True), wr.double().requires_grad_(True)
+    yref = R.conv2d(xg, wg, (s, s), pad, bias.double())
+    assert relerr(nchw(y), yref.detach()) < tol
+    assert relerr(ssum, yref.detach().sum(dim=(0, 2, 3))) < 1e-4
+    assert relerr(ssq, (yref.detach() ** 2).sum(dim=(0, 2, 3))) < 1e-4
+    _, dwref = torch.autograd.grad(yref, (xg, wg), dyr.double())
+    dw = torch.full((cout, cin, k, k), 7.0, device=cuda)
+    ops.conv2d_rowfold_wgrad(dyd, img, k, k, (s, s), dw)
+    assert relerr(dw, dwref) < tol
+
+
 def test_conv_epilogue_residual_relu_stats(cuda):
     ops = _ops()
     g = torch.Generator().manual_seed(5)
