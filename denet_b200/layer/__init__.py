@@ -19,7 +19,7 @@ from torch import nn
 # global switches (the reference keeps train flag / epoch / iteration as module-level Theano symbols,
 # denet/layer/__init__.py:5-28)
 _state = {"train": False, "epoch": 0, "iteration": 0, "precision": "bf16", "device": "cuda", "param_version": 0,
-          "fuse_bn_stats": True}
+          "fuse_bn_stats": True, "device_targets": True, "gt": None}
 
 
 def get_train():
@@ -28,6 +28,25 @@ def get_train():
 
 def set_train(v):
     _state["train"] = bool(v)
+
+
+def device_targets():
+    """build the corner / detection targets on the device from the ground-truth boxes (csrc/targets.cu) instead of in
+    numpy on the host; active when the model has uploaded the boxes of the current batch (set_ground_truth)"""
+    return _state["device_targets"] and _state["gt"] is not None
+
+
+def set_device_targets(v):
+    _state["device_targets"] = bool(v)
+
+
+def get_ground_truth():
+    return _state["gt"]
+
+
+def set_ground_truth(gt):
+    """(gt_bbox (B,G,4) f64, gt_class (B,G) i32, gt_count (B) i32) device tensors of the current batch, or None"""
+    _state["gt"] = gt
 
 
 def get_epoch():

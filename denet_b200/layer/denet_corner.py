@@ -11,7 +11,8 @@ import numpy
 import torch
 
 from .. import ops
-from . import AbstractLayer, InitialLayer, get_train, h2d, set_param, get_param
+from . import (AbstractLayer, InitialLayer, d2h, device_targets, get_ground_truth, get_train, h2d, set_param,
+               get_param)
 from .convolution import ConvLayer
 
 
@@ -50,6 +51,7 @@ class DeNetCornerLayer(AbstractLayer):
         self.grad_factor = 1.0
         self.cost_value = None
         self._target = None
+        self._target_dev = None     # persistent (B,2,cn,H,W) buffer filled by denet_corner_target
         self._z = self._dz = None
         self._sample_grad = None
 
@@ -68,7 +70,14 @@ class DeNetCornerLayer(AbstractLayer):
         return json
 
     def get_target(self, model, samples, metas):
-        """one-hot corner maps of the ground-truth boxes (denet_corner.py:81-123)"""
+        """one-hot corner maps of the ground-truth boxes (denet_corner.py:81-123).  With device targets on, the same
+        map is produced by denet_corner_target inside forward() and this returns None."""
+        if device_targets() and self.dropout == 0.0:
+            self._target = None
+            return None
+        return self.get_target_host(metas)
+
+    def get_target_host(self, metas):
         corner_pr = numpy.zeros(self.corner_shape, dtype=numpy.float32)
         W, H = self.width, self.height
         for b, meta in enumerate(metas):
@@ -112,6 +121,11 @@ class DeNetCornerLayer(AbstractLayer):
         if self.cost_value is None:
             self.cost_value = torch.zeros((1,), dtype=torch.float32, device=x.device)
         if get_train():
+            if self._target is None and device_targets():
+                if self._target_dev is None:
+                    self._target_dev = torch.empty(self.corner_shape, dtype=torch.float32, device=x.device)
+                self._target = ops.corner_target(get_ground_truth(), self.corner_num, self.height, self.width,
+                                                 self._target_dev)
             assert self._target is not None, "denet-corner: get_target/set_target must precede a training forward"
             self._dz = ops.alloc_like(z)
             ops.corner_cost(z, self.corner_num, self._target, float(self.cost_factor), self.grad_factor, self._dz,
@@ -120,6 +134,10 @@ class DeNetCornerLayer(AbstractLayer):
 
     def cost(self, yt_index=None, yt_value=None):
         return self.cost_value
+
+    def last_target(self):
+        """(yt_index, yt_value) of the last training forward in the reference's format, whichever side built it"""
+        return numpy.array([], dtype=numpy.int64), d2h(self._target.reshape(-1))
 
     def set_sample_grad(self, dfmap):
         """gradient wrt `sample` (B,H,W,F) fp32 from the sparse layer's scatter"""

@@ -11,7 +11,7 @@ import numpy
 import torch
 
 from .. import common, ops
-from . import AbstractLayer, InitialLayer, get_train, h2d
+from . import AbstractLayer, InitialLayer, d2h, device_targets, get_ground_truth, get_train, h2d
 from .convolution import ConvLayer
 
 
@@ -71,6 +71,7 @@ class DeNetDetectLayer(AbstractLayer):
         self.grad_factor = 1.0
         self.cost_value = None     # device tensor [detection cost, box cost] of the last training forward
         self._targets = None
+        self._targets_dev = None    # persistent target buffers filled by denet_detect_target
         self._dout = None
         self.logits = None
 
@@ -101,6 +102,14 @@ class DeNetDetectLayer(AbstractLayer):
         return (t[0], t[1]) if isinstance(t, (tuple, list)) else (t, t)
 
     def get_target(self, model, samples, metas):
+        """denet_detect.py:147-235.  With device targets on, denet_detect_target builds the same arrays inside forward()
+        from the ground-truth boxes and the RoIs already in HBM, and this returns None."""
+        if device_targets():
+            self._targets = None
+            return None
+        return self.get_target_host(metas)
+
+    def get_target_host(self, metas):
         """denet_detect.py:147-235 on the host arrays of the sparse layer (no per-RoI python tuples)"""
         thr0, thr1 = self._thresholds()
         sn = self.sample_num
@@ -163,6 +172,19 @@ class DeNetDetectLayer(AbstractLayer):
         if self.cost_value is None:
             self.cost_value = torch.zeros((2,), dtype=torch.float32, device=x.device)
         if get_train():
+            if self._targets is None and device_targets():
+                if self._targets_dev is None:
+                    dev, sn = x.device, self.sample_num
+                    self._targets_dev = (
+                        torch.empty(self.det_shape, dtype=torch.float32, device=dev),
+                        torch.empty((self.batch_size, sn, sn), dtype=torch.float32, device=dev) if self.use_bbox_reg
+                        else None,
+                        torch.empty((self.batch_size, 8, sn, sn), dtype=torch.float32, device=dev) if self.use_bbox_reg
+                        else None)
+                thr0, thr1 = self._thresholds()
+                ops.detect_target(get_ground_truth(), self.sparse_layer.sample_bbox64, self.sample_num, self.class_num,
+                                  thr0, thr1, self.use_bbox_reg, *self._targets_dev)
+                self._targets = self._targets_dev
             assert self._targets is not None, "denet-detect: get_target/set_target must precede a training forward"
             self._dout = ops.alloc_like(o)
             t_det, t_valid, t_reg = self._targets
@@ -173,6 +195,11 @@ class DeNetDetectLayer(AbstractLayer):
 
     def cost(self, yt_index=None, yt_value=None):
         return None if self.cost_value is None else self.cost_value.sum()
+
+    def last_target(self):
+        """(yt_index, yt_value) of the last training forward in the reference's flattened format (:229-235)"""
+        parts = [t.reshape(-1) for t in self._targets if t is not None]
+        return numpy.array([], dtype=numpy.int64), d2h(torch.cat(parts))
 
     def backward(self, dy):
         dx = self.layers[0].backward(self._dout)

@@ -66,6 +66,7 @@ class DeNetSparseLayer(AbstractLayer):
         object.__setattr__(self, "corner_layer", corner_layer)
 
         self.sample_bbox = None           # (B,sn,sn,4) fp32 device tensor consumed by the gather kernel
+        self.sample_bbox64 = None         # (B,sn*sn,4) float64 device copy for denet_detect_target
         self.sample_bbox_host = None      # (B,sn*sn,4) float64: what the reference keeps as python floats
         self.sample_pr_host = None        # (B,sn*sn)   float64
         self._sample_bbox_list = None
@@ -124,6 +125,8 @@ class DeNetSparseLayer(AbstractLayer):
         arr = numpy.ascontiguousarray(bbox.astype(numpy.float32).reshape(self.batch_size, self.sample_num,
                                                                          self.sample_num, 4))
         self.sample_bbox = h2d(arr)
+        # the doubles feed the device-side detection targets (python floats in the reference, denet_detect.py:200-212)
+        self.sample_bbox64 = h2d(numpy.ascontiguousarray(bbox, dtype=numpy.float64))
         return arr
 
     def set_samples(self, sample_bboxs):

@@ -376,10 +376,32 @@ class ModelCNN:
             return img.fill(t)
         return ops.nchw_to_nhwc(t, layer_mod.act_dtype())
 
+    def upload_metas(self, data_m):
+        """ground-truth boxes / classes of the batch as fixed-shape device arrays for the device-side target builders
+        (a few KB); None when there are no metas, no DSS head, or an image has more boxes than the kernels handle"""
+        if not data_m or not layer_mod._state["device_targets"] or \
+                not any(l.type_name == "denet-corner" for l in self.layers):
+            return None
+        G = ops.MAX_GT
+        b = len(data_m)
+        if max(len(m.get("bbox", [])) for m in data_m) > G:
+            return None
+        box = numpy.zeros((b, G, 4), dtype=numpy.float64)
+        cls = numpy.zeros((b, G), dtype=numpy.int32)
+        cnt = numpy.zeros((b,), dtype=numpy.int32)
+        for i, m in enumerate(data_m):
+            n = len(m["bbox"])
+            cnt[i] = n
+            if n:
+                box[i, :n] = numpy.asarray(m["bbox"], dtype=numpy.float64)
+                cls[i, :n] = numpy.asarray(m["class"], dtype=numpy.int32)
+        return layer_mod.h2d(box, self.device), layer_mod.h2d(cls, self.device), layer_mod.h2d(cnt, self.device)
+
     def forward(self, data_x, data_m=None, train=False):
         """one pass over the layer list; in train mode every layer's get_target runs right before its forward so
         that the sparse layer can sample from the corner maps of this very pass"""
         layer_mod.set_train(train)
+        layer_mod.set_ground_truth(self.upload_metas(data_m) if train else None)
         x = self.upload(data_x)
         self.layers[0].output = x
         for l in self.layers[1:]:

@@ -499,6 +499,27 @@ def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, loc
     return pr, bbox, ibox, count, ncand
 
 
+# ---------------------------------------------------------------------------------------------- targets
+MAX_GT = 64   # ground-truth boxes per image the device target builders handle (csrc/targets.cu kMaxGt)
+
+
+def corner_target(gt, cn, H, W, out):
+    """gt = (gt_bbox (B,G,4) f64, gt_class (B,G) i32, gt_count (B) i32) device tensors -> out (B,2,cn,H,W) fp32"""
+    gt_bbox, _, gt_count = gt
+    b, g = gt_bbox.shape[:2]
+    call("denet_corner_target", gt_bbox.data_ptr(), gt_count.data_ptr(), b, g, cn, H, W, out.data_ptr(), _stream())
+    return out
+
+
+def detect_target(gt, sample_bbox64, sn, class_num, thr0, thr1, use_bbox, det, valid, reg):
+    gt_bbox, gt_class, gt_count = gt
+    b, g = gt_bbox.shape[:2]
+    assert sample_bbox64.dtype == torch.float64 and sample_bbox64.is_contiguous()
+    call("denet_detect_target", gt_bbox.data_ptr(), gt_class.data_ptr(), gt_count.data_ptr(),
+         sample_bbox64.data_ptr(), b, g, sn, class_num, float(thr0), float(thr1), int(use_bbox), det.data_ptr(),
+         _ptr(valid), _ptr(reg), _stream())
+
+
 # ---------------------------------------------------------------------------------------------- costs
 def _loss_ws(device):
     return workspace(lib.load().denet_loss_workspace_bytes(), device, "loss")

@@ -219,6 +219,20 @@ int denet_detect_cost(const void* o, int dtype, long long ld, int B, int sn, int
 int denet_softmax_nll(const void* o, int dtype, long long ld, int B, int classes, const int* label, float grad_factor,
                       void* dout, float* logp_out, float* cost, float* workspace, cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ targets
+ * The host target builders of the reference, evaluated on the device from the ground-truth boxes:
+ * corner_target: DeNetCornerLayer.get_target (denet/layer/denet_corner.py:81-123, dropout 0) -> (B,2,cn,H,W) fp32.
+ * detect_target: DeNetDetectLayer.get_target (denet/layer/denet_detect.py:147-235, IoU of common/theano_util.py:38-59)
+ *   -> target_det (B,classNum+1,sn,sn), target_valid (B,sn,sn), target_reg (B,8,sn,sn) fp32 (the three pieces of the
+ *   reference's flattened yt_value).  gt_bbox (B,G,4) and sample_bbox (B,sn*sn,4) are DOUBLES (x0,y0,x1,y1) - python
+ *   floats in the reference; gt_class (B,G) int32; gt_count (B) int32 (<= G <= 64).  Results equal the host
+ *   builders' bit for bit. */
+int denet_corner_target(const double* gt_bbox, const int* gt_count, int B, int G, int cn, int H, int W, float* target,
+                        cudaStream_t stream);
+int denet_detect_target(const double* gt_bbox, const int* gt_class, const int* gt_count, const double* sample_bbox,
+                        int B, int G, int sn, int class_num, float thr0, float thr1, int use_bbox, float* target_det,
+                        float* target_valid, float* target_reg, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ solver
  * ModelCNN.build_train_func update rules (model/model_cnn.py:282-305, 320-324) for ALL parameter
  * tensors in one launch.  `entries` is a device array of denet_solver_entry_bytes()-sized records

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 import oracle
 from oracle import ref_ops as R
-from util import busy_corner_map, nchw, nhwc, relerr
+from util import synthetic_metas, busy_corner_map, nchw, nhwc, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -447,6 +447,60 @@ def test_build_samples_matches_compiled_reference(cuda):
             key = tuple(bbox[b, i])
             if pr[b, i] > cut or ncand[b] <= sn * sn:
                 assert key in want and want[key] == pr[b, i]
+
+
+# ------------------------------------------------------------------------------------------------ targets
+@pytest.mark.parametrize("B,H,sn,classes,use_bbox", [(32, 64, 24, 80, True), (3, 16, 5, 20, False), (2, 32, 8, 4, True)])
+def test_device_targets_bit_exact(cuda, B, H, sn, classes, use_bbox):
+    """denet_corner_target / denet_detect_target == the oracle's restatement of the host builders, bit for bit"""
+    import random
+    ops = _ops()
+    metas = synthetic_metas(B, classes, seed=B + sn)
+    metas[0]["bbox"], metas[0]["class"] = [], []                      # an image without objects
+    rnd = random.Random(5)
+    K = sn * sn
+    samples = []
+    for b in range(B):
+        lst = []
+        for i in range(K):
+            gts = metas[b]["bbox"]
+            if gts and i % 3 == 0:                                    # jittered ground truth: positives, shared RoIs
+                g = gts[rnd.randrange(len(gts))]
+                j = [rnd.uniform(-0.03, 0.03) for _ in range(4)]
+                lst.append((0.5, (g[0] + j[0], g[1] + j[1], g[2] + j[2], g[3] + j[3])))
+            elif gts and i % 7 == 1:
+                lst.append((1.0, tuple(gts[rnd.randrange(len(gts))])))    # exact ground truth (IoU 1)
+            else:
+                x0, y0 = rnd.uniform(0, 1), rnd.uniform(0, 1)
+                lst.append((0.0, (x0, y0, rnd.uniform(x0, 1), rnd.uniform(y0, 1))))
+        samples.append(lst)
+    if len(metas[1]["bbox"]) >= 2:                                    # two objects of different class on one RoI
+        metas[1]["bbox"][1] = metas[1]["bbox"][0]
+        metas[1]["class"][1] = (metas[1]["class"][0] + 1) % classes
+    G = ops.MAX_GT
+    box = numpy.zeros((B, G, 4)); cls = numpy.zeros((B, G), numpy.int32); cnt = numpy.zeros((B,), numpy.int32)
+    for b, m in enumerate(metas):
+        cnt[b] = len(m["bbox"])
+        if cnt[b]:
+            box[b, :cnt[b]] = m["bbox"]
+            cls[b, :cnt[b]] = m["class"]
+    gt = (torch.from_numpy(box).cuda(), torch.from_numpy(cls).cuda(), torch.from_numpy(cnt).cuda())
+    for cn in (4, 5):
+        tgt = torch.empty((B, 2, cn, H, H), device="cuda")
+        ops.corner_target(gt, cn, H, H, tgt)
+        ref = R.corner_target(metas, (B, 2, cn, H, H), cn == 5)[1]
+        assert numpy.array_equal(tgt.cpu().numpy().reshape(-1), ref)
+    s64 = torch.from_numpy(numpy.array([[bb for _, bb in lst] for lst in samples], dtype=numpy.float64)).cuda()
+    det = torch.empty((B, classes + 1, sn, sn), device="cuda")
+    valid = torch.empty((B, sn, sn), device="cuda") if use_bbox else None
+    reg = torch.empty((B, 8, sn, sn), device="cuda") if use_bbox else None
+    ops.detect_target(gt, s64, sn, classes, 0.5, 0.5, use_bbox, det, valid, reg)
+    ref = R.detect_target(metas, samples, B, sn, classes, 0.5, use_bbox)[1]
+    got = torch.cat([t.reshape(-1) for t in (det, valid, reg) if t is not None]).cpu().numpy()
+    n0 = det.numel()
+    assert numpy.array_equal(got[:n0], ref[:n0]), "class targets"
+    assert (ref[:n0].reshape(B, classes + 1, -1)[:, :classes] > 0).sum() > 0, "the case must contain positives"
+    assert numpy.array_equal(got, ref)
 
 
 # ------------------------------------------------------------------------------------------------ costs

@@ -80,27 +80,40 @@ def pool_argmax(model):
     return out
 
 
+def oracle_targets(model, metas):
+    """[(layer type, (yt_index, yt_value))] in cost-layer order, built by the ORACLE's restatement of the reference's
+    host target builders from the metas and the RoIs the step used; the targets the CUDA path built for itself
+    (on the device, csrc/targets.cu) must equal them bit for bit"""
+    out = []
+    dns = [l for l in model.layers if l.type_name == "denet-sparse"]
+    for l in model.layers:
+        if l.type_name == "denet-corner":
+            t = R.corner_target(metas, l.corner_shape, l.use_center)
+        elif l.type_name == "denet-detect":
+            t = R.detect_target(metas, dns[0].sample_bbox_list, l.batch_size, l.sample_num, l.class_num,
+                                l.overlap_threshold, l.use_bbox_reg)
+        elif l.type_name == "regression":
+            classes = l.output_shape[1]
+            t = (numpy.array([b * classes + int(m["image_class"]) for b, m in enumerate(metas)], dtype=numpy.int64),
+                 numpy.array([], dtype=numpy.float32))
+        else:
+            continue
+        if hasattr(l, "last_target"):
+            mine = l.last_target()
+            assert numpy.array_equal(mine[1], t[1]), "%s: target built by the CUDA path differs from the oracle" % \
+                l.type_name
+        out.append((l.type_name, t))
+    return out
+
+
 def run_step(model, x, metas, solver="nesterov", lr=0.05, mom=(0.9, 0.9), decay=1e-4, it=1, seed=5):
     """GPU train step; returns what is needed to replay it on the oracle"""
     js = model.export_json()["layers"]
     before = {k: p.detach().cpu().double().clone() for k, p in named_params(model).items()}
     random.seed(seed)
     numpy.random.seed(seed)
-    captured = []
-    for l in model.layers:
-        if l.has_cost or l.type_name == "denet-sparse":
-            orig = l.get_target
-
-            def wrapped(m, dx, dm, _orig=orig, _l=l):
-                t = _orig(m, dx, dm)
-                if t is not None:
-                    captured.append((_l.type_name, t))
-                return t
-            l.get_target = wrapped
     cost, costs = model.train_step(x, metas, 0, it, lr, list(mom), decay)
-    for l in model.layers:
-        if "get_target" in l.__dict__:
-            del l.__dict__["get_target"]
+    captured = oracle_targets(model, metas)
     return js, before, captured, cost, costs
 
 
