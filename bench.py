@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=2, help="images per CPU-baseline step")
     ap.add_argument("--cpu-sample-steps", type=int, default=4)
+    ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--detail", action="store_true", help="also print a per-layer conv timing table to stderr")
     return ap.parse_args()
 
@@ -229,34 +230,59 @@ def run_b200(args):
         return v
 
     it = 0
-    for _ in range(args.warmup):
+
+    def step_device():
+        nonlocal it
         model._train_step_device(x_dev, metas, 0, it, hp["lr"], hp["momentum"], hp["decay"])
         it += 1
-    cost = model.train_step(x_pinned, metas, 0, it, hp["lr"], hp["momentum"], hp["decay"])[0]
-    it += 1
+
+    def step_host():
+        nonlocal it
+        c = model.train_step(x_pinned, metas, 0, it, hp["lr"], hp["momentum"], hp["decay"])[0]
+        it += 1
+        return c
+
+    # ---- conv kernel timing (roofline): eager launches of the same steps, every conv entry point bracketed by CUDA
+    # events on its stream (events cannot be recorded inside a replayed graph)
+    timed_names = ["denet_conv2d_fprop", "denet_conv2d_wgrad", "denet_conv2d_rowfold_fprop",
+                   "denet_conv2d_rowfold_wgrad"]
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    lib.start_timing(timed_names)
+    le0 = clib.denet_launch_count()
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record()
+    for _ in range(args.steps):
+        step_device()
+    t1e.record()
+    barrier()
+    ms_eager = max_over_ranks(t0e.elapsed_time(t1e))
+    launches = (clib.denet_launch_count() - le0) / args.steps     # kernels per step (graph mode replays the same nodes)
+    timings = lib.stop_timing()
+
+    graphs = not args.eager
+    if graphs:
+        model.enable_cuda_graphs(True)
+    for _ in range(max(args.warmup, 3)):          # in graph mode: eager warm-up, capture, replay
+        step_device()
+    cost = step_host()
     if not numpy.isfinite(cost):
         raise SystemExit("bench.py: cost is not finite after warm-up (%r)" % cost)
 
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
 
-    # ---- region A: inputs resident in HBM (value), conv entry points bracketed by CUDA events (roofline)
-    timed_names = ["denet_conv2d_fprop", "denet_conv2d_wgrad", "denet_conv2d_rowfold_fprop",
-                   "denet_conv2d_rowfold_wgrad"]
+    # ---- region A: inputs resident in HBM (value)
     barrier()
-    lib.start_timing(timed_names)
-    l0 = clib.denet_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        model._train_step_device(x_dev, metas, 0, it, hp["lr"], hp["momentum"], hp["decay"])
-        it += 1
+        step_device()
     e1.record()
     barrier()
     ms_a = max_over_ranks(e0.elapsed_time(e1))
-    launches = (clib.denet_launch_count() - l0) / args.steps
-    timings = lib.stop_timing()
 
     # ---- region B: through the public API with HOST buffers: H2D of the batch and D2H of the costs every step
     barrier()
@@ -265,8 +291,7 @@ def run_b200(args):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.steps):
-        cost = model.train_step(x_pinned, metas, 0, it, hp["lr"], hp["momentum"], hp["decay"])[0]
-        it += 1
+        cost = step_host()
     e3.record()
     barrier()
     ms_b = max_over_ranks(e2.elapsed_time(e3))
@@ -313,6 +338,8 @@ def run_b200(args):
                 "launches_per_step": n_conv_launch / args.steps,
                 "conv_ms_per_step": conv_ms / args.steps,
                 "conv_share_of_step": (conv_ms / args.steps) / (ms_a / args.steps),
+                "timed_in": "eager launches of the same steps (%.2f ms/step eager); value/e2e are %s" % (
+                    ms_eager / args.steps, "CUDA-graph replays" if graphs else "eager too"),
                 "families": {k: {"tflops": (v[1] / (v[0] / 1000.0) / 1e12 if v[0] > 0 else None),
                                  "ms_per_step": v[0] / args.steps} for k, v in fam.items()},
                 "algorithmic_gflop_per_image": train_flops / batch / 1e9}
@@ -325,7 +352,8 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup + 1, "ms_per_step": ms_a / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": workload_config(args.workload, batch, world, data_shape, classes, solver),
+            "config": dict(workload_config(args.workload, batch, world, data_shape, classes, solver),
+                           launch_mode="cuda-graphs" if graphs else "eager"),
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_b / args.steps,
                     "h2d_bytes_per_step": (tb1["h2d"] - tb0["h2d"]) // args.steps,

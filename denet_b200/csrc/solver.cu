@@ -25,7 +25,17 @@ __global__ void __launch_bounds__(256) solver_update_kernel(const SolverEntry* _
                                                              const int* __restrict__ block_tensor,
                                                              const long long* __restrict__ block_offset, int solver,
                                                              float lr, float mu, float mu2, float rho, float decay,
-                                                             int iteration, int bias_decay, float grad_scale) {
+                                                             int iteration, int bias_decay, float grad_scale,
+                                                             const float* __restrict__ hp) {
+    if (hp) {   // hyper-parameters of THIS step from device memory: a captured CUDA graph replays with new values
+        lr = hp[0];
+        mu = hp[1];
+        mu2 = hp[2];
+        decay = hp[3];
+        iteration = (int)hp[4];
+        grad_scale = hp[5];
+        rho = iteration > 0 ? mu : 0.f;
+    }
     const SolverEntry e = entries[block_tensor[blockIdx.x]];
     const long long start = block_offset[blockIdx.x];
     const long long end = start + kChunk < e.n ? start + kChunk : e.n;
@@ -72,7 +82,18 @@ extern "C" int denet_solver_update(const void* entries, const int* block_tensor,
     const float rho = iteration > 0 ? momentum0 : 0.0f;
     solver_update_kernel<<<DN_G(nblocks), 256, 0, stream>>>((const SolverEntry*)entries, block_tensor, block_offset, solver, lr,
                                                       momentum0, momentum1, rho, decay, iteration, bias_decay,
-                                                      grad_scale);
+                                                      grad_scale, nullptr);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_solver_update_dev(const void* entries, const int* block_tensor, const long long* block_offset,
+                                       int nblocks, int solver, const float* hp, int bias_decay, cudaStream_t stream) {
+    DN_REQUIRE(entries && block_tensor && block_offset && hp, "solver_update_dev: null pointer");
+    DN_REQUIRE(solver >= 0 && solver <= 2, "solver_update_dev: solver must be 0 (sgd), 1 (nesterov/torch) or 2 (adam)");
+    if (nblocks == 0) return 0;
+    solver_update_kernel<<<DN_G(nblocks), 256, 0, stream>>>((const SolverEntry*)entries, block_tensor, block_offset, solver,
+                                                            0.f, 0.f, 0.f, 0.f, 0.f, 0, bias_decay, 1.f, hp);
     DN_CHECK_LAUNCH();
     return 0;
 }

@@ -138,21 +138,63 @@ def import_json(json_layers, x, x_shape, layer_range=None):
 transfer_bytes = {"h2d": 0, "d2h": 0}
 
 
-def h2d(array, device=None):
-    """host numpy array / CPU tensor -> device tensor through pinned memory, asynchronous on the current stream"""
+_slots = {}     # slot name -> (pinned host tensor, device tensor, copy-done event)
+
+
+def h2d(array, device=None, slot=None):
+    """host numpy array / CPU tensor -> device tensor, asynchronous on the current stream.
+
+    With `slot`, the copy goes through a PERSISTENT pinned staging buffer into a PERSISTENT device tensor (same
+    address every step: no cudaHostAlloc per call, and the device tensor can be an input of a captured CUDA graph).
+    Without it a fresh pinned buffer is used.  CUDA tensors pass through (or are copied into the slot)."""
     t = array if torch.is_tensor(array) else torch.from_numpy(numpy.ascontiguousarray(array))
+    dev = device if device is not None else (_state["device"] or "cuda")
+    if slot is None:
+        if t.is_cuda:
+            return t
+        transfer_bytes["h2d"] += t.numel() * t.element_size()
+        if not t.is_pinned():
+            t = t.pin_memory()
+        return t.to(dev, non_blocking=True)
+    ent = _slots.get(slot)
+    if ent is None or ent[1].shape != t.shape or ent[1].dtype != t.dtype:
+        ent = (torch.empty(t.shape, dtype=t.dtype).pin_memory(), torch.empty(t.shape, dtype=t.dtype, device=dev),
+               torch.cuda.Event())
+        _slots[slot] = ent
+    pinned, dst, done = ent
     if t.is_cuda:
-        return t
+        if t.data_ptr() != dst.data_ptr():
+            dst.copy_(t, non_blocking=True)
+        return dst
     transfer_bytes["h2d"] += t.numel() * t.element_size()
-    if not t.is_pinned():
-        t = t.pin_memory()
-    return t.to(device if device is not None else (_state["device"] or "cuda"), non_blocking=True)
+    if t.is_pinned():
+        dst.copy_(t, non_blocking=True)          # caller-owned pinned memory (e.g. the image batch): no staging copy
+        return dst
+    done.synchronize()                            # the previous copy out of the staging buffer has finished
+    pinned.copy_(t)
+    dst.copy_(pinned, non_blocking=True)
+    done.record()
+    return dst
 
 
-def d2h(tensor):
-    """device tensor -> numpy (synchronises the current stream)"""
+def slot_tensor(slot):
+    ent = _slots.get(slot)
+    return None if ent is None else ent[1]
+
+
+def d2h(tensor, slot=None):
+    """device tensor -> numpy (synchronises the current stream); with `slot` through a persistent pinned buffer"""
     transfer_bytes["d2h"] += tensor.numel() * tensor.element_size()
-    return tensor.cpu().numpy()
+    if slot is None:
+        return tensor.cpu().numpy()
+    key = ("d2h", slot)
+    ent = _slots.get(key)
+    if ent is None or ent[0].shape != tensor.shape or ent[0].dtype != tensor.dtype:
+        ent = (torch.empty(tensor.shape, dtype=tensor.dtype).pin_memory(), None, None)
+        _slots[key] = ent
+    ent[0].copy_(tensor, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return ent[0].numpy()
 
 
 def new_param(array):

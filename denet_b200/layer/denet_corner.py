@@ -121,7 +121,7 @@ class DeNetCornerLayer(AbstractLayer):
         if self.cost_value is None:
             self.cost_value = torch.zeros((1,), dtype=torch.float32, device=x.device)
         if get_train():
-            if self._target is None and device_targets():
+            if device_targets() and self.dropout == 0.0:
                 if self._target_dev is None:
                     self._target_dev = torch.empty(self.corner_shape, dtype=torch.float32, device=x.device)
                 self._target = ops.corner_target(get_ground_truth(), self.corner_num, self.height, self.width,

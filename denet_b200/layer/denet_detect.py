@@ -172,7 +172,7 @@ class DeNetDetectLayer(AbstractLayer):
         if self.cost_value is None:
             self.cost_value = torch.zeros((2,), dtype=torch.float32, device=x.device)
         if get_train():
-            if self._targets is None and device_targets():
+            if device_targets():
                 if self._targets_dev is None:
                     dev, sn = x.device, self.sample_num
                     self._targets_dev = (

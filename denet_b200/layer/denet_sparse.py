@@ -31,7 +31,7 @@ def py_random_doubles(k):
     rs.set_state(("MT19937", numpy.array(internal[:-1], dtype=numpy.uint32), int(internal[-1])))
     out = rs.random_sample(k)
     st = rs.get_state()
-    random.setstate((version, tuple(int(v) for v in st[1]) + (int(st[2]),), gauss))
+    random.setstate((version, tuple(st[1].tolist()) + (int(st[2]),), gauss))
     return out
 
 
@@ -70,6 +70,7 @@ class DeNetSparseLayer(AbstractLayer):
         self.sample_bbox_host = None      # (B,sn*sn,4) float64: what the reference keeps as python floats
         self.sample_pr_host = None        # (B,sn*sn)   float64
         self._sample_bbox_list = None
+        self._packed_dev = None
         self.output_feat = self.grid_size * self.grid_size * corner_layer.sample_shape[1] + 2
         self.output_shape = (self.batch_size, self.output_feat, self.sample_num, self.sample_num)
 
@@ -90,18 +91,31 @@ class DeNetSparseLayer(AbstractLayer):
         return json
 
     # ---------------------------------------------------------------------------------------------- sampling
-    def get_samples_arrays(self, corner_pr=None):
-        """device sampler -> host arrays: pr (B,K) f32, bbox (B,K,4) f32, count (B) (one small device->host copy)"""
+    def enqueue_samples(self, corner_pr=None):
+        """enqueue the device sampler on the corner maps of this forward pass; results land in persistent device
+        buffers packed as [pr (B,K) | bbox (B,K,4) | count (B)] fp32 (capturable in a CUDA graph: no host access)"""
         if corner_pr is None:
             corner_pr = self.corner_layer.corner_pr
         assert corner_pr is not None, "denet-sparse: the corner layer has not run a forward pass yet"
         pr, bbox, _, count, _ = ops.build_samples(corner_pr, self.corner_threshold, self.sample_num, self.corner_max,
                                                   self.local_max)
-        k = self.sample_count
-        packed = d2h(torch.cat([pr.reshape(-1), bbox.reshape(-1), count.to(torch.float32)]))
-        b = self.batch_size
+        b, k = self.batch_size, self.sample_count
+        if self._packed_dev is None:
+            self._packed_dev = torch.empty((5 * b * k + b,), dtype=torch.float32, device=corner_pr.device)
+        torch.cat([pr.reshape(-1), bbox.reshape(-1), count.to(torch.float32)], out=self._packed_dev)
+        return self._packed_dev
+
+    def collect_samples(self):
+        """device -> host copy of the packed sampler output (one small synchronising copy):
+        pr (B,K) f32, bbox (B,K,4) f32, count (B)"""
+        packed = d2h(self._packed_dev, slot="denet-sparse/samples")
+        b, k = self.batch_size, self.sample_count
         return (packed[:b * k].reshape(b, k), packed[b * k:5 * b * k].reshape(b, k, 4),
                 packed[5 * b * k:].astype(numpy.int64))
+
+    def get_samples_arrays(self, corner_pr=None):
+        self.enqueue_samples(corner_pr)
+        return self.collect_samples()
 
     def get_samples(self, data_x=None, train=False, store_shared=False):
         """reference return format (denet_sparse.py:117-145): per image a list of (pr, (x0,y0,x1,y1))"""
@@ -124,9 +138,9 @@ class DeNetSparseLayer(AbstractLayer):
         self._sample_bbox_list = None
         arr = numpy.ascontiguousarray(bbox.astype(numpy.float32).reshape(self.batch_size, self.sample_num,
                                                                          self.sample_num, 4))
-        self.sample_bbox = h2d(arr)
+        self.sample_bbox = h2d(arr, slot="denet-sparse/bbox32")
         # the doubles feed the device-side detection targets (python floats in the reference, denet_detect.py:200-212)
-        self.sample_bbox64 = h2d(numpy.ascontiguousarray(bbox, dtype=numpy.float64))
+        self.sample_bbox64 = h2d(numpy.ascontiguousarray(bbox, dtype=numpy.float64), slot="denet-sparse/bbox64")
         return arr
 
     def set_samples(self, sample_bboxs):
@@ -142,7 +156,11 @@ class DeNetSparseLayer(AbstractLayer):
 
     def get_target(self, model, data_x, metas):
         """denet_sparse.py:164-206, vectorised; consumes python's `random` stream exactly like the reference loops"""
-        pr32, bbox32, count = self.get_samples_arrays()
+        return self.finish_target(metas, *self.get_samples_arrays())
+
+    def finish_target(self, metas, pr32, bbox32, count):
+        """host half of get_target: the reference's python-`random` post-processing of the ranked RoIs, then the
+        upload of the final (B,sn,sn,4) box tensor"""
         k = self.sample_count
         n_keep = k - math.floor(self.random_sample * k)
         pr = numpy.zeros((self.batch_size, k), dtype=numpy.float64)

@@ -115,6 +115,9 @@ class ModelCNN:
         self._ready = False
         self.last_costs_device = None
         self._image = None          # padded input buffer of a row-folded stem conv
+        self._static_inputs = False # copy every batch into one persistent device buffer (needed by CUDA graphs)
+        self._graphs = None         # captured CUDA graphs of the training step (enable_cuda_graphs)
+        self._use_graphs = False
 
     # ---------------------------------------------------------------------------------------------- shapes
     def get_input_shape(self):
@@ -363,7 +366,7 @@ class ModelCNN:
         """host NCHW fp32 batch (numpy or pinned tensor) -> NHWC device activation"""
         if isinstance(data_x, numpy.ndarray):
             data_x = numpy.ascontiguousarray(data_x, dtype=numpy.float32)
-        t = layer_mod.h2d(data_x, self.device).contiguous()
+        t = layer_mod.h2d(data_x, self.device, slot="model/image" if self._static_inputs else None).contiguous()
         first = self.layers[1] if len(self.layers) > 1 else None
         geom = getattr(first, "rowfold", None)
         if geom is not None:
@@ -395,7 +398,8 @@ class ModelCNN:
             if n:
                 box[i, :n] = numpy.asarray(m["bbox"], dtype=numpy.float64)
                 cls[i, :n] = numpy.asarray(m["class"], dtype=numpy.int32)
-        return layer_mod.h2d(box, self.device), layer_mod.h2d(cls, self.device), layer_mod.h2d(cnt, self.device)
+        return (layer_mod.h2d(box, self.device, slot="model/gt_bbox"), layer_mod.h2d(cls, self.device, slot="model/gt_class"),
+                layer_mod.h2d(cnt, self.device, slot="model/gt_count"))
 
     def forward(self, data_x, data_m=None, train=False):
         """one pass over the layer list; in train mode every layer's get_target runs right before its forward so
@@ -404,8 +408,11 @@ class ModelCNN:
         layer_mod.set_ground_truth(self.upload_metas(data_m) if train else None)
         x = self.upload(data_x)
         self.layers[0].output = x
-        for l in self.layers[1:]:
-            if train:
+        return self.forward_layers(x, 1, len(self.layers), data_x, data_m, train)
+
+    def forward_layers(self, x, start, end, data_x=None, data_m=None, train=False, with_targets=True):
+        for l in self.layers[start:end]:
+            if train and with_targets:
                 target = l.get_target(self, data_x, data_m)
                 if target is not None:
                     l.set_target(*target)
@@ -421,42 +428,154 @@ class ModelCNN:
                 hook(index)
         return dy
 
-    def solver_step(self, learning_rate, momentum, decay, iteration, grad_scale=1.0):
-        mom = list(momentum) + [0.0, 0.0]
-        lib.call("denet_solver_update", self._solver_entries.data_ptr(), self._solver_block_tensor.data_ptr(),
-                 self._solver_block_offset.data_ptr(), self._solver_nblocks, SOLVER_CODES[self.solver_mode],
-                 float(learning_rate), float(mom[0]), float(mom[1]), float(decay), int(iteration),
-                 int(self.bias_decay), float(grad_scale), ops._stream())
+    def solver_step(self, learning_rate, momentum, decay, iteration, grad_scale=1.0, hp_dev=None):
+        """one multi-tensor update launch; with hp_dev the per-step scalars are read from device memory (CUDA graphs)"""
+        if hp_dev is not None:
+            lib.call("denet_solver_update_dev", self._solver_entries.data_ptr(), self._solver_block_tensor.data_ptr(),
+                     self._solver_block_offset.data_ptr(), self._solver_nblocks, SOLVER_CODES[self.solver_mode],
+                     hp_dev.data_ptr(), int(self.bias_decay), ops._stream())
+        else:
+            mom = list(momentum) + [0.0, 0.0]
+            lib.call("denet_solver_update", self._solver_entries.data_ptr(), self._solver_block_tensor.data_ptr(),
+                     self._solver_block_offset.data_ptr(), self._solver_nblocks, SOLVER_CODES[self.solver_mode],
+                     float(learning_rate), float(mom[0]), float(mom[1]), float(decay), int(iteration),
+                     int(self.bias_decay), float(grad_scale), ops._stream())
         layer_mod.bump_param_version()
+
+    def _pack_costs(self):
+        costs = torch.stack([l.cost().reshape(()) for l in self.cost_layers])
+        if self._cost_factor_t is None:
+            self._cost_factor_t = torch.tensor(self.cost_factors, dtype=torch.float32).to(costs.device)
+        total = (costs * self._cost_factor_t).sum().reshape(1)
+        return torch.cat([total, costs])
 
     def _train_step_device(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):
         """forward + backward + update on the device; returns the device tensor [total, cost_0, cost_1, ...]"""
         layer_mod.set_epoch(epoch)
         layer_mod.set_iteration(it)
-        self.bn_stat_buffer.zero_()
         ops.pin_stream(True)
         try:
-            return self._train_step_pinned(data_x, data_m, it, learning_rate, momentum, decay)
+            with torch.no_grad():
+                if self._use_graphs:
+                    return self._train_step_graphed(data_x, data_m, it, learning_rate, momentum, decay)
+                return self._train_step_eager(data_x, data_m, it, learning_rate, momentum, decay)
         finally:
             ops.pin_stream(False)
             layer_mod.set_train(False)
 
-    def _train_step_pinned(self, data_x, data_m, it, learning_rate, momentum, decay):
-        with torch.no_grad():
-            self.forward(data_x, data_m, train=True)
-            if self.ddp is not None:
-                self.ddp.begin_step()
-            self.backward()
-            grad_scale = 1.0
-            if self.ddp is not None:
-                grad_scale = self.ddp.finish_step()
-            self.solver_step(learning_rate, momentum, decay, it, grad_scale)
-            costs = torch.stack([l.cost().reshape(()) for l in self.cost_layers])
-            if self._cost_factor_t is None:
-                self._cost_factor_t = torch.tensor(self.cost_factors, dtype=torch.float32).to(costs.device)
-            total = (costs * self._cost_factor_t).sum().reshape(1)
-            self.last_costs_device = torch.cat([total, costs])
+    def _train_step_eager(self, data_x, data_m, it, learning_rate, momentum, decay):
+        self.bn_stat_buffer.zero_()
+        self.forward(data_x, data_m, train=True)
+        if self.ddp is not None:
+            self.ddp.begin_step()
+        self.backward()
+        grad_scale = 1.0
+        if self.ddp is not None:
+            grad_scale = self.ddp.finish_step()
+        self.solver_step(learning_rate, momentum, decay, it, grad_scale)
+        self.last_costs_device = self._pack_costs()
         return self.last_costs_device
+
+    # ---------------------------------------------------------------------------------------------- CUDA graphs
+    def enable_cuda_graphs(self, on=True):
+        """Replay the training step from captured CUDA graphs instead of ~520 eager launches.  The step is cut where
+        the HOST has to look at device results: after the corner layer + device sampler (the reference's
+        python-`random` post-processing of the RoIs runs on the host between the two graphs).  Models without a
+        sparse layer are one graph.  Inputs (image batch, ground truth, RoI boxes, solver scalars) live in persistent
+        device buffers refreshed by small copies before each replay.  The first graphed step runs eagerly (creates
+        every persistent buffer), the second captures."""
+        self._use_graphs = bool(on)
+        self._static_inputs = bool(on)
+        self._graphs = None
+        self._graph_warm = False
+
+    def _sparse_index(self):
+        for i, l in enumerate(self.layers):
+            if l.type_name == "denet-sparse":
+                return i
+        return None
+
+    def _write_hp(self, it, learning_rate, momentum, decay):
+        mom = list(momentum) + [0.0, 0.0]
+        world = self.ddp.world if self.ddp is not None else 1
+        hp = numpy.array([learning_rate, mom[0], mom[1], decay, float(it), 1.0 / world], dtype=numpy.float32)
+        return layer_mod.h2d(hp, self.device, slot="model/hp")
+
+    def _segment_a(self, si):
+        """image -> ... -> corner layer (+ device targets, corner cost) -> device sampler"""
+        self.bn_stat_buffer.zero_()
+        x = self.upload(layer_mod.slot_tensor("model/image"))
+        self.layers[0].output = x
+        end = si if si is not None else len(self.layers)
+        x = self.forward_layers(x, 1, end, train=True, with_targets=False)
+        if si is not None:
+            self.layers[si].enqueue_samples()
+        return x
+
+    def _segment_b(self, x, si, hp_dev):
+        """sparse gather -> head -> costs -> backward (+ gradient all-reduce) -> solver"""
+        if si is not None:
+            x = self.forward_layers(x, si, len(self.layers), train=True, with_targets=False)
+        if self.ddp is not None:
+            self.ddp.begin_step()
+        self.backward()
+        if self.ddp is not None:
+            self.ddp.finish_step()
+        self.solver_step(None, None, None, None, hp_dev=hp_dev)
+        self._g_costs.copy_(self._pack_costs())
+
+    def _train_step_graphed(self, data_x, data_m, it, learning_rate, momentum, decay):
+        if not self._graph_warm:
+            # eager step through the persistent input buffers: allocates them, the workspaces and the cost tensors
+            self._graph_warm = True
+            return self._train_step_eager(data_x, data_m, it, learning_rate, momentum, decay)
+        si = self._sparse_index()
+        layer_mod.set_train(True)
+        # refresh the static inputs of this step
+        layer_mod.h2d(data_x, self.device, slot="model/image")
+        gt = self.upload_metas(data_m)
+        layer_mod.set_ground_truth(gt)
+        for l in self.layers[1:]:
+            if l.type_name == "regression":          # labels are the only host-built target left
+                l.set_target(*l.get_target(self, data_x, data_m))
+        hp_dev = self._write_hp(it, learning_rate, momentum, decay)
+        if self._graphs is None:
+            self._capture(si, hp_dev)
+        ga, gb = self._graphs
+        ga.replay()
+        if si is not None:
+            sp = self.layers[si]
+            sp.finish_target(data_m, *sp.collect_samples())
+        if gb is not None:
+            gb.replay()
+        layer_mod.bump_param_version()
+        self.last_costs_device = self._g_costs
+        return self.last_costs_device
+
+    def _capture(self, si, hp_dev):
+        assert any(l.type_name == "denet-corner" for l in self.layers) == (layer_mod.get_ground_truth() is not None), \
+            "CUDA graphs need the device-side target builders (<= %d boxes per image)" % ops.MAX_GT
+        for l in _walk(self.layers):
+            if hasattr(l, "_wver"):
+                l._wver = -1                         # weight operand preparation must be part of the graph
+        self._g_costs = torch.zeros((1 + len(self.cost_layers),), dtype=torch.float32, device=self.device)
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga, pool=pool):
+            ops.pin_stream(True)
+            x = self._segment_a(si)
+            if si is None:
+                self._segment_b(x, si, hp_dev)
+        gb = None
+        if si is not None:
+            # the RoI box buffers are persistent slots created by the eager warm-up step: record against them
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, pool=pool):
+                ops.pin_stream(True)
+                self._segment_b(x, si, hp_dev)
+        ops.pin_stream(True)
+        self._graphs = (ga, gb)
 
     def train_step(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):
         """reference contract (model_cnn.py:407-445): returns (cost, [layer costs]) as python floats"""

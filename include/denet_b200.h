@@ -244,6 +244,10 @@ int denet_solver_chunk(void);
 int denet_solver_update(const void* entries, const int* block_tensor, const long long* block_offset, int nblocks,
                         int solver, float lr, float momentum0, float momentum1, float decay, int iteration,
                         int bias_decay, float grad_scale, cudaStream_t stream);
+/* same update with the per-step scalars read from DEVICE memory, hp = {lr, momentum0, momentum1, decay, iteration,
+ * grad_scale} (6 floats), so that a CUDA graph captured once replays with the values of the current step. */
+int denet_solver_update_dev(const void* entries, const int* block_tensor, const long long* block_offset, int nblocks,
+                            int solver, const float* hp, int bias_decay, cudaStream_t stream);
 
 #ifdef __cplusplus
 }
