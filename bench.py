@@ -264,7 +264,8 @@ def run_b200(args):
     graphs = not args.eager
     if graphs:
         model.enable_cuda_graphs(True)
-    for _ in range(max(args.warmup, 3)):          # in graph mode: eager warm-up, capture, replay
+    for _ in range(max(args.warmup, 3) + (3 if graphs else 0)):   # graph mode: eager warm-up, capture, then replays
+                                                                  # (the first two replays of a fresh graph are slow)
         step_device()
     cost = step_host()
     if not numpy.isfinite(cost):
@@ -278,11 +279,23 @@ def run_b200(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    marks = []
     for _ in range(args.steps):
         step_device()
+        if args.detail:
+            m = torch.cuda.Event(enable_timing=True)
+            m.record()
+            marks.append(m)
     e1.record()
     barrier()
     ms_a = max_over_ranks(e0.elapsed_time(e1))
+    if args.detail and rank == 0:
+        prev = e0
+        per = []
+        for m in marks:
+            per.append(round(prev.elapsed_time(m), 2))
+            prev = m
+        print("region A per-step ms:", per, file=sys.stderr)
 
     # ---- region B: through the public API with HOST buffers: H2D of the batch and D2H of the costs every step
     barrier()

@@ -30,6 +30,31 @@ constexpr int kBM = 128;      // UMMA M (TMEM lanes)
 constexpr int kBK = 64;       // K elements per pipeline stage (= 128 B of bf16 = one swizzle row)
 constexpr int kThreads = 192; // 6 warps
 
+// Division by a run-time constant in two instructions (the producer / MMA roles are single threads: every dependent
+// scalar instruction costs ~5 cycles, an integer division by a kernel parameter ~40 of them).
+struct FastDiv {
+    uint32_t d, mul, shr;
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> shr); }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
+static FastDiv make_fastdiv(int d) {   // valid for dividends < 2^31
+    FastDiv f;
+    f.d = (uint32_t)d;
+    f.mul = 0;
+    f.shr = 0;
+    if (d > 1) {
+        int lg = 0;
+        while ((1u << lg) < (uint32_t)d) ++lg;
+        const int pw = 31 + lg;
+        f.mul = (uint32_t)(((1ull << pw) + (uint64_t)d - 1) / (uint64_t)d);
+        f.shr = (uint32_t)(pw - 32);
+    }
+    return f;
+}
+
 struct ConvFpropParams {
     CUtensorMap tmA[2];  // input  (C, W, H, N) bf16, [0] = hi, [1] = lo
     CUtensorMap tmB[2];  // weight (KtotPad, Cout) bf16
@@ -40,6 +65,7 @@ struct ConvFpropParams {
     int Wo, Ho, No;      // output extent
     int TW, TH, TN;      // patch (TW*TH*TN == 128)
     int tiles_w, tiles_h, tiles_n, tiles_co;
+    FastDiv fd_co, fd_w, fd_h, fd_tw, fd_th;   // tile -> (ct, tw, th, tn), row -> (w, h, n) without divisions
     int num_tiles;
     int Cout;
     long long ldy;       // output pixel pitch (elements)
@@ -63,10 +89,17 @@ struct ConvWgradParams {
     int total_kblocks;
     int splits;
     int co_tiles, ci_tiles;
+    FastDiv fd_cot, fd_cit, fd_taps, fd_w, fd_h;   // tile / k-block decoding without divisions
+    int log2_tw;          // TW is a power of two
     int num_tiles;
     int Cout, Cin;
     int ldws;             // workspace cin pitch (elements)
     float* ws;            // [splits][Cout][taps][ldws]
+    // row-shared variant (conv_wgrad_rows_kernel): one X box with a (S-1)-pixel halo serves the S taps of a filter row
+    int xrows;            // rows of one 64-channel X sub-box = (TW + S - 1) * TH * TN
+    int xbox_bytes;       // its smem footprint (xrows * 128 rounded up to 1024)
+    int a_boxes;          // 64-channel dY sub-boxes actually loaded (1 when Cout <= 64)
+    int debug;            // profiling knobs: bit0 skip the MMAs, bit1 skip the TMA loads (results are garbage)
 };
 
 template <int BN, int STAGES>
@@ -192,31 +225,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int ct = tile % p.tiles_co;
-                int mt = tile / p.tiles_co;
-                const int tw = mt % p.tiles_w;
-                mt /= p.tiles_w;
-                const int th = mt % p.tiles_h;
-                const int tn = mt / p.tiles_h;
+                uint32_t ct, mt, tw, th, tn;
+                p.fd_co.divmod(tile, mt, ct);
+                p.fd_w.divmod(mt, mt, tw);
+                p.fd_h.divmod(mt, tn, th);
                 // input-space origin of the patch: the tensor map walks the image with element strides (stride_w,
                 // stride_h), so a strided convolution is the same box fetch started at (w0*stride + tap offset)
-                const int w0 = tw * p.TW * p.stride_w, h0 = th * p.TH * p.stride_h, n0 = tn * p.TN, co0 = ct * BN;
+                const int w0 = tw * p.TW * p.stride_w - p.pad_w, h0 = th * p.TH * p.stride_h - p.pad_h;
+                const int n0 = tn * p.TN, co0 = ct * BN;
                 for (int term = 0; term < p.nterms; ++term) {
-                    const int ai = (term == 1) ? 1 : 0;  // terms: (hi,hi) (lo,hi) (hi,lo)
-                    const int bi = (term == 2) ? 1 : 0;
-                    for (int tap = 0; tap < ntaps; ++tap) {
-                        const int dh = tap / p.S - p.pad_h;
-                        const int dw = tap % p.S - p.pad_w;
-                        for (int kc = 0; kc < p.kchunks; ++kc) {
-                            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                            uint8_t* sA = smem + stage * L::kStageBytes;
-                            uint8_t* sB = sA + L::kABytes;
-                            ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-                            ptx::tma_load_4d(sA, &p.tmA[ai], &full_bar[stage], kc * kBK, w0 + dw, h0 + dh, n0);
-                            ptx::tma_load_2d(sB, &p.tmB[bi], &full_bar[stage], (tap * p.kchunks + kc) * kBK, co0);
-                            if (++stage == STAGES) {
-                                stage = 0;
-                                phase ^= 1;
+                    const CUtensorMap* mapA = &p.tmA[(term == 1) ? 1 : 0];   // terms: (hi,hi) (lo,hi) (hi,lo)
+                    const CUtensorMap* mapB = &p.tmB[(term == 2) ? 1 : 0];
+                    int kcol = 0;                                            // K column of the weight operand
+                    for (int r = 0; r < p.R; ++r) {
+                        for (int sx = 0; sx < p.S; ++sx) {
+                            for (int kc = 0; kc < p.kchunks; ++kc, kcol += kBK) {
+                                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                                uint8_t* sA = smem + stage * L::kStageBytes;
+                                ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                                ptx::tma_load_4d(sA, mapA, &full_bar[stage], kc * kBK, w0 + sx, h0 + r, n0);
+                                ptx::tma_load_2d(sA + L::kABytes, mapB, &full_bar[stage], kcol, co0);
+                                if (++stage == STAGES) {
+                                    stage = 0;
+                                    phase ^= 1;
+                                }
                             }
                         }
                     }
@@ -227,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         // ------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 0, 0);
+            const uint64_t adesc0 = ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -239,10 +272,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t sA = ptx::smem_u32(smem + stage * L::kStageBytes);
-                    const uint32_t sB = sA + L::kABytes;
-                    const uint64_t adesc = ptx::make_smem_desc(sA, 16, 1024);
-                    const uint64_t bdesc = ptx::make_smem_desc(sB, 16, 1024);
+                    // descriptors of stage 0 + the stage offset in 16-byte units (the address field is addr >> 4)
+                    const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (L::kStageBytes >> 4));
+                    const uint64_t bdesc = adesc + (L::kABytes >> 4);
 #pragma unroll
                     for (int j = 0; j < kBK / 16; ++j) {
                         // advance 16 bf16 (32 B) along K inside the 128B-swizzled row
@@ -283,19 +315,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int ct = tile % p.tiles_co;
+            uint32_t uct, mt, tw, th, tn;
+            p.fd_co.divmod(tile, mt, uct);
+            const int ct = static_cast<int>(uct);
             if (ct != acc_ct) {
                 flush_stats();
                 acc_ct = ct;
             }
-            int mt = tile / p.tiles_co;
-            const int tw = mt % p.tiles_w;
-            mt /= p.tiles_w;
-            const int th = mt % p.tiles_h;
-            const int tn = mt / p.tiles_h;
-            const int w = tw * p.TW + (row % p.TW);
-            const int h = th * p.TH + (row / p.TW) % p.TH;
-            const int n = tn * p.TN + row / (p.TW * p.TH);
+            p.fd_w.divmod(mt, mt, tw);
+            p.fd_h.divmod(mt, tn, th);
+            uint32_t rq, rw, rn, rh;
+            p.fd_tw.divmod(row, rq, rw);
+            p.fd_th.divmod(rq, rn, rh);
+            const int w = tw * p.TW + rw;
+            const int h = th * p.TH + rh;
+            const int n = tn * p.TN + rn;
             const bool row_ok = (w < p.Wo) && (h < p.Ho) && (n < p.No);
             const long long pix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;
             const int co0 = ct * BN;
@@ -411,12 +445,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     // tile -> (co tile, ci tile, tap, split); split is the slowest index so that concurrently running CTAs
     // share the same pixel range (L2 reuse of dY / X boxes).
     auto decode = [&](int tile, int& cot, int& cit, int& tap, int& kb0, int& kb1) {
-        cot = tile % p.co_tiles;
-        int t = tile / p.co_tiles;
-        cit = t % p.ci_tiles;
-        t /= p.ci_tiles;
-        tap = t % ntaps;
-        const int split = t / ntaps;
+        uint32_t t, a, b, c;
+        p.fd_cot.divmod(tile, t, a);
+        p.fd_cit.divmod(t, t, b);
+        p.fd_taps.divmod(t, t, c);
+        cot = a; cit = b; tap = c;
+        const int split = t;
         kb0 = static_cast<int>(static_cast<long long>(p.total_kblocks) * split / p.splits);
         kb1 = static_cast<int>(static_cast<long long>(p.total_kblocks) * (split + 1) / p.splits);
     };
@@ -432,11 +466,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                 decode(tile, cot, cit, tap, kb0, kb1);
                 const int dh = tap / p.S - p.pad_h;
                 const int dw = tap % p.S - p.pad_w;
+                // k-block kb0 -> patch position, then advanced incrementally (no division in the loop)
+                uint32_t tw, th, tn, t2;
+                p.fd_w.divmod(kb0, t2, tw);
+                p.fd_h.divmod(t2, tn, th);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    const int tw = kb % p.tiles_w;
-                    const int t2 = kb / p.tiles_w;
-                    const int th = t2 % p.tiles_h;
-                    const int tn = t2 / p.tiles_h;
                     const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
                     for (int term = 0; term < p.nterms; ++term) {
                         const int ai = (term == 1) ? 1 : 0;
@@ -444,18 +478,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sA = smem + stage * L::kStageBytes;
                         uint8_t* sB = sA + L::kABytes;
-                        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                        if (p.debug & 2) {
+                            ptx::mbar_arrive(&full_bar[stage]);
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
 #pragma unroll
-                        for (int i = 0; i < kBM / 64; ++i)
-                            ptx::tma_load_4d(sA + i * kBoxBytes, &p.tmDY[ai], &full_bar[stage], cot * kBM + i * 64, w0,
-                                             h0, n0);
+                            for (int i = 0; i < kBM / 64; ++i)
+                                ptx::tma_load_4d(sA + i * kBoxBytes, &p.tmDY[ai], &full_bar[stage], cot * kBM + i * 64,
+                                                 w0, h0, n0);
 #pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            ptx::tma_load_4d(sB + i * kBoxBytes, &p.tmX[bi], &full_bar[stage], cit * BN + i * 64,
-                                             w0 * p.stride_w + dw, h0 * p.stride_h + dh, n0);
+                            for (int i = 0; i < BN / 64; ++i)
+                                ptx::tma_load_4d(sB + i * kBoxBytes, &p.tmX[bi], &full_bar[stage], cit * BN + i * 64,
+                                                 w0 * p.stride_w + dw, h0 * p.stride_h + dh, n0);
+                        }
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
+                        }
+                    }
+                    if (++tw == static_cast<uint32_t>(p.tiles_w)) {
+                        tw = 0;
+                        if (++th == static_cast<uint32_t>(p.tiles_h)) {
+                            th = 0;
+                            ++tn;
                         }
                     }
                 }
@@ -464,6 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 1, 1);
+            const uint64_t adesc0 = ptx::make_smem_desc(ptx::smem_u32(smem), kBoxBytes, 1024);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -479,15 +525,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                 for (int kb = 0; kb < nk; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t sA = ptx::smem_u32(smem + stage * L::kStageBytes);
-                    const uint32_t sB = sA + L::kABytes;
                     // MN-major: LBO = next 64-channel box, SBO = next group of 8 pixel rows
-                    const uint64_t adesc = ptx::make_smem_desc(sA, kBoxBytes, 1024);
-                    const uint64_t bdesc = ptx::make_smem_desc(sB, kBoxBytes, 1024);
+                    const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (L::kStageBytes >> 4));
+                    const uint64_t bdesc = adesc + (L::kABytes >> 4);
 #pragma unroll
                     for (int j = 0; j < kBK / 16; ++j) {
                         // advance 16 pixel rows = 2048 B
-                        ptx::umma_f16(d_tmem, adesc + 128 * j, bdesc + 128 * j, idesc, (kb | j) != 0);
+                        if (!(p.debug & 1))
+                            ptx::umma_f16(d_tmem, adesc + 128 * j, bdesc + 128 * j, idesc, (kb | j) != 0);
                     }
                     ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) {
@@ -505,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             int cot, cit, tap, kb0, kb1;
             decode(tile, cot, cit, tap, kb0, kb1);
-            const int split = (tile / p.co_tiles / p.ci_tiles) / ntaps;
+            const int split = static_cast<int>(p.fd_taps.div(p.fd_cit.div(p.fd_cot.div(tile))));
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int co = cot * kBM + row;
@@ -528,6 +573,225 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                     store_row_chunk(dst_row, 1, ci, v, nvalid);
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad, row-shared
+// Stride-1 filter gradient with the S taps of one filter row computed from ONE pair of TMA loads per k-block: the X
+// box is fetched with an (S-1)-pixel halo along W and tap s reads it through a descriptor that starts s rows (s*128 B)
+// into the box.  Tile = (Cout tile, Cin tile, filter row r, split); accumulators = S x BN TMEM columns.  Compared
+// with conv_wgrad_kernel (one tap per tile) the L2 -> shared-memory traffic of a 3x3 layer drops 3x, which is what
+// bounds the small-channel layers.
+template <int BN>
+struct RowsLayout {
+    static constexpr int kABytes = kBM * kBK * 2;                  // dY: 2 sub-boxes [64 px][64 co]
+    static constexpr int kBMaxBytes = (BN / 64) * 10240;           // X: BN/64 sub-boxes of <= 80 rows
+    static constexpr int kStageBytes = kABytes + kBMaxBytes;
+    static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __grid_constant__ ConvWgradParams p) {
+    using L = RowsLayout<BN>;
+    constexpr int STAGES = L::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 512;
+    constexpr int kBoxBytes = kBK * 128;
+    const int nbuf = (2 * p.S * BN <= 512) ? 2 : 1;    // accumulator sets (S * BN columns each)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int tile, int& cot, int& cit, int& r, int& kb0, int& kb1, int& split) {
+        uint32_t t, a, b, c;
+        p.fd_cot.divmod(tile, t, a);
+        p.fd_cit.divmod(t, t, b);
+        p.fd_taps.divmod(t, t, c);      // here: filter rows (R)
+        cot = a; cit = b; r = c;
+        split = t;
+        kb0 = static_cast<int>(static_cast<long long>(p.total_kblocks) * split / p.splits);
+        kb1 = static_cast<int>(static_cast<long long>(p.total_kblocks) * (split + 1) / p.splits);
+    };
+    const uint32_t stage_tx = p.a_boxes * kBoxBytes + (BN / 64) * p.xrows * 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::tma_prefetch_desc(&p.tmDY[0]);
+            ptx::tma_prefetch_desc(&p.tmX[0]);
+            int stage = 0;
+            uint32_t phase = 0;
+            const bool two_a = p.a_boxes > 1;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int cot, cit, r, kb0, kb1, split;
+                decode(tile, cot, cit, r, kb0, kb1, split);
+                const int dh = r - p.pad_h;
+                uint32_t tw, th, tn, t2;
+                p.fd_w.divmod(kb0, t2, tw);
+                p.fd_h.divmod(t2, tn, th);
+                const int cA = cot * kBM, cB = cit * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+                    for (int term = 0; term < p.nterms; ++term) {
+                        const CUtensorMap* mapA = &p.tmDY[(term == 1) ? 1 : 0];
+                        const CUtensorMap* mapB = &p.tmX[(term == 2) ? 1 : 0];
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * L::kStageBytes;
+                        uint8_t* sB = sA + L::kABytes;
+                        if (p.debug & 2) {
+                            ptx::mbar_arrive(&full_bar[stage]);
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
+                            ptx::tma_load_4d(sA, mapA, &full_bar[stage], cA, w0, h0, n0);
+                            if (two_a) ptx::tma_load_4d(sA + kBoxBytes, mapA, &full_bar[stage], cA + 64, w0, h0, n0);
+#pragma unroll
+                            for (int i = 0; i < BN / 64; ++i)
+                                ptx::tma_load_4d(sB + i * p.xbox_bytes, mapB, &full_bar[stage], cB + i * 64,
+                                                 w0 - p.pad_w, h0 + dh, n0);
+                        }
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    if (++tw == static_cast<uint32_t>(p.tiles_w)) {
+                        tw = 0;
+                        if (++th == static_cast<uint32_t>(p.tiles_h)) {
+                            th = 0;
+                            ++tn;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 1, 1);
+            const int xw = p.TW + p.S - 1;                 // X rows per image row of the patch
+            // one K=16 MMA = two 8-row groups of dY; with TW == 8 they sit in consecutive image rows of the X box
+            const uint32_t sbo_x = (p.TW >= 16) ? 1024u : static_cast<uint32_t>(xw) * 128u;
+            // descriptors of stage 0; everything else is an offset in 16-byte units added to the address field:
+            //   stage        -> stage * kStageBytes / 16
+            //   MMA j (K=16) -> dY: 16 rows = 2048 B;  X: rows of pixel (16j) of the patch inside the halo'd box
+            //   tap s        -> X: s rows = s * 128 B.   The base-offset field stays 0: the hardware derives the
+            //   128B-swizzle phase from the absolute shared-memory address, which is also how TMA wrote the box
+            //   (measured: with the field set the result is wrong).
+            const uint32_t smem0 = ptx::smem_u32(smem);
+            const uint64_t adesc0 = ptx::make_smem_desc(smem0, kBoxBytes, 1024);
+            const uint64_t bdesc0 = ptx::make_smem_desc(smem0 + L::kABytes, p.xbox_bytes, sbo_x);
+            uint32_t xoff[kBK / 16];
+#pragma unroll
+            for (int j = 0; j < kBK / 16; ++j)
+                xoff[j] = static_cast<uint32_t>(((16 * j) >> p.log2_tw) * xw + ((16 * j) & (p.TW - 1))) * 8u;
+            const int S = p.S;
+            const bool do_mma = !(p.debug & 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                int cot, cit, r, kb0, kb1, split;
+                decode(tile, cot, cit, r, kb0, kb1, split);
+                const int as = (nbuf == 2) ? (it & 1) : 0;
+                const uint32_t aphase = (nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * (S * BN);
+                const int nk = (kb1 - kb0) * p.nterms;
+                for (int kb = 0; kb < nk; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t soff = static_cast<uint64_t>(stage * (L::kStageBytes >> 4));
+                    const uint64_t adesc = adesc0 + soff;
+                    const uint64_t bdesc = bdesc0 + soff;
+                    if (do_mma) {
+#pragma unroll
+                        for (int j = 0; j < kBK / 16; ++j) {
+                            const uint64_t bj = bdesc + xoff[j];
+                            for (int sx = 0; sx < S; ++sx)
+                                ptx::umma_f16(d_tmem + sx * BN, adesc + 128 * j, bj + 8 * sx, idesc, (kb | j) != 0);
+                        }
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            int cot, cit, r, kb0, kb1, split;
+            decode(tile, cot, cit, r, kb0, kb1, split);
+            const int as = (nbuf == 2) ? (it & 1) : 0;
+            const uint32_t aphase = (nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
+            const int co = cot * kBM + row;
+            const bool row_ok = co < p.Cout;
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            for (int s = 0; s < p.S; ++s) {
+                float* dst_row = p.ws + ((static_cast<long long>(split) * p.Cout + co) * (p.R * p.S) + r * p.S + s) *
+                                            static_cast<long long>(p.ldws);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t rr[32];
+                    const uint32_t taddr =
+                        tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * (p.S * BN) + s * BN + c0;
+                    ptx::tmem_ld_32x32b_x32(taddr, rr);
+                    ptx::tmem_ld_wait();
+                    const int ci = cit * BN + c0;
+                    int nvalid = p.Cin - ci;
+                    nvalid = nvalid > 32 ? 32 : nvalid;
+                    if (row_ok && nvalid > 0) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+                        store_row_chunk(dst_row, 1, ci, v, nvalid);
+                    }
                 }
             }
             ptx::tc_fence_before();
@@ -642,6 +906,17 @@ static int launch_wgrad(const ConvWgradParams& p, cudaStream_t stream) {
     return 0;
 }
 
+template <int BN>
+static int launch_wgrad_rows(const ConvWgradParams& p, cudaStream_t stream) {
+    using L = RowsLayout<BN>;
+    auto kern = conv_wgrad_rows_kernel<BN>;
+    DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    kern<<<DN_G(grid), kThreads, L::kTotal, stream>>>(p);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
 // sw/sh: traversal (element) strides along W/H.  With a stride s the box must span TW*s input columns to deliver
 // TW elements (cuTensorMapEncodeTiled loads ceil(box/stride) elements per dimension).
 static int make_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int N, long long ld, int TW, int TH,
@@ -662,6 +937,11 @@ int fprop_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStr
     const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
     p.tiles_co = ceil_div(Cout, BN);
     p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
+    p.fd_co = make_fastdiv(p.tiles_co);
+    p.fd_w = make_fastdiv(p.tiles_w);
+    p.fd_h = make_fastdiv(p.tiles_h);
+    p.fd_tw = make_fastdiv(p.TW);
+    p.fd_th = make_fastdiv(p.TH);
     int rc;
     const uint64_t ktot = (uint64_t)p.R * p.S * p.kchunks * 64;
     uint64_t dims[2] = {ktot, (uint64_t)Cout};
@@ -762,15 +1042,47 @@ extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int
     return fprop_finish(p, b_hi, b_lo, stream);
 }
 
+namespace dn {
+
+// Tiling plan of the filter gradient.  rows_path: the row-shared kernel (stride 1, S > 1, patch >= 8 pixels wide,
+// halo box within the shared-memory budget); otherwise one tap per tile.
+struct WgradPlan {
+    int TW, TH, TN, total_kb, BN, co_tiles, ci_tiles, base_tiles, splits, rows_path, xrows;
+};
+
+static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cout, int Cin, int R, int S, int stride_h, int stride_w,
+                            int want_rows) {
+    WgradPlan pl;
+    pick_patch(Wo, Ho, N, 64, pl.TW, pl.TH, pl.TN);
+    pl.total_kb = ceil_div(Wo, pl.TW) * ceil_div(Ho, pl.TH) * ceil_div(N, pl.TN);
+    pl.BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
+    pl.xrows = (pl.TW + S - 1) * pl.TH * pl.TN;
+    pl.rows_path = want_rows && stride_h == 1 && stride_w == 1 && S > 1 && S <= 8 && pl.TW >= 8 && pl.xrows <= 80;
+    if (pl.rows_path)
+        while (S * pl.BN > 512) pl.BN /= 2;
+    pl.co_tiles = ceil_div(Cout, 128);
+    pl.ci_tiles = ceil_div(Cin, pl.BN);
+    pl.base_tiles = pl.co_tiles * pl.ci_tiles * R * (pl.rows_path ? 1 : S);
+    pl.splits = wgrad_splits(pl.total_kb, pl.base_tiles);
+    return pl;
+}
+
+static int g_wgrad_rows = 1;         // 0: always one tap per tile (A/B switch for tests / profiling)
+
+}  // namespace dn
+
+static int g_wgrad_debug = 0;
+extern "C" int denet_conv2d_wgrad_set_mode(int row_shared) {
+    g_wgrad_rows = row_shared & 1;
+    g_wgrad_debug = row_shared >> 1;      // undocumented profiling knobs (bit1: no MMA, bit2: no TMA)
+    return 0;
+}
+
 extern "C" size_t denet_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cout, int Cin, int R, int S) {
-    int TW, TH, TN;
-    pick_patch(Wo, Ho, N, 64, TW, TH, TN);
-    const int total_kb = ceil_div(Wo, TW) * ceil_div(Ho, TH) * ceil_div(N, TN);
-    const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
-    const int base_tiles = ceil_div(Cout, 128) * ceil_div(Cin, BN) * R * S;
-    int splits = ceil_div(2 * num_sms(), base_tiles);
-    if (splits > total_kb) splits = total_kb;
-    if (splits < 1) splits = 1;
+    // the stride is not known here: size for whichever plan needs more
+    const WgradPlan a = plan_wgrad(N, Ho, Wo, Cout, Cin, R, S, 1, 1, 1);
+    const WgradPlan b = plan_wgrad(N, Ho, Wo, Cout, Cin, R, S, 2, 2, 0);
+    const int splits = a.splits > b.splits ? a.splits : b.splits;
     const int ldws = (Cin + 3) / 4 * 4;
     return (size_t)splits * Cout * R * S * ldws * sizeof(float);
 }
@@ -782,49 +1094,62 @@ extern "C" int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, i
     DN_REQUIRE(dy_hi && x_hi && dw && workspace, "conv2d_wgrad: null pointer");
     DN_REQUIRE((dy_lo == nullptr) == (x_lo == nullptr), "conv2d_wgrad: dy_lo and x_lo must both be given or both null");
     DN_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0, "conv2d_wgrad: pixel pitches must be multiples of 8 elements");
+    DN_REQUIRE(stride_h >= 1 && stride_h <= 8 && stride_w >= 1 && stride_w <= 8, "conv2d_wgrad: stride must be in [1,8]");
+    const WgradPlan pl = plan_wgrad(N, Ho, Wo, Cout, Cin, R, S, stride_h, stride_w, g_wgrad_rows);
     ConvWgradParams p;
     memset(&p, 0, sizeof(p));
-    DN_REQUIRE(stride_h >= 1 && stride_h <= 8 && stride_w >= 1 && stride_w <= 8, "conv2d_wgrad: stride must be in [1,8]");
     p.nterms = dy_lo ? 3 : 1;
     p.R = R; p.S = S; p.pad_h = pad_h; p.pad_w = pad_w;
     p.stride_h = stride_h; p.stride_w = stride_w;
-    pick_patch(Wo, Ho, N, 64, p.TW, p.TH, p.TN);
+    p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN;
     p.tiles_w = ceil_div(Wo, p.TW);
     p.tiles_h = ceil_div(Ho, p.TH);
     p.tiles_n = ceil_div(N, p.TN);
-    p.total_kblocks = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
-    p.co_tiles = ceil_div(Cout, 128);
-    p.ci_tiles = ceil_div(Cin, BN);
-    const int base_tiles = p.co_tiles * p.ci_tiles * R * S;
-    int splits = ceil_div(2 * num_sms(), base_tiles);
-    if (splits > p.total_kblocks) splits = p.total_kblocks;
-    if (splits < 1) splits = 1;
-    p.splits = splits;
-    p.num_tiles = base_tiles * splits;
+    p.total_kblocks = pl.total_kb;
+    p.co_tiles = pl.co_tiles;
+    p.ci_tiles = pl.ci_tiles;
+    p.splits = pl.splits;
+    p.num_tiles = pl.base_tiles * pl.splits;
     p.Cout = Cout; p.Cin = Cin;
     p.ldws = (Cin + 3) / 4 * 4;
     p.ws = workspace;
-    const size_t need = (size_t)splits * Cout * R * S * p.ldws * sizeof(float);
+    p.fd_cot = make_fastdiv(p.co_tiles);
+    p.fd_cit = make_fastdiv(p.ci_tiles);
+    p.fd_taps = make_fastdiv(pl.rows_path ? R : R * S);
+    p.fd_w = make_fastdiv(p.tiles_w);
+    p.fd_h = make_fastdiv(p.tiles_h);
+    for (p.log2_tw = 0; (1 << p.log2_tw) < p.TW; ++p.log2_tw) {
+    }
+    p.xrows = pl.xrows;
+    p.xbox_bytes = (pl.xrows * 128 + 1023) / 1024 * 1024;
+    p.a_boxes = Cout <= 64 ? 1 : 2;
+    p.debug = g_wgrad_debug;
+    const size_t need = (size_t)pl.splits * Cout * R * S * p.ldws * sizeof(float);
     DN_REQUIRE(workspace_bytes >= need, "conv2d_wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
 
     int rc;
     if ((rc = make_act_map(&p.tmDY[0], dy_hi, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
     if (dy_lo && (rc = make_act_map(&p.tmDY[1], dy_lo, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
-    if ((rc = make_act_map(&p.tmX[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h))) return rc;
-    if (x_lo && (rc = make_act_map(&p.tmX[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h)))
-        return rc;
-
-    switch (BN) {
-        case 64: rc = launch_wgrad<64, 8>(p, stream); break;
-        case 128: rc = launch_wgrad<128, 6>(p, stream); break;
-        default: rc = launch_wgrad<256, 4>(p, stream); break;
+    if (pl.rows_path) {
+        const int xw = p.TW + S - 1;
+        if ((rc = make_act_map(&p.tmX[0], x_hi, Cin, Wi, Hi, N, ldx, xw, p.TH, p.TN))) return rc;
+        if (x_lo && (rc = make_act_map(&p.tmX[1], x_lo, Cin, Wi, Hi, N, ldx, xw, p.TH, p.TN))) return rc;
+        switch (pl.BN) {
+            case 64: rc = launch_wgrad_rows<64>(p, stream); break;
+            case 128: rc = launch_wgrad_rows<128>(p, stream); break;
+            default: rc = launch_wgrad_rows<256>(p, stream); break;
+        }
+    } else {
+        if ((rc = make_act_map(&p.tmX[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h))) return rc;
+        if (x_lo && (rc = make_act_map(&p.tmX[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h)))
+            return rc;
+        rc = wgrad_launch(p, stream);
     }
     if (rc) return rc;
     const long long total = (long long)Cout * Cin * R * S;
     const int block = 256;
     const int grid = (int)std::min<long long>(ceil_div_ll(total, block), 148LL * 16);
-    wgrad_reduce_kernel<<<DN_G(grid), block, 0, stream>>>(workspace, dw, splits, Cout, Cin, R, S, p.ldws, accumulate);
+    wgrad_reduce_kernel<<<DN_G(grid), block, 0, stream>>>(workspace, dw, pl.splits, Cout, Cin, R, S, p.ldws, accumulate);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -1016,6 +1341,11 @@ extern "C" int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, 
     p.ci_tiles = 1;
     p.splits = wgrad_splits(p.total_kblocks, p.co_tiles * R);
     p.num_tiles = p.co_tiles * R * p.splits;
+    p.fd_cot = make_fastdiv(p.co_tiles);
+    p.fd_cit = make_fastdiv(1);
+    p.fd_taps = make_fastdiv(R);
+    p.fd_w = make_fastdiv(p.tiles_w);
+    p.fd_h = make_fastdiv(p.tiles_h);
     p.Cout = Cout; p.Cin = 64;             // GEMM N extent: the 64 folded columns of a filter row
     p.ldws = 64;
     p.ws = workspace;

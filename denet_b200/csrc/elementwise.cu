@@ -134,31 +134,63 @@ __global__ void bn_stats_finalize_kernel(const T* __restrict__ x, const float* _
     if (run_stdinv) run_stdinv[c] = momentum * run_stdinv[c] + (1.0f - momentum) * is;
 }
 
+// Thread layout shared by the batch-norm passes: a thread owns ONE channel pack (8 channels = 16 B) for the whole
+// kernel, so the per-channel constants live in registers, and walks the rows of its slab `rlanes` apart with the
+// loads of kBnUnroll rows in flight.  A warp covers 32 consecutive packs = 512 contiguous bytes of a pixel row (or of
+// several rows when C < 256).
+constexpr int kBnUnroll = 4;      // forward apply: 2 streams x 4 rows in flight
+constexpr int kBnUnrollBwd = 2;   // backward passes: 3 streams x 2 rows (register budget)
+
 // y = [relu]( (x - mean) * (gamma * invstd) + beta [+ residual] )
 template <typename T, int VEC>
-__global__ void bn_apply_kernel(const T* __restrict__ x, long long M, int C, long long ld,
-                                const float* __restrict__ mean, const float* __restrict__ invstd,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const T* __restrict__ residual, int relu, T* __restrict__ y) {
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, long long M, int C, long long ld,
+                                                              int rows_per_block, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              const T* __restrict__ residual, int relu,
+                                                              T* __restrict__ y) {
     const int CV = C / VEC;
-    const long long total = M * CV;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int cv = (int)(idx % CV);
-        const long long r = idx / CV;
-        const long long off = r * ld + (long long)cv * VEC;
-        Pack<T, VEC> p, q;
-        p.load(x + off);
-        if (residual) q.load(residual + off);
+    const int cvt = CV < kBnThreads ? CV : kBnThreads;
+    const int rlanes = kBnThreads / cvt;
+    const int cv = blockIdx.y * cvt + threadIdx.x % cvt;
+    const int rl = threadIdx.x / cvt;
+    if (cv >= CV || rl >= rlanes) return;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    float mu[VEC], a[VEC], b[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const int c = cv * VEC + i;
-            float v = (p.v[i] - __ldg(mean + c)) * (__ldg(gamma + c) * __ldg(invstd + c)) + __ldg(beta + c);
-            if (residual) v += q.v[i];
-            if (relu) v = fmaxf(v, 0.f);
-            p.v[i] = v;
+    for (int i = 0; i < VEC; ++i) {
+        const int c = cv * VEC + i;
+        mu[i] = mean[c];
+        a[i] = gamma[c] * invstd[c];
+        b[i] = beta[c];
+    }
+    const long long coff = (long long)cv * VEC;
+    for (long long r = r0 + rl; r < r1; r += (long long)rlanes * kBnUnroll) {
+        Pack<T, VEC> p[kBnUnroll], q[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const long long rr = r + (long long)u * rlanes;
+            if (rr < r1) {
+                p[u].load(x + rr * ld + coff);
+                if (residual) q[u].load(residual + rr * ld + coff);
+            }
         }
-        p.store(y + off);
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const long long rr = r + (long long)u * rlanes;
+            if (rr < r1) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    float v = (p[u].v[i] - mu[i]) * a[i] + b[i];
+                    if (residual) v += q[u].v[i];
+                    if (relu) v = fmaxf(v, 0.f);
+                    p[u].v[i] = v;
+                }
+                p[u].store(y + rr * ld + coff);
+            }
+        }
     }
 }
 
@@ -189,18 +221,30 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const T* __r
             mu[i] = mean[cv * VEC + i];
             is[i] = invstd[cv * VEC + i];
         }
-        for (long long r = r0 + rl; r < r1; r += rlanes) {
-            const long long off = r * ld + (long long)cv * VEC;
-            Pack<T, VEC> g, xv, yo;
-            g.load(dy + off);
-            xv.load(x + off);
-            if (relu) yo.load(yout + off);
+        const long long coff = (long long)cv * VEC;
+        for (long long r = r0 + rl; r < r1; r += (long long)rlanes * kBnUnrollBwd) {
+            Pack<T, VEC> g[kBnUnrollBwd], xv[kBnUnrollBwd], yo[kBnUnrollBwd];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                float d = g.v[i];
-                if (relu && !(yo.v[i] > 0.f)) d = 0.f;
-                s[i] += d;
-                s2[i] += d * ((xv.v[i] - mu[i]) * is[i]);
+            for (int u = 0; u < kBnUnrollBwd; ++u) {
+                const long long rr = r + (long long)u * rlanes;
+                if (rr < r1) {
+                    g[u].load(dy + rr * ld + coff);
+                    xv[u].load(x + rr * ld + coff);
+                    if (relu) yo[u].load(yout + rr * ld + coff);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBnUnrollBwd; ++u) {
+                const long long rr = r + (long long)u * rlanes;
+                if (rr < r1) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        float d = g[u].v[i];
+                        if (relu && !(yo[u].v[i] > 0.f)) d = 0.f;
+                        s[i] += d;
+                        s2[i] += d * ((xv[u].v[i] - mu[i]) * is[i]);
+                    }
+                }
             }
         }
     }
@@ -241,35 +285,63 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ns
 
 // backward stage 2: dx = gamma*invstd * (dy' - sum_dy/M - xhat * sum_dy_xhat/M); optionally export dy' (residual grad)
 template <typename T, int VEC>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yout, const T* __restrict__ x,
-                                    long long M, int C, long long ld, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ sum_dy, const float* __restrict__ sum_dy_xhat, int relu,
-                                    T* __restrict__ dx, T* __restrict__ dres) {
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yout,
+                                                                  const T* __restrict__ x, long long M, int C,
+                                                                  long long ld, int rows_per_block,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ sum_dy,
+                                                                  const float* __restrict__ sum_dy_xhat, int relu,
+                                                                  T* __restrict__ dx, T* __restrict__ dres) {
     const int CV = C / VEC;
-    const long long total = M * CV;
+    const int cvt = CV < kBnThreads ? CV : kBnThreads;
+    const int rlanes = kBnThreads / cvt;
+    const int cv = blockIdx.y * cvt + threadIdx.x % cvt;
+    const int rl = threadIdx.x / cvt;
+    if (cv >= CV || rl >= rlanes) return;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
     const float inv_m = 1.0f / (float)M;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int cv = (int)(idx % CV);
-        const long long r = idx / CV;
-        const long long off = r * ld + (long long)cv * VEC;
-        Pack<T, VEC> g, xv, yo, o;
-        g.load(dy + off);
-        xv.load(x + off);
-        if (relu) yo.load(yout + off);
+    float mu[VEC], is[VEC], k1[VEC], c1[VEC], c2[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const int c = cv * VEC + i;
-            float d = g.v[i];
-            if (relu && !(yo.v[i] > 0.f)) d = 0.f;
-            g.v[i] = d;
-            const float is = __ldg(invstd + c);
-            const float xh = (xv.v[i] - __ldg(mean + c)) * is;
-            o.v[i] = __ldg(gamma + c) * is * (d - __ldg(sum_dy + c) * inv_m - xh * __ldg(sum_dy_xhat + c) * inv_m);
+    for (int i = 0; i < VEC; ++i) {
+        const int c = cv * VEC + i;
+        mu[i] = mean[c];
+        is[i] = invstd[c];
+        k1[i] = gamma[c] * is[i];
+        c1[i] = sum_dy[c] * inv_m;
+        c2[i] = sum_dy_xhat[c] * inv_m;
+    }
+    const long long coff = (long long)cv * VEC;
+    for (long long r = r0 + rl; r < r1; r += (long long)rlanes * kBnUnrollBwd) {
+        Pack<T, VEC> g[kBnUnrollBwd], xv[kBnUnrollBwd], yo[kBnUnrollBwd];
+#pragma unroll
+        for (int u = 0; u < kBnUnrollBwd; ++u) {
+            const long long rr = r + (long long)u * rlanes;
+            if (rr < r1) {
+                g[u].load(dy + rr * ld + coff);
+                xv[u].load(x + rr * ld + coff);
+                if (relu) yo[u].load(yout + rr * ld + coff);
+            }
         }
-        o.store(dx + off);
-        if (dres) g.store(dres + off);
+#pragma unroll
+        for (int u = 0; u < kBnUnrollBwd; ++u) {
+            const long long rr = r + (long long)u * rlanes;
+            if (rr < r1) {
+                Pack<T, VEC> o;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    float d = g[u].v[i];
+                    if (relu && !(yo[u].v[i] > 0.f)) d = 0.f;
+                    g[u].v[i] = d;
+                    const float xh = (xv[u].v[i] - mu[i]) * is[i];
+                    o.v[i] = k1[i] * (d - c1[i] - xh * c2[i]);
+                }
+                o.store(dx + rr * ld + coff);
+                if (dres) g[u].store(dres + rr * ld + coff);
+            }
+        }
     }
 }
 
@@ -725,6 +797,19 @@ static int bn_slabs(long long M, int C, int vec, int* rows_per_block, int* ychun
     return (int)ceil_div_ll(M, *rows_per_block);
 }
 
+// row slabs for the non-reducing passes (apply kernels): ~8 resident blocks per SM, at least kBnUnroll rows per lane
+static int ew_slabs(long long M, int C, int vec, int* rows_per_block, int* ychunks) {
+    const int CV = C / vec;
+    const int cvt = CV < kBnThreads ? CV : kBnThreads;
+    *ychunks = ceil_div(CV, cvt);
+    const int rlanes = kBnThreads / cvt;
+    long long rpb = ceil_div_ll(M, (long long)num_sms() * 8);
+    const long long quantum = (long long)rlanes * kBnUnroll;
+    rpb = ceil_div_ll(rpb, quantum) * quantum;
+    *rows_per_block = (int)std::min<long long>(rpb, 1 << 30);
+    return (int)ceil_div_ll(M, *rows_per_block);
+}
+
 }  // namespace dn
 
 using namespace dn;
@@ -761,9 +846,11 @@ extern "C" int denet_bn_apply(const void* x, int dtype, long long M, int C, long
                               int relu, void* y, cudaStream_t stream) {
     DN_REQUIRE(x && y && mean && invstd && gamma && beta, "bn_apply: null pointer");
     const bool v = vec8_ok(C, ld, x, y, residual);
+    int rpb, yc;
+    const int nslabs = ew_slabs(M, C, v ? 8 : 1, &rpb, &yc);
     DN_DISPATCH(dtype, v, {
-        bn_apply_kernel<T, VEC><<<DN_G(ew_grid(M * (C / VEC), 256)), 256, 0, stream>>>(
-            (const T*)x, M, C, ld, mean, invstd, gamma, beta, (const T*)residual, relu, (T*)y);
+        bn_apply_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>(
+            (const T*)x, M, C, ld, rpb, mean, invstd, gamma, beta, (const T*)residual, relu, (T*)y);
     });
     DN_CHECK_LAUNCH();
     return 0;
@@ -792,9 +879,11 @@ extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x
             (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb, mean, invstd, relu, workspace);
         bn_bwd_finalize_kernel<<<DN_G(ceil_div(C, 32)), kFinThreads, 0, stream>>>(workspace, nslabs, C, sums, sums + C, dgamma, dbeta,
                                                                      accumulate);
-        bn_bwd_apply_kernel<T, VEC><<<DN_G(ew_grid(M * (C / VEC), 256)), 256, 0, stream>>>(
-            (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, mean, invstd, gamma, sums, sums + C, relu, (T*)dx,
-            (T*)dres);
+        int rpb2, yc2;
+        const int nslabs2 = ew_slabs(M, C, VEC, &rpb2, &yc2);
+        bn_bwd_apply_kernel<T, VEC><<<DN_G(dim3(nslabs2, yc2)), kBnThreads, 0, stream>>>(
+            (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb2, mean, invstd, gamma, sums, sums + C, relu,
+            (T*)dx, (T*)dres);
     });
     DN_CHECK_LAUNCH();
     return 0;

@@ -165,6 +165,25 @@ class DeNetSparseLayer(AbstractLayer):
         n_keep = k - math.floor(self.random_sample * k)
         pr = numpy.zeros((self.batch_size, k), dtype=numpy.float64)
         bbox = numpy.zeros((self.batch_size, k, 4), dtype=numpy.float64)
+        count = numpy.asarray(count[:len(metas)], dtype=numpy.int64)
+        if len(metas) == self.batch_size and not (count > n_keep).any():
+            # no image needs random.sample: the draws of all images are consecutive in python's stream (image order,
+            # then RoI order, 4 per box), so one vectorised block of random() values serves the whole batch
+            pad = numpy.arange(k)[None, :] >= count[:, None]                  # (B,K) True where a random box goes
+            keep = ~pad
+            pr[keep] = pr32[keep]
+            bbox[keep] = bbox32[keep]
+            u = py_random_doubles(4 * int(pad.sum())).reshape(-1, 4)
+            x0 = 0.0 + (1.0 - 0.0) * u[:, 0]
+            y0 = 0.0 + (1.0 - 0.0) * u[:, 1]
+            bbox[pad] = numpy.stack([x0, y0, x0 + (1.0 - x0) * u[:, 2], y0 + (1.0 - y0) * u[:, 3]], axis=1)
+            if self.sample_gt:
+                for b, meta in enumerate(metas):
+                    for index, gt in enumerate(meta["bbox"]):
+                        pr[b, k - (index + 1)] = 1.0
+                        bbox[b, k - (index + 1)] = gt
+            self.set_samples_arrays(pr, bbox)
+            return None
         for b, meta in enumerate(metas):
             cnt = int(count[b])
             if cnt > n_keep:

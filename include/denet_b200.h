@@ -77,6 +77,10 @@ int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int 
                        int pad_h, int pad_w, int stride_h, int stride_w, float* dw, int accumulate, float* workspace,
                        size_t workspace_bytes, cudaStream_t stream);
 
+/* Kernel selection of conv2d_wgrad (profiling / A-B tests): row_shared = 1 (default) lets stride-1 S>1 layers use the
+ * row-shared kernel (one halo'd X box serves the S taps of a filter row), 0 forces one tap per tile. */
+int denet_conv2d_wgrad_set_mode(int row_shared);
+
 /* Zero-insertion upsampling y[n, h*sh, w*sw, :] = x[n,h,w,:] (zero elsewhere), (Hd, Wd) = extent of y: turns the
  * data gradient of a strided convolution into a stride-1 correlation (cuDNN bwd-data of convolution.py:83). */
 int denet_dilate(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sh, int sw, void* y, int Hd,

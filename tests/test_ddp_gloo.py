@@ -1,0 +1,69 @@
+"""The N>1 path on the CPU: world_size-2 `gloo` processes run the bucket planner and the bucketed gradient all-reduce
+(denet_b200/multi/ddp.py) that replaces the reference's host-side parameter averaging (multi/shared.py:105-119)."""
+import os
+import socket
+
+import numpy
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from denet_b200.multi import ddp
+
+
+def test_plan_buckets_covers_every_gradient_once_in_backward_order():
+    ranges = [(1, 0, 100), (2, 100, 100), (3, 100, 1100), (5, 1100, 1200), (9, 1200, 5000)]
+    buckets = ddp.plan_buckets(ranges, 1000)
+    covered = sorted((s, e) for _, s, e in buckets)
+    assert covered[0][0] == 0 and covered[-1][1] == 5000
+    for (s0, e0), (s1, e1) in zip(covered[:-1], covered[1:]):
+        assert e0 == s1                                   # contiguous, no overlap
+    ready = [r for r, _, _ in buckets]
+    assert ready == sorted(ready, reverse=True)           # launched as backward descends through the layers
+    for r, s, e in buckets:
+        owners = [l for l, ls, le in ranges if ls < e and le > s and le > ls]
+        assert min(owners) >= r                           # every owner of the bucket has finished by layer r
+
+
+def test_shard_batch():
+    assert ddp.shard_batch(64, 0, 2) == (0, 32) and ddp.shard_batch(64, 1, 2) == (32, 64)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w = ddp.init_process_group("gloo")
+    assert (r, w) == (rank, world)
+    rs = numpy.random.RandomState(100 + rank)
+    flat = torch.from_numpy(rs.randn(5000).astype(numpy.float32))
+    mine = flat.clone()
+    bn_stat = torch.full((7,), float(rank + 1))
+    ranges = [(1, 0, 100), (3, 100, 1100), (5, 1100, 1200), (9, 1200, 5000)]
+    red = ddp.GradientAllReduce(flat, ranges, bucket_bytes=4000, extra_mean_tensors=[bn_stat])
+    red.begin_step()
+    for layer in range(9, 0, -1):                         # the backward pass retires layers in descending order
+        red.layer_done(layer)
+    scale = red.finish_step()
+    out.put((rank, mine.numpy(), flat.numpy().copy(), scale, bn_stat.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = res[0][1] + res[1][1]
+    for rank, _, reduced, scale, bn in res:
+        assert numpy.allclose(reduced, total, rtol=1e-6, atol=1e-6)      # sum over ranks in every bucket
+        assert scale == 0.5                                              # the solver applies 1/world
+        assert numpy.allclose(bn, 1.5)                                   # running statistics are averaged

@@ -36,6 +36,10 @@ CONV_CASES = [
     (2, 32, 32, 64, 128, 1, 2, 0),
     (1, 20, 20, 128, 40, 7, 1, 0),
     (2, 9, 9, 256, 512, 3, 1, 2),
+    (1, 64, 64, 64, 64, 3, 1, 1),      # wgrad row-shared kernel: 64-pixel patch in one image row
+    (2, 32, 32, 128, 136, 3, 1, 1),    # 32 x 2 patch, two Cout tiles
+    (4, 8, 8, 64, 96, 3, 1, 1),        # 8 x 8 patch: one MMA spans two image rows
+    (2, 16, 16, 72, 64, 5, 1, 2),      # 5 taps per filter row
 ]
 
 

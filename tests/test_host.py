@@ -1,0 +1,149 @@
+"""Host-side logic of the Layer API mirror on the CPU: model-desc grammar and shapes, the reference's recipes, JSON
+round trip, the host target builders and the python-`random` post-processing against the oracle's restatements."""
+import math
+import random
+
+import numpy
+import pytest
+import torch
+
+from oracle import ref_ops as R
+from util import synthetic_metas
+
+
+def build(desc, shape, batch, classes, convert=False, seed=1):
+    from denet_b200.model import model_cnn
+    numpy.random.seed(seed)
+    m = model_cnn.ModelCNN()
+    m.batch_size, m.class_num = batch, classes
+    m.build(desc.split(), shape, "relu", "half", ["he-backward"])
+    if convert:
+        m.convert_bn_relu()
+    return m
+
+
+def test_recipes_shapes_and_flops():
+    """the three BASELINE.json workloads parse through parse_desc; conv FLOPs match SURVEY.md §8d"""
+    from denet_b200.model import model_cnn, recipes
+    want = {"cifar-cnn": ((32, 10), 0.920e9), "resnet34": ((256, 1000), 21.74e9), "denet34-skip": (None, 163.05e9)}
+    for name, (desc, shape, batch, classes, convert, _) in recipes.WORKLOADS.items():
+        b = 2 if name != "cifar-cnn" else batch
+        m = build(desc, shape, b, classes, convert)
+        convs = [l for l in model_cnn._walk(m.layers) if l.type_name == "conv" and l.enabled]
+        fwd = sum(l.fprop_flops() for l in convs) / b
+        train = 3 * fwd - sum(l.fprop_flops() for l in convs if l.is_first) / b
+        assert abs(train - want[name][1]) / want[name][1] < 2e-3, (name, train)
+        if name == "denet34-skip":
+            assert m.layers[-1].type_name == "denet-detect"
+            dns = [l for l in m.layers if l.type_name == "denet-sparse"][0]
+            assert dns.output_shape == (b, 7 * 7 * 96 + 2, 24, 24)
+            dnc = [l for l in m.layers if l.type_name == "denet-corner"][0]
+            assert dnc.corner_shape == (b, 2, 4, 64, 64)
+            assert m.get_parameter_num() > 32e6
+        else:
+            assert tuple(m.get_output_shape()) == (b, classes) or tuple(m.get_output_shape())[:2] == (b, classes)
+
+
+def test_desc_grammar_tags_and_errors():
+    from denet_b200.model import model_cnn
+    m = build("C.B[8,3] BN A P[2] C.X[4,3,1,2,1] BNA PI[2] SPLIT R", (3, 16, 16), 2, 5)
+    types = [l.type_name for l in m.layers[1:]]
+    assert types[:4] == ["conv", "batchnorm", "activation", "pool"]
+    assert m.layers[1].use_bias and m.layers[1].filter_shape == (8, 3, 3, 3)
+    assert m.layers[5].filter_shape == (4, 8, 3, 1) and m.layers[5].stride == (2, 1)
+    with pytest.raises(Exception):
+        build("C[8,3] NOPE[1]", (3, 8, 8), 1, 2)
+
+
+def test_json_roundtrip_on_host():
+    from denet_b200.model import model_cnn
+    m = build("C.B[8,7,2] BN A P[3,2,1] nRSN.O[1,8,3] nRSN.O[1,16,3,2] P.A[2] R.TB", (3, 32, 32), 2, 4)
+    js = m.export_json()
+    m2 = model_cnn.load_from_json(js, batch_size=2)
+    js2 = m2.export_json()
+    assert [l["type"] for l in js["layers"]] == [l["type"] for l in js2["layers"]]
+    w1 = numpy.asarray(js["layers"][0]["weight"])
+    assert numpy.array_equal(w1, numpy.asarray(js2["layers"][0]["weight"])) and w1.shape == (8, 3, 7, 7)
+
+
+def _denet(batch=3, classes=6):
+    desc = ("C.B[8,7,2] BN A P[3,2,1] nRSN.O[1,8,3] SKIPSRC[0] nRSN.O[1,16,3,2] PI[2] C[8,3] SKIP[0] BNA DNC[8,100] "
+            "DNS[3,4,0.01,0.25] C[16,1] BNA DND[0.5,1,1]")
+    return build(desc, (3, 64, 64), batch, classes, True)
+
+
+def test_host_target_builders_match_oracle():
+    m = _denet()
+    metas = synthetic_metas(3, 6, seed=4, max_boxes=5)
+    metas[1]["bbox"], metas[1]["class"] = [], []
+    dnc = [l for l in m.layers if l.type_name == "denet-corner"][0]
+    dns = [l for l in m.layers if l.type_name == "denet-sparse"][0]
+    dnd = [l for l in m.layers if l.type_name == "denet-detect"][0]
+    assert numpy.array_equal(dnc.get_target_host(metas)[1], R.corner_target(metas, dnc.corner_shape, False)[1])
+    rnd = random.Random(2)
+    k = dns.sample_count
+    pr = numpy.zeros((3, k))
+    bbox = numpy.zeros((3, k, 4))
+    for b in range(3):
+        for i in range(k):
+            if metas[b]["bbox"] and i % 2 == 0:
+                g = metas[b]["bbox"][i % len(metas[b]["bbox"])]
+                bbox[b, i] = [g[0] + rnd.uniform(-.02, .02), g[1], g[2], g[3] + rnd.uniform(-.02, .02)]
+            else:
+                x0, y0 = rnd.uniform(0, 1), rnd.uniform(0, 1)
+                bbox[b, i] = [x0, y0, rnd.uniform(x0, 1), rnd.uniform(y0, 1)]
+    dns.sample_pr_host, dns.sample_bbox_host = pr, bbox
+    samples = [[(0.0, tuple(bbox[b, i])) for i in range(k)] for b in range(3)]
+    want = R.detect_target(metas, samples, 3, dns.sample_num, 6, 0.5, True)[1]
+    got = dnd.get_target_host(metas)[1]
+    assert numpy.array_equal(got, want)
+    assert (want[:3 * 7 * k].reshape(3, 7, k)[:, :6] > 0).any()
+
+
+@pytest.mark.parametrize("counts", [[0, 3, 16], [16, 16, 16], [2, 14, 5], [13, 16, 1]])
+def test_sparse_postprocess_consumes_python_random_like_the_reference(counts, monkeypatch):
+    """DeNetSparseLayer.finish_target == the oracle's loop restatement of denet_sparse.py:184-201, including the exact
+    consumption of python's `random` stream (both the vectorised whole-batch path and the per-image path)"""
+    m = _denet()
+    dns = [l for l in m.layers if l.type_name == "denet-sparse"][0]
+    k = dns.sample_count                                   # 16, random_sample 0.25 -> keep at most 12
+    metas = synthetic_metas(3, 6, seed=9, max_boxes=3)
+    rs = numpy.random.RandomState(1)
+    pr32 = numpy.sort(rs.rand(3, k).astype(numpy.float32), axis=1)[:, ::-1].copy()
+    bbox32 = rs.rand(3, k, 4).astype(numpy.float32)
+    captured = {}
+    monkeypatch.setattr(dns, "set_samples_arrays", lambda pr, bbox: captured.update(pr=pr.copy(), bbox=bbox.copy()))
+    random.seed(77)
+    dns.finish_target(metas, pr32, bbox32, numpy.array(counts))
+    after_mine = random.random()
+    lists = [[(float(pr32[b, i]), tuple(float(v) for v in bbox32[b, i])) for i in range(counts[b])] for b in range(3)]
+    random.seed(77)
+    want = R.sparse_postprocess(lists, metas, k, dns.random_sample, True, random)
+    after_ref = random.random()
+    assert after_mine == after_ref, "python random stream consumed differently"
+    for b in range(3):
+        assert len(want[b]) == k
+        for i in range(k):
+            assert captured["pr"][b, i] == want[b][i][0]
+            assert tuple(captured["bbox"][b, i]) == tuple(want[b][i][1])
+
+
+def test_py_random_doubles_is_pythons_stream():
+    from denet_b200.layer.denet_sparse import py_random_doubles
+    for k in (1, 31, 32, 1000):
+        random.seed(5)
+        a = py_random_doubles(k)
+        nxt = random.random()
+        random.seed(5)
+        b = [random.random() for _ in range(k)]
+        assert list(a) == b and nxt == random.random()
+
+
+def test_no_cpu_fallback():
+    from denet_b200 import lib, ops
+    m = _denet()
+    if not torch.cuda.is_available():
+        with pytest.raises(lib.DenetError):
+            m.to_device()
+    with pytest.raises(lib.DenetError):
+        ops.act_operand(torch.zeros(1, 2, 2, 8))
