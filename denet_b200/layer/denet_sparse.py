@@ -9,6 +9,7 @@ meaning AND in random-stream consumption (:184-201): sub-sample to make room for
 overwrite the tail with the ground truth.  forward() is the sparse RoI feature gather (DeNetSparseOp,
 denet_sparse_op.py:42-85), backward() its scatter-add (:171-212).
 """
+import ctypes
 import math
 import random
 
@@ -16,6 +17,7 @@ import numpy
 import torch
 
 from .. import common, ops
+from ..lib import call
 from . import AbstractLayer, act_dtype, d2h, get_train, h2d
 
 
@@ -32,6 +34,26 @@ def py_random_doubles(k):
     out = rs.random_sample(k)
     st = rs.get_state()
     random.setstate((version, tuple(st[1].tolist()) + (int(st[2]),), gauss))
+    return out
+
+
+def mt_export():
+    """python `random` state -> (624-word numpy array, c_int position, version, gauss_next) for the native helpers"""
+    version, internal, gauss = random.getstate()
+    arr = numpy.array(internal, dtype=numpy.uint32)
+    return numpy.ascontiguousarray(arr[:624]), ctypes.c_int(int(arr[624])), version, gauss
+
+
+def mt_import(mt, pos, version, gauss):
+    random.setstate((version, tuple(mt.tolist()) + (int(pos.value),), gauss))
+
+
+def py_random_sample(n, k):
+    """random.sample(range(n), k), natively, consuming the interpreter's stream identically"""
+    mt, pos, version, gauss = mt_export()
+    out = numpy.empty((k,), dtype=numpy.int32)
+    call("denet_pyrandom_sample", mt.ctypes.data, ctypes.addressof(pos), int(n), int(k), out.ctypes.data)
+    mt_import(mt, pos, version, gauss)
     return out
 
 
@@ -165,48 +187,20 @@ class DeNetSparseLayer(AbstractLayer):
         n_keep = k - math.floor(self.random_sample * k)
         pr = numpy.zeros((self.batch_size, k), dtype=numpy.float64)
         bbox = numpy.zeros((self.batch_size, k, 4), dtype=numpy.float64)
-        count = numpy.asarray(count[:len(metas)], dtype=numpy.int64)
-        if len(metas) == self.batch_size and not (count > n_keep).any():
-            # no image needs random.sample: the draws of all images are consecutive in python's stream (image order,
-            # then RoI order, 4 per box), so one vectorised block of random() values serves the whole batch
-            pad = numpy.arange(k)[None, :] >= count[:, None]                  # (B,K) True where a random box goes
-            keep = ~pad
-            pr[keep] = pr32[keep]
-            bbox[keep] = bbox32[keep]
-            u = py_random_doubles(4 * int(pad.sum())).reshape(-1, 4)
-            x0 = 0.0 + (1.0 - 0.0) * u[:, 0]
-            y0 = 0.0 + (1.0 - 0.0) * u[:, 1]
-            bbox[pad] = numpy.stack([x0, y0, x0 + (1.0 - x0) * u[:, 2], y0 + (1.0 - y0) * u[:, 3]], axis=1)
-            if self.sample_gt:
-                for b, meta in enumerate(metas):
-                    for index, gt in enumerate(meta["bbox"]):
-                        pr[b, k - (index + 1)] = 1.0
-                        bbox[b, k - (index + 1)] = gt
-            self.set_samples_arrays(pr, bbox)
-            return None
-        for b, meta in enumerate(metas):
-            cnt = int(count[b])
-            if cnt > n_keep:
-                keep = random.sample(range(cnt), n_keep)     # same draws as random.sample(list_of_cnt_items, n_keep)
-                pr[b, :n_keep] = pr32[b, keep]
-                bbox[b, :n_keep] = bbox32[b, keep]
-                cnt = n_keep
-            else:
-                pr[b, :cnt] = pr32[b, :cnt]
-                bbox[b, :cnt] = bbox32[b, :cnt]
-            m = k - cnt
-            if m > 0:
-                # random.uniform(a, b) = a + (b-a)*random():  x0,y0 ~ U(0,1), x1 ~ U(x0,1), y1 ~ U(y0,1)
-                u = py_random_doubles(4 * m).reshape(m, 4)
-                x0 = 0.0 + (1.0 - 0.0) * u[:, 0]
-                y0 = 0.0 + (1.0 - 0.0) * u[:, 1]
-                bbox[b, cnt:, 0] = x0
-                bbox[b, cnt:, 1] = y0
-                bbox[b, cnt:, 2] = x0 + (1.0 - x0) * u[:, 2]
-                bbox[b, cnt:, 3] = y0 + (1.0 - y0) * u[:, 3]
-                pr[b, cnt:] = 0.0
-            if self.sample_gt:
-                for index, gt in enumerate(meta["bbox"]):
+        nb = len(metas)
+        count = numpy.ascontiguousarray(count[:nb], dtype=numpy.int64)
+        pr32 = numpy.ascontiguousarray(pr32[:nb], dtype=numpy.float32)
+        bbox32 = numpy.ascontiguousarray(bbox32[:nb], dtype=numpy.float32)
+        # sub-sample / pad with python-`random` semantics for the whole batch in one native call
+        # (csrc/pyrandom.cu: the interpreter's Mersenne-Twister state goes in and comes back advanced exactly as the
+        # reference's loops over random.sample / random.uniform would have advanced it)
+        mt, pos, version, gauss = mt_export()
+        call("denet_sparse_postprocess", mt.ctypes.data, ctypes.addressof(pos), pr32.ctypes.data, bbox32.ctypes.data,
+             count.ctypes.data, nb, k, n_keep, pr.ctypes.data, bbox.ctypes.data)
+        mt_import(mt, pos, version, gauss)
+        if self.sample_gt:
+            for b, meta in enumerate(metas):
+                for index, gt in enumerate(meta["bbox"]):       # the LAST len(GT) slots become the ground truth
                     pr[b, k - (index + 1)] = 1.0
                     bbox[b, k - (index + 1)] = gt
         self.set_samples_arrays(pr, bbox)

@@ -14,7 +14,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "denet_b200.h")
 DENET_F32 = 0
 DENET_BF16 = 1
 
-_SCALARS = {"int": ctypes.c_int, "double": ctypes.c_double, "long long": ctypes.c_longlong, "float": ctypes.c_float, "size_t": ctypes.c_size_t,
+_SCALARS = {"int": ctypes.c_int, "double": ctypes.c_double, "long long": ctypes.c_longlong, "float": ctypes.c_float, "size_t": ctypes.c_size_t, "uint32_t": ctypes.c_uint32,
             "cudaStream_t": ctypes.c_void_p}
 
 

@@ -223,6 +223,18 @@ int denet_detect_cost(const void* o, int dtype, long long ld, int B, int sn, int
 int denet_softmax_nll(const void* o, int dtype, long long ld, int B, int classes, const int* label, float grad_factor,
                       void* dout, float* logp_out, float* cost, float* workspace, cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ RoI post-processing
+ * HOST functions (no device work).  sparse_postprocess is the python-`random` post-processing of the ranked RoIs in
+ * DeNetSparseLayer.get_target (denet/layer/denet_sparse.py:184-201) for a whole batch: sub-sample to n_keep with
+ * random.sample, pad to K with random boxes.  mt_state (624 words) / mt_pos are the interpreter's Mersenne-Twister
+ * state (random.getstate()), advanced in place exactly as the reference's python loops would advance it.
+ * pr32 (B,K) / bbox32 (B,K,4) fp32 ranked samples, count (B) int64; outputs pr (B,K) / bbox (B,K,4) doubles.
+ * pyrandom_sample = random.sample(range(n), k); pyrandom_random = n x random.random(). */
+int denet_sparse_postprocess(uint32_t* mt_state, int* mt_pos, const float* pr32, const float* bbox32,
+                             const long long* count, int B, int K, int n_keep, double* pr, double* bbox);
+int denet_pyrandom_sample(uint32_t* mt_state, int* mt_pos, int n, int k, int* out_index);
+int denet_pyrandom_random(uint32_t* mt_state, int* mt_pos, long long n, double* out);
+
 /* ------------------------------------------------------------------------------------------------ targets
  * The host target builders of the reference, evaluated on the device from the ground-truth boxes:
  * corner_target: DeNetCornerLayer.get_target (denet/layer/denet_corner.py:81-123, dropout 0) -> (B,2,cn,H,W) fp32.

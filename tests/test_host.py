@@ -147,3 +147,28 @@ def test_no_cpu_fallback():
             m.to_device()
     with pytest.raises(lib.DenetError):
         ops.act_operand(torch.zeros(1, 2, 2, 8))
+
+
+def test_native_pyrandom_matches_the_interpreter():
+    """csrc/pyrandom.cu restates CPython's Mersenne Twister, random.random, _randbelow and both variants of
+    random.sample: same results AND the same stream position afterwards, for populations around powers of two"""
+    from denet_b200.layer.denet_sparse import py_random_sample, mt_export, mt_import
+    from denet_b200 import lib
+    import ctypes
+    for seed, (n, k) in enumerate([(576, 519), (576, 576), (1, 1), (2, 1), (512, 100), (513, 3), (64, 5), (2304, 2074),
+                                   (5000, 6), (100000, 50), (1023, 1000), (21, 21), (22, 5), (30, 0)]):
+        random.seed(seed)
+        want = random.sample(range(n), k)
+        after = random.random()
+        random.seed(seed)
+        got = py_random_sample(n, k)
+        assert list(got) == want, (n, k)
+        assert random.random() == after, (n, k)
+    random.seed(9)
+    want = [random.random() for _ in range(1500)]      # crosses a 624-word regeneration
+    random.seed(9)
+    mt, pos, version, gauss = mt_export()
+    out = numpy.empty(1500)
+    lib.call("denet_pyrandom_random", mt.ctypes.data, ctypes.addressof(pos), 1500, out.ctypes.data)
+    mt_import(mt, pos, version, gauss)
+    assert list(out) == want and random.random() == [random.seed(9), [random.random() for _ in range(1501)]][1][-1]
