@@ -153,12 +153,33 @@ __device__ __forceinline__ void load_row_chunk(const void* y, int y_fp32, long l
                                                int ncols_valid) {
     if (y_fp32) {
         const float* src = reinterpret_cast<const float*>(y) + elem_off;
+        if (ncols_valid == 32 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (i < ncols_valid) ? src[i] : 0.f;
+            for (int i = 0; i < 8; ++i) {
+                const float4 f = reinterpret_cast<const float4*>(src)[i];
+                v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (i < ncols_valid) ? src[i] : 0.f;
+        }
     } else {
         const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(y) + elem_off;
+        if (ncols_valid == 32 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (i < ncols_valid) ? __bfloat162float(src[i]) : 0.f;
+            for (int i = 0; i < 4; ++i) {
+                const uint4 u = reinterpret_cast<const uint4*>(src)[i];
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
+                    v[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (i < ncols_valid) ? __bfloat162float(src[i]) : 0.f;
+        }
     }
 }
 
@@ -219,9 +240,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
-        if (lane == 0) {
-            ptx::tma_prefetch_desc(&p.tmA[0]);
-            ptx::tma_prefetch_desc(&p.tmB[0]);
+        // The whole warp runs the loops (so that every address / coordinate is warp-uniform and lives in uniform
+        // registers); one elected lane issues the TMA instructions.  Running the loops under `if (lane == 0)` makes
+        // the compiler wrap every TMA / MMA issue in a register -> uniform-register "waterfall" loop (~200 cycles).
+        {
+            if (ptx::elect_one()) {
+                ptx::tma_prefetch_desc(&p.tmA[0]);
+                ptx::tma_prefetch_desc(&p.tmB[0]);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -242,9 +268,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                             for (int kc = 0; kc < p.kchunks; ++kc, kcol += kBK) {
                                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                                 uint8_t* sA = smem + stage * L::kStageBytes;
-                                ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-                                ptx::tma_load_4d(sA, mapA, &full_bar[stage], kc * kBK, w0 + sx, h0 + r, n0);
-                                ptx::tma_load_2d(sA + L::kABytes, mapB, &full_bar[stage], kcol, co0);
+                                if (ptx::elect_one()) {
+                                    ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                                    ptx::tma_load_4d(sA, mapA, &full_bar[stage], kc * kBK, w0 + sx, h0 + r, n0);
+                                    ptx::tma_load_2d(sA + L::kABytes, mapB, &full_bar[stage], kcol, co0);
+                                }
+                                __syncwarp();
                                 if (++stage == STAGES) {
                                     stage = 0;
                                     phase ^= 1;
@@ -257,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 0, 0);
             const uint64_t adesc0 = ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024);
             int stage = 0;
@@ -275,18 +304,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                     // descriptors of stage 0 + the stage offset in 16-byte units (the address field is addr >> 4)
                     const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (L::kStageBytes >> 4));
                     const uint64_t bdesc = adesc + (L::kABytes >> 4);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < kBK / 16; ++j) {
-                        // advance 16 bf16 (32 B) along K inside the 128B-swizzled row
-                        ptx::umma_f16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | j) != 0);
+                        for (int j = 0; j < kBK / 16; ++j) {
+                            // advance 16 bf16 (32 B) along K inside the 128B-swizzled row
+                            ptx::umma_f16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | j) != 0);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::umma_commit(&tfull_bar[as]);
+                if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[as]);
+                __syncwarp();
             }
         }
     } else {
@@ -456,9 +489,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            ptx::tma_prefetch_desc(&p.tmDY[0]);
-            ptx::tma_prefetch_desc(&p.tmX[0]);
+        {
+            if (ptx::elect_one()) {
+                ptx::tma_prefetch_desc(&p.tmDY[0]);
+                ptx::tma_prefetch_desc(&p.tmX[0]);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -478,19 +513,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sA = smem + stage * L::kStageBytes;
                         uint8_t* sB = sA + L::kABytes;
-                        if (p.debug & 2) {
-                            ptx::mbar_arrive(&full_bar[stage]);
-                        } else {
-                            ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                        if (ptx::elect_one()) {
+                            if (p.debug & 2) {
+                                ptx::mbar_arrive(&full_bar[stage]);
+                            } else {
+                                // Cout <= 64: the second 64-channel dY box would be all TMA zero fill; skip it (its
+                                // accumulator rows are never read)
+                                ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes - (2 - p.a_boxes) * kBoxBytes);
+                                for (int i = 0; i < p.a_boxes; ++i)
+                                    ptx::tma_load_4d(sA + i * kBoxBytes, &p.tmDY[ai], &full_bar[stage],
+                                                     cot * kBM + i * 64, w0, h0, n0);
 #pragma unroll
-                            for (int i = 0; i < kBM / 64; ++i)
-                                ptx::tma_load_4d(sA + i * kBoxBytes, &p.tmDY[ai], &full_bar[stage], cot * kBM + i * 64,
-                                                 w0, h0, n0);
-#pragma unroll
-                            for (int i = 0; i < BN / 64; ++i)
-                                ptx::tma_load_4d(sB + i * kBoxBytes, &p.tmX[bi], &full_bar[stage], cit * BN + i * 64,
-                                                 w0 * p.stride_w + dw, h0 * p.stride_h + dh, n0);
+                                for (int i = 0; i < BN / 64; ++i)
+                                    ptx::tma_load_4d(sB + i * kBoxBytes, &p.tmX[bi], &full_bar[stage],
+                                                     cit * BN + i * 64, w0 * p.stride_w + dw, h0 * p.stride_h + dh, n0);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -507,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 1, 1);
             const uint64_t adesc0 = ptx::make_smem_desc(ptx::smem_u32(smem), kBoxBytes, 1024);
             int stage = 0;
@@ -528,19 +567,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                     // MN-major: LBO = next 64-channel box, SBO = next group of 8 pixel rows
                     const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (L::kStageBytes >> 4));
                     const uint64_t bdesc = adesc + (L::kABytes >> 4);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < kBK / 16; ++j) {
-                        // advance 16 pixel rows = 2048 B
-                        if (!(p.debug & 1))
-                            ptx::umma_f16(d_tmem, adesc + 128 * j, bdesc + 128 * j, idesc, (kb | j) != 0);
+                        for (int j = 0; j < kBK / 16; ++j) {
+                            // advance 16 pixel rows = 2048 B
+                            if (!(p.debug & 1))
+                                ptx::umma_f16(d_tmem, adesc + 128 * j, bdesc + 128 * j, idesc, (kb | j) != 0);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::umma_commit(&tfull_bar[as]);
+                if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[as]);
+                __syncwarp();
             }
         }
     } else {
@@ -568,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                 const int ci = cit * BN + c0;
                 int nvalid = p.Cin - ci;
                 nvalid = nvalid > 32 ? 32 : nvalid;
-                if (row_ok && nvalid > 0) {
+                if (row_ok && nvalid > 0 && !(p.debug & 4)) {
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -656,9 +699,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
     const uint32_t stage_tx = p.a_boxes * kBoxBytes + (BN / 64) * p.xrows * 128;
 
     if (warp == 0) {
-        if (lane == 0) {
-            ptx::tma_prefetch_desc(&p.tmDY[0]);
-            ptx::tma_prefetch_desc(&p.tmX[0]);
+        {
+            if (ptx::elect_one()) {
+                ptx::tma_prefetch_desc(&p.tmDY[0]);
+                ptx::tma_prefetch_desc(&p.tmX[0]);
+            }
             int stage = 0;
             uint32_t phase = 0;
             const bool two_a = p.a_boxes > 1;
@@ -678,17 +723,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sA = smem + stage * L::kStageBytes;
                         uint8_t* sB = sA + L::kABytes;
-                        if (p.debug & 2) {
-                            ptx::mbar_arrive(&full_bar[stage]);
-                        } else {
-                            ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
-                            ptx::tma_load_4d(sA, mapA, &full_bar[stage], cA, w0, h0, n0);
-                            if (two_a) ptx::tma_load_4d(sA + kBoxBytes, mapA, &full_bar[stage], cA + 64, w0, h0, n0);
+                        if (ptx::elect_one()) {
+                            if (p.debug & 2) {
+                                ptx::mbar_arrive(&full_bar[stage]);
+                            } else {
+                                ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
+                                ptx::tma_load_4d(sA, mapA, &full_bar[stage], cA, w0, h0, n0);
+                                if (two_a)
+                                    ptx::tma_load_4d(sA + kBoxBytes, mapA, &full_bar[stage], cA + 64, w0, h0, n0);
 #pragma unroll
-                            for (int i = 0; i < BN / 64; ++i)
-                                ptx::tma_load_4d(sB + i * p.xbox_bytes, mapB, &full_bar[stage], cB + i * 64,
-                                                 w0 - p.pad_w, h0 + dh, n0);
+                                for (int i = 0; i < BN / 64; ++i)
+                                    ptx::tma_load_4d(sB + i * p.xbox_bytes, mapB, &full_bar[stage], cB + i * 64,
+                                                     w0 - p.pad_w, h0 + dh, n0);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -705,7 +754,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 1, 1);
             const int xw = p.TW + p.S - 1;                 // X rows per image row of the patch
             // one K=16 MMA = two 8-row groups of dY; with TW == 8 they sit in consecutive image rows of the X box
@@ -743,21 +792,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                     const uint64_t soff = static_cast<uint64_t>(stage * (L::kStageBytes >> 4));
                     const uint64_t adesc = adesc0 + soff;
                     const uint64_t bdesc = bdesc0 + soff;
-                    if (do_mma) {
+                    if (ptx::elect_one()) {
+                        if (do_mma) {
 #pragma unroll
-                        for (int j = 0; j < kBK / 16; ++j) {
-                            const uint64_t bj = bdesc + xoff[j];
-                            for (int sx = 0; sx < S; ++sx)
-                                ptx::umma_f16(d_tmem + sx * BN, adesc + 128 * j, bj + 8 * sx, idesc, (kb | j) != 0);
+                            for (int j = 0; j < kBK / 16; ++j) {
+                                const uint64_t bj = bdesc + xoff[j];
+                                for (int sx = 0; sx < S; ++sx)
+                                    ptx::umma_f16(d_tmem + sx * BN, adesc + 128 * j, bj + 8 * sx, idesc, (kb | j) != 0);
+                            }
                         }
+                        ptx::umma_commit(&empty_bar[stage]);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::umma_commit(&tfull_bar[as]);
+                if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[as]);
+                __syncwarp();
             }
         }
     } else {
@@ -786,7 +839,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                     const int ci = cit * BN + c0;
                     int nvalid = p.Cin - ci;
                     nvalid = nvalid > 32 ? 32 : nvalid;
-                    if (row_ok && nvalid > 0) {
+                    if (row_ok && nvalid > 0 && !(p.debug & 4)) {
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
@@ -1057,7 +1110,10 @@ static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cout, int Cin, int R, int
     pl.total_kb = ceil_div(Wo, pl.TW) * ceil_div(Ho, pl.TH) * ceil_div(N, pl.TN);
     pl.BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
     pl.xrows = (pl.TW + S - 1) * pl.TH * pl.TN;
-    pl.rows_path = want_rows && stride_h == 1 && stride_w == 1 && S > 1 && S <= 8 && pl.TW >= 8 && pl.xrows <= 80;
+    // measured on B200 (scripts/bench_wgrad.py): the row-shared kernel wins for Cin <= 64 (266 vs 181 TFLOP/s at
+    // 64->64 3x3 128^2); from 128 channels on, its smaller Cin tile and single accumulator set lose to one tap per tile
+    pl.rows_path = want_rows && stride_h == 1 && stride_w == 1 && S > 1 && S <= 8 && pl.TW >= 8 && pl.xrows <= 80 &&
+                   Cin <= 64;
     if (pl.rows_path)
         while (S * pl.BN > 512) pl.BN /= 2;
     pl.co_tiles = ceil_div(Cout, 128);
@@ -1346,6 +1402,7 @@ extern "C" int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, 
     p.fd_taps = make_fastdiv(R);
     p.fd_w = make_fastdiv(p.tiles_w);
     p.fd_h = make_fastdiv(p.tiles_h);
+    p.a_boxes = Cout <= 64 ? 1 : 2;
     p.Cout = Cout; p.Cin = 64;             // GEMM N extent: the 64 folded columns of a filter row
     p.ldws = 64;
     p.ws = workspace;

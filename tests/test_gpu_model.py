@@ -267,7 +267,7 @@ def _steps(model, x, metas, n, graphs):
     model.enable_cuda_graphs(graphs)
     out = []
     for it in range(n):
-        out.append(model.train_step(x, metas, 0, it, 0.02, [0.9, 0.9], 1e-4))
+        out.append(model.train_step(x, metas, 0, it, 0.002, [0.9, 0.9], 1e-4))   # small lr: the tiny models are chaotic
     return out
 
 
@@ -300,7 +300,7 @@ def test_cuda_graph_step_equals_eager_step(cuda, which):
     # two EAGER runs of this tiny model already differ (fp32 atomics order in the batch-norm statistics and the
     # sparse scatter, amplified step by step): the graphed run must stay within a few times that run-to-run noise
     for (t0, _), (t1, _), (t2, _) in zip(ca, ca2, cb):
-        assert abs(t0 - t2) <= 3 * abs(t0 - t1) + 5e-3 * abs(t0), (ca, ca2, cb)
+        assert abs(t0 - t2) <= 3 * abs(t0 - t1) + 3e-3 * abs(t0), (ca, ca2, cb)
     pa, pa2, pb = named_params(a), named_params(a2), named_params(b)
     for name in pa:
         if pa[name].norm().item() > 1e-2:
