@@ -914,6 +914,55 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Ci
     }
 }
 
+// All conv layers' operands in ONE launch (86 small launches per step otherwise): block i prepares elements
+// [block_offset[i], +kPrepChunk) of operand block_entry[i] of a device-resident table.
+// mode 0 / 1 as weight_prep_kernel, mode 2 = row-folded stem operand [Cout][R][64] (weight_prep_rowfold_kernel).
+struct PrepEntry {
+    const float* w;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+    long long total;
+    int Cout, Cin, R, S, mode, Cp;
+};
+constexpr int kPrepChunk = 4096;
+
+__global__ void __launch_bounds__(256) weight_prep_multi_kernel(const PrepEntry* __restrict__ entries,
+                                                                 const int* __restrict__ block_entry,
+                                                                 const long long* __restrict__ block_offset) {
+    const PrepEntry e = entries[block_entry[blockIdx.x]];
+    const long long start = block_offset[blockIdx.x];
+    const long long end = start + kPrepChunk < e.total ? start + kPrepChunk : e.total;
+    const int R = e.R, S = e.S, Cin = e.Cin;
+    const int ntaps = R * S;
+    const int kin = e.mode == 0 ? e.Cin : e.Cout;
+    const int kp = (kin + 63) / 64 * 64;
+    for (long long idx = start + threadIdx.x; idx < end; idx += blockDim.x) {
+        float v = 0.f;
+        if (e.mode == 2) {
+            const int k = static_cast<int>(idx % 64);
+            const int r = static_cast<int>((idx / 64) % R);
+            const int co = static_cast<int>(idx / (64LL * R));
+            const int sx = k / e.Cp, c = k % e.Cp;
+            if (sx < S && c < Cin) v = e.w[((static_cast<long long>(co) * Cin + c) * R + (R - 1 - r)) * S + (S - 1 - sx)];
+        } else {
+            const int k = static_cast<int>(idx % kp);
+            const long long t = idx / kp;
+            const int tap = static_cast<int>(t % ntaps);
+            const int row = static_cast<int>(t / ntaps);
+            if (k < kin) {
+                const int r = tap / S, sx = tap % S;
+                if (e.mode == 0)
+                    v = e.w[((static_cast<long long>(row) * Cin + k) * R + (R - 1 - r)) * S + (S - 1 - sx)];
+                else
+                    v = e.w[((static_cast<long long>(k) * Cin + row) * R + r) * S + sx];
+            }
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        e.hi[idx] = hi;
+        if (e.lo) e.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
 // fp32 -> bf16 hi/lo split of an activation tensor (parity mode operand preparation).
 __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long n) {
@@ -1039,6 +1088,18 @@ extern "C" int denet_conv_weight_prep(const float* w, int Cout, int Cin, int R, 
     const int block = 256;
     const int grid = (int)std::min<long long>(ceil_div_ll(total, block), 148LL * 16);
     weight_prep_kernel<<<DN_G(grid), block, 0, stream>>>(w, Cout, Cin, R, S, mode, (__nv_bfloat16*)b_hi, (__nv_bfloat16*)b_lo);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_weight_prep_entry_bytes(void) { return (int)sizeof(PrepEntry); }
+extern "C" int denet_weight_prep_chunk(void) { return kPrepChunk; }
+
+extern "C" int denet_conv_weight_prep_multi(const void* entries, const int* block_entry, const long long* block_offset,
+                                            int nblocks, cudaStream_t stream) {
+    DN_REQUIRE(entries && block_entry && block_offset, "weight_prep_multi: null pointer");
+    if (nblocks == 0) return 0;
+    weight_prep_multi_kernel<<<DN_G(nblocks), 256, 0, stream>>>((const PrepEntry*)entries, block_entry, block_offset);
     DN_CHECK_LAUNCH();
     return 0;
 }

@@ -201,7 +201,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const T* __r
                                                                       long long ld, int rows_per_block,
                                                                       const float* __restrict__ mean,
                                                                       const float* __restrict__ invstd, int relu,
-                                                                      float* __restrict__ partial) {
+                                                                      float* __restrict__ partial,
+                                                                      const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta) {
     const int CV = C / VEC;
     const int cvt = CV < kBnThreads ? CV : kBnThreads;
     const int rlanes = kBnThreads / cvt;
@@ -215,11 +217,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const T* __r
     for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
     const bool active = (cv < CV) && (rl < rlanes);
     if (active) {
-        float mu[VEC], is[VEC];
+        // relu mask: y > 0.  Without a residual input y = relu((x - mean) * (gamma*invstd) + beta), so the mask is
+        // recomputed from x with the forward pass's exact expression (yout == nullptr) instead of reading y back.
+        const bool mask_from_x = relu && (yout == nullptr);
+        float mu[VEC], is[VEC], fa[VEC], fb[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             mu[i] = mean[cv * VEC + i];
             is[i] = invstd[cv * VEC + i];
+            fa[i] = mask_from_x ? gamma[cv * VEC + i] * is[i] : 0.f;
+            fb[i] = mask_from_x ? beta[cv * VEC + i] : 0.f;
         }
         const long long coff = (long long)cv * VEC;
         for (long long r = r0 + rl; r < r1; r += (long long)rlanes * kBnUnrollBwd) {
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const T* __r
                 if (rr < r1) {
                     g[u].load(dy + rr * ld + coff);
                     xv[u].load(x + rr * ld + coff);
-                    if (relu) yo[u].load(yout + rr * ld + coff);
+                    if (relu && !mask_from_x) yo[u].load(yout + rr * ld + coff);
                 }
             }
 #pragma unroll
@@ -240,7 +247,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const T* __r
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
                         float d = g[u].v[i];
-                        if (relu && !(yo[u].v[i] > 0.f)) d = 0.f;
+                        if (mask_from_x) {
+                            if (!((xv[u].v[i] - mu[i]) * fa[i] + fb[i] > 0.f)) d = 0.f;
+                        } else if (relu && !(yo[u].v[i] > 0.f)) {
+                            d = 0.f;
+                        }
                         s[i] += d;
                         s2[i] += d * ((xv[u].v[i] - mu[i]) * is[i]);
                     }
@@ -293,7 +304,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
                                                                   const float* __restrict__ gamma,
                                                                   const float* __restrict__ sum_dy,
                                                                   const float* __restrict__ sum_dy_xhat, int relu,
-                                                                  T* __restrict__ dx, T* __restrict__ dres) {
+                                                                  T* __restrict__ dx, T* __restrict__ dres,
+                                                                  const float* __restrict__ beta) {
     const int CV = C / VEC;
     const int cvt = CV < kBnThreads ? CV : kBnThreads;
     const int rlanes = kBnThreads / cvt;
@@ -303,7 +315,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
     const float inv_m = 1.0f / (float)M;
-    float mu[VEC], is[VEC], k1[VEC], c1[VEC], c2[VEC];
+    const bool mask_from_x = relu && (yout == nullptr);
+    float mu[VEC], is[VEC], k1[VEC], c1[VEC], c2[VEC], fb[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         const int c = cv * VEC + i;
@@ -312,6 +325,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
         k1[i] = gamma[c] * is[i];
         c1[i] = sum_dy[c] * inv_m;
         c2[i] = sum_dy_xhat[c] * inv_m;
+        fb[i] = mask_from_x ? beta[c] : 0.f;
     }
     const long long coff = (long long)cv * VEC;
     for (long long r = r0 + rl; r < r1; r += (long long)rlanes * kBnUnrollBwd) {
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
             if (rr < r1) {
                 g[u].load(dy + rr * ld + coff);
                 xv[u].load(x + rr * ld + coff);
-                if (relu) yo[u].load(yout + rr * ld + coff);
+                if (relu && !mask_from_x) yo[u].load(yout + rr * ld + coff);
             }
         }
 #pragma unroll
@@ -333,7 +347,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
                     float d = g[u].v[i];
-                    if (relu && !(yo[u].v[i] > 0.f)) d = 0.f;
+                    if (mask_from_x) {   // k1 = gamma * invstd: the forward pass's (x - mean) * (gamma*invstd) + beta
+                        if (!((xv[u].v[i] - mu[i]) * k1[i] + fb[i] > 0.f)) d = 0.f;
+                    } else if (relu && !(yo[u].v[i] > 0.f)) {
+                        d = 0.f;
+                    }
                     g[u].v[i] = d;
                     const float xh = (xv[u].v[i] - mu[i]) * is[i];
                     o.v[i] = k1[i] * (d - c1[i] - xh * c2[i]);
@@ -530,12 +548,27 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
                 const int wo = wn / sw;
                 if (wo >= Wo) continue;
                 const long long opix = ((long long)n * Ho + ho) * Wo + wo;
-                Pack<T, VEC> g;
-                g.load(dy + opix * ldy + (long long)cv * VEC);
                 const int tap = r * kw + s;
+                if (VEC == 8) {
+                    // the 8 tap bytes of this pack in one 8-byte load; dy is only fetched when some channel matches
+                    const uint2 am = *reinterpret_cast<const uint2*>(argmax + opix * C + cv * 8);
+                    const uint32_t w2[2] = {am.x, am.y};
+                    bool any = false;
 #pragma unroll
-                for (int i = 0; i < VEC; ++i)
-                    if (argmax[opix * C + cv * VEC + i] == tap) acc[i] += g.v[i];
+                    for (int i = 0; i < 8; ++i) any |= (((w2[i >> 2] >> (8 * (i & 3))) & 0xffu) == (uint32_t)tap);
+                    if (!any) continue;
+                    Pack<T, VEC> g;
+                    g.load(dy + opix * ldy + (long long)cv * VEC);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i)
+                        if (((w2[(i & 7) >> 2] >> (8 * (i & 3))) & 0xffu) == (uint32_t)tap) acc[i] += g.v[i];
+                } else {
+                    Pack<T, VEC> g;
+                    g.load(dy + opix * ldy + (long long)cv * VEC);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i)
+                        if (argmax[opix * C + cv * VEC + i] == tap) acc[i] += g.v[i];
+                }
             }
         }
         Pack<T, VEC> o;
@@ -864,11 +897,11 @@ extern "C" int denet_bn_inference_invstd(const float* run_stdinv, float eps, flo
 }
 
 extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x, int dtype, long long M, int C,
-                                 long long ld, const float* mean, const float* invstd, const float* gamma, int relu,
-                                 void* dx, void* dres, float* dgamma, float* dbeta, int accumulate, float* workspace,
-                                 size_t workspace_bytes, cudaStream_t stream) {
+                                 long long ld, const float* mean, const float* invstd, const float* gamma,
+                                 const float* beta, int relu, void* dx, void* dres, float* dgamma, float* dbeta,
+                                 int accumulate, float* workspace, size_t workspace_bytes, cudaStream_t stream) {
     DN_REQUIRE(dy && x && dx && mean && invstd && gamma && workspace, "bn_backward: null pointer");
-    DN_REQUIRE(!relu || yout, "bn_backward: relu mask needs the forward output");
+    DN_REQUIRE(!relu || yout || beta, "bn_backward: the relu mask needs the forward output, or beta to recompute it");
     DN_REQUIRE(workspace_bytes >= denet_bn_workspace_bytes(M, C), "bn_backward: workspace too small");
     const bool v = vec8_ok(C, ld, dy, x, dx, yout) && vec8_ok(C, ld, dres);
     int rpb, yc;
@@ -876,14 +909,14 @@ extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x
     float* sums = workspace + (size_t)nslabs * 2 * C;
     DN_DISPATCH(dtype, v, {
         bn_bwd_partial_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>(
-            (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb, mean, invstd, relu, workspace);
+            (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb, mean, invstd, relu, workspace, gamma, beta);
         bn_bwd_finalize_kernel<<<DN_G(ceil_div(C, 32)), kFinThreads, 0, stream>>>(workspace, nslabs, C, sums, sums + C, dgamma, dbeta,
                                                                      accumulate);
         int rpb2, yc2;
         const int nslabs2 = ew_slabs(M, C, VEC, &rpb2, &yc2);
         bn_bwd_apply_kernel<T, VEC><<<DN_G(dim3(nslabs2, yc2)), kBnThreads, 0, stream>>>(
             (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb2, mean, invstd, gamma, sums, sums + C, relu,
-            (T*)dx, (T*)dres);
+            (T*)dx, (T*)dres, beta);
     });
     DN_CHECK_LAUNCH();
     return 0;

@@ -114,7 +114,9 @@ class BatchNormLayer(AbstractLayer):
             else:
                 ops.bn_stats(x, self.eps, mean, invstd, self.mean, self.stdinv, self.momentum)
             y = ops.bn_apply(x, mean, invstd, self.omega, self.beta, residual=residual, relu=relu)
-            self._saved = (x, y if relu else None, mean, invstd, relu)
+            # backward needs y only for the relu mask, and only when a residual was added (otherwise the mask is
+            # recomputed from x: one tensor read less in both backward passes)
+            self._saved = (x, y if (relu and residual is not None) else None, mean, invstd, relu)
         else:
             invstd = ops.bn_inference_invstd(self.stdinv, self.eps)
             y = ops.bn_apply(x, self.mean, invstd, self.omega, self.beta, residual=residual, relu=relu)
@@ -128,7 +130,7 @@ class BatchNormLayer(AbstractLayer):
         x, y, mean, invstd, relu = self._saved
         self._saved = None
         dx, dres = ops.bn_backward(dy, y, x, mean, invstd, self.omega, relu, self.omega.grad, self.beta.grad,
-                                   want_dres=want_dres)
+                                   want_dres=want_dres, beta=self.beta)
         return (dx, dres) if want_dres else dx
 
 

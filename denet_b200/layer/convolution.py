@@ -169,6 +169,36 @@ class ConvLayer(AbstractLayer):
             self._wver = param_version()
         return self._wop_f, self._wop_d
 
+    def prep_entries(self):
+        """(w, operand, mode, Cp) records for ModelCNN's one-launch operand preparation, or None when this layer
+        prepares its own operands (im2col variant); allocates the operand buffers on first use"""
+        if not self.enabled or self.use_im2col:
+            return None
+        split = get_precision() == "fp32"
+        if self._wop_f is not None and (self._wop_f.lo is not None) != split:
+            self._wop_f = self._wop_d = None
+        cout, cin, R, S = self.filter_shape
+        dev = self.omega.device
+
+        def alloc(shape, rows, kin):
+            hi = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+            return ops.ConvOperand(hi, torch.empty_like(hi) if split else None, rows, kin, R, S)
+        if self.rowfold is not None:
+            if self._wop_f is None:
+                self._wop_f = alloc((cout, R, 64), cout, cin)
+            return [(self.omega, self._wop_f, 2, self.rowfold[0])]
+        if self._wop_f is None:
+            self._wop_f = alloc((cout, R * S, (cin + 63) // 64 * 64), cout, cin)
+        out = [(self.omega, self._wop_f, 0, 0)]
+        if not self.is_first:
+            if self._wop_d is None:
+                self._wop_d = alloc((cin, R * S, (cout + 63) // 64 * 64), cin, cout)
+            out.append((self.omega, self._wop_d, 1, 0))
+        return out
+
+    def mark_operands_current(self):
+        self._wver = param_version()
+
     def _as_operand(self, t):
         """activation / gradient tensor -> MMA operand of the current precision mode"""
         if get_precision() == "bf16" and t.dtype == torch.float32:

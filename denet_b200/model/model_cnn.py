@@ -117,6 +117,10 @@ class ModelCNN:
         self._image = None          # padded input buffer of a row-folded stem conv
         self._static_inputs = False # copy every batch into one persistent device buffer (needed by CUDA graphs)
         self._graphs = None         # captured CUDA graphs of the training step (enable_cuda_graphs)
+        self._prep_table = None     # device table of the one-launch conv operand preparation
+        self._prep_version = -1
+        self._prep_precision = None
+        self._prep_layers = []
         self._use_graphs = False
 
     # ---------------------------------------------------------------------------------------------- shapes
@@ -401,11 +405,54 @@ class ModelCNN:
         return (layer_mod.h2d(box, self.device, slot="model/gt_bbox"), layer_mod.h2d(cls, self.device, slot="model/gt_class"),
                 layer_mod.h2d(cnt, self.device, slot="model/gt_count"))
 
+    def prepare_operands(self):
+        """bf16 GEMM operands of every conv layer from the fp32 master weights in ONE kernel launch (after each
+        solver step); layers not covered (im2col variant) refresh their own operands lazily"""
+        if self._prep_version == layer_mod.param_version() or self.device is None:
+            return
+        precision = layer_mod.get_precision()
+        if self._prep_table is None or self._prep_precision != precision:
+            convs = [l for l in _walk(self.layers) if l.type_name == "conv"]
+            records = []
+            self._prep_layers = []
+            for l in convs:
+                ent = l.prep_entries()
+                if ent is not None:
+                    records += ent
+                    self._prep_layers.append(l)
+            ebytes = lib.load().denet_weight_prep_entry_bytes()
+            chunk = lib.load().denet_weight_prep_chunk()
+            assert ebytes == 56, ebytes
+            table = numpy.zeros((max(len(records), 1), 7), dtype=numpy.int64)
+            ints = table.view(numpy.int32).reshape(len(table), 14)
+            block_entry, block_offset = [], []
+            for i, (w, op, mode, cp) in enumerate(records):
+                cout, cin, R, S = w.shape
+                table[i, 0] = w.data_ptr()
+                table[i, 1] = op.hi.data_ptr()
+                table[i, 2] = op.lo.data_ptr() if op.lo is not None else 0
+                table[i, 3] = op.hi.numel()
+                ints[i, 8:14] = [cout, cin, R, S, mode, cp]
+                for o in range(0, op.hi.numel(), chunk):
+                    block_entry.append(i)
+                    block_offset.append(o)
+            self._prep_table = (torch.from_numpy(table).to(self.device),
+                                torch.tensor(block_entry, dtype=torch.int32, device=self.device),
+                                torch.tensor(block_offset, dtype=torch.int64, device=self.device), len(block_entry))
+            self._prep_precision = precision
+        entries, be, bo, nblocks = self._prep_table
+        lib.call("denet_conv_weight_prep_multi", entries.data_ptr(), be.data_ptr(), bo.data_ptr(), nblocks,
+                 ops._stream())
+        for l in self._prep_layers:
+            l.mark_operands_current()
+        self._prep_version = layer_mod.param_version()
+
     def forward(self, data_x, data_m=None, train=False):
         """one pass over the layer list; in train mode every layer's get_target runs right before its forward so
         that the sparse layer can sample from the corner maps of this very pass"""
         layer_mod.set_train(train)
         layer_mod.set_ground_truth(self.upload_metas(data_m) if train else None)
+        self.prepare_operands()
         x = self.upload(data_x)
         self.layers[0].output = x
         return self.forward_layers(x, 1, len(self.layers), data_x, data_m, train)
@@ -504,6 +551,8 @@ class ModelCNN:
     def _segment_a(self, si):
         """image -> ... -> corner layer (+ device targets, corner cost) -> device sampler"""
         self.bn_stat_buffer.zero_()
+        self._prep_version = -1                  # the operand preparation is part of the captured graph
+        self.prepare_operands()
         x = self.upload(layer_mod.slot_tensor("model/image"))
         self.layers[0].output = x
         end = si if si is not None else len(self.layers)

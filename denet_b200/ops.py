@@ -338,7 +338,9 @@ def bn_inference_invstd(run_stdinv, eps):
     return out
 
 
-def bn_backward(dy, yout, x, mean, invstd, gamma, relu, dgamma, dbeta, accumulate=False, want_dres=False, dx=None):
+def bn_backward(dy, yout, x, mean, invstd, gamma, relu, dgamma, dbeta, accumulate=False, want_dres=False, dx=None,
+                beta=None):
+    """yout=None with relu: the mask is recomputed from x (needs beta; only valid when the forward had no residual)"""
     M, C = _rows(x), x.shape[-1]
     ws = _bn_ws(M, C, x.device)
     if dx is None:
@@ -347,7 +349,8 @@ def bn_backward(dy, yout, x, mean, invstd, gamma, relu, dgamma, dbeta, accumulat
     ld = _pitch(x)
     assert _pitch(dy) == ld and _pitch(dx) == ld and (yout is None or _pitch(yout) == ld)
     call("denet_bn_backward", dy.data_ptr(), _ptr(yout), x.data_ptr(), _dtype_code(x), M, C, ld, mean.data_ptr(),
-         invstd.data_ptr(), gamma.data_ptr(), int(relu), dx.data_ptr(), _ptr(dres), _ptr(dgamma), _ptr(dbeta),
+         invstd.data_ptr(), gamma.data_ptr(), _ptr(beta), int(relu), dx.data_ptr(), _ptr(dres), _ptr(dgamma),
+         _ptr(dbeta),
          int(accumulate), ws.data_ptr(), ws.numel() * 4, _stream())
     return dx, dres
 

@@ -53,6 +53,15 @@ long long denet_launch_count(void);
 int denet_conv_weight_prep(const float* w, int Cout, int Cin, int R, int S, int mode, void* b_hi, void* b_lo,
                            cudaStream_t stream);
 
+/* The operands of ALL conv layers in one launch.  `entries` is a device array of denet_weight_prep_entry_bytes()-sized
+ * records {const float* w; bf16* hi; bf16* lo (or NULL); long long total; int Cout, Cin, R, S, mode, Cp} with mode
+ * 0 / 1 as above and 2 = row-folded stem operand (Cp = padded channels); block i prepares elements
+ * [block_offset[i], +denet_weight_prep_chunk()) of operand block_entry[i]. */
+int denet_weight_prep_entry_bytes(void);
+int denet_weight_prep_chunk(void);
+int denet_conv_weight_prep_multi(const void* entries, const int* block_entry, const long long* block_offset,
+                                 int nblocks, cudaStream_t stream);
+
 /* fp32 -> bf16 hi (+ lo = bf16(x - hi)) operand split.  lo may be NULL. */
 int denet_split_bf16(const float* x, void* hi, void* lo, long long n, cudaStream_t stream);
 
@@ -125,7 +134,9 @@ int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, int N, int 
  * bn_finalize_sums: same outputs from the sum / sum-of-squares accumulated by denet_conv2d_fprop's epilogue.
  * bn_apply: y = [relu]((x-mean)*gamma*invstd + beta [+ residual]).
  * bn_inference_invstd: the reference's test-time quirk var = (1/stdinv)^2, eps added again (batch_norm.py:50-52).
- * bn_backward: dy' = dy*[y>0] if relu; dx = gamma*invstd*(dy' - mean(dy') - xhat*mean(dy'*xhat));
+ * bn_backward: dy' = dy*[y>0] if relu (yout = the forward output; when the forward had no residual input, yout may be
+ *   NULL and the mask is recomputed from x, gamma, beta with the forward's exact expression - one tensor read less);
+ *   dx = gamma*invstd*(dy' - mean(dy') - xhat*mean(dy'*xhat));
  *   dgamma/dbeta (+)=; dres (optional) receives dy' (gradient of the residual input). */
 size_t denet_bn_workspace_bytes(long long M, int C);
 int denet_bn_stats(const void* x, int dtype, long long M, int C, long long ld, float eps, float* mean, float* invstd,
@@ -138,7 +149,8 @@ int denet_bn_apply(const void* x, int dtype, long long M, int C, long long ld, c
                    cudaStream_t stream);
 int denet_bn_inference_invstd(const float* run_stdinv, float eps, float* out, int C, cudaStream_t stream);
 int denet_bn_backward(const void* dy, const void* yout, const void* x, int dtype, long long M, int C, long long ld,
-                      const float* mean, const float* invstd, const float* gamma, int relu, void* dx, void* dres,
+                      const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
+                      void* dx, void* dres,
                       float* dgamma, float* dbeta, int accumulate, float* workspace, size_t workspace_bytes,
                       cudaStream_t stream);
 

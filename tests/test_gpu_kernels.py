@@ -242,6 +242,33 @@ def test_bn_forward_backward(cuda, dtype, shape):
     assert relerr(dgamma, dgr) < tol and relerr(dbeta, dbr) < tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bn_backward_mask_recomputed_from_x(cuda, dtype):
+    """BN+ReLU without a residual: the backward recomputes the relu mask from x (yout = None) and must give exactly
+    what the mask read back from the stored forward output gives"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    shape = (4, 72, 12, 10)
+    c = shape[1]
+    x = (torch.randn(shape, generator=g) * 1.5 - 0.2).to(dtype).float()
+    dy = torch.randn(shape, generator=g).to(dtype).float()
+    gamma = (torch.rand(c, generator=g) + 0.5).to(cuda)
+    gamma[::5] *= -1                                        # negative scales flip the sign relation
+    beta = torch.randn(c, generator=g).to(cuda)
+    xd, dyd = nhwc(x, dtype, cuda), nhwc(dy, dtype, cuda)
+    mean, invstd = torch.empty(c, device=cuda), torch.empty(c, device=cuda)
+    ops.bn_stats(xd, 1e-5, mean, invstd)
+    y = ops.bn_apply(xd, mean, invstd, gamma, beta, relu=True)
+    outs = []
+    for yout in (y, None):
+        dgamma, dbeta = torch.zeros(c, device=cuda), torch.zeros(c, device=cuda)
+        dx, _ = ops.bn_backward(dyd, yout, xd, mean, invstd, gamma, True, dgamma, dbeta, beta=beta)
+        outs.append((dx.clone(), dgamma, dbeta))
+    assert (nchw(y) > 0).float().mean().item() > 0.2
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
 def test_bn_test_mode_quirk(cuda):
     ops = _ops()
     rs = torch.rand(32) + 0.5
