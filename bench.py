@@ -311,7 +311,11 @@ def run_b200(args):
     tb1 = dict(layer_mod.transfer_bytes)
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
-        return
+        # leave together with rank 0; skip interpreter / NCCL teardown (captured graphs hold NCCL work: a one-sided
+        # destroy_process_group hung the launcher for its whole timeout)
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
     images = batch * world * args.steps
     value = images / (ms_a / 1000.0)
@@ -377,7 +381,9 @@ def run_b200(args):
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
