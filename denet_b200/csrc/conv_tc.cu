@@ -963,6 +963,59 @@ __global__ void __launch_bounds__(256) weight_prep_multi_kernel(const PrepEntry*
     }
 }
 
+// The split-K reductions of ALL filter gradients in ONE launch (one small launch per conv layer otherwise): block i
+// reduces elements [block_offset[i], +kReduceChunk) of entry block_entry[i].  Same fixed summation order and the same
+// output layouts as wgrad_reduce_kernel (mode 0) / wgrad_reduce_rowfold_kernel (mode 1).
+struct ReduceEntry {
+    const float* ws;
+    float* dw;
+    long long total;    // Cout * Cin * R * S
+    int splits, Cout, Cin, R, S, ldws, mode, Cp, accumulate, pad_;
+};
+constexpr int kReduceChunk = 1024;
+
+__global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const ReduceEntry* __restrict__ entries,
+                                                                  const int* __restrict__ block_entry,
+                                                                  const long long* __restrict__ block_offset) {
+    const ReduceEntry e = entries[block_entry[blockIdx.x]];
+    const long long start = block_offset[blockIdx.x];
+    const long long end = start + kReduceChunk < e.total ? start + kReduceChunk : e.total;
+    const int R = e.R, S = e.S, Cin = e.Cin, Cout = e.Cout;
+    const int ntaps = R * S;
+    for (long long idx = start + threadIdx.x; idx < end; idx += blockDim.x) {
+        const float* src;
+        long long step, o;
+        if (e.mode == 0) {
+            // idx enumerates (co, tap, ci): coalesced workspace reads
+            const int ci = static_cast<int>(idx % Cin);
+            const long long t = idx / Cin;
+            const int tap = static_cast<int>(t % ntaps);
+            const int co = static_cast<int>(t / ntaps);
+            src = e.ws + (static_cast<long long>(co) * ntaps + tap) * e.ldws + ci;
+            step = static_cast<long long>(Cout) * ntaps * e.ldws;
+            const int r = tap / S, sx = tap % S;
+            o = ((static_cast<long long>(co) * Cin + ci) * R + (R - 1 - r)) * S + (S - 1 - sx);
+        } else {
+            const int sf = static_cast<int>(idx % S);
+            const int rf = static_cast<int>((idx / S) % R);
+            const int c = static_cast<int>((idx / (static_cast<long long>(S) * R)) % Cin);
+            const int co = static_cast<int>(idx / (static_cast<long long>(S) * R * Cin));
+            src = e.ws + (static_cast<long long>(co) * R + (R - 1 - rf)) * e.ldws + (S - 1 - sf) * e.Cp + c;
+            step = static_cast<long long>(Cout) * R * e.ldws;
+            o = idx;
+        }
+        float acc = 0.f;
+        int sp = 0;
+        for (; sp + 4 <= e.splits; sp += 4) {
+            const float a0 = src[0], a1 = src[step], a2 = src[2 * step], a3 = src[3 * step];
+            acc += a0; acc += a1; acc += a2; acc += a3;
+            src += 4 * step;
+        }
+        for (; sp < e.splits; ++sp, src += step) acc += *src;
+        e.dw[o] = e.accumulate ? e.dw[o] + acc : acc;
+    }
+}
+
 // fp32 -> bf16 hi/lo split of an activation tensor (parity mode operand preparation).
 __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long n) {
@@ -1058,10 +1111,39 @@ int fprop_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStr
     }
 }
 
-int wgrad_splits(int total_kblocks, int base_tiles) {
-    int splits = ceil_div(2 * num_sms(), base_tiles);
-    if (splits > total_kblocks) splits = total_kblocks;
-    return splits < 1 ? 1 : splits;
+// Split-K factor of the filter gradient.  A persistent grid of num_sms() CTAs runs the base_tiles * splits tiles in
+// ceil(tiles / SMs) rounds of ceil(total_kblocks / splits) k-blocks each, so a tile count just above a multiple of the
+// SM count wastes most of a round (the former rule ceil(2*SMs / base_tiles) produced 297..306 tiles on 148 SMs for the
+// ResNet layers: 3 rounds for 2.0x waves).  Pick the factor that minimises
+//     rounds * kblocks_per_split * t_kblock  +  splits * t_reduce
+// where t_kblock is the larger of the MMA time and the L2 -> shared-memory time of one k-block on one SM and t_reduce
+// the workspace write + read of one split (the fixed-order reduction pass).  Ties go to fewer splits.
+static int g_wgrad_legacy_splits = 0;
+int wgrad_splits(int total_kblocks, int base_tiles, int bn_cols, int stage_bytes, long long out_elems) {
+    const int sms = num_sms();
+    if (g_wgrad_legacy_splits) {
+        int splits = ceil_div(2 * sms, base_tiles);
+        if (splits > total_kblocks) splits = total_kblocks;
+        return splits < 1 ? 1 : splits;
+    }
+    const double t_mma = 2.0 * 128 * bn_cols * 64 / 10.0e6;          // us: ~10 TFLOP/s of bf16 MMA per SM
+    const double t_l2 = stage_bytes / 84.0e3;                         // us: ~12.4 TB/s chip-wide over 148 SMs
+    const double t_kb = t_mma > t_l2 ? t_mma : t_l2;
+    const double t_red = 8.0 * out_elems / 4.0e6;                     // us per split: fp32 write + read at ~4 TB/s
+    int max_splits = ceil_div(8 * sms, base_tiles);
+    if (max_splits > total_kblocks) max_splits = total_kblocks;
+    if (max_splits < 1) max_splits = 1;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= max_splits; ++s) {
+        const int rounds = ceil_div(base_tiles * s, sms);
+        const double cost = rounds * (ceil_div(total_kblocks, s) * t_kb + 0.3) + s * t_red;
+        if (cost < best_cost * 0.999) {
+            best_cost = cost;
+            best = s;
+        }
+    }
+    return best;
 }
 
 // dispatch of the wgrad GEMM; p holds the maps, the k-block tiling, Cout/Cin (GEMM N extent), R, S and the workspace
@@ -1100,6 +1182,18 @@ extern "C" int denet_conv_weight_prep_multi(const void* entries, const int* bloc
     DN_REQUIRE(entries && block_entry && block_offset, "weight_prep_multi: null pointer");
     if (nblocks == 0) return 0;
     weight_prep_multi_kernel<<<DN_G(nblocks), 256, 0, stream>>>((const PrepEntry*)entries, block_entry, block_offset);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_wgrad_reduce_entry_bytes(void) { return (int)sizeof(ReduceEntry); }
+extern "C" int denet_wgrad_reduce_chunk(void) { return kReduceChunk; }
+
+extern "C" int denet_wgrad_reduce_multi(const void* entries, const int* block_entry, const long long* block_offset,
+                                        int nblocks, cudaStream_t stream) {
+    DN_REQUIRE(entries && block_entry && block_offset, "wgrad_reduce_multi: null pointer");
+    if (nblocks == 0) return 0;
+    wgrad_reduce_multi_kernel<<<DN_G(nblocks), 256, 0, stream>>>((const ReduceEntry*)entries, block_entry, block_offset);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -1180,7 +1274,13 @@ static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cout, int Cin, int R, int
     pl.co_tiles = ceil_div(Cout, 128);
     pl.ci_tiles = ceil_div(Cin, pl.BN);
     pl.base_tiles = pl.co_tiles * pl.ci_tiles * R * (pl.rows_path ? 1 : S);
-    pl.splits = wgrad_splits(pl.total_kb, pl.base_tiles);
+    {
+        const int a_boxes = Cout <= 64 ? 1 : 2;
+        const int stage_bytes = pl.rows_path ? a_boxes * 8192 + (pl.BN / 64) * pl.xrows * 128
+                                             : a_boxes * 8192 + pl.BN * 128;
+        pl.splits = wgrad_splits(pl.total_kb, pl.base_tiles, pl.rows_path ? S * pl.BN : pl.BN, stage_bytes,
+                                 (long long)Cout * Cin * R * S);
+    }
     return pl;
 }
 
@@ -1191,7 +1291,8 @@ static int g_wgrad_rows = 1;         // 0: always one tap per tile (A/B switch f
 static int g_wgrad_debug = 0;
 extern "C" int denet_conv2d_wgrad_set_mode(int row_shared) {
     g_wgrad_rows = row_shared & 1;
-    g_wgrad_debug = row_shared >> 1;      // undocumented profiling knobs (bit1: no MMA, bit2: no TMA)
+    g_wgrad_debug = (row_shared >> 1) & 7;      // undocumented profiling knobs (bit1: no MMA, bit2: no TMA)
+    g_wgrad_legacy_splits = (row_shared >> 4) & 1;   // bit4: the former split-K rule (A/B measurements)
     return 0;
 }
 
@@ -1204,11 +1305,16 @@ extern "C" size_t denet_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cout, 
     return (size_t)splits * Cout * R * S * ldws * sizeof(float);
 }
 
+extern "C" int denet_conv2d_wgrad_splits(int N, int Ho, int Wo, int Cout, int Cin, int R, int S, int stride_h,
+                                         int stride_w) {
+    return plan_wgrad(N, Ho, Wo, Cout, Cin, R, S, stride_h, stride_w, g_wgrad_rows).splits;
+}
+
 extern "C" int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int Wo, int Cout, long long lddy,
                                   const void* x_hi, const void* x_lo, int Hi, int Wi, int Cin, long long ldx, int R,
                                   int S, int pad_h, int pad_w, int stride_h, int stride_w, float* dw, int accumulate,
                                   float* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    DN_REQUIRE(dy_hi && x_hi && dw && workspace, "conv2d_wgrad: null pointer");
+    DN_REQUIRE(dy_hi && x_hi && workspace, "conv2d_wgrad: null pointer");
     DN_REQUIRE((dy_lo == nullptr) == (x_lo == nullptr), "conv2d_wgrad: dy_lo and x_lo must both be given or both null");
     DN_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0, "conv2d_wgrad: pixel pitches must be multiples of 8 elements");
     DN_REQUIRE(stride_h >= 1 && stride_h <= 8 && stride_w >= 1 && stride_w <= 8, "conv2d_wgrad: stride must be in [1,8]");
@@ -1263,6 +1369,7 @@ extern "C" int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, i
         rc = wgrad_launch(p, stream);
     }
     if (rc) return rc;
+    if (!dw) return 0;      // partial sums only: the caller reduces them later (denet_wgrad_reduce_multi)
     const long long total = (long long)Cout * Cin * R * S;
     const int block = 256;
     const int grid = (int)std::min<long long>(ceil_div_ll(total, block), 148LL * 16);
@@ -1431,15 +1538,24 @@ extern "C" size_t denet_conv2d_rowfold_wgrad_workspace(int N, int Ho, int Wo, in
     int TW, TH, TN;
     pick_patch(Wo, Ho, N, 64, TW, TH, TN);
     const int total_kb = ceil_div(Wo, TW) * ceil_div(Ho, TH) * ceil_div(N, TN);
-    const int splits = wgrad_splits(total_kb, ceil_div(Cout, 128) * R);
+    const int splits = wgrad_splits(total_kb, ceil_div(Cout, 128) * R, 64, (Cout <= 64 ? 1 : 2) * 8192 + 8192,
+                                    (long long)Cout * R * 64);
     return (size_t)splits * Cout * R * 64 * sizeof(float);
+}
+
+extern "C" int denet_conv2d_rowfold_wgrad_splits(int N, int Ho, int Wo, int Cout, int R) {
+    int TW, TH, TN;
+    pick_patch(Wo, Ho, N, 64, TW, TH, TN);
+    const int total_kb = ceil_div(Wo, TW) * ceil_div(Ho, TH) * ceil_div(N, TN);
+    return wgrad_splits(total_kb, ceil_div(Cout, 128) * R, 64, (Cout <= 64 ? 1 : 2) * 8192 + 8192,
+                        (long long)Cout * R * 64);
 }
 
 extern "C" int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int Wo, int Cout,
                                           long long lddy, const void* x_hi, const void* x_lo, int Hp, int Wp, int Cp,
                                           int Cin, int R, int S, int stride_h, int stride_w, float* dw, int accumulate,
                                           float* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    DN_REQUIRE(dy_hi && x_hi && dw && workspace, "conv2d_rowfold_wgrad: null pointer");
+    DN_REQUIRE(dy_hi && x_hi && workspace, "conv2d_rowfold_wgrad: null pointer");
     DN_REQUIRE((dy_lo == nullptr) == (x_lo == nullptr), "conv2d_rowfold_wgrad: dy_lo and x_lo must come together");
     DN_REQUIRE(lddy % 8 == 0, "conv2d_rowfold_wgrad: dy pitch must be a multiple of 8 elements");
     int rc;
@@ -1456,7 +1572,8 @@ extern "C" int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, 
     p.total_kblocks = p.tiles_w * p.tiles_h * p.tiles_n;
     p.co_tiles = ceil_div(Cout, 128);
     p.ci_tiles = 1;
-    p.splits = wgrad_splits(p.total_kblocks, p.co_tiles * R);
+    p.splits = wgrad_splits(p.total_kblocks, p.co_tiles * R, 64, (Cout <= 64 ? 1 : 2) * 8192 + 8192,
+                            (long long)Cout * R * 64);
     p.num_tiles = p.co_tiles * R * p.splits;
     p.fd_cot = make_fastdiv(p.co_tiles);
     p.fd_cit = make_fastdiv(1);
@@ -1475,6 +1592,7 @@ extern "C" int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, 
     if (x_lo && (rc = make_rowfold_map(&p.tmX[1], x_lo, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, p.TH, p.TN)))
         return rc;
     if ((rc = wgrad_launch(p, stream))) return rc;
+    if (!dw) return 0;      // partial sums only (see denet_wgrad_reduce_multi)
     const long long total = (long long)Cout * Cin * R * S;
     const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 16);
     wgrad_reduce_rowfold_kernel<<<DN_G(grid), 256, 0, stream>>>(workspace, dw, p.splits, Cout, Cin, R, S, Cp, p.ldws,

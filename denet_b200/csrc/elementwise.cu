@@ -518,58 +518,84 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int N, int H, int W,
     }
 }
 
-// gather form (deterministic): every input pixel sums dy of the windows whose recorded argmax points at it
+// gather form (deterministic): every input pixel sums dy of the windows whose recorded argmax points at it.
+// The windows covering input row h are ho in [ceil((h+ph-kh+1)/sh), floor((h+ph)/sh)] (at most ceil(kh/sh) of them,
+// 2 x 2 for the 3x3 stride-2 stem pool); they are enumerated directly - no scan over the kh*kw taps - and the tap
+// bytes and dy packs of all of them are requested before the first use, so that the loads overlap.
 template <typename T, int VEC>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ argmax, int N, int H, int W,
                                    int C, long long ldx, int kh, int kw, int sh, int sw, int ph, int pw, int Ho, int Wo,
                                    long long ldy, T* __restrict__ dx) {
     const int CV = C / VEC;
     const long long total = (long long)N * H * W * CV;
+    const bool small = total < 0x7fffffffLL;
+    const bool quad = (kh + sh - 1) / sh <= 2 && (kw + sw - 1) / sw <= 2;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int cv = (int)(idx % CV);
-        long long t = idx / CV;
-        const int w = (int)(t % W);
-        t /= W;
-        const int h = (int)(t % H);
-        const int n = (int)(t / H);
+        int cv, w, h, n;
+        if (small) {
+            unsigned u = (unsigned)idx;
+            cv = (int)(u % (unsigned)CV); u /= (unsigned)CV;
+            w = (int)(u % (unsigned)W); u /= (unsigned)W;
+            h = (int)(u % (unsigned)H);
+            n = (int)(u / (unsigned)H);
+        } else {
+            cv = (int)(idx % CV);
+            long long t = idx / CV;
+            w = (int)(t % W);
+            t /= W;
+            h = (int)(t % H);
+            n = (int)(t / H);
+        }
         float acc[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-        // windows (ho, wo) with ho*sh - ph + r == h, 0 <= r < kh
-        for (int r = 0; r < kh; ++r) {
-            const int hn = h + ph - r;
-            if (hn < 0 || hn % sh != 0) continue;
-            const int ho = hn / sh;
-            if (ho >= Ho) continue;
-            for (int s = 0; s < kw; ++s) {
-                const int wn = w + pw - s;
-                if (wn < 0 || wn % sw != 0) continue;
-                const int wo = wn / sw;
-                if (wo >= Wo) continue;
-                const long long opix = ((long long)n * Ho + ho) * Wo + wo;
-                const int tap = r * kw + s;
-                if (VEC == 8) {
-                    // the 8 tap bytes of this pack in one 8-byte load; dy is only fetched when some channel matches
-                    const uint2 am = *reinterpret_cast<const uint2*>(argmax + opix * C + cv * 8);
-                    const uint32_t w2[2] = {am.x, am.y};
-                    bool any = false;
+        const int hp = h + ph, wp = w + pw;
+        int ho_hi = hp / sh, wo_hi = wp / sw;
+        if (ho_hi > Ho - 1) ho_hi = Ho - 1;
+        if (wo_hi > Wo - 1) wo_hi = Wo - 1;
+        const int hlo = hp - kh + 1, wlo = wp - kw + 1;
+        const int ho_lo = hlo <= 0 ? 0 : (hlo + sh - 1) / sh;
+        const int wo_lo = wlo <= 0 ? 0 : (wlo + sw - 1) / sw;
+        if (VEC == 8 && quad) {
+            uint2 am[4];
+            Pack<T, VEC> g[4];
+            int tap[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) any |= (((w2[i >> 2] >> (8 * (i & 3))) & 0xffu) == (uint32_t)tap);
-                    if (!any) continue;
-                    Pack<T, VEC> g;
-                    g.load(dy + opix * ldy + (long long)cv * VEC);
+            for (int a = 0; a < 2; ++a)
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i)
-                        if (((w2[(i & 7) >> 2] >> (8 * (i & 3))) & 0xffu) == (uint32_t)tap) acc[i] += g.v[i];
-                } else {
+                for (int b = 0; b < 2; ++b) {
+                    const int ho = ho_hi - a, wo = wo_hi - b;
+                    const bool ok = ho >= ho_lo && wo >= wo_lo;
+                    const long long opix = ((long long)n * Ho + (ok ? ho : ho_hi)) * Wo + (ok ? wo : wo_hi);
+                    tap[2 * a + b] = ok ? (hp - ho * sh) * kw + (wp - wo * sw) : 0x100;
+                    if (ok) {
+                        am[2 * a + b] = *reinterpret_cast<const uint2*>(argmax + opix * C + cv * 8);
+                        g[2 * a + b].load(dy + opix * ldy + (long long)cv * VEC);
+                    } else {
+                        am[2 * a + b] = make_uint2(0xffffffffu, 0xffffffffu);
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) g[2 * a + b].v[i] = 0.f;
+                    }
+                }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t w2[2] = {am[q].x, am[q].y};
+#pragma unroll
+                for (int i = 0; i < VEC; ++i)
+                    if (((w2[(i & 7) >> 2] >> (8 * (i & 3))) & 0xffu) == (uint32_t)tap[q]) acc[i] += g[q].v[i];
+            }
+        } else {
+            for (int ho = ho_hi; ho >= ho_lo; --ho)
+                for (int wo = wo_hi; wo >= wo_lo; --wo) {
+                    const long long opix = ((long long)n * Ho + ho) * Wo + wo;
+                    const int tap = (hp - ho * sh) * kw + (wp - wo * sw);
                     Pack<T, VEC> g;
                     g.load(dy + opix * ldy + (long long)cv * VEC);
 #pragma unroll
                     for (int i = 0; i < VEC; ++i)
                         if (argmax[opix * C + cv * VEC + i] == tap) acc[i] += g.v[i];
                 }
-            }
         }
         Pack<T, VEC> o;
 #pragma unroll

@@ -19,7 +19,7 @@ from torch import nn
 # global switches (the reference keeps train flag / epoch / iteration as module-level Theano symbols,
 # denet/layer/__init__.py:5-28)
 _state = {"train": False, "epoch": 0, "iteration": 0, "precision": "bf16", "device": "cuda", "param_version": 0,
-          "fuse_bn_stats": True, "device_targets": True, "gt": None}
+          "fuse_bn_stats": True, "device_targets": True, "gt": None, "wgrad_pending": None}
 
 
 def get_train():
@@ -28,6 +28,16 @@ def get_train():
 
 def set_train(v):
     _state["train"] = bool(v)
+
+
+def wgrad_pending():
+    """list collecting the filter gradients whose split-K reduction is deferred to one multi-tensor launch
+    (ModelCNN.backward owns it), or None: every conv layer reduces its own gradient right away"""
+    return _state["wgrad_pending"]
+
+
+def set_wgrad_pending(v):
+    _state["wgrad_pending"] = v
 
 
 def device_targets():

@@ -11,7 +11,8 @@ import numpy
 import torch
 
 from .. import lib, ops
-from . import (AbstractLayer, act_dtype, get_param, get_precision, new_param, param_version, set_param)
+from . import (AbstractLayer, act_dtype, get_param, get_precision, new_param, param_version, set_param,
+               wgrad_pending)
 
 
 def conv_output_hw(in_hw, size, stride, border_mode):
@@ -249,8 +250,10 @@ class ConvLayer(AbstractLayer):
             ops.colsum(dy, self.beta.grad)
         gdt = act_dtype()
         dx = None
+        pending = wgrad_pending()
+        defer = (pending, self) if pending is not None else None
         if self.rowfold is not None:
-            ops.conv2d_rowfold_wgrad(dyop, self._xop, R, S, self.stride, self.omega.grad)
+            ops.conv2d_rowfold_wgrad(dyop, self._xop, R, S, self.stride, self.omega.grad, defer=defer)
         elif self.use_im2col:
             dw2 = ops.conv2d_wgrad(dyop, self._xop, 1, 1, (0, 0))
             ops.weight_grad_from_im2col(dw2, self.omega.grad)
@@ -260,7 +263,7 @@ class ConvLayer(AbstractLayer):
                 if add_to is not None:
                     dx = ops.add(dx, add_to, out=dx)
         else:
-            ops.conv2d_wgrad(dyop, self._xop, R, S, self.pad, self.stride, dw=self.omega.grad)
+            ops.conv2d_wgrad(dyop, self._xop, R, S, self.pad, self.stride, dw=self.omega.grad, defer=defer)
             if not self.is_first:
                 if self.stride == (1, 1):
                     dx = ops.conv2d_fprop(dyop, wop_d, (R - 1 - self.pad[0], S - 1 - self.pad[1]), (h, w), gdt,

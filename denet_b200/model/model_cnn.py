@@ -112,6 +112,7 @@ class ModelCNN:
         self.input = None
         self.device = None
         self.ddp = None             # denet_b200.multi.GradientAllReduce when running data parallel
+        self.defer_wgrad_reduce = True   # one multi-tensor split-K reduction launch instead of one per conv layer
         self._ready = False
         self.last_costs_device = None
         self._image = None          # padded input buffer of a row-folded stem conv
@@ -467,12 +468,24 @@ class ModelCNN:
         return x
 
     def backward(self):
+        """reverse pass over the layer list.  The split-K reductions of the filter gradients are deferred and run as
+        ONE multi-tensor launch: at the end of the pass, or - with data parallelism - whenever a top-level layer
+        retires, right before its gradients may enter an all-reduce bucket."""
         dy = None
         hook = self.ddp.layer_done if self.ddp is not None else None
-        for index in range(len(self.layers) - 1, 0, -1):
-            dy = self.layers[index].backward(dy)
-            if hook is not None:
-                hook(index)
+        pending = [] if self.defer_wgrad_reduce else None
+        layer_mod.set_wgrad_pending(pending)
+        try:
+            for index in range(len(self.layers) - 1, 0, -1):
+                dy = self.layers[index].backward(dy)
+                if hook is not None:
+                    if pending and self.ddp.will_launch(index):
+                        ops.wgrad_reduce_pending(pending)
+                    hook(index)
+            if pending:
+                ops.wgrad_reduce_pending(pending)
+        finally:
+            layer_mod.set_wgrad_pending(None)
         return dy
 
     def solver_step(self, learning_rate, momentum, decay, iteration, grad_scale=1.0, hp_dev=None):

@@ -83,6 +83,11 @@ class GradientAllReduce:
         else:
             self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def will_launch(self, layer_index):
+        """True when layer_done(layer_index) is going to start the all-reduce of at least one bucket (the caller must
+        have finished every pending gradient write of the layers >= layer_index before that)"""
+        return self.world > 1 and self._next < len(self.buckets) and self.buckets[self._next][0] >= layer_index
+
     def layer_done(self, layer_index):
         """called by the backward pass after layer `layer_index` has written its gradients"""
         if self.world <= 1:

@@ -4,6 +4,7 @@ torch is used for device memory and streams only; every op here is one or more c
 on the current CUDA stream.  Activations are NHWC tensors (N, H, W, C) whose last-dim pitch may be padded to a
 multiple of 8 elements (TMA needs 16-byte strides).  Nothing here falls back to torch arithmetic.
 """
+import numpy
 import torch
 
 from . import lib
@@ -172,8 +173,31 @@ def conv2d_fprop(xop, wop, pad, out_hw, out_dtype, stride=(1, 1), bias=None, res
     return out
 
 
-def conv2d_wgrad(dyop, xop, R, S, pad, stride=(1, 1), dw=None, accumulate=False):
-    """Filter gradient in the reference layout (Cout, Cin, R, S). dy: (N,Ho,Wo,Cout), x: (N,Hi,Wi,Cin)."""
+class WgradPending:
+    """split-K partial sums of one filter gradient waiting for the multi-tensor reduction (denet_wgrad_reduce_multi)"""
+
+    def __init__(self, ws, dw, splits, cout, cin, R, S, ldws, mode=0, cp=0, accumulate=False):
+        self.ws, self.dw, self.splits, self.cout, self.cin, self.R, self.S = ws, dw, splits, cout, cin, R, S
+        self.ldws, self.mode, self.cp, self.accumulate = ldws, mode, cp, accumulate
+
+    def key(self):
+        return (self.ws.data_ptr(), self.dw.data_ptr(), self.splits, self.cout, self.cin, self.R, self.S, self.ldws,
+                self.mode, self.cp, int(self.accumulate))
+
+
+def _own_workspace(owner, nbytes, device):
+    """per-layer persistent workspace (deferred reductions must not share one scratch buffer)"""
+    ws = getattr(owner, "_wgrad_ws", None)
+    if ws is None or ws.numel() * 4 < nbytes or ws.device != device:
+        ws = torch.empty((max(1024, (nbytes + 3) // 4),), dtype=torch.float32, device=device)
+        owner._wgrad_ws = ws
+    return ws
+
+
+def conv2d_wgrad(dyop, xop, R, S, pad, stride=(1, 1), dw=None, accumulate=False, defer=None):
+    """Filter gradient in the reference layout (Cout, Cin, R, S). dy: (N,Ho,Wo,Cout), x: (N,Hi,Wi,Cin).
+    defer = (pending list, owner): leave the split-K partials in the owner's private workspace and append a
+    WgradPending record instead of reducing now (ModelCNN reduces all layers in one launch)."""
     dy, x = dyop.hi, xop.hi
     n, ho, wo, cout = dy.shape
     n2, hi_, wi_, cin = x.shape
@@ -186,12 +210,63 @@ def conv2d_wgrad(dyop, xop, R, S, pad, stride=(1, 1), dw=None, accumulate=False)
         n_, ho_, wo_, hi2, wi2 = 1, 1, n * ho * wo, 1, n * ho * wo
     else:
         n_, ho_, wo_, hi2, wi2 = n, ho, wo, hi_, wi_
-    nbytes = lib.load().denet_conv2d_wgrad_workspace(n_, ho_, wo_, cout, cin, R, S)
-    ws = workspace(nbytes, x.device, "wgrad")
+    L = lib.load()
+    nbytes = L.denet_conv2d_wgrad_workspace(n_, ho_, wo_, cout, cin, R, S)
+    if defer is not None:
+        pending, owner = defer
+        ws = _own_workspace(owner, nbytes, x.device)
+        splits = L.denet_conv2d_wgrad_splits(n_, ho_, wo_, cout, cin, R, S, stride[0], stride[1])
+        pending.append(WgradPending(ws, dw, splits, cout, cin, R, S, (cin + 3) // 4 * 4, 0, 0, accumulate))
+        dw_ptr = None
+    else:
+        ws = workspace(nbytes, x.device, "wgrad")
+        dw_ptr = dw.data_ptr()
+    if defer is not None and accumulate and len(defer[0]) > 1:
+        wgrad_reduce_pending(defer[0][:-1])      # a launch must not hold two writers of one gradient tensor
+        del defer[0][:-1]
     call("denet_conv2d_wgrad", dy.data_ptr(), _ptr(dyop.lo), n_, ho_, wo_, cout, _pitch(dy),
          x.data_ptr(), _ptr(xop.lo), hi2, wi2, cin, _pitch(x), R, S, pad[0], pad[1], stride[0], stride[1],
-         dw.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel() * 4, _stream())
+         dw_ptr, int(accumulate), ws.data_ptr(), ws.numel() * 4, _stream())
+    if defer is not None and accumulate:
+        wgrad_reduce_pending(defer[0])
     return dw
+
+
+_reduce_tables = {}
+
+
+def wgrad_reduce_pending(pending):
+    """one launch reducing every WgradPending record of the list (fixed summation order, reference filter layout);
+    the device table of a given list of records is built once and reused (the step structure is static)"""
+    if not pending:
+        return
+    key = tuple(e.key() for e in pending)
+    tab = _reduce_tables.get(key)
+    if tab is None:
+        L = lib.load()
+        assert L.denet_wgrad_reduce_entry_bytes() == 64
+        chunk = L.denet_wgrad_reduce_chunk()
+        dev = pending[0].ws.device
+        table = numpy.zeros((len(pending), 8), dtype=numpy.int64)
+        ints = table.view(numpy.int32).reshape(len(pending), 16)
+        block_entry, block_offset = [], []
+        for i, e in enumerate(pending):
+            total = e.cout * e.cin * e.R * e.S
+            table[i, 0] = e.ws.data_ptr()
+            table[i, 1] = e.dw.data_ptr()
+            table[i, 2] = total
+            ints[i, 6:16] = [e.splits, e.cout, e.cin, e.R, e.S, e.ldws, e.mode, e.cp, int(e.accumulate), 0]
+            for o in range(0, total, chunk):
+                block_entry.append(i)
+                block_offset.append(o)
+        tab = (torch.from_numpy(table).to(dev), torch.tensor(block_entry, dtype=torch.int32, device=dev),
+               torch.tensor(block_offset, dtype=torch.int64, device=dev), len(block_entry))
+        if len(_reduce_tables) > 256:
+            _reduce_tables.clear()
+        _reduce_tables[key] = tab
+    entries, be, bo, nblocks = tab
+    call("denet_wgrad_reduce_multi", entries.data_ptr(), be.data_ptr(), bo.data_ptr(), nblocks, _stream())
+    del pending[:]
 
 
 # ---------------------------------------------------------------------------------------------- row-folded stem conv
@@ -250,14 +325,23 @@ def conv2d_rowfold_fprop(img, wop, stride, out_hw, out_dtype, bias=None, relu=Fa
     return out
 
 
-def conv2d_rowfold_wgrad(dyop, img, R, S, stride, dw, accumulate=False):
+def conv2d_rowfold_wgrad(dyop, img, R, S, stride, dw, accumulate=False, defer=None):
     dy = dyop.hi
     n, ho, wo, cout = dy.shape
     assert (dyop.lo is None) == (img.lo is None)
-    nbytes = lib.load().denet_conv2d_rowfold_wgrad_workspace(n, ho, wo, cout, R)
-    ws = workspace(nbytes, dy.device, "wgrad")
+    L = lib.load()
+    nbytes = L.denet_conv2d_rowfold_wgrad_workspace(n, ho, wo, cout, R)
+    if defer is not None:
+        pending, owner = defer
+        ws = _own_workspace(owner, nbytes, dy.device)
+        splits = L.denet_conv2d_rowfold_wgrad_splits(n, ho, wo, cout, R)
+        pending.append(WgradPending(ws, dw, splits, cout, img.c, R, S, 64, 1, img.cp, accumulate))
+        dw_ptr = None
+    else:
+        ws = workspace(nbytes, dy.device, "wgrad")
+        dw_ptr = dw.data_ptr()
     call("denet_conv2d_rowfold_wgrad", dy.data_ptr(), _ptr(dyop.lo), n, ho, wo, cout, _pitch(dy), img.hi.data_ptr(),
-         _ptr(img.lo), img.hp, img.wp, img.cp, img.c, R, S, stride[0], stride[1], dw.data_ptr(), int(accumulate),
+         _ptr(img.lo), img.hp, img.wp, img.cp, img.c, R, S, stride[0], stride[1], dw_ptr, int(accumulate),
          ws.data_ptr(), ws.numel() * 4, _stream())
     return dw
 

@@ -86,6 +86,20 @@ int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int 
                        int pad_h, int pad_w, int stride_h, int stride_w, float* dw, int accumulate, float* workspace,
                        size_t workspace_bytes, cudaStream_t stream);
 
+/* Deferred reduction: conv2d_wgrad / conv2d_rowfold_wgrad called with dw = NULL leave their split-K partial sums in
+ * `workspace` ([splits][Cout][R*S][pad4(Cin)] fp32, resp. [splits][Cout][R][64] for the row-folded stem; the split
+ * count comes from denet_conv2d_wgrad_splits / denet_conv2d_rowfold_wgrad_splits) and denet_wgrad_reduce_multi
+ * reduces the partials of MANY layers in one launch, in the same fixed order and into the same reference layout.
+ * `entries` is a device array of denet_wgrad_reduce_entry_bytes()-sized records {const float* ws; float* dw;
+ * long long total (= Cout*Cin*R*S); int splits, Cout, Cin, R, S, ldws, mode (0 generic, 1 row-folded), Cp,
+ * accumulate, pad}; block i reduces elements [block_offset[i], +denet_wgrad_reduce_chunk()) of entry block_entry[i]. */
+int denet_conv2d_wgrad_splits(int N, int Ho, int Wo, int Cout, int Cin, int R, int S, int stride_h, int stride_w);
+int denet_conv2d_rowfold_wgrad_splits(int N, int Ho, int Wo, int Cout, int R);
+int denet_wgrad_reduce_entry_bytes(void);
+int denet_wgrad_reduce_chunk(void);
+int denet_wgrad_reduce_multi(const void* entries, const int* block_entry, const long long* block_offset, int nblocks,
+                             cudaStream_t stream);
+
 /* Kernel selection of conv2d_wgrad (profiling / A-B tests): row_shared = 1 (default) lets stride-1 S>1 layers use the
  * row-shared kernel (one halo'd X box serves the S taps of a filter row), 0 forces one tap per tile. */
 int denet_conv2d_wgrad_set_mode(int row_shared);

@@ -75,6 +75,14 @@ def test_conv_fprop_dgrad_wgrad(cuda, case, split):
 
     dw = ops.conv2d_wgrad(dyd, xd, k, k, (pad, pad), (s, s))
     assert relerr(dw, dwref) < tol
+    # deferred split-K reduction (one multi-tensor launch, as ModelCNN.backward runs it): same fixed order -> same bits
+    class Owner:
+        pass
+    pending, dw2 = [], torch.full((cout, cin, k, k), 3.0, device=cuda)
+    ops.conv2d_wgrad(dyd, xd, k, k, (pad, pad), (s, s), dw=dw2, defer=(pending, Owner()))
+    assert len(pending) == 1
+    ops.wgrad_reduce_pending(pending)
+    assert pending == [] and torch.equal(dw2, dw)
 
     wop_d = ops.conv_weight_prep(wdev, 1, split)
     if s == 1:
@@ -134,6 +142,12 @@ def test_conv_rowfold_stem(cuda, case, split):
     dw = torch.full((cout, cin, k, k), 7.0, device=cuda)
     ops.conv2d_rowfold_wgrad(dyd, img, k, k, (s, s), dw)
     assert relerr(dw, dwref) < tol
+    class Owner:
+        pass
+    pending, dw2 = [], torch.full((cout, cin, k, k), 3.0, device=cuda)
+    ops.conv2d_rowfold_wgrad(dyd, img, k, k, (s, s), dw2, defer=(pending, Owner()))
+    ops.wgrad_reduce_pending(pending)
+    assert torch.equal(dw2, dw)
 
 
 def test_conv_epilogue_residual_relu_stats(cuda):

@@ -300,7 +300,7 @@ def test_cuda_graph_step_equals_eager_step(cuda, which):
     # two EAGER runs of this tiny model already differ (fp32 atomics order in the batch-norm statistics and the
     # sparse scatter, amplified step by step): the graphed run must stay within a few times that run-to-run noise
     for (t0, _), (t1, _), (t2, _) in zip(ca, ca2, cb):
-        assert abs(t0 - t2) <= 3 * abs(t0 - t1) + 3e-3 * abs(t0) + 1e-3, (ca, ca2, cb)
+        assert abs(t0 - t2) <= 3 * abs(t0 - t1) + 1e-2 * abs(t0) + 1e-3, (ca, ca2, cb)   # bf16: 1 ulp = 0.4 %
     pa, pa2, pb = named_params(a), named_params(a2), named_params(b)
     for name in pa:
         if pa[name].norm().item() > 1e-2:
