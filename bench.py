@@ -245,7 +245,7 @@ def run_b200(args):
     # ---- conv kernel timing (roofline): eager launches of the same steps, every conv entry point bracketed by CUDA
     # events on its stream (events cannot be recorded inside a replayed graph)
     timed_names = ["denet_conv2d_fprop", "denet_conv2d_wgrad", "denet_conv2d_rowfold_fprop",
-                   "denet_conv2d_rowfold_wgrad"]
+                   "denet_conv2d_rowfold_wgrad", "denet_wgrad_reduce_multi"]
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
@@ -334,6 +334,9 @@ def run_b200(args):
     fam = {"fprop": [0.0, 0.0, 0], "dgrad": [0.0, 0.0, 0], "wgrad": [0.0, 0.0, 0]}     # ms, flops, launches
     for name, evs in timings.items():
         for ms, tag in evs:
+            if name == "denet_wgrad_reduce_multi":
+                fam["wgrad"][0] += ms          # the deferred split-K reduction of all filter gradients: time, no FLOPs
+                continue
             if tag is None:
                 continue
             kind, layer = tag
@@ -348,7 +351,7 @@ def run_b200(args):
     conv_fl = sum(v[1] for v in fam.values())
     n_conv_launch = sum(v[2] for v in fam.values())
     achieved = conv_fl / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_fprop_kernel / conv_wgrad_kernel (tcgen05 implicit GEMM, bf16)",
+    roofline = {"bound": "tensor", "kernel": "conv_fprop_halo_kernel / conv_fprop_kernel / conv_wgrad_kernel (+ split-K reduction) (tcgen05 implicit GEMM, bf16)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src,
                 "flops_per_launch": conv_fl / max(n_conv_launch, 1), "ms_per_launch": conv_ms / max(n_conv_launch, 1),

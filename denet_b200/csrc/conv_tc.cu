@@ -76,6 +76,23 @@ struct ConvFpropParams {
     const void* residual;    // same layout/dtype as y, or null
     float* stat_sum;         // optional per-channel sum / sum of squares accumulators (fp32 atomics), or null
     float* stat_sqsum;
+    // ---- tap-group variant (conv_fprop_halo_kernel): ONE halo'd A box per 64-channel chunk serves all R*S taps
+    int a_loads;             // TMA loads per A stage: 1, or 2 = even / odd input rows of a stride-2 row-folded stem
+    int a_dw, a_dh;          // start of load 0 relative to the patch origin (w0*stride_w, h0*stride_h), in map coords
+    int a_dh_step;           // start row of load i = a_dh + i * a_dh_step
+    uint32_t a_load_bytes;   // bytes one load delivers (the whole box, out-of-image rows are zero filled)
+    uint32_t a_load_stride;  // shared-memory distance between the loads of a stage (1024-byte multiple)
+    uint32_t a_stage_bytes;  // a_loads * a_load_stride
+    uint32_t a_sbo;          // descriptor stride between 8-pixel groups of the M tile (bytes)
+    uint32_t tap_off16[64];  // A descriptor start of tap t relative to the stage start, in 16-byte units
+    int kmmas;               // K=16 MMAs per 64-wide K block (4, fewer when the tail of the block is structurally zero)
+    int a_stages, b_stages;  // ring depths (run-time: the A stage size depends on the patch)
+    int b_resident;          // all B tiles stay in shared memory for the life of the CTA (small filters, Cout <= BN)
+    uint32_t a_region_bytes; // a_stages * a_stage_bytes
+    uint32_t b_region_bytes; // B ring, or the resident filter bank
+    int debug;               // profiling knobs (results are garbage): bit0 epilogue = TMEM read only, bit1 no statistics,
+                             // bit2 no MMAs, bit3 no A / B loads
+    long long* timeline;     // profiling: CTA 0 records clock64() stamps [role][tile][4] (roles: producer, MMA, epilogue)
 };
 
 struct ConvWgradParams {
@@ -199,6 +216,135 @@ __device__ __forceinline__ void butterfly_colsum(float (&v)[32], int lane) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ fprop epilogue
+// warps 2..5 -> TMEM lane quarter warp%4: TMEM -> registers -> bias / batch-norm statistics / residual / ReLU -> global.
+// Shared by conv_fprop_kernel and conv_fprop_halo_kernel (same tile decoding, same accumulator double buffering).
+template <int BN>
+__device__ __forceinline__ void fprop_epilogue(const ConvFpropParams& p, float2* stat_smem, uint32_t tmem_base,
+                                               uint64_t* tfull_bar, uint64_t* tempty_bar, int warp, int lane) {
+    // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarter warp%4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    // running per-channel sums of this warp (warp-private shared memory: entry [c][0] = sum, [c][1] = sum of squares)
+    float2* sacc = stat_smem + q * BN;
+    if (p.stat_sum)
+        for (int c = lane; c < BN; c += 32) sacc[c] = make_float2(0.f, 0.f);
+    int acc_ct = -1;
+    auto flush_stats = [&]() {
+        if (p.stat_sum && acc_ct >= 0) {
+            for (int i = lane; i < BN; i += 32) {
+                const int c = acc_ct * BN + i;
+                const float2 a = sacc[i];
+                if (c < p.Cout) {
+                    atomicAdd(p.stat_sum + c, a.x);
+                    atomicAdd(p.stat_sqsum + c, a.y);
+                }
+                sacc[i] = make_float2(0.f, 0.f);
+            }
+        }
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        uint32_t uct, mt, tw, th, tn;
+        p.fd_co.divmod(tile, mt, uct);
+        const int ct = static_cast<int>(uct);
+        if (ct != acc_ct) {
+            flush_stats();
+            acc_ct = ct;
+        }
+        p.fd_w.divmod(mt, mt, tw);
+        p.fd_h.divmod(mt, tn, th);
+        uint32_t rq, rw, rn, rh;
+        p.fd_tw.divmod(row, rq, rw);
+        p.fd_th.divmod(rq, rn, rh);
+        const int w = tw * p.TW + rw;
+        const int h = th * p.TH + rh;
+        const int n = tn * p.TN + rn;
+        const bool row_ok = (w < p.Wo) && (h < p.Ho) && (n < p.No);
+        const long long pix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;
+        const int co0 = ct * BN;
+
+        const bool stamp = p.timeline && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 64;
+        if (stamp) p.timeline[(2 * 64 + it) * 4 + 0] = clock64();
+        ptx::mbar_wait(&tfull_bar[as], aphase);
+        ptx::tc_fence_after();
+        if (stamp) p.timeline[(2 * 64 + it) * 4 + 1] = clock64();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0;
+            ptx::tmem_ld_32x32b_x32(taddr, r);
+            ptx::tmem_ld_wait();
+            const int co = co0 + c0;
+            int nvalid = p.Cout - co;
+            nvalid = nvalid > 32 ? 32 : nvalid;
+            if (nvalid > 0 && !(p.debug & 1)) {
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                if (p.bias) {
+                    // 8 independent 16-byte loads (32 dependent scalar loads cost ~1600 cycles per chunk)
+                    const float* bp = p.bias + co;
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+                        float4 b4[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bp) + i);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            v[4 * i] += b4[i].x; v[4 * i + 1] += b4[i].y; v[4 * i + 2] += b4[i].z; v[4 * i + 3] += b4[i].w;
+                        }
+                    } else {
+                        float bb[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) bb[i] = (i < nvalid) ? __ldg(bp + i) : 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += bb[i];
+                    }
+                }
+                if (p.stat_sum && !(p.debug & 2)) {
+                    // per-channel batch statistics of the (pre-activation) conv output.  Lane = pixel row, v[] = 32
+                    // channels: a halving butterfly (16+8+4+2+1 exchanges per quantity instead of 32 x 5) leaves
+                    // lane l with the 32-row sum of channel co + l; it is accumulated in registers across the
+                    // tiles of this CTA and flushed with one atomic per lane when the channel tile changes.
+                    float s[32], sq[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        s[i] = row_ok ? v[i] : 0.f;
+                        sq[i] = s[i] * s[i];
+                    }
+                    butterfly_colsum(s, lane);
+                    butterfly_colsum(sq, lane);
+                    float2 a = sacc[c0 + lane];
+                    a.x += s[0];
+                    a.y += sq[0];
+                    sacc[c0 + lane] = a;
+                }
+                if (row_ok) {
+                    const long long off = pix * p.ldy + co;
+                    if (p.residual) {
+                        float rres[32];
+                        load_row_chunk(p.residual, p.y_fp32, off, rres, nvalid);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += rres[i];
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    store_row_chunk(p.y, p.y_fp32, off, v, nvalid);
+                }
+            }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+        if (stamp) p.timeline[(2 * 64 + it) * 4 + 2] = clock64();
+    }
+    flush_stats();
+}
+
 // ------------------------------------------------------------------------------------------------ fprop / dgrad
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_constant__ ConvFpropParams p) {
@@ -237,6 +383,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
 
     const int ntaps = p.R * p.S;
     const int num_kb = p.nterms * ntaps * p.kchunks;
+    // loop-invariant parameters in registers: the single-instruction-stream roles must not re-read them per k-block
+    const int R = p.R, S = p.S, kchunks = p.kchunks, nterms = p.nterms, num_tiles = p.num_tiles, debug = p.debug;
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
@@ -250,28 +398,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             }
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int tile_w = p.TW * p.stride_w, tile_h = p.TH * p.stride_h, pad_w = p.pad_w, pad_h = p.pad_h, TN = p.TN;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 uint32_t ct, mt, tw, th, tn;
                 p.fd_co.divmod(tile, mt, ct);
                 p.fd_w.divmod(mt, mt, tw);
                 p.fd_h.divmod(mt, tn, th);
                 // input-space origin of the patch: the tensor map walks the image with element strides (stride_w,
                 // stride_h), so a strided convolution is the same box fetch started at (w0*stride + tap offset)
-                const int w0 = tw * p.TW * p.stride_w - p.pad_w, h0 = th * p.TH * p.stride_h - p.pad_h;
-                const int n0 = tn * p.TN, co0 = ct * BN;
-                for (int term = 0; term < p.nterms; ++term) {
+                const int w0 = tw * tile_w - pad_w, h0 = th * tile_h - pad_h;
+                const int n0 = tn * TN, co0 = ct * BN;
+                for (int term = 0; term < nterms; ++term) {
                     const CUtensorMap* mapA = &p.tmA[(term == 1) ? 1 : 0];   // terms: (hi,hi) (lo,hi) (hi,lo)
                     const CUtensorMap* mapB = &p.tmB[(term == 2) ? 1 : 0];
                     int kcol = 0;                                            // K column of the weight operand
-                    for (int r = 0; r < p.R; ++r) {
-                        for (int sx = 0; sx < p.S; ++sx) {
-                            for (int kc = 0; kc < p.kchunks; ++kc, kcol += kBK) {
+                    for (int r = 0; r < R; ++r) {
+                        for (int sx = 0; sx < S; ++sx) {
+                            for (int kc = 0; kc < kchunks; ++kc, kcol += kBK) {
                                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                                 uint8_t* sA = smem + stage * L::kStageBytes;
                                 if (ptx::elect_one()) {
-                                    ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-                                    ptx::tma_load_4d(sA, mapA, &full_bar[stage], kc * kBK, w0 + sx, h0 + r, n0);
-                                    ptx::tma_load_2d(sA + L::kABytes, mapB, &full_bar[stage], kcol, co0);
+                                    if (debug & 8) {
+                                        ptx::mbar_arrive(&full_bar[stage]);
+                                    } else {
+                                        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                                        ptx::tma_load_4d(sA, mapA, &full_bar[stage], kc * kBK, w0 + sx, h0 + r, n0);
+                                        ptx::tma_load_2d(sA + L::kABytes, mapB, &full_bar[stage], kcol, co0);
+                                    }
                                 }
                                 __syncwarp();
                                 if (++stage == STAGES) {
@@ -292,12 +445,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const bool do_mma = !(debug & 4);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
+#pragma unroll 1
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
@@ -305,10 +460,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                     const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (L::kStageBytes >> 4));
                     const uint64_t bdesc = adesc + (L::kABytes >> 4);
                     if (ptx::elect_one()) {
+                        if (do_mma) {
 #pragma unroll
-                        for (int j = 0; j < kBK / 16; ++j) {
-                            // advance 16 bf16 (32 B) along K inside the 128B-swizzled row
-                            ptx::umma_f16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | j) != 0);
+                            for (int j = 0; j < kBK / 16; ++j) {
+                                // advance 16 bf16 (32 B) along K inside the 128B-swizzled row
+                                ptx::umma_f16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | j) != 0);
+                            }
                         }
                         ptx::umma_commit(&empty_bar[stage]);
                     }
@@ -323,109 +480,283 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             }
         }
     } else {
-        // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarter warp%4)
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        int it = 0;
-        // running per-channel sums of this warp (warp-private shared memory: entry [c][0] = sum, [c][1] = sum of squares)
-        float2* sacc = reinterpret_cast<float2*>(smem + L::kStatOffset) + q * BN;
-        if (p.stat_sum)
-            for (int c = lane; c < BN; c += 32) sacc[c] = make_float2(0.f, 0.f);
-        int acc_ct = -1;
-        auto flush_stats = [&]() {
-            if (p.stat_sum && acc_ct >= 0) {
-                for (int i = lane; i < BN; i += 32) {
-                    const int c = acc_ct * BN + i;
-                    const float2 a = sacc[i];
-                    if (c < p.Cout) {
-                        atomicAdd(p.stat_sum + c, a.x);
-                        atomicAdd(p.stat_sqsum + c, a.y);
-                    }
-                    sacc[i] = make_float2(0.f, 0.f);
-                }
+        fprop_epilogue<BN>(p, reinterpret_cast<float2*>(smem + L::kStatOffset), tmem_base, tfull_bar, tempty_bar, warp,
+                           lane);
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fprop, tap groups
+// Stride-1 R x S convolutions (and the row-folded stem) with the A operand fetched ONCE per 64-channel chunk for all
+// taps: the patch of 128 output pixels is loaded with its (R-1, S-1) halo as one TMA box, and tap (r, s) reads the box
+// through a shared-memory descriptor that starts r*(TW+S-1)+s pixel rows (128 B each) into it, with the stride between
+// 8-pixel groups set to one box row (TW = 8, so a group is one image row of the patch).  The 128B-swizzle phase follows
+// the absolute shared-memory address, which is how TMA wrote the box, so unaligned starts read consistent data.
+// conv_fprop_kernel fetches 9 boxes of 16 KB per chunk for a 3x3 filter; this kernel fetches one of 22.5 KB - the
+// L2 -> shared-memory traffic (the bound of the <= 256-channel layers, ~12 TB/s chip-wide) drops by the same factor for
+// A.  Filters that fit (64-channel 3x3 layers: 72 KB, the stem: 56 KB) stay resident in shared memory instead of being
+// streamed per tile.  Row-folded stem with stride 2: two boxes (even / odd input rows), tap r reads box r&1 at row r>>1.
+// NT = number of taps when known at compile time (the tap loop is then fully unrolled with the descriptor offsets in
+// registers), 0 = run-time count.  RESIDENT = the filter bank lives in shared memory for the whole kernel.  KM = K=16
+// MMAs per 64-wide K block when known at compile time (0 = run-time p.kmmas).
+// The producer and MMA roles are single instruction streams whose per-iteration latency bounds the small-N layers (a
+// 128 x 64 x 16 MMA executes in 32 cycles): every loop-invariant parameter is hoisted into registers, and the only
+// work left per tap is the barrier handshake (streaming filters) and the address adds of the K=16 MMAs.
+template <int BN, int NT, bool RESIDENT, int KM>
+__global__ void __launch_bounds__(kThreads, 1) conv_fprop_halo_kernel(const __grid_constant__ ConvFpropParams p) {
+    constexpr int kBBytes = BN * kBK * 2;
+    constexpr uint32_t kB16 = kBBytes >> 4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_b = smem + p.a_region_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + p.b_region_bytes);
+    uint64_t* a_empty = a_full + 8;
+    uint64_t* b_full = a_empty + 8;
+    uint64_t* b_empty = b_full + 16;
+    uint64_t* tfull_bar = b_empty + 16;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* bres_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+    float2* stat_smem = reinterpret_cast<float2*>(smem_b + p.b_region_bytes + 512);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 8; ++s) {
+            ptx::mbar_init(&a_full[s], 1);
+            ptx::mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < 16; ++s) {
+            ptx::mbar_init(&b_full[s], 1);
+            ptx::mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 4);
+        }
+        ptx::mbar_init(bres_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // loop-invariant parameters (kept in registers: the role loops below must not re-read them)
+    const int ntaps = NT > 0 ? NT : p.R * p.S;
+    const int kchunks = p.kchunks, nterms = p.nterms, num_tiles = p.num_tiles;
+    const int a_stages = p.a_stages, b_stages = p.b_stages;
+    const uint32_t a_stage_bytes = p.a_stage_bytes;
+    const int debug = p.debug;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer (warp-uniform loops, elected issue)
+        if (ptx::elect_one()) {
+            ptx::tma_prefetch_desc(&p.tmA[0]);
+            ptx::tma_prefetch_desc(&p.tmB[0]);
+        }
+        if (RESIDENT) {
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(bres_bar, p.b_region_bytes);
+                const int nb = ntaps * kchunks;
+                for (int i = 0; i < nb; ++i)
+                    ptx::tma_load_2d(smem_b + i * kBBytes, &p.tmB[0], bres_bar, i * kBK, 0);
             }
-        };
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            uint32_t uct, mt, tw, th, tn;
-            p.fd_co.divmod(tile, mt, uct);
-            const int ct = static_cast<int>(uct);
-            if (ct != acc_ct) {
-                flush_stats();
-                acc_ct = ct;
-            }
+            __syncwarp();
+        }
+        const int a_loads = p.a_loads, a_dh_step = p.a_dh_step;
+        const uint32_t a_load_stride = p.a_load_stride, a_tx = p.a_loads * p.a_load_bytes;
+        const int tile_w = p.TW * p.stride_w, tile_h = p.TH * p.stride_h, a_dw = p.a_dw, a_dh = p.a_dh, TN = p.TN;
+        const int tap_kstep = kchunks * kBK;
+        int as = 0, bs = 0;
+        uint32_t aphase = 0, bphase = 0;
+        int pit = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++pit) {
+            if (p.timeline && blockIdx.x == 0 && lane == 0 && pit < 64) p.timeline[(0 * 64 + pit) * 4 + 0] = clock64();
+            uint32_t ct, mt, tw, th, tn;
+            p.fd_co.divmod(tile, mt, ct);
             p.fd_w.divmod(mt, mt, tw);
             p.fd_h.divmod(mt, tn, th);
-            uint32_t rq, rw, rn, rh;
-            p.fd_tw.divmod(row, rq, rw);
-            p.fd_th.divmod(rq, rn, rh);
-            const int w = tw * p.TW + rw;
-            const int h = th * p.TH + rh;
-            const int n = tn * p.TN + rn;
-            const bool row_ok = (w < p.Wo) && (h < p.Ho) && (n < p.No);
-            const long long pix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;
-            const int co0 = ct * BN;
-
-            ptx::mbar_wait(&tfull_bar[as], aphase);
-            ptx::tc_fence_after();
+            const int w0 = tw * tile_w + a_dw, h0 = th * tile_h + a_dh;
+            const int n0 = tn * TN, co0 = ct * BN;
+            for (int term = 0; term < nterms; ++term) {
+                const CUtensorMap* mapA = &p.tmA[(term == 1) ? 1 : 0];   // terms: (hi,hi) (lo,hi) (hi,lo)
+                const CUtensorMap* mapB = &p.tmB[(term == 2) ? 1 : 0];
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    ptx::mbar_wait(&a_empty[as], aphase ^ 1);
+                    uint8_t* sA = smem + as * a_stage_bytes;
+                    if (ptx::elect_one()) {
+                        if (debug & 8) {
+                            ptx::mbar_arrive(&a_full[as]);
+                        } else {
+                            ptx::mbar_expect_tx(&a_full[as], a_tx);
+                            for (int i = 0; i < a_loads; ++i)
+                                ptx::tma_load_4d(sA + i * a_load_stride, mapA, &a_full[as], kc * kBK, w0,
+                                                 h0 + i * a_dh_step, n0);
+                        }
+                    }
+                    __syncwarp();
+                    if (p.timeline && blockIdx.x == 0 && lane == 0 && pit < 64 && kc == 0)
+                        p.timeline[(0 * 64 + pit) * 4 + 1] = clock64();
+                    if (++as == a_stages) {
+                        as = 0;
+                        aphase ^= 1;
+                    }
+                    if (!RESIDENT) {
+                        int kcol = kc * kBK;                       // B column of (tap 0, chunk kc)
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0;
-                ptx::tmem_ld_32x32b_x32(taddr, r);
-                ptx::tmem_ld_wait();
-                const int co = co0 + c0;
-                int nvalid = p.Cout - co;
-                nvalid = nvalid > 32 ? 32 : nvalid;
-                if (nvalid > 0) {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (p.bias) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < nvalid) v[i] += __ldg(p.bias + co + i);
-                    }
-                    if (p.stat_sum) {
-                        // per-channel batch statistics of the (pre-activation) conv output.  Lane = pixel row, v[] = 32
-                        // channels: a halving butterfly (16+8+4+2+1 exchanges per quantity instead of 32 x 5) leaves
-                        // lane l with the 32-row sum of channel co + l; it is accumulated in registers across the
-                        // tiles of this CTA and flushed with one atomic per lane when the channel tile changes.
-                        float s[32], sq[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            s[i] = row_ok ? v[i] : 0.f;
-                            sq[i] = s[i] * s[i];
+                        for (int t = 0; t < ntaps; ++t, kcol += tap_kstep) {
+                            ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
+                            if (ptx::elect_one()) {
+                                if (debug & 8) {
+                                    ptx::mbar_arrive(&b_full[bs]);
+                                } else {
+                                    ptx::mbar_expect_tx(&b_full[bs], kBBytes);
+                                    ptx::tma_load_2d(smem_b + bs * kBBytes, mapB, &b_full[bs], kcol, co0);
+                                }
+                            }
+                            __syncwarp();
+                            if (++bs == b_stages) {
+                                bs = 0;
+                                bphase ^= 1;
+                            }
                         }
-                        butterfly_colsum(s, lane);
-                        butterfly_colsum(sq, lane);
-                        float2 a = sacc[c0 + lane];
-                        a.x += s[0];
-                        a.y += sq[0];
-                        sacc[c0 + lane] = a;
-                    }
-                    if (row_ok) {
-                        const long long off = pix * p.ldy + co;
-                        if (p.residual) {
-                            float rres[32];
-                            load_row_chunk(p.residual, p.y_fp32, off, rres, nvalid);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] += rres[i];
-                        }
-                        if (p.relu) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                        }
-                        store_row_chunk(p.y, p.y_fp32, off, v, nvalid);
                     }
                 }
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
         }
-        flush_stats();
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 0, 0);
+        const uint64_t adesc0 = ptx::make_smem_desc(ptx::smem_u32(smem), 16, p.a_sbo);
+        const uint64_t bdesc0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), 16, 1024);
+        const uint32_t a_stage16 = a_stage_bytes >> 4;
+        const int kmmas = p.kmmas;
+        const bool do_mma = !(debug & 4);
+        constexpr int NTR = NT > 0 ? NT : 1;
+        uint32_t toff[NTR];
+#pragma unroll
+        for (int t = 0; t < NTR; ++t) toff[t] = p.tap_off16[t];
+        if (RESIDENT) {
+            ptx::mbar_wait(bres_bar, 0);
+            ptx::tc_fence_after();
+        }
+        int as = 0, bs = 0;
+        uint32_t aphase = 0, bphase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t accphase = (it >> 1) & 1;
+            const bool stamp = p.timeline && blockIdx.x == 0 && lane == 0 && it < 64;
+            if (stamp) p.timeline[(1 * 64 + it) * 4 + 0] = clock64();
+            ptx::mbar_wait(&tempty_bar[acc], accphase ^ 1);
+            ptx::tc_fence_after();
+            if (stamp) p.timeline[(1 * 64 + it) * 4 + 1] = clock64();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            uint32_t accflag = 0;                                   // 0 only for the first MMA of the tile
+            for (int term = 0; term < nterms; ++term) {
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    ptx::mbar_wait(&a_full[as], aphase);
+                    ptx::tc_fence_after();
+                    if (stamp && kc == 0 && term == 0) p.timeline[(1 * 64 + it) * 4 + 2] = clock64();
+                    const uint64_t ad = adesc0 + static_cast<uint64_t>(as * a_stage16);
+                    if (NT > 0 && RESIDENT) {
+                        // the whole chunk (NT taps x 4 MMAs) is one straight-line issue sequence
+                        const uint64_t bd = bdesc0 + static_cast<uint64_t>(kc * kB16);
+                        const uint32_t bstep = kchunks * kB16;
+                        if (ptx::elect_one()) {
+                            if (do_mma) {
+#pragma unroll
+                                for (int t = 0; t < NTR; ++t) {
+#pragma unroll
+                                    for (int j = 0; j < (KM > 0 ? KM : 4); ++j)
+                                        if (KM > 0 || j < kmmas)
+                                            ptx::umma_f16(d_tmem, ad + toff[t] + 2 * j, bd + t * bstep + 2 * j, idesc,
+                                                          (t | j) != 0 ? 1u : accflag);
+                                }
+                            }
+                            ptx::umma_commit(&a_empty[as]);
+                        }
+                        __syncwarp();
+                    } else if (NT > 0) {
+#pragma unroll
+                        for (int t = 0; t < NTR; ++t) {
+                            ptx::mbar_wait(&b_full[bs], bphase);
+                            ptx::tc_fence_after();
+                            const uint64_t bd = bdesc0 + static_cast<uint64_t>(bs * kB16);
+                            if (ptx::elect_one()) {
+                                if (do_mma) {
+#pragma unroll
+                                    for (int j = 0; j < (KM > 0 ? KM : 4); ++j)
+                                        if (KM > 0 || j < kmmas)
+                                            ptx::umma_f16(d_tmem, ad + toff[t] + 2 * j, bd + 2 * j, idesc,
+                                                          (t | j) != 0 ? 1u : accflag);
+                                }
+                                ptx::umma_commit(&b_empty[bs]);
+                                if (t == NTR - 1) ptx::umma_commit(&a_empty[as]);
+                            }
+                            __syncwarp();
+                            if (++bs == b_stages) {
+                                bs = 0;
+                                bphase ^= 1;
+                            }
+                        }
+                    } else {
+                        // run-time tap count (5x5, 7x7 ... filters): same protocol, offsets read from the parameters
+#pragma unroll 1
+                        for (int t = 0; t < ntaps; ++t) {
+                            uint64_t bd;
+                            if (RESIDENT) {
+                                bd = bdesc0 + static_cast<uint64_t>((t * kchunks + kc) * kB16);
+                            } else {
+                                ptx::mbar_wait(&b_full[bs], bphase);
+                                ptx::tc_fence_after();
+                                bd = bdesc0 + static_cast<uint64_t>(bs * kB16);
+                            }
+                            const uint64_t at = ad + p.tap_off16[t];
+                            if (ptx::elect_one()) {
+                                if (do_mma) {
+#pragma unroll
+                                    for (int j = 0; j < (KM > 0 ? KM : 4); ++j)
+                                        if (KM > 0 || j < kmmas)
+                                            ptx::umma_f16(d_tmem, at + 2 * j, bd + 2 * j, idesc,
+                                                          (t | j) != 0 ? 1u : accflag);
+                                }
+                                if (!RESIDENT) ptx::umma_commit(&b_empty[bs]);
+                                if (t == ntaps - 1) ptx::umma_commit(&a_empty[as]);
+                            }
+                            __syncwarp();
+                            if (!RESIDENT && ++bs == b_stages) {
+                                bs = 0;
+                                bphase ^= 1;
+                            }
+                        }
+                    }
+                    accflag = 1;
+                    if (++as == a_stages) {
+                        as = 0;
+                        aphase ^= 1;
+                    }
+                }
+            }
+            if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[acc]);
+            __syncwarp();
+            if (stamp) p.timeline[(1 * 64 + it) * 4 + 3] = clock64();
+        }
+    } else {
+        fprop_epilogue<BN>(p, stat_smem, tmem_base, tfull_bar, tempty_bar, warp, lane);
     }
 
     ptx::tc_fence_before();
@@ -474,6 +805,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     const int ntaps = p.R * p.S;
+    // loop-invariant parameters in registers (the producer / MMA roles are single instruction streams)
+    const int nterms = p.nterms, debug = p.debug, num_tiles = p.num_tiles;
 
     // tile -> (co tile, ci tile, tap, split); split is the slowest index so that concurrently running CTAs
     // share the same pixel range (L2 reuse of dY / X boxes).
@@ -496,37 +829,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
             }
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int TW = p.TW, TH = p.TH, TN = p.TN, a_boxes = p.a_boxes, stride_w = p.stride_w, stride_h = p.stride_h;
+            const uint32_t tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+            const uint32_t stage_tx = L::kStageBytes - (2 - a_boxes) * kBoxBytes;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int cot, cit, tap, kb0, kb1;
                 decode(tile, cot, cit, tap, kb0, kb1);
                 const int dh = tap / p.S - p.pad_h;
                 const int dw = tap % p.S - p.pad_w;
+                const int cA = cot * kBM, cB = cit * BN;
                 // k-block kb0 -> patch position, then advanced incrementally (no division in the loop)
                 uint32_t tw, th, tn, t2;
                 p.fd_w.divmod(kb0, t2, tw);
                 p.fd_h.divmod(t2, tn, th);
+#pragma unroll 1
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
-                    for (int term = 0; term < p.nterms; ++term) {
+                    const int w0 = tw * TW, h0 = th * TH, n0 = tn * TN;
+                    for (int term = 0; term < nterms; ++term) {
                         const int ai = (term == 1) ? 1 : 0;
                         const int bi = (term == 2) ? 1 : 0;
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sA = smem + stage * L::kStageBytes;
                         uint8_t* sB = sA + L::kABytes;
                         if (ptx::elect_one()) {
-                            if (p.debug & 2) {
+                            if (debug & 2) {
                                 ptx::mbar_arrive(&full_bar[stage]);
                             } else {
                                 // Cout <= 64: the second 64-channel dY box would be all TMA zero fill; skip it (its
                                 // accumulator rows are never read)
-                                ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes - (2 - p.a_boxes) * kBoxBytes);
-                                for (int i = 0; i < p.a_boxes; ++i)
-                                    ptx::tma_load_4d(sA + i * kBoxBytes, &p.tmDY[ai], &full_bar[stage],
-                                                     cot * kBM + i * 64, w0, h0, n0);
+                                ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
+                                ptx::tma_load_4d(sA, &p.tmDY[ai], &full_bar[stage], cA, w0, h0, n0);
+                                if (a_boxes > 1)
+                                    ptx::tma_load_4d(sA + kBoxBytes, &p.tmDY[ai], &full_bar[stage], cA + 64, w0, h0, n0);
 #pragma unroll
                                 for (int i = 0; i < BN / 64; ++i)
                                     ptx::tma_load_4d(sB + i * kBoxBytes, &p.tmX[bi], &full_bar[stage],
-                                                     cit * BN + i * 64, w0 * p.stride_w + dw, h0 * p.stride_h + dh, n0);
+                                                     cB + i * 64, w0 * stride_w + dw, h0 * stride_h + dh, n0);
                             }
                         }
                         __syncwarp();
@@ -535,9 +873,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                             phase ^= 1;
                         }
                     }
-                    if (++tw == static_cast<uint32_t>(p.tiles_w)) {
+                    if (++tw == tiles_w) {
                         tw = 0;
-                        if (++th == static_cast<uint32_t>(p.tiles_h)) {
+                        if (++th == tiles_h) {
                             th = 0;
                             ++tn;
                         }
@@ -552,7 +890,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const bool do_mma = !(debug & 1);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 int cot, cit, tap, kb0, kb1;
                 decode(tile, cot, cit, tap, kb0, kb1);
                 const int as = it & 1;
@@ -560,7 +899,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
-                const int nk = (kb1 - kb0) * p.nterms;
+                const int nk = (kb1 - kb0) * nterms;
+#pragma unroll 1
                 for (int kb = 0; kb < nk; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
@@ -568,11 +908,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                     const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (L::kStageBytes >> 4));
                     const uint64_t bdesc = adesc + (L::kABytes >> 4);
                     if (ptx::elect_one()) {
+                        if (do_mma) {
 #pragma unroll
-                        for (int j = 0; j < kBK / 16; ++j) {
-                            // advance 16 pixel rows = 2048 B
-                            if (!(p.debug & 1))
+                            for (int j = 0; j < kBK / 16; ++j) {
+                                // advance 16 pixel rows = 2048 B
                                 ptx::umma_f16(d_tmem, adesc + 128 * j, bdesc + 128 * j, idesc, (kb | j) != 0);
+                            }
                         }
                         ptx::umma_commit(&empty_bar[stage]);
                     }
@@ -707,7 +1048,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
             int stage = 0;
             uint32_t phase = 0;
             const bool two_a = p.a_boxes > 1;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int TW = p.TW, TH = p.TH, TN = p.TN, nterms = p.nterms, debug = p.debug, pad_w = p.pad_w;
+            const int num_tiles = p.num_tiles, xbox_bytes = p.xbox_bytes;
+            const uint32_t tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int cot, cit, r, kb0, kb1, split;
                 decode(tile, cot, cit, r, kb0, kb1, split);
                 const int dh = r - p.pad_h;
@@ -715,16 +1059,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                 p.fd_w.divmod(kb0, t2, tw);
                 p.fd_h.divmod(t2, tn, th);
                 const int cA = cot * kBM, cB = cit * BN;
+#pragma unroll 1
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
-                    for (int term = 0; term < p.nterms; ++term) {
+                    const int w0 = tw * TW, h0 = th * TH, n0 = tn * TN;
+                    for (int term = 0; term < nterms; ++term) {
                         const CUtensorMap* mapA = &p.tmDY[(term == 1) ? 1 : 0];
                         const CUtensorMap* mapB = &p.tmX[(term == 2) ? 1 : 0];
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sA = smem + stage * L::kStageBytes;
                         uint8_t* sB = sA + L::kABytes;
                         if (ptx::elect_one()) {
-                            if (p.debug & 2) {
+                            if (debug & 2) {
                                 ptx::mbar_arrive(&full_bar[stage]);
                             } else {
                                 ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
@@ -733,8 +1078,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                                     ptx::tma_load_4d(sA + kBoxBytes, mapA, &full_bar[stage], cA + 64, w0, h0, n0);
 #pragma unroll
                                 for (int i = 0; i < BN / 64; ++i)
-                                    ptx::tma_load_4d(sB + i * p.xbox_bytes, mapB, &full_bar[stage], cB + i * 64,
-                                                     w0 - p.pad_w, h0 + dh, n0);
+                                    ptx::tma_load_4d(sB + i * xbox_bytes, mapB, &full_bar[stage], cB + i * 64,
+                                                     w0 - pad_w, h0 + dh, n0);
                             }
                         }
                         __syncwarp();
@@ -743,9 +1088,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                             phase ^= 1;
                         }
                     }
-                    if (++tw == static_cast<uint32_t>(p.tiles_w)) {
+                    if (++tw == tiles_w) {
                         tw = 0;
-                        if (++th == static_cast<uint32_t>(p.tiles_h)) {
+                        if (++th == tiles_h) {
                             th = 0;
                             ++tn;
                         }
@@ -777,7 +1122,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int nterms = p.nterms, num_tiles = p.num_tiles;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 int cot, cit, r, kb0, kb1, split;
                 decode(tile, cot, cit, r, kb0, kb1, split);
                 const int as = (nbuf == 2) ? (it & 1) : 0;
@@ -785,7 +1131,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * (S * BN);
-                const int nk = (kb1 - kb0) * p.nterms;
+                const int nk = (kb1 - kb0) * nterms;
+#pragma unroll 1
                 for (int kb = 0; kb < nk; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
@@ -794,11 +1141,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                     const uint64_t bdesc = bdesc0 + soff;
                     if (ptx::elect_one()) {
                         if (do_mma) {
+                            if (S == 3) {          // the 3x3 layers: 12 MMAs as one straight-line sequence
 #pragma unroll
-                            for (int j = 0; j < kBK / 16; ++j) {
-                                const uint64_t bj = bdesc + xoff[j];
-                                for (int sx = 0; sx < S; ++sx)
-                                    ptx::umma_f16(d_tmem + sx * BN, adesc + 128 * j, bj + 8 * sx, idesc, (kb | j) != 0);
+                                for (int j = 0; j < kBK / 16; ++j) {
+                                    const uint64_t bj = bdesc + xoff[j];
+#pragma unroll
+                                    for (int sx = 0; sx < 3; ++sx)
+                                        ptx::umma_f16(d_tmem + sx * BN, adesc + 128 * j, bj + 8 * sx, idesc,
+                                                      (kb | j) != 0);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < kBK / 16; ++j) {
+                                    const uint64_t bj = bdesc + xoff[j];
+                                    for (int sx = 0; sx < S; ++sx)
+                                        ptx::umma_f16(d_tmem + sx * BN, adesc + 128 * j, bj + 8 * sx, idesc,
+                                                      (kb | j) != 0);
+                                }
                             }
                         }
                         ptx::umma_commit(&empty_bar[stage]);
@@ -1111,6 +1470,83 @@ int fprop_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStr
     }
 }
 
+// ---- tap-group (halo) fprop: ring sizing, weight map, dispatch.  The caller has filled the A map(s), the patch
+// geometry (TW/TH/TN, tiles_w/h/n) and the a_* / tap-offset fields.  Returns 1 when the layer does not fit (caller falls
+// back to conv_fprop_kernel), 0 on success, < 0 on error.
+static int g_fprop_mode = 3;      // bit0: use the tap-group kernel where eligible, bit1: resident filters
+static int g_fprop_debug = 0;     // ConvFpropParams::debug
+static long long* g_fprop_timeline = nullptr;
+
+template <int BN, int NT, bool RESIDENT, int KM>
+static int launch_fprop_halo(const ConvFpropParams& p, cudaStream_t stream) {
+    const size_t smem = 1024 + (size_t)p.a_region_bytes + p.b_region_bytes + 512 + 4 * BN * 8;
+    auto kern = conv_fprop_halo_kernel<BN, NT, RESIDENT, KM>;
+    DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    kern<<<DN_G(grid), kThreads, smem, stream>>>(p);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+// specialised instances: 3x3 filters (9 taps, 4 MMAs per K block) and the 7-row stride-2 stem (K = 28 -> 2 MMAs);
+// everything else runs the run-time-count instance
+template <int BN>
+static int dispatch_fprop_halo(const ConvFpropParams& p, cudaStream_t stream) {
+    const int ntaps = p.R * p.S;
+    constexpr int BR = BN <= 128 ? BN : 128;      // resident filters exist for BN <= 128 only
+    if (p.b_resident) {
+        if (BN == 64 && ntaps == 9 && p.kmmas == 4) return launch_fprop_halo<64, 9, true, 4>(p, stream);
+        if (BN == 64 && ntaps == 7 && p.kmmas == 2) return launch_fprop_halo<64, 7, true, 2>(p, stream);
+        return launch_fprop_halo<BR, 0, true, 0>(p, stream);
+    }
+    if (ntaps == 9 && p.kmmas == 4) return launch_fprop_halo<BN, 9, false, 4>(p, stream);
+    if (BN == 64 && ntaps == 7 && p.kmmas == 2) return launch_fprop_halo<64, 7, false, 2>(p, stream);
+    return launch_fprop_halo<BN, 0, false, 0>(p, stream);
+}
+
+int halo_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStream_t stream) {
+    const int Cout = p.Cout;
+    const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    const uint32_t b_bytes = BN * 128;
+    const uint32_t budget = 200 * 1024;
+    const int ntaps = p.R * p.S;
+    p.a_stage_bytes = p.a_loads * p.a_load_stride;
+    p.b_resident = (g_fprop_mode & 2) && p.nterms == 1 && BN <= 128 && Cout <= BN &&
+                   (uint32_t)(ntaps * p.kchunks) * b_bytes <= 80 * 1024;
+    if (p.b_resident) {
+        p.b_region_bytes = ntaps * p.kchunks * b_bytes;
+        p.b_stages = 1;
+        p.a_stages = (int)((budget - p.b_region_bytes) / p.a_stage_bytes);
+        if (p.a_stages > 6) p.a_stages = 6;
+    } else {
+        p.b_stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+        p.b_region_bytes = p.b_stages * b_bytes;
+        p.a_stages = (int)((budget - p.b_region_bytes) / p.a_stage_bytes);
+        if (p.a_stages > 4) p.a_stages = 4;
+    }
+    if (p.a_stages < 2) return 1;
+    p.a_region_bytes = p.a_stages * p.a_stage_bytes;
+    p.tiles_co = ceil_div(Cout, BN);
+    p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
+    p.fd_co = make_fastdiv(p.tiles_co);
+    p.fd_w = make_fastdiv(p.tiles_w);
+    p.fd_h = make_fastdiv(p.tiles_h);
+    p.fd_tw = make_fastdiv(p.TW);
+    p.fd_th = make_fastdiv(p.TH);
+    int rc;
+    const uint64_t ktot = (uint64_t)ntaps * p.kchunks * 64;
+    uint64_t dims[2] = {ktot, (uint64_t)Cout};
+    uint64_t strides[1] = {ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    if ((rc = encode_tmap_bf16(&p.tmB[0], b_hi, 2, dims, strides, box, nullptr))) return rc;
+    if (b_lo && (rc = encode_tmap_bf16(&p.tmB[1], b_lo, 2, dims, strides, box, nullptr))) return rc;
+    switch (BN) {
+        case 64: return dispatch_fprop_halo<64>(p, stream);
+        case 128: return dispatch_fprop_halo<128>(p, stream);
+        default: return dispatch_fprop_halo<256>(p, stream);
+    }
+}
+
 // Split-K factor of the filter gradient.  A persistent grid of num_sms() CTAs runs the base_tiles * splits tiles in
 // ceil(tiles / SMs) rounds of ceil(total_kblocks / splits) k-blocks each, so a tile count just above a multiple of the
 // SM count wastes most of a round (the former rule ceil(2*SMs / base_tiles) produced 297..306 tiles on 148 SMs for the
@@ -1225,6 +1661,8 @@ extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int
     ConvFpropParams p;
     memset(&p, 0, sizeof(p));
     p.nterms = x_lo ? 3 : 1;
+    p.debug = g_fprop_debug;
+    p.timeline = g_fprop_timeline;
     p.R = R; p.S = S; p.pad_h = pad_h; p.pad_w = pad_w;
     p.stride_h = stride_h; p.stride_w = stride_w;
     p.kchunks = ceil_div(Cin, 64);
@@ -1244,10 +1682,44 @@ extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int
     p.stat_sqsum = stat_sqsum;
 
     int rc;
+    // stride-1 multi-tap filters: one halo'd A box per channel chunk serves all taps (conv_fprop_halo_kernel).  The
+    // patch is 8 x 16 pixels of ONE image so that an 8-pixel group of the M tile is one row of the box.
+    if ((g_fprop_mode & 1) && stride_h == 1 && stride_w == 1 && R * S > 1 && R <= 8 && S <= 8 && Ho >= 12 && Wo >= 8) {
+        ConvFpropParams h = p;
+        h.TW = 8; h.TH = 16; h.TN = 1;
+        h.tiles_w = ceil_div(Wo, 8);
+        h.tiles_h = ceil_div(Ho, 16);
+        h.tiles_n = N;
+        const int bw = 8 + S - 1, bh = 16 + R - 1;
+        h.a_loads = 1;
+        h.a_dw = -pad_w; h.a_dh = -pad_h; h.a_dh_step = 0;
+        h.a_load_bytes = (uint32_t)bw * bh * 128;
+        h.a_load_stride = (h.a_load_bytes + 1023) / 1024 * 1024;
+        h.a_sbo = (uint32_t)bw * 128;
+        for (int r = 0; r < R; ++r)
+            for (int sx = 0; sx < S; ++sx) h.tap_off16[r * S + sx] = (uint32_t)(r * bw + sx) * 8;   // 128 B per box row
+        h.kmmas = 4;
+        if ((rc = make_act_map(&h.tmA[0], x_hi, Cin, Wi, Hi, N, ldx, bw, bh, 1))) return rc;
+        if (x_lo && (rc = make_act_map(&h.tmA[1], x_lo, Cin, Wi, Hi, N, ldx, bw, bh, 1))) return rc;
+        rc = halo_finish(h, b_hi, b_lo, stream);
+        if (rc <= 0) return rc;
+    }
     if ((rc = make_act_map(&p.tmA[0], x_hi, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h))) return rc;
     if (x_lo && (rc = make_act_map(&p.tmA[1], x_lo, Cin, Wi, Hi, N, ldx, p.TW, p.TH, p.TN, stride_w, stride_h)))
         return rc;
     return fprop_finish(p, b_hi, b_lo, stream);
+}
+
+// profiling: device buffer of 3 * 64 * 4 int64 receiving CTA 0's per-tile clock stamps (NULL = off)
+extern "C" int denet_conv2d_fprop_set_timeline(void* buf) {
+    g_fprop_timeline = (long long*)buf;
+    return 0;
+}
+
+extern "C" int denet_conv2d_fprop_set_mode(int mode) {
+    g_fprop_mode = mode & 15;
+    g_fprop_debug = mode >> 4;        // undocumented profiling knobs, see ConvFpropParams::debug
+    return 0;
 }
 
 namespace dn {
@@ -1392,6 +1864,7 @@ namespace dn {
 
 static int rowfold_k(int S, int Cp) { return (S * Cp + 7) / 8 * 8; }   // dim0 extent (elements), <= 64
 
+// TH = rows the box delivers (the box spans TH * stride_h input rows walked with element stride stride_h)
 static int make_rowfold_map(CUtensorMap* tm, const void* base, int Cp, int S, int Wo, int Hp, int Wp, int N,
                             int stride_w, int stride_h, int TW, int TH, int TN) {
     const int kf = rowfold_k(S, Cp);
@@ -1512,6 +1985,8 @@ extern "C" int denet_conv2d_rowfold_fprop(const void* x_hi, const void* x_lo, in
     ConvFpropParams p;
     memset(&p, 0, sizeof(p));
     p.nterms = x_lo ? 3 : 1;
+    p.debug = g_fprop_debug;
+    p.timeline = g_fprop_timeline;
     p.R = R; p.S = 1; p.pad_h = 0; p.pad_w = 0;       // taps = filter rows; the padding lives in the buffer
     p.stride_h = stride_h; p.stride_w = 1;             // the column stride lives in the tensor map
     p.kchunks = 1;
@@ -1528,6 +2003,31 @@ extern "C" int denet_conv2d_rowfold_fprop(const void* x_hi, const void* x_lo, in
     p.bias = bias;
     p.stat_sum = stat_sum;
     p.stat_sqsum = stat_sqsum;
+    // filter rows sharing one fetch of the input rows (conv_fprop_halo_kernel): the rows 2*ho + r of a stride-2 stem
+    // are loaded as two boxes, even and odd input rows; filter row r reads box r & 1 starting r >> 1 rows in
+    if ((g_fprop_mode & 1) && stride_h <= 2 && R > 1 && R <= 16 && Wo >= 8) {
+        ConvFpropParams h = p;
+        h.TW = Wo >= 16 ? 16 : 8; h.TH = 128 / h.TW; h.TN = 1;
+        h.tiles_w = ceil_div(Wo, h.TW);
+        h.tiles_h = ceil_div(Ho, h.TH);
+        h.tiles_n = N;
+        const int rows = h.TH + (R - 1) / stride_h;
+        h.a_loads = stride_h < R ? stride_h : R;
+        h.a_dw = 0; h.a_dh = 0; h.a_dh_step = 1;
+        h.a_load_bytes = (uint32_t)rows * h.TW * 128;
+        h.a_load_stride = (h.a_load_bytes + 1023) / 1024 * 1024;
+        h.a_sbo = 1024;
+        for (int r = 0; r < R; ++r)      // filter row r: box r % stride_h, r / stride_h rows of TW pixels in
+            h.tap_off16[r] = ((uint32_t)(r % stride_h) * h.a_load_stride + (uint32_t)(r / stride_h) * h.TW * 128) >> 4;
+        h.kmmas = (rowfold_k(S, Cp) + 15) / 16;
+        if (rows * stride_h <= 256) {
+            if ((rc = make_rowfold_map(&h.tmA[0], x_hi, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, h.TW, rows, 1))) return rc;
+            if (x_lo && (rc = make_rowfold_map(&h.tmA[1], x_lo, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, h.TW, rows, 1)))
+                return rc;
+            rc = halo_finish(h, b_hi, b_lo, stream);
+            if (rc <= 0) return rc;
+        }
+    }
     if ((rc = make_rowfold_map(&p.tmA[0], x_hi, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, p.TH, p.TN))) return rc;
     if (x_lo && (rc = make_rowfold_map(&p.tmA[1], x_lo, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, p.TH, p.TN)))
         return rc;

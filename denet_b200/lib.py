@@ -71,6 +71,11 @@ def load():
     if lib.denet_abi_version() != 3:
         raise DenetError("denet_b200: ABI version mismatch (library %d, binding 3) - rebuild" % lib.denet_abi_version())
     _lib = lib
+    # profiling / A-B switches (kernel variants only; every variant is a CUDA kernel of this library)
+    if os.environ.get("DENET_FPROP_MODE"):
+        lib.denet_conv2d_fprop_set_mode(int(os.environ["DENET_FPROP_MODE"]))
+    if os.environ.get("DENET_WGRAD_MODE"):
+        lib.denet_conv2d_wgrad_set_mode(int(os.environ["DENET_WGRAD_MODE"]))
     return lib
 
 

@@ -76,6 +76,14 @@ int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int Hi, int Wi
                        int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo, const float* bias,
                        const void* residual, int relu, float* stat_sum, float* stat_sqsum, cudaStream_t stream);
 
+/* Kernel selection of conv2d_fprop / conv2d_rowfold_fprop (profiling / A-B tests): bit 0 (default on) lets stride-1
+ * multi-tap filters and the row-folded stem use the tap-group kernel (one halo'd input box per channel chunk serves
+ * all filter taps), bit 1 (default on) keeps filters that fit resident in shared memory; 0 = one box per tap. */
+int denet_conv2d_fprop_set_mode(int mode);
+/* Profiling aid: device buffer of 3*64*4 int64 in which CTA 0 of the tap-group kernel records per-tile clock64()
+ * stamps of its producer / MMA / epilogue roles (NULL switches it off). */
+int denet_conv2d_fprop_set_timeline(void* buf);
+
 /* Filter gradient in the reference layout:
  *   dw[co][ci][R-1-r][S-1-s] (+)= sum_pixels dy[p,co] * x[p*stride+(r,s)-pad, ci].
  * Split-K partial sums go through `workspace` (size from denet_conv2d_wgrad_workspace) and are reduced in a
