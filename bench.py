@@ -276,6 +276,8 @@ def run_b200(args):
         sampler.start()
 
     # ---- region A: inputs resident in HBM (value)
+    for _ in range(2):        # untimed: the first step after switching the input source (host batch -> resident batch)
+        step_device()         # re-binds the static input slot and runs ~10 ms slower than the steady state
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -300,6 +302,9 @@ def run_b200(args):
     # ---- region B: through the public API with HOST buffers: H2D of the batch and D2H of the costs every step
     barrier()
     from denet_b200 import layer as layer_mod
+    for _ in range(2):        # untimed transition back to host batches
+        cost = step_host()
+    barrier()
     tb0 = dict(layer_mod.transfer_bytes)
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()

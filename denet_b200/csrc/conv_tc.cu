@@ -1280,7 +1280,7 @@ struct PrepEntry {
     const float* w;
     __nv_bfloat16* hi;
     __nv_bfloat16* lo;
-    long long total;
+    long long total;      // work items = operand rows x padded K columns (rows x 64 for the row-folded operand)
     int Cout, Cin, R, S, mode, Cp;
 };
 constexpr int kPrepChunk = 4096;
@@ -1288,37 +1288,46 @@ constexpr int kPrepChunk = 4096;
 __global__ void __launch_bounds__(256) weight_prep_multi_kernel(const PrepEntry* __restrict__ entries,
                                                                  const int* __restrict__ block_entry,
                                                                  const long long* __restrict__ block_offset) {
+    // One work item = one (operand row, K column) pair; the item writes that column for every filter tap.  Reading the
+    // R*S taps of a (co, ci) filter as one contiguous run keeps the fp32 reads coalesced (a per-element mapping reads
+    // 4 bytes out of every 36), consecutive items write consecutive bf16 of each tap row; all index math is 32-bit.
     const PrepEntry e = entries[block_entry[blockIdx.x]];
-    const long long start = block_offset[blockIdx.x];
-    const long long end = start + kPrepChunk < e.total ? start + kPrepChunk : e.total;
-    const int R = e.R, S = e.S, Cin = e.Cin;
-    const int ntaps = R * S;
-    const int kin = e.mode == 0 ? e.Cin : e.Cout;
-    const int kp = (kin + 63) / 64 * 64;
-    for (long long idx = start + threadIdx.x; idx < end; idx += blockDim.x) {
-        float v = 0.f;
-        if (e.mode == 2) {
-            const int k = static_cast<int>(idx % 64);
-            const int r = static_cast<int>((idx / 64) % R);
-            const int co = static_cast<int>(idx / (64LL * R));
-            const int sx = k / e.Cp, c = k % e.Cp;
-            if (sx < S && c < Cin) v = e.w[((static_cast<long long>(co) * Cin + c) * R + (R - 1 - r)) * S + (S - 1 - sx)];
-        } else {
-            const int k = static_cast<int>(idx % kp);
-            const long long t = idx / kp;
-            const int tap = static_cast<int>(t % ntaps);
-            const int row = static_cast<int>(t / ntaps);
-            if (k < kin) {
-                const int r = tap / S, sx = tap % S;
-                if (e.mode == 0)
-                    v = e.w[((static_cast<long long>(row) * Cin + k) * R + (R - 1 - r)) * S + (S - 1 - sx)];
-                else
-                    v = e.w[((static_cast<long long>(k) * Cin + row) * R + r) * S + sx];
+    const unsigned items = (unsigned)e.total;
+    const unsigned start = (unsigned)block_offset[blockIdx.x];
+    const unsigned end = start + kPrepChunk < items ? start + kPrepChunk : items;
+    const unsigned R = e.R, S = e.S, Cin = e.Cin, Cout = e.Cout;
+    if (e.mode == 2) {
+        const unsigned Cp = e.Cp;
+        for (unsigned it = start + threadIdx.x; it < end; it += blockDim.x) {
+            const unsigned k = it & 63u, co = it >> 6;
+            const unsigned sx = k / Cp, c = k - sx * Cp;
+            const bool live = sx < S && c < Cin;
+            const float* src = e.w + ((size_t)co * Cin + c) * R * S + (S - 1 - sx);
+            for (unsigned r = 0; r < R; ++r) {
+                const float v = live ? src[(R - 1 - r) * S] : 0.f;
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                const size_t o = ((size_t)co * R + r) * 64 + k;
+                e.hi[o] = hi;
+                if (e.lo) e.lo[o] = __float2bfloat16_rn(v - __bfloat162float(hi));
             }
         }
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        e.hi[idx] = hi;
-        if (e.lo) e.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        return;
+    }
+    const unsigned ntaps = R * S;
+    const unsigned kin = e.mode == 0 ? Cin : Cout;
+    const unsigned kp = (kin + 63u) / 64u * 64u;
+    for (unsigned it = start + threadIdx.x; it < end; it += blockDim.x) {
+        const unsigned row = it / kp, k = it - row * kp;
+        const bool live = k < kin;
+        // mode 0: B[co=row][tap][ci=k] = W[row][k][R-1-r][S-1-s] = run[ntaps-1-tap];  mode 1: B[ci=row][tap][co=k] = W[k][row][tap]
+        const float* run = e.w + (e.mode == 0 ? ((size_t)row * Cin + k) : ((size_t)k * Cin + row)) * ntaps;
+        size_t o = (size_t)row * ntaps * kp + k;
+        for (unsigned t = 0; t < ntaps; ++t, o += kp) {
+            const float v = live ? run[e.mode == 0 ? ntaps - 1 - t : t] : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            e.hi[o] = hi;
+            if (e.lo) e.lo[o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
     }
 }
 
@@ -1331,7 +1340,7 @@ struct ReduceEntry {
     long long total;    // Cout * Cin * R * S
     int splits, Cout, Cin, R, S, ldws, mode, Cp, accumulate, pad_;
 };
-constexpr int kReduceChunk = 1024;
+constexpr int kReduceChunk = 256;       // one element per thread: the split loop is the only serial work
 
 __global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const ReduceEntry* __restrict__ entries,
                                                                   const int* __restrict__ block_entry,

@@ -139,7 +139,7 @@ __global__ void bn_stats_finalize_kernel(const T* __restrict__ x, const float* _
 // loads of kBnUnroll rows in flight.  A warp covers 32 consecutive packs = 512 contiguous bytes of a pixel row (or of
 // several rows when C < 256).
 constexpr int kBnUnroll = 4;      // forward apply: 2 streams x 4 rows in flight
-constexpr int kBnUnrollBwd = 2;   // backward passes: 3 streams x 2 rows (register budget)
+constexpr int kBnUnrollBwd = 4;   // backward passes: 2-3 streams x 4 rows, held as raw 16-byte packs
 
 // y = [relu]( (x - mean) * (gamma * invstd) + beta [+ residual] )
 template <typename T, int VEC>
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
     }
     const long long coff = (long long)cv * VEC;
     for (long long r = r0 + rl; r < r1; r += (long long)rlanes * kBnUnroll) {
-        Pack<T, VEC> p[kBnUnroll], q[kBnUnroll];
+        Raw<T, VEC> p[kBnUnroll], q[kBnUnroll];
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
             const long long rr = r + (long long)u * rlanes;
@@ -181,14 +181,15 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
         for (int u = 0; u < kBnUnroll; ++u) {
             const long long rr = r + (long long)u * rlanes;
             if (rr < r1) {
+                Pack<T, VEC> o;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
-                    float v = (p[u].v[i] - mu[i]) * a[i] + b[i];
-                    if (residual) v += q[u].v[i];
+                    float v = (p[u].get(i) - mu[i]) * a[i] + b[i];
+                    if (residual) v += q[u].get(i);
                     if (relu) v = fmaxf(v, 0.f);
-                    p[u].v[i] = v;
+                    o.v[i] = v;
                 }
-                p[u].store(y + rr * ld + coff);
+                o.store(y + rr * ld + coff);
             }
         }
     }
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const T* __r
         }
         const long long coff = (long long)cv * VEC;
         for (long long r = r0 + rl; r < r1; r += (long long)rlanes * kBnUnrollBwd) {
-            Pack<T, VEC> g[kBnUnrollBwd], xv[kBnUnrollBwd], yo[kBnUnrollBwd];
+            Raw<T, VEC> g[kBnUnrollBwd], xv[kBnUnrollBwd], yo[kBnUnrollBwd];
 #pragma unroll
             for (int u = 0; u < kBnUnrollBwd; ++u) {
                 const long long rr = r + (long long)u * rlanes;
@@ -246,14 +247,15 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const T* __r
                 if (rr < r1) {
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        float d = g[u].v[i];
+                        float d = g[u].get(i);
+                        const float xc = xv[u].get(i) - mu[i];
                         if (mask_from_x) {
-                            if (!((xv[u].v[i] - mu[i]) * fa[i] + fb[i] > 0.f)) d = 0.f;
-                        } else if (relu && !(yo[u].v[i] > 0.f)) {
+                            if (!(xc * fa[i] + fb[i] > 0.f)) d = 0.f;
+                        } else if (relu && !(yo[u].get(i) > 0.f)) {
                             d = 0.f;
                         }
                         s[i] += d;
-                        s2[i] += d * ((xv[u].v[i] - mu[i]) * is[i]);
+                        s2[i] += d * (xc * is[i]);
                     }
                 }
             }
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
     }
     const long long coff = (long long)cv * VEC;
     for (long long r = r0 + rl; r < r1; r += (long long)rlanes * kBnUnrollBwd) {
-        Pack<T, VEC> g[kBnUnrollBwd], xv[kBnUnrollBwd], yo[kBnUnrollBwd];
+        Raw<T, VEC> g[kBnUnrollBwd], xv[kBnUnrollBwd], yo[kBnUnrollBwd];
 #pragma unroll
         for (int u = 0; u < kBnUnrollBwd; ++u) {
             const long long rr = r + (long long)u * rlanes;
@@ -343,21 +345,22 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
         for (int u = 0; u < kBnUnrollBwd; ++u) {
             const long long rr = r + (long long)u * rlanes;
             if (rr < r1) {
-                Pack<T, VEC> o;
+                Pack<T, VEC> o, gm;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
-                    float d = g[u].v[i];
+                    float d = g[u].get(i);
+                    const float xc = xv[u].get(i) - mu[i];
                     if (mask_from_x) {   // k1 = gamma * invstd: the forward pass's (x - mean) * (gamma*invstd) + beta
-                        if (!((xv[u].v[i] - mu[i]) * k1[i] + fb[i] > 0.f)) d = 0.f;
-                    } else if (relu && !(yo[u].v[i] > 0.f)) {
+                        if (!(xc * k1[i] + fb[i] > 0.f)) d = 0.f;
+                    } else if (relu && !(yo[u].get(i) > 0.f)) {
                         d = 0.f;
                     }
-                    g[u].v[i] = d;
-                    const float xh = (xv[u].v[i] - mu[i]) * is[i];
+                    gm.v[i] = d;
+                    const float xh = xc * is[i];
                     o.v[i] = k1[i] * (d - c1[i] - xh * c2[i]);
                 }
                 o.store(dx + rr * ld + coff);
-                if (dres) g[u].store(dres + rr * ld + coff);
+                if (dres) gm.store(dres + rr * ld + coff);
             }
         }
     }
@@ -559,31 +562,34 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
         const int wo_lo = wlo <= 0 ? 0 : (wlo + sw - 1) / sw;
         if (VEC == 8 && quad) {
             uint2 am[4];
-            Pack<T, VEC> g[4];
-            int tap[4];
+            Raw<T, VEC> g[4];
+            uint32_t tapw[4];
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     const int ho = ho_hi - a, wo = wo_hi - b;
                     const bool ok = ho >= ho_lo && wo >= wo_lo;
-                    const long long opix = ((long long)n * Ho + (ok ? ho : ho_hi)) * Wo + (ok ? wo : wo_hi);
-                    tap[2 * a + b] = ok ? (hp - ho * sh) * kw + (wp - wo * sw) : 0x100;
+                    const int q = 2 * a + b;
                     if (ok) {
-                        am[2 * a + b] = *reinterpret_cast<const uint2*>(argmax + opix * C + cv * 8);
-                        g[2 * a + b].load(dy + opix * ldy + (long long)cv * VEC);
+                        const long long opix = ((long long)n * Ho + ho) * Wo + wo;
+                        tapw[q] = (uint32_t)((hp - ho * sh) * kw + (wp - wo * sw)) * 0x01010101u;
+                        am[q] = *reinterpret_cast<const uint2*>(argmax + opix * C + cv * 8);
+                        g[q].load(dy + opix * ldy + (long long)cv * VEC);
                     } else {
-                        am[2 * a + b] = make_uint2(0xffffffffu, 0xffffffffu);
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) g[2 * a + b].v[i] = 0.f;
+                        tapw[q] = 0;
+                        am[q] = make_uint2(0xffffffffu, 0xffffffffu);      // matches no tap
+                        g[q].load(dy);                                      // never used
                     }
                 }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint32_t w2[2] = {am[q].x, am[q].y};
+                // byte-wise compare of the 8 recorded taps with this pixel's tap: 0xff per matching channel
+                const uint32_t m0 = __vcmpeq4(am[q].x, tapw[q]), m1 = __vcmpeq4(am[q].y, tapw[q]);
+                if ((m0 | m1) == 0) continue;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i)
-                    if (((w2[(i & 7) >> 2] >> (8 * (i & 3))) & 0xffu) == (uint32_t)tap[q]) acc[i] += g[q].v[i];
+                    if (((i < 4 ? m0 : m1) >> (8 * (i & 3))) & 1u) acc[i] += g[q].get(i);
             }
         } else {
             for (int ho = ho_hi; ho >= ho_lo; --ho)

@@ -99,6 +99,26 @@ struct Pack<__nv_bfloat16, 4> {
     }
 };
 
+// Raw<T, VEC>: a pack kept in its memory representation until it is used (8 bf16 = 4 registers instead of the 8 of
+// Pack<>): the streaming kernels hold several rows of several tensors in flight per thread, and their occupancy - and
+// with it the bytes in flight per SM - is bounded by registers.
+template <typename T, int VEC>
+struct Raw {
+    Pack<T, VEC> p;
+    __device__ __forceinline__ void load(const T* ptr) { p.load(ptr); }
+    __device__ __forceinline__ float get(int i) const { return p.v[i]; }
+};
+
+template <>
+struct Raw<__nv_bfloat16, 8> {
+    uint4 u;
+    __device__ __forceinline__ void load(const __nv_bfloat16* ptr) { u = *reinterpret_cast<const uint4*>(ptr); }
+    __device__ __forceinline__ float get(int i) const {
+        const uint32_t w = (i >> 1) == 0 ? u.x : ((i >> 1) == 1 ? u.y : ((i >> 1) == 2 ? u.z : u.w));
+        return (i & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
+    }
+};
+
 // dispatch on dtype code and on whether 8-wide vector access is legal (C % 8 == 0, pitch % 8 == 0, 16B base)
 #define DN_DISPATCH(dtype, vec_ok, ...)                                    \
     do {                                                                   \

@@ -432,9 +432,10 @@ class ModelCNN:
                 table[i, 0] = w.data_ptr()
                 table[i, 1] = op.hi.data_ptr()
                 table[i, 2] = op.lo.data_ptr() if op.lo is not None else 0
-                table[i, 3] = op.hi.numel()
+                items = op.hi.numel() // (R if mode == 2 else R * S)      # (operand row, K column) pairs
+                table[i, 3] = items
                 ints[i, 8:14] = [cout, cin, R, S, mode, cp]
-                for o in range(0, op.hi.numel(), chunk):
+                for o in range(0, items, chunk):
                     block_entry.append(i)
                     block_offset.append(o)
             self._prep_table = (torch.from_numpy(table).to(self.device),

@@ -55,7 +55,8 @@ int denet_conv_weight_prep(const float* w, int Cout, int Cin, int R, int S, int 
 
 /* The operands of ALL conv layers in one launch.  `entries` is a device array of denet_weight_prep_entry_bytes()-sized
  * records {const float* w; bf16* hi; bf16* lo (or NULL); long long total; int Cout, Cin, R, S, mode, Cp} with mode
- * 0 / 1 as above and 2 = row-folded stem operand (Cp = padded channels); block i prepares elements
+ * 0 / 1 as above and 2 = row-folded stem operand (Cp = padded channels); `total` counts work items = operand rows x
+ * padded K columns (an item covers that column for all filter taps); block i prepares items
  * [block_offset[i], +denet_weight_prep_chunk()) of operand block_entry[i]. */
 int denet_weight_prep_entry_bytes(void);
 int denet_weight_prep_chunk(void);

@@ -305,3 +305,29 @@ def test_cuda_graph_step_equals_eager_step(cuda, which):
     for name in pa:
         if pa[name].norm().item() > 1e-2:
             assert relerr(pb[name], pa[name]) < 3 * relerr(pa2[name], pa[name]) + 2e-2, name
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_one_launch_operand_preparation_matches_per_layer_kernels(cuda, precision):
+    """ModelCNN.prepare_operands (all conv layers in one launch, denet_conv_weight_prep_multi) writes exactly the
+    operands of the per-layer kernels: fprop / dgrad layouts, the row-folded stem, bf16 hi (+ lo in parity mode)"""
+    from denet_b200 import ops
+    model = build(DENET_SMALL, (3, 128, 128), 2, 20, precision, convert=True)
+    model.to_device(precision=precision)
+    model.prepare_operands()
+    split = precision == "fp32"
+    seen = 0
+    for l in model._prep_layers:
+        if l.rowfold is not None:
+            ref = [(l._wop_f, ops.conv_weight_prep_rowfold(l.omega, l.rowfold[0], split))]
+        else:
+            ref = [(l._wop_f, ops.conv_weight_prep(l.omega, 0, split))]
+            if not l.is_first:
+                ref.append((l._wop_d, ops.conv_weight_prep(l.omega, 1, split)))
+        for got, want in ref:
+            assert torch.equal(got.hi, want.hi), l.filter_shape
+            assert (got.lo is None) == (want.lo is None)
+            if split:
+                assert torch.equal(got.lo, want.lo), l.filter_shape
+            seen += 1
+    assert seen > 20
