@@ -1119,6 +1119,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                 xoff[j] = static_cast<uint32_t>(((16 * j) >> p.log2_tw) * xw + ((16 * j) & (p.TW - 1))) * 8u;
             const int S = p.S;
             const bool do_mma = !(p.debug & 1);
+            // Cin tile of 64 channels and S * 64 <= 256: ONE MMA per K step covers all S taps.  The B operand is
+            // described as S column groups of 64 channels whose group stride (LBO) is one pixel row of the box
+            // (128 B), i.e. group g is the same X box shifted by g pixels = tap g; its accumulator columns are
+            // [g*64, g*64+64), exactly where the per-tap MMAs put them.  3x fewer MMA instructions for a 3x3 filter
+            // (the single issuing thread is what bounds N = 64 MMAs).
+            const bool stacked = (BN == 64) && (S * 64 <= 256) && !(p.debug & 8);
+            const uint32_t idesc_stacked = ptx::make_idesc_bf16(S * 64, 1, 1);
+            const uint64_t bdesc0_stacked = ptx::make_smem_desc(smem0 + L::kABytes, 128, sbo_x);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -1140,7 +1148,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
                     const uint64_t adesc = adesc0 + soff;
                     const uint64_t bdesc = bdesc0 + soff;
                     if (ptx::elect_one()) {
-                        if (do_mma) {
+                        if (do_mma && stacked) {
+                            const uint64_t bst = bdesc0_stacked + soff;
+#pragma unroll
+                            for (int j = 0; j < kBK / 16; ++j)
+                                ptx::umma_f16(d_tmem, adesc + 128 * j, bst + xoff[j], idesc_stacked, (kb | j) != 0);
+                        } else if (do_mma) {
                             if (S == 3) {          // the 3x3 layers: 12 MMAs as one straight-line sequence
 #pragma unroll
                                 for (int j = 0; j < kBK / 16; ++j) {
@@ -1340,29 +1353,67 @@ struct ReduceEntry {
     long long total;    // Cout * Cin * R * S
     int splits, Cout, Cin, R, S, ldws, mode, Cp, accumulate, pad_;
 };
-constexpr int kReduceChunk = 256;       // one element per thread: the split loop is the only serial work
+constexpr int kReduceChunk = 1024;      // elementwise path: elements per block
+constexpr int kReduceItems = 4;         // tiled path: (co, 32-channel group) items per block
 
 __global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const ReduceEntry* __restrict__ entries,
                                                                   const int* __restrict__ block_entry,
                                                                   const long long* __restrict__ block_offset) {
     const ReduceEntry e = entries[block_entry[blockIdx.x]];
-    const long long start = block_offset[blockIdx.x];
-    const long long end = start + kReduceChunk < e.total ? start + kReduceChunk : e.total;
     const int R = e.R, S = e.S, Cin = e.Cin, Cout = e.Cout;
     const int ntaps = R * S;
+    if (e.mode == 0 && ntaps > 1) {
+        // Tiled path (multi-tap filters): the workspace is [split][co][tap][ci], the reference gradient [co][ci][tap'].
+        // A block sums the splits of (co, 32 consecutive ci, all taps) with coalesced 128-byte reads per tap row,
+        // transposes through shared memory and writes the 32 * ntaps contiguous output floats coalesced (a
+        // per-element mapping writes 4 bytes out of every 4 * ntaps).
+        __shared__ float tile[32][65];
+        const int groups = (Cin + 31) / 32;
+        const long long units = static_cast<long long>(Cout) * groups;
+        const long long first = block_offset[blockIdx.x];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const long long step = static_cast<long long>(Cout) * ntaps * e.ldws;
+        for (long long item = first; item < first + kReduceItems && item < units; ++item) {
+            const int co = static_cast<int>(item / groups);
+            const int ci0 = static_cast<int>(item % groups) * 32;
+            const int ci = ci0 + lane;
+            for (int t = warp; t < ntaps; t += 8) {
+                float acc = 0.f;
+                if (ci < Cin) {
+                    const float* src = e.ws + (static_cast<long long>(co) * ntaps + t) * e.ldws + ci;
+                    int sp = 0;
+                    for (; sp + 4 <= e.splits; sp += 4) {
+                        const float a0 = src[0], a1 = src[step], a2 = src[2 * step], a3 = src[3 * step];
+                        acc += a0; acc += a1; acc += a2; acc += a3;
+                        src += 4 * step;
+                    }
+                    for (; sp < e.splits; ++sp, src += step) acc += *src;
+                }
+                tile[lane][ntaps - 1 - t] = acc;       // tap (r, s) of the correlation = element (R-1-r, S-1-s)
+            }
+            __syncthreads();
+            const int nci = Cin - ci0 < 32 ? Cin - ci0 : 32;
+            float* dst = e.dw + (static_cast<long long>(co) * Cin + ci0) * ntaps;
+            for (int i = threadIdx.x; i < nci * ntaps; i += blockDim.x) {
+                const float v = tile[i / ntaps][i % ntaps];
+                dst[i] = e.accumulate ? dst[i] + v : v;
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    const long long start = block_offset[blockIdx.x];
+    const long long end = start + kReduceChunk < e.total ? start + kReduceChunk : e.total;
     for (long long idx = start + threadIdx.x; idx < end; idx += blockDim.x) {
         const float* src;
         long long step, o;
         if (e.mode == 0) {
-            // idx enumerates (co, tap, ci): coalesced workspace reads
+            // 1x1 filters: workspace [split][co][ci] and gradient [co][ci] enumerate alike
             const int ci = static_cast<int>(idx % Cin);
-            const long long t = idx / Cin;
-            const int tap = static_cast<int>(t % ntaps);
-            const int co = static_cast<int>(t / ntaps);
-            src = e.ws + (static_cast<long long>(co) * ntaps + tap) * e.ldws + ci;
-            step = static_cast<long long>(Cout) * ntaps * e.ldws;
-            const int r = tap / S, sx = tap % S;
-            o = ((static_cast<long long>(co) * Cin + ci) * R + (R - 1 - r)) * S + (S - 1 - sx);
+            const int co = static_cast<int>(idx / Cin);
+            src = e.ws + static_cast<long long>(co) * e.ldws + ci;
+            step = static_cast<long long>(Cout) * e.ldws;
+            o = idx;
         } else {
             const int sf = static_cast<int>(idx % S);
             const int rf = static_cast<int>((idx / S) % R);
@@ -1633,6 +1684,7 @@ extern "C" int denet_conv_weight_prep_multi(const void* entries, const int* bloc
 
 extern "C" int denet_wgrad_reduce_entry_bytes(void) { return (int)sizeof(ReduceEntry); }
 extern "C" int denet_wgrad_reduce_chunk(void) { return kReduceChunk; }
+extern "C" int denet_wgrad_reduce_items(void) { return kReduceItems; }
 
 extern "C" int denet_wgrad_reduce_multi(const void* entries, const int* block_entry, const long long* block_offset,
                                         int nblocks, cudaStream_t stream) {
@@ -1772,7 +1824,8 @@ static int g_wgrad_rows = 1;         // 0: always one tap per tile (A/B switch f
 static int g_wgrad_debug = 0;
 extern "C" int denet_conv2d_wgrad_set_mode(int row_shared) {
     g_wgrad_rows = row_shared & 1;
-    g_wgrad_debug = (row_shared >> 1) & 7;      // undocumented profiling knobs (bit1: no MMA, bit2: no TMA)
+    g_wgrad_debug = ((row_shared >> 1) & 7) | (((row_shared >> 5) & 1) << 3);   // undocumented profiling knobs (bit1: no
+                                                  // MMA, bit2: no TMA, bit3: no store; bit5: per-tap MMAs in the rows kernel)
     g_wgrad_legacy_splits = (row_shared >> 4) & 1;   // bit4: the former split-K rule (A/B measurements)
     return 0;
 }

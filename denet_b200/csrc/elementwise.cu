@@ -9,6 +9,7 @@
 //   relu              denet/layer/activation.py:32-34
 // All kernels are grid-stride over 8-channel packs (16 B bf16 / 32 B fp32 per access, channels contiguous) and are
 // sized in multiples of the SM count; reductions are two-stage with a fixed order (deterministic).
+#include <string.h>
 #include <algorithm>
 
 #include "common.cuh"
@@ -141,6 +142,22 @@ __global__ void bn_stats_finalize_kernel(const T* __restrict__ x, const float* _
 constexpr int kBnUnroll = 4;      // forward apply: 2 streams x 4 rows in flight
 constexpr int kBnUnrollBwd = 4;   // backward passes: 2-3 streams x 4 rows, held as raw 16-byte packs
 
+// Statistics handed over as raw per-channel sums (the producing convolution's epilogue accumulated them): the apply
+// kernel derives mean / inverse std itself - same arithmetic as bn_finalize_sums_kernel, one thread per channel of the
+// block's channel range, shared through shared memory - and the blocks of row slab 0 publish them (backward needs
+// them) and update the running statistics.  Saves one tiny launch per batch-norm layer.
+struct BnSums {
+    const float* sum;        // null: mean / invstd are given
+    const float* sqsum;
+    long long M;
+    float eps;
+    float* mean_out;
+    float* invstd_out;
+    float* run_mean;
+    float* run_stdinv;
+    float momentum;
+};
+
 // y = [relu]( (x - mean) * (gamma * invstd) + beta [+ residual] )
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, long long M, int C, long long ld,
@@ -149,12 +166,36 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta,
                                                               const T* __restrict__ residual, int relu,
-                                                              T* __restrict__ y) {
+                                                              T* __restrict__ y, const BnSums sums) {
     const int CV = C / VEC;
     const int cvt = CV < kBnThreads ? CV : kBnThreads;
     const int rlanes = kBnThreads / cvt;
     const int cv = blockIdx.y * cvt + threadIdx.x % cvt;
     const int rl = threadIdx.x / cvt;
+    __shared__ float s_mu[kBnThreads * (VEC == 8 ? 8 : 1)], s_is[kBnThreads * (VEC == 8 ? 8 : 1)];
+    if (sums.sum) {
+        const int c0 = blockIdx.y * cvt * VEC, nc = cvt * VEC;
+        for (int j = threadIdx.x; j < nc; j += blockDim.x) {
+            const int c = c0 + j;
+            if (c < C) {
+                const double m = (double)sums.sum[c] / (double)sums.M;
+                double var = (double)sums.sqsum[c] / (double)sums.M - m * m;
+                if (var < 0.0) var = 0.0;
+                const float mf = (float)m;
+                const float is = (float)(1.0 / sqrt(var + (double)sums.eps));
+                s_mu[j] = mf;
+                s_is[j] = is;
+                if (blockIdx.x == 0) {
+                    sums.mean_out[c] = mf;
+                    sums.invstd_out[c] = is;
+                    if (sums.run_mean) sums.run_mean[c] = sums.momentum * sums.run_mean[c] + (1.0f - sums.momentum) * mf;
+                    if (sums.run_stdinv)
+                        sums.run_stdinv[c] = sums.momentum * sums.run_stdinv[c] + (1.0f - sums.momentum) * is;
+                }
+            }
+        }
+        __syncthreads();
+    }
     if (cv >= CV || rl >= rlanes) return;
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
@@ -162,8 +203,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         const int c = cv * VEC + i;
-        mu[i] = mean[c];
-        a[i] = gamma[c] * invstd[c];
+        const int j = (threadIdx.x % cvt) * VEC + i;
+        mu[i] = sums.sum ? s_mu[j] : mean[c];
+        a[i] = gamma[c] * (sums.sum ? s_is[j] : invstd[c]);
         b[i] = beta[c];
     }
     const long long coff = (long long)cv * VEC;
@@ -913,9 +955,31 @@ extern "C" int denet_bn_apply(const void* x, int dtype, long long M, int C, long
     const bool v = vec8_ok(C, ld, x, y, residual);
     int rpb, yc;
     const int nslabs = ew_slabs(M, C, v ? 8 : 1, &rpb, &yc);
+    BnSums none;
+    memset(&none, 0, sizeof(none));
     DN_DISPATCH(dtype, v, {
         bn_apply_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>(
-            (const T*)x, M, C, ld, rpb, mean, invstd, gamma, beta, (const T*)residual, relu, (T*)y);
+            (const T*)x, M, C, ld, rpb, mean, invstd, gamma, beta, (const T*)residual, relu, (T*)y, none);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_bn_apply_sums(const void* x, int dtype, long long M, int C, long long ld, const float* sum,
+                                   const float* sqsum, float eps, const float* gamma, const float* beta,
+                                   const void* residual, int relu, void* y, float* mean, float* invstd, float* run_mean,
+                                   float* run_stdinv, float momentum, cudaStream_t stream) {
+    DN_REQUIRE(x && y && sum && sqsum && mean && invstd && gamma && beta, "bn_apply_sums: null pointer");
+    DN_REQUIRE(M > 0, "bn_apply_sums: empty tensor");
+    const bool v = vec8_ok(C, ld, x, y, residual);
+    int rpb, yc;
+    const int nslabs = ew_slabs(M, C, v ? 8 : 1, &rpb, &yc);
+    BnSums sm;
+    sm.sum = sum; sm.sqsum = sqsum; sm.M = M; sm.eps = eps; sm.mean_out = mean; sm.invstd_out = invstd;
+    sm.run_mean = run_mean; sm.run_stdinv = run_stdinv; sm.momentum = momentum;
+    DN_DISPATCH(dtype, v, {
+        bn_apply_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>(
+            (const T*)x, M, C, ld, rpb, nullptr, nullptr, gamma, beta, (const T*)residual, relu, (T*)y, sm);
     });
     DN_CHECK_LAUNCH();
     return 0;

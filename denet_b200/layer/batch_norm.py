@@ -107,13 +107,13 @@ class BatchNormLayer(AbstractLayer):
             mean = torch.empty((c,), dtype=torch.float32, device=x.device)
             invstd = torch.empty_like(mean)
             if self._fused_ready:
-                m = x.shape[0] * x.shape[1] * x.shape[2]
-                ops.bn_finalize_sums(self._fused[0], self._fused[1], m, self.eps, mean, invstd, self.mean, self.stdinv,
-                                     self.momentum)
+                # the conv epilogue left per-channel sums: statistics are finalised inside the apply launch
+                y = ops.bn_apply_sums(x, self._fused[0], self._fused[1], self.eps, self.omega, self.beta, mean, invstd,
+                                      self.mean, self.stdinv, self.momentum, residual=residual, relu=relu)
                 self._fused_ready = False
             else:
                 ops.bn_stats(x, self.eps, mean, invstd, self.mean, self.stdinv, self.momentum)
-            y = ops.bn_apply(x, mean, invstd, self.omega, self.beta, residual=residual, relu=relu)
+                y = ops.bn_apply(x, mean, invstd, self.omega, self.beta, residual=residual, relu=relu)
             # backward needs y only for the relu mask, and only when a residual was added (otherwise the mask is
             # recomputed from x: one tensor read less in both backward passes)
             self._saved = (x, y if (relu and residual is not None) else None, mean, invstd, relu)

@@ -246,6 +246,7 @@ def wgrad_reduce_pending(pending):
         L = lib.load()
         assert L.denet_wgrad_reduce_entry_bytes() == 64
         chunk = L.denet_wgrad_reduce_chunk()
+        items = L.denet_wgrad_reduce_items()
         dev = pending[0].ws.device
         table = numpy.zeros((len(pending), 8), dtype=numpy.int64)
         ints = table.view(numpy.int32).reshape(len(pending), 16)
@@ -256,7 +257,11 @@ def wgrad_reduce_pending(pending):
             table[i, 1] = e.dw.data_ptr()
             table[i, 2] = total
             ints[i, 6:16] = [e.splits, e.cout, e.cin, e.R, e.S, e.ldws, e.mode, e.cp, int(e.accumulate), 0]
-            for o in range(0, total, chunk):
+            if e.mode == 0 and e.R * e.S > 1:      # tiled path: units of (co, 32-channel group)
+                units, per_block = e.cout * ((e.cin + 31) // 32), items
+            else:
+                units, per_block = total, chunk
+            for o in range(0, units, per_block):
                 block_entry.append(i)
                 block_offset.append(o)
         tab = (torch.from_numpy(table).to(dev), torch.tensor(block_entry, dtype=torch.int32, device=dev),
@@ -413,6 +418,18 @@ def bn_apply(x, mean, invstd, gamma, beta, residual=None, relu=False, out=None):
     assert _pitch(out) == _pitch(x) and (residual is None or _pitch(residual) == _pitch(x))
     call("denet_bn_apply", x.data_ptr(), _dtype_code(x), _rows(x), x.shape[-1], _pitch(x), mean.data_ptr(),
          invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(residual), int(relu), out.data_ptr(), _stream())
+    return out
+
+
+def bn_apply_sums(x, sums, sqsums, eps, gamma, beta, mean, invstd, run_mean=None, run_stdinv=None, momentum=0.9,
+                  residual=None, relu=False, out=None):
+    """bn_apply fed with the conv epilogue's per-channel sums: finalises the statistics inside the apply launch"""
+    if out is None:
+        out = alloc_like(x)
+    assert _pitch(out) == _pitch(x) and (residual is None or _pitch(residual) == _pitch(x))
+    call("denet_bn_apply_sums", x.data_ptr(), _dtype_code(x), _rows(x), x.shape[-1], _pitch(x), sums.data_ptr(),
+         sqsums.data_ptr(), eps, gamma.data_ptr(), beta.data_ptr(), _ptr(residual), int(relu), out.data_ptr(),
+         mean.data_ptr(), invstd.data_ptr(), _ptr(run_mean), _ptr(run_stdinv), momentum, _stream())
     return out
 
 

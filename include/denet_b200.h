@@ -101,11 +101,15 @@ int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int 
  * reduces the partials of MANY layers in one launch, in the same fixed order and into the same reference layout.
  * `entries` is a device array of denet_wgrad_reduce_entry_bytes()-sized records {const float* ws; float* dw;
  * long long total (= Cout*Cin*R*S); int splits, Cout, Cin, R, S, ldws, mode (0 generic, 1 row-folded), Cp,
- * accumulate, pad}; block i reduces elements [block_offset[i], +denet_wgrad_reduce_chunk()) of entry block_entry[i]. */
+ * accumulate, pad}.  Work of block i on entry block_entry[i]: for 1x1 filters and the row-folded stem, the elements
+ * [block_offset[i], +denet_wgrad_reduce_chunk()); for multi-tap filters (mode 0, R*S > 1) the items
+ * [block_offset[i], +denet_wgrad_reduce_items()) out of Cout * ceil(Cin/32), an item being one output channel times 32
+ * consecutive input channels times all taps (transposed through shared memory so that both sides are coalesced). */
 int denet_conv2d_wgrad_splits(int N, int Ho, int Wo, int Cout, int Cin, int R, int S, int stride_h, int stride_w);
 int denet_conv2d_rowfold_wgrad_splits(int N, int Ho, int Wo, int Cout, int R);
 int denet_wgrad_reduce_entry_bytes(void);
 int denet_wgrad_reduce_chunk(void);
+int denet_wgrad_reduce_items(void);
 int denet_wgrad_reduce_multi(const void* entries, const int* block_entry, const long long* block_offset, int nblocks,
                              cudaStream_t stream);
 
@@ -170,6 +174,13 @@ int denet_bn_finalize_sums(const float* sum, const float* sqsum, long long M, in
 int denet_bn_apply(const void* x, int dtype, long long M, int C, long long ld, const float* mean, const float* invstd,
                    const float* gamma, const float* beta, const void* residual, int relu, void* y,
                    cudaStream_t stream);
+/* bn_apply with the statistics given as the raw per-channel sums a convolution epilogue accumulated (sum, sqsum over M
+ * rows): derives mean / invstd like denet_bn_finalize_sums, writes them to `mean` / `invstd` (the backward pass reads
+ * them) and updates the running statistics - one launch instead of two per batch-norm layer. */
+int denet_bn_apply_sums(const void* x, int dtype, long long M, int C, long long ld, const float* sum,
+                        const float* sqsum, float eps, const float* gamma, const float* beta, const void* residual,
+                        int relu, void* y, float* mean, float* invstd, float* run_mean, float* run_stdinv,
+                        float momentum, cudaStream_t stream);
 int denet_bn_inference_invstd(const float* run_stdinv, float eps, float* out, int C, cudaStream_t stream);
 int denet_bn_backward(const void* dy, const void* yout, const void* x, int dtype, long long M, int C, long long ld,
                       const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,

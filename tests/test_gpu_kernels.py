@@ -257,6 +257,33 @@ def test_bn_forward_backward(cuda, dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(4, 64, 9, 9), (3, 100, 5, 7), (2, 512, 4, 4), (2, 2304, 3, 3)])
+def test_bn_apply_from_epilogue_sums(cuda, dtype, shape):
+    """bn_apply_sums (statistics finalised inside the apply launch) == bn_finalize_sums + bn_apply, bit for bit:
+    output, published mean / invstd and the running-statistics update"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(shape[1] + 1)
+    n, c, h, w = shape
+    x = (torch.randn(shape, generator=g) * 2 + 0.5).to(dtype).float()
+    res = torch.randn(shape, generator=g).to(dtype).float()
+    xd, resd = nhwc(x, dtype, cuda), nhwc(res, dtype, cuda)
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(cuda), torch.randn(c, generator=g).to(cuda)
+    xf = xd[..., :c].float().reshape(-1, c)
+    ssum, ssq = xf.sum(0).contiguous(), (xf * xf).sum(0).contiguous()
+    M = xf.shape[0]
+    mean_a, is_a, rm_a, rs_a = (torch.empty(c, device=cuda), torch.empty(c, device=cuda),
+                                torch.full((c,), 0.25, device=cuda), torch.full((c,), 1.5, device=cuda))
+    ops.bn_finalize_sums(ssum, ssq, M, 1e-5, mean_a, is_a, rm_a, rs_a, 0.9)
+    ya = ops.bn_apply(xd, mean_a, is_a, gamma, beta, residual=resd, relu=True)
+    mean_b, is_b, rm_b, rs_b = (torch.empty(c, device=cuda), torch.empty(c, device=cuda),
+                                torch.full((c,), 0.25, device=cuda), torch.full((c,), 1.5, device=cuda))
+    yb = ops.bn_apply_sums(xd, ssum, ssq, 1e-5, gamma, beta, mean_b, is_b, rm_b, rs_b, 0.9, residual=resd, relu=True)
+    assert torch.equal(mean_a, mean_b) and torch.equal(is_a, is_b)
+    assert torch.equal(rm_a, rm_b) and torch.equal(rs_a, rs_b)
+    assert torch.equal(ya[..., :c], yb[..., :c])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_bn_backward_mask_recomputed_from_x(cuda, dtype):
     """BN+ReLU without a residual: the backward recomputes the relu mask from x (yout = None) and must give exactly
     what the mask read back from the stored forward output gives"""

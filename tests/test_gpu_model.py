@@ -273,8 +273,13 @@ def _steps(model, x, metas, n, graphs):
 
 @pytest.mark.parametrize("which", ["denet", "classifier"])
 def test_cuda_graph_step_equals_eager_step(cuda, which):
-    """the captured-graph training step (ModelCNN.enable_cuda_graphs) follows the eager step: same costs and the same
-    parameters after 3 steps, up to the order-nondeterminism of the fp32 atomics both modes share"""
+    """the captured-graph training step (ModelCNN.enable_cuda_graphs) follows the eager step.  With the batch-norm
+    statistics taken by the deterministic two-stage reduction the classifier must match BIT FOR BIT (costs and
+    parameters after 3 steps); the conv-epilogue statistics (fp32 atomics, the throughput default) and the sparse
+    scatter of the DeNet head are order-nondeterministic in both modes, so there the graphed run only has to stay within
+    the run-to-run spread of these tiny, chaotic models"""
+    from denet_b200 import layer as layer_mod
+
     def make():
         if which == "denet":
             m = build(DENET_SMALL, (3, 128, 128), 4, 20, "bf16", convert=True)
@@ -290,21 +295,34 @@ def test_cuda_graph_step_equals_eager_step(cuda, which):
     else:
         x = numpy.random.uniform(0, 1, (8, 3, 64, 64)).astype(numpy.float32)
         metas = [{"image_class": int(c), "bbox": [], "class": []} for c in numpy.random.randint(0, 10, 8)]
-    a = make()
-    ca = _steps(a, x, metas, 3, graphs=False)
-    a2 = make()
-    ca2 = _steps(a2, x, metas, 3, graphs=False)
-    b = make()
-    cb = _steps(b, x, metas, 3, graphs=True)     # step 0 eager warm-up, step 1 captures + replays, step 2 replays
-    assert b._graphs is not None, "the graphs were not captured"
-    # two EAGER runs of this tiny model already differ (fp32 atomics order in the batch-norm statistics and the
-    # sparse scatter, amplified step by step): the graphed run must stay within a few times that run-to-run noise
-    for (t0, _), (t1, _), (t2, _) in zip(ca, ca2, cb):
-        assert abs(t0 - t2) <= 3 * abs(t0 - t1) + 1e-2 * abs(t0) + 1e-3, (ca, ca2, cb)   # bf16: 1 ulp = 0.4 %
-    pa, pa2, pb = named_params(a), named_params(a2), named_params(b)
-    for name in pa:
-        if pa[name].norm().item() > 1e-2:
-            assert relerr(pb[name], pa[name]) < 3 * relerr(pa2[name], pa[name]) + 2e-2, name
+    try:
+        if which == "classifier":
+            layer_mod.set_fuse_bn_stats(False)
+            a = make()
+            ca = _steps(a, x, metas, 3, graphs=False)
+            b = make()
+            cb = _steps(b, x, metas, 3, graphs=True)
+            assert b._graphs is not None, "the graphs were not captured"
+            assert ca == cb, (ca, cb)
+            pa, pb = named_params(a), named_params(b)
+            for name in pa:
+                assert torch.equal(pa[name], pb[name]), name
+        layer_mod.set_fuse_bn_stats(True)
+        a = make()
+        ca = _steps(a, x, metas, 3, graphs=False)
+        a2 = make()
+        ca2 = _steps(a2, x, metas, 3, graphs=False)
+        b = make()
+        cb = _steps(b, x, metas, 3, graphs=True)     # step 0 eager warm-up, step 1 captures + replays, step 2 replays
+        assert b._graphs is not None, "the graphs were not captured"
+        for (t0, _), (t1, _), (t2, _) in zip(ca, ca2, cb):
+            assert abs(t0 - t2) <= 3 * abs(t0 - t1) + 0.1 * abs(t0) + 1e-3, (ca, ca2, cb)
+        pa, pa2, pb = named_params(a), named_params(a2), named_params(b)
+        for name in pa:
+            if pa[name].norm().item() > 1e-2:
+                assert relerr(pb[name], pa[name]) < 3 * relerr(pa2[name], pa[name]) + 5e-2, name
+    finally:
+        layer_mod.set_fuse_bn_stats(True)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
