@@ -117,6 +117,12 @@ struct ConvWgradParams {
     int xbox_bytes;       // its smem footprint (xrows * 128 rounded up to 1024)
     int a_boxes;          // 64-channel dY sub-boxes actually loaded (1 when Cout <= 64)
     int debug;            // profiling knobs: bit0 skip the MMAs, bit1 skip the TMA loads (results are garbage)
+    // row-folded stem variant (conv_wgrad_stem_kernel): all R filter rows per tile
+    int x_loads;          // X boxes per stage: 1 (stride_h 1) or 2 (even / odd input rows of a stride-2 stem)
+    int xbox_stride;      // shared-memory distance between them (1024-byte multiple)
+    int stem_stages;      // ring depth
+    int stem_stage_bytes; // a_boxes * 8192 + x_loads * xbox_stride
+    int ntap[2];          // filter rows served by X box 0 / 1 (N of its MMA = ntap * 64)
 };
 
 template <int BN, int STAGES>
@@ -1233,6 +1239,207 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rows_kernel(const __gr
     }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, stem
+// Filter gradient of the row-folded stem (the S taps of a filter row are folded into K = 64 columns): ALL R filter rows
+// in one tile.  Per k-block of 8 x 8 output pixels the dY box is fetched once (conv_wgrad_kernel fetches it once per
+// filter row) together with the input rows the block touches - one box for stride 1, the even and the odd input rows as
+// two boxes for stride 2 - and filter row r = p + stride * j reads box p starting j image rows (TW * 128 B) in.  The j's
+// of one box are stacked along N: the B operand is described as ntap column groups of 64 whose group stride (LBO) is
+// one image row of the box, so ONE MMA per K step computes every filter row of that parity (N = 256 + N = 192 for the
+// 7-row stem instead of 7 MMAs of N = 64, and 2 instead of 7 barrier round trips per 64 pixels).
+// Accumulators: R * 64 TMEM columns, column block of row r = (r % stride) * ntap[0] * 64 + (r / stride) * 64.
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_stem_kernel(const __grid_constant__ ConvWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int STAGES = p.stem_stages;
+    const int stage_bytes = p.stem_stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* tfull_bar = empty_bar + 8;
+    uint64_t* tempty_bar = tfull_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 512;
+    constexpr int kBoxBytes = kBK * 128;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 8; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::mbar_init(tempty_bar, 4);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = p.num_tiles, nterms = p.nterms, a_boxes = p.a_boxes, x_loads = p.x_loads;
+    const int a_bytes = a_boxes * kBoxBytes, xbox_stride = p.xbox_stride;
+    // tile -> (co tile, split)
+    auto decode = [&](int tile, int& cot, int& split, int& kb0, int& kb1) {
+        uint32_t t, a;
+        p.fd_cot.divmod(tile, t, a);
+        cot = a;
+        split = t;
+        kb0 = static_cast<int>(static_cast<long long>(p.total_kblocks) * split / p.splits);
+        kb1 = static_cast<int>(static_cast<long long>(p.total_kblocks) * (split + 1) / p.splits);
+    };
+
+    if (warp == 0) {
+        if (ptx::elect_one()) {
+            ptx::tma_prefetch_desc(&p.tmDY[0]);
+            ptx::tma_prefetch_desc(&p.tmX[0]);
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        const int TW = p.TW, TH = p.TH, TN = p.TN, stride_h = p.stride_h, debug = p.debug;
+        const uint32_t tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+        const uint32_t stage_tx = a_bytes + x_loads * (p.xrows * 128);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int cot, split, kb0, kb1;
+            decode(tile, cot, split, kb0, kb1);
+            uint32_t tw, th, tn, t2;
+            p.fd_w.divmod(kb0, t2, tw);
+            p.fd_h.divmod(t2, tn, th);
+            const int cA = cot * kBM;
+#pragma unroll 1
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int w0 = tw * TW, h0 = th * TH, n0 = tn * TN;
+                for (int term = 0; term < nterms; ++term) {
+                    const CUtensorMap* mapA = &p.tmDY[(term == 1) ? 1 : 0];
+                    const CUtensorMap* mapB = &p.tmX[(term == 2) ? 1 : 0];
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * stage_bytes;
+                    uint8_t* sB = sA + a_bytes;
+                    if (ptx::elect_one()) {
+                        if (debug & 2) {
+                            ptx::mbar_arrive(&full_bar[stage]);
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
+                            ptx::tma_load_4d(sA, mapA, &full_bar[stage], cA, w0, h0, n0);
+                            if (a_boxes > 1) ptx::tma_load_4d(sA + kBoxBytes, mapA, &full_bar[stage], cA + 64, w0, h0, n0);
+                            for (int i = 0; i < x_loads; ++i)
+                                ptx::tma_load_4d(sB + i * xbox_stride, mapB, &full_bar[stage], 0, w0, h0 * stride_h + i, n0);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                if (++tw == tiles_w) {
+                    tw = 0;
+                    if (++th == tiles_h) {
+                        th = 0;
+                        ++tn;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t smem0 = ptx::smem_u32(smem);
+        // dY: MN-major, 64-channel sub-boxes kBoxBytes apart, 8-pixel groups 1024 B apart.  X: MN-major, column group g
+        // = filter row j = g of this box, one image row (TW * 128 B) further in; 8-pixel groups 1024 B apart (the box
+        // has no halo along W, so the 64 pixels of the k-block are contiguous rows of it).
+        const uint64_t adesc0 = ptx::make_smem_desc(smem0, kBoxBytes, 1024);
+        const uint64_t bdesc0 = ptx::make_smem_desc(smem0 + a_bytes, p.TW * 128, 1024);
+        const uint32_t idesc0 = ptx::make_idesc_bf16(p.ntap[0] * 64, 1, 1);
+        const uint32_t idesc1 = ptx::make_idesc_bf16(p.ntap[1] > 0 ? p.ntap[1] * 64 : 64, 1, 1);
+        const uint32_t col1 = p.ntap[0] * 64;
+        const uint32_t xb16 = static_cast<uint32_t>(xbox_stride) >> 4;
+        const bool two = x_loads > 1;
+        const bool do_mma = !(p.debug & 1);
+        const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int cot, split, kb0, kb1;
+            decode(tile, cot, split, kb0, kb1);
+            ptx::mbar_wait(tempty_bar, (it & 1) ^ 1);
+            ptx::tc_fence_after();
+            const int nk = (kb1 - kb0) * nterms;
+#pragma unroll 1
+            for (int kb = 0; kb < nk; ++kb) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                const uint64_t soff = static_cast<uint64_t>(stage * stage16);
+                const uint64_t adesc = adesc0 + soff;
+                const uint64_t bdesc = bdesc0 + soff;
+                if (ptx::elect_one()) {
+                    if (do_mma) {
+#pragma unroll
+                        for (int j = 0; j < kBK / 16; ++j) {        // 16 pixels = 2048 B in both operands
+                            ptx::umma_f16(tmem_base, adesc + 128 * j, bdesc + 128 * j, idesc0, (kb | j) != 0);
+                            if (two)
+                                ptx::umma_f16(tmem_base + col1, adesc + 128 * j, bdesc + xb16 + 128 * j, idesc1,
+                                              (kb | j) != 0);
+                        }
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (ptx::elect_one()) ptx::umma_commit(tfull_bar);
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int R = p.R, stride_h = p.stride_h;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int cot, split, kb0, kb1;
+            decode(tile, cot, split, kb0, kb1);
+            const int co = cot * kBM + row;
+            const bool row_ok = co < p.Cout;
+            ptx::mbar_wait(tfull_bar, it & 1);
+            ptx::tc_fence_after();
+            for (int r = 0; r < R; ++r) {
+                const uint32_t col = static_cast<uint32_t>((r % stride_h) * p.ntap[0] * 64 + (r / stride_h) * 64);
+                float* dst_row = p.ws + ((static_cast<long long>(split) * p.Cout + co) * R + r) * static_cast<long long>(p.ldws);
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t rr[32];
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col + c0;
+                    ptx::tmem_ld_32x32b_x32(taddr, rr);
+                    ptx::tmem_ld_wait();
+                    if (row_ok && !(p.debug & 4)) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+                        store_row_chunk(dst_row, 1, c0, v, 32);
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 // Sum the split-K partials and scatter into the reference filter layout (Cout, Cin, R, S) of the *true*
 // convolution (tap (r,s) of the correlation is element (R-1-r, S-1-s) of the reference filter).
 // accumulate != 0 adds into dw (used when a layer's weight receives gradient from two paths).
@@ -2096,21 +2303,55 @@ extern "C" int denet_conv2d_rowfold_fprop(const void* x_hi, const void* x_lo, in
     return fprop_finish(p, b_hi, b_lo, stream);
 }
 
-extern "C" size_t denet_conv2d_rowfold_wgrad_workspace(int N, int Ho, int Wo, int Cout, int R) {
-    int TW, TH, TN;
-    pick_patch(Wo, Ho, N, 64, TW, TH, TN);
-    const int total_kb = ceil_div(Wo, TW) * ceil_div(Ho, TH) * ceil_div(N, TN);
-    const int splits = wgrad_splits(total_kb, ceil_div(Cout, 128) * R, 64, (Cout <= 64 ? 1 : 2) * 8192 + 8192,
-                                    (long long)Cout * R * 64);
-    return (size_t)splits * Cout * R * 64 * sizeof(float);
+namespace dn {
+
+// Tiling plan of the row-folded filter gradient.  stem: conv_wgrad_stem_kernel (all R filter rows per tile, 8 x 8 pixel
+// k-blocks of one image); otherwise conv_wgrad_kernel with one filter row per tile.
+struct RowfoldWgradPlan {
+    int stem, TW, TH, TN, total_kb, base_tiles, splits, rows, x_loads, ntap0, ntap1, xbox_stride, stage_bytes, stages;
+};
+
+static RowfoldWgradPlan plan_rowfold_wgrad(int N, int Ho, int Wo, int Cout, int R, int stride_h) {
+    RowfoldWgradPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    const int a_boxes = Cout <= 64 ? 1 : 2;
+    const int co_tiles = ceil_div(Cout, 128);
+    pl.ntap0 = ceil_div(R, stride_h);
+    pl.ntap1 = stride_h == 2 ? R / 2 : 0;
+    pl.stem = g_wgrad_rows && R > 1 && (stride_h == 1 || stride_h == 2) && pl.ntap0 * 64 <= 256 && R * 64 <= 512 &&
+              Wo >= 8 && Ho >= 4;
+    if (pl.stem) {
+        pl.TW = 8; pl.TH = 8; pl.TN = 1;
+        pl.total_kb = ceil_div(Wo, 8) * ceil_div(Ho, 8) * N;
+        pl.base_tiles = co_tiles;
+        pl.rows = pl.TH + (R - 1) / stride_h;
+        pl.x_loads = stride_h < R ? stride_h : R;
+        pl.xbox_stride = (pl.rows * pl.TW * 128 + 1023) / 1024 * 1024;
+        pl.stage_bytes = a_boxes * 8192 + pl.x_loads * pl.xbox_stride;
+        pl.stages = (200 * 1024) / pl.stage_bytes;
+        if (pl.stages > 8) pl.stages = 8;
+        if (pl.stages < 2) pl.stem = 0;
+    }
+    if (pl.stem) {
+        pl.splits = wgrad_splits(pl.total_kb, pl.base_tiles, R * 64, pl.stage_bytes, (long long)Cout * R * 64);
+    } else {
+        pick_patch(Wo, Ho, N, 64, pl.TW, pl.TH, pl.TN);
+        pl.total_kb = ceil_div(Wo, pl.TW) * ceil_div(Ho, pl.TH) * ceil_div(N, pl.TN);
+        pl.base_tiles = co_tiles * R;
+        pl.splits = wgrad_splits(pl.total_kb, pl.base_tiles, 64, a_boxes * 8192 + 8192, (long long)Cout * R * 64);
+    }
+    return pl;
 }
 
-extern "C" int denet_conv2d_rowfold_wgrad_splits(int N, int Ho, int Wo, int Cout, int R) {
-    int TW, TH, TN;
-    pick_patch(Wo, Ho, N, 64, TW, TH, TN);
-    const int total_kb = ceil_div(Wo, TW) * ceil_div(Ho, TH) * ceil_div(N, TN);
-    return wgrad_splits(total_kb, ceil_div(Cout, 128) * R, 64, (Cout <= 64 ? 1 : 2) * 8192 + 8192,
-                        (long long)Cout * R * 64);
+}  // namespace dn
+
+extern "C" size_t denet_conv2d_rowfold_wgrad_workspace(int N, int Ho, int Wo, int Cout, int R, int stride_h) {
+    const RowfoldWgradPlan pl = plan_rowfold_wgrad(N, Ho, Wo, Cout, R, stride_h);
+    return (size_t)pl.splits * Cout * R * 64 * sizeof(float);
+}
+
+extern "C" int denet_conv2d_rowfold_wgrad_splits(int N, int Ho, int Wo, int Cout, int R, int stride_h) {
+    return plan_rowfold_wgrad(N, Ho, Wo, Cout, R, stride_h).splits;
 }
 
 extern "C" int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int Wo, int Cout,
@@ -2127,16 +2368,17 @@ extern "C" int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, 
     p.nterms = dy_lo ? 3 : 1;
     p.R = R; p.S = 1; p.pad_h = 0; p.pad_w = 0;
     p.stride_h = stride_h; p.stride_w = 1;
-    pick_patch(Wo, Ho, N, 64, p.TW, p.TH, p.TN);
+    const RowfoldWgradPlan pl = plan_rowfold_wgrad(N, Ho, Wo, Cout, R, stride_h);
+    p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN;
     p.tiles_w = ceil_div(Wo, p.TW);
     p.tiles_h = ceil_div(Ho, p.TH);
     p.tiles_n = ceil_div(N, p.TN);
-    p.total_kblocks = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.total_kblocks = pl.total_kb;
     p.co_tiles = ceil_div(Cout, 128);
     p.ci_tiles = 1;
-    p.splits = wgrad_splits(p.total_kblocks, p.co_tiles * R, 64, (Cout <= 64 ? 1 : 2) * 8192 + 8192,
-                            (long long)Cout * R * 64);
-    p.num_tiles = p.co_tiles * R * p.splits;
+    p.splits = pl.splits;
+    p.num_tiles = pl.base_tiles * pl.splits;
+    p.debug = g_wgrad_debug;
     p.fd_cot = make_fastdiv(p.co_tiles);
     p.fd_cit = make_fastdiv(1);
     p.fd_taps = make_fastdiv(R);
@@ -2150,10 +2392,26 @@ extern "C" int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, 
     DN_REQUIRE(workspace_bytes >= need, "conv2d_rowfold_wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
     if ((rc = make_act_map(&p.tmDY[0], dy_hi, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
     if (dy_lo && (rc = make_act_map(&p.tmDY[1], dy_lo, Cout, Wo, Ho, N, lddy, p.TW, p.TH, p.TN))) return rc;
-    if ((rc = make_rowfold_map(&p.tmX[0], x_hi, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, p.TH, p.TN))) return rc;
-    if (x_lo && (rc = make_rowfold_map(&p.tmX[1], x_lo, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, p.TH, p.TN)))
+    const int xbox_rows = pl.stem ? pl.rows : p.TH;
+    if ((rc = make_rowfold_map(&p.tmX[0], x_hi, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, xbox_rows, p.TN))) return rc;
+    if (x_lo && (rc = make_rowfold_map(&p.tmX[1], x_lo, Cp, S, Wo, Hp, Wp, N, stride_w, stride_h, p.TW, xbox_rows, p.TN)))
         return rc;
-    if ((rc = wgrad_launch(p, stream))) return rc;
+    if (pl.stem) {
+        p.x_loads = pl.x_loads;
+        p.xbox_stride = pl.xbox_stride;
+        p.xrows = pl.rows * pl.TW;
+        p.stem_stages = pl.stages;
+        p.stem_stage_bytes = pl.stage_bytes;
+        p.ntap[0] = pl.ntap0;
+        p.ntap[1] = pl.ntap1;
+        const size_t smem = 1024 + (size_t)pl.stages * pl.stage_bytes + 256;
+        DN_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+        conv_wgrad_stem_kernel<<<DN_G(grid), kThreads, smem, stream>>>(p);
+        DN_CHECK_LAUNCH();
+    } else if ((rc = wgrad_launch(p, stream))) {
+        return rc;
+    }
     if (!dw) return 0;      // partial sums only (see denet_wgrad_reduce_multi)
     const long long total = (long long)Cout * Cin * R * S;
     const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148LL * 16);

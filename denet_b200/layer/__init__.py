@@ -187,6 +187,34 @@ def h2d(array, device=None, slot=None):
     return dst
 
 
+def h2d_on_stream(array, device, slot, stream, after=None):
+    """like h2d(..., slot=...) for HOST data, but enqueued on `stream` (a copy stream) after the event `after` (the last
+    consumer of the slot's device tensor): the transfer overlaps whatever the compute stream is still doing.  Returns
+    (device tensor, event that fires when the data has landed); the consumer's stream must wait on that event."""
+    t = array if torch.is_tensor(array) else torch.from_numpy(numpy.ascontiguousarray(array))
+    assert not t.is_cuda
+    ent = _slots.get(slot)
+    if ent is None or ent[1].shape != t.shape or ent[1].dtype != t.dtype:
+        ent = (torch.empty(t.shape, dtype=t.dtype).pin_memory(), torch.empty(t.shape, dtype=t.dtype, device=device),
+               torch.cuda.Event())
+        _slots[slot] = ent
+    pinned, dst, done = ent
+    transfer_bytes["h2d"] += t.numel() * t.element_size()
+    ready = torch.cuda.Event()
+    with torch.cuda.stream(stream):
+        if after is not None:
+            stream.wait_event(after)
+        if t.is_pinned():
+            dst.copy_(t, non_blocking=True)      # caller-owned pinned memory: no staging copy
+        else:
+            done.synchronize()                    # the previous copy out of the staging buffer has finished
+            pinned.copy_(t)
+            dst.copy_(pinned, non_blocking=True)
+            done.record(stream)
+        ready.record(stream)
+    return dst, ready
+
+
 def slot_tensor(slot):
     ent = _slots.get(slot)
     return None if ent is None else ent[1]

@@ -68,8 +68,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.denet_abi_version() != 3:
-        raise DenetError("denet_b200: ABI version mismatch (library %d, binding 3) - rebuild" % lib.denet_abi_version())
+    if lib.denet_abi_version() != 4:
+        raise DenetError("denet_b200: ABI version mismatch (library %d, binding 4) - rebuild" % lib.denet_abi_version())
     _lib = lib
     # profiling / A-B switches (kernel variants only; every variant is a CUDA kernel of this library)
     if os.environ.get("DENET_FPROP_MODE"):

@@ -123,6 +123,11 @@ class ModelCNN:
         self._prep_precision = None
         self._prep_layers = []
         self._use_graphs = False
+        self._copy_stream = None       # graphed steps: image upload / cost download off the compute stream
+        self._img_consumed = self._cost_ready = self._cost_copied = None
+        self._img_consumed_valid = False
+        self._costs_pinned = None
+        self._host_costs = None
 
     # ---------------------------------------------------------------------------------------------- shapes
     def get_input_shape(self):
@@ -575,27 +580,50 @@ class ModelCNN:
             self.layers[si].enqueue_samples()
         return x
 
-    def _segment_b(self, x, si, hp_dev):
-        """sparse gather -> head -> costs -> backward (+ gradient all-reduce) -> solver"""
+    def _segment_b1(self, x, si):
+        """sparse gather -> head -> costs (the end of the forward pass)"""
         if si is not None:
             x = self.forward_layers(x, si, len(self.layers), train=True, with_targets=False)
+        self._g_costs.copy_(self._pack_costs())
+
+    def _segment_b2(self, hp_dev):
+        """backward (+ gradient all-reduce) -> solver"""
         if self.ddp is not None:
             self.ddp.begin_step()
         self.backward()
         if self.ddp is not None:
             self.ddp.finish_step()
         self.solver_step(None, None, None, None, hp_dev=hp_dev)
-        self._g_costs.copy_(self._pack_costs())
 
     def _train_step_graphed(self, data_x, data_m, it, learning_rate, momentum, decay):
+        """Replays the captured step.  Two things are taken off the critical path of a caller that feeds HOST batches
+        and reads the costs back (train_step): the image upload runs on a copy stream and only waits for the previous
+        step's stem to have consumed the staging tensor, and the costs - final once the forward pass is done - are
+        copied to pinned host memory on that stream while the backward pass and the update still run; train_step
+        returns as soon as they have landed, so the next call's upload overlaps this step's backward pass."""
         if not self._graph_warm:
             # eager step through the persistent input buffers: allocates them, the workspaces and the cost tensors
             self._graph_warm = True
+            self._host_costs = None
             return self._train_step_eager(data_x, data_m, it, learning_rate, momentum, decay)
         si = self._sparse_index()
         layer_mod.set_train(True)
+        cur = torch.cuda.current_stream()
         # refresh the static inputs of this step
-        layer_mod.h2d(data_x, self.device, slot="model/image")
+        img_ready = None
+        host_image = not (torch.is_tensor(data_x) and data_x.is_cuda)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._img_consumed = torch.cuda.Event()
+            self._cost_ready = torch.cuda.Event()
+            self._cost_copied = torch.cuda.Event()
+        if host_image:
+            if isinstance(data_x, numpy.ndarray):
+                data_x = numpy.ascontiguousarray(data_x, dtype=numpy.float32)
+            _, img_ready = layer_mod.h2d_on_stream(data_x, self.device, "model/image", self._copy_stream,
+                                                   self._img_consumed if self._img_consumed_valid else None)
+        else:
+            layer_mod.h2d(data_x, self.device, slot="model/image")
         gt = self.upload_metas(data_m)
         layer_mod.set_ground_truth(gt)
         for l in self.layers[1:]:
@@ -603,14 +631,31 @@ class ModelCNN:
                 l.set_target(*l.get_target(self, data_x, data_m))
         hp_dev = self._write_hp(it, learning_rate, momentum, decay)
         if self._graphs is None:
+            if img_ready is not None:
+                img_ready.synchronize()
             self._capture(si, hp_dev)
-        ga, gb = self._graphs
+        ga, gb1, gb2 = self._graphs
+        if img_ready is not None:
+            cur.wait_event(img_ready)
         ga.replay()
+        self._img_consumed.record(cur)               # the staging tensor of the image may be overwritten from here on
+        self._img_consumed_valid = True
         if si is not None:
             sp = self.layers[si]
             sp.finish_target(data_m, *sp.collect_samples())
-        if gb is not None:
-            gb.replay()
+            gb1.replay()
+        self._host_costs = None
+        if host_image:
+            # costs are final here: fetch them on the copy stream while the backward pass runs
+            if self._costs_pinned is None or self._costs_pinned.shape != self._g_costs.shape:
+                self._costs_pinned = torch.empty(self._g_costs.shape, dtype=torch.float32).pin_memory()
+            self._cost_ready.record(cur)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._cost_ready)
+                self._costs_pinned.copy_(self._g_costs, non_blocking=True)
+                self._cost_copied.record(self._copy_stream)
+            self._host_costs = (self._costs_pinned, self._cost_copied)
+        gb2.replay()
         layer_mod.bump_param_version()
         self.last_costs_device = self._g_costs
         return self.last_costs_device
@@ -629,21 +674,35 @@ class ModelCNN:
             ops.pin_stream(True)
             x = self._segment_a(si)
             if si is None:
-                self._segment_b(x, si, hp_dev)
-        gb = None
+                self._segment_b1(x, si)
+        gb1 = None
         if si is not None:
             # the RoI box buffers are persistent slots created by the eager warm-up step: record against them
-            gb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gb, pool=pool):
+            gb1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb1, pool=pool):
                 ops.pin_stream(True)
-                self._segment_b(x, si, hp_dev)
+                self._segment_b1(x, si)
+        gb2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb2, pool=pool):
+            ops.pin_stream(True)
+            self._segment_b2(hp_dev)
         ops.pin_stream(True)
-        self._graphs = (ga, gb)
+        self._graphs = (ga, gb1, gb2)
 
     def train_step(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):
         """reference contract (model_cnn.py:407-445): returns (cost, [layer costs]) as python floats"""
         assert "train_step" in self.func, "Call build_train_func() before calling train_step()"
-        costs = layer_mod.d2h(self._train_step_device(data_x, data_m, epoch, it, learning_rate, momentum, decay))
+        dev = self._train_step_device(data_x, data_m, epoch, it, learning_rate, momentum, decay)
+        if self._host_costs is not None:
+            # graphed step: the costs were copied to pinned memory right after the forward pass; the backward pass and
+            # the update may still be running (every later call is ordered behind them on the compute stream)
+            pinned, landed = self._host_costs
+            self._host_costs = None
+            landed.synchronize()
+            layer_mod.transfer_bytes["d2h"] += pinned.numel() * 4
+            costs = pinned.numpy().copy()
+        else:
+            costs = layer_mod.d2h(dev)
         return float(costs[0]), [float(c) for c in costs[1:]]
 
     def train_epoch(self, dataset, epoch, learning_rate, momentum=[0, 1, 0], decay=0.0, solver_mode="sgd"):

@@ -335,11 +335,11 @@ def conv2d_rowfold_wgrad(dyop, img, R, S, stride, dw, accumulate=False, defer=No
     n, ho, wo, cout = dy.shape
     assert (dyop.lo is None) == (img.lo is None)
     L = lib.load()
-    nbytes = L.denet_conv2d_rowfold_wgrad_workspace(n, ho, wo, cout, R)
+    nbytes = L.denet_conv2d_rowfold_wgrad_workspace(n, ho, wo, cout, R, stride[0])
     if defer is not None:
         pending, owner = defer
         ws = _own_workspace(owner, nbytes, dy.device)
-        splits = L.denet_conv2d_rowfold_wgrad_splits(n, ho, wo, cout, R)
+        splits = L.denet_conv2d_rowfold_wgrad_splits(n, ho, wo, cout, R, stride[0])
         pending.append(WgradPending(ws, dw, splits, cout, img.c, R, S, 64, 1, img.cp, accumulate))
         dw_ptr = None
     else:

@@ -28,7 +28,7 @@ typedef struct CUstream_st* cudaStream_t;
 extern "C" {
 #endif
 
-#define DENET_ABI_VERSION 3
+#define DENET_ABI_VERSION 4
 
 #define DENET_F32 0
 #define DENET_BF16 1
@@ -106,7 +106,7 @@ int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int 
  * [block_offset[i], +denet_wgrad_reduce_items()) out of Cout * ceil(Cin/32), an item being one output channel times 32
  * consecutive input channels times all taps (transposed through shared memory so that both sides are coalesced). */
 int denet_conv2d_wgrad_splits(int N, int Ho, int Wo, int Cout, int Cin, int R, int S, int stride_h, int stride_w);
-int denet_conv2d_rowfold_wgrad_splits(int N, int Ho, int Wo, int Cout, int R);
+int denet_conv2d_rowfold_wgrad_splits(int N, int Ho, int Wo, int Cout, int R, int stride_h);
 int denet_wgrad_reduce_entry_bytes(void);
 int denet_wgrad_reduce_chunk(void);
 int denet_wgrad_reduce_items(void);
@@ -147,7 +147,7 @@ int denet_conv2d_rowfold_fprop(const void* x_hi, const void* x_lo, int N, int Hp
                                const void* b_hi, const void* b_lo, int Cout, int R, int S, int stride_h, int stride_w,
                                void* y, int y_dtype, long long ldy, int Ho, int Wo, const float* bias, int relu,
                                float* stat_sum, float* stat_sqsum, cudaStream_t stream);
-size_t denet_conv2d_rowfold_wgrad_workspace(int N, int Ho, int Wo, int Cout, int R);
+size_t denet_conv2d_rowfold_wgrad_workspace(int N, int Ho, int Wo, int Cout, int R, int stride_h);
 int denet_conv2d_rowfold_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int Wo, int Cout, long long lddy,
                                const void* x_hi, const void* x_lo, int Hp, int Wp, int Cp, int Cin, int R, int S,
                                int stride_h, int stride_w, float* dw, int accumulate, float* workspace,
