@@ -244,7 +244,7 @@ def run_b200(args):
 
     # ---- conv kernel timing (roofline): eager launches of the same steps, every conv entry point bracketed by CUDA
     # events on its stream (events cannot be recorded inside a replayed graph)
-    timed_names = ["denet_conv2d_fprop", "denet_conv2d_wgrad", "denet_conv2d_rowfold_fprop",
+    timed_names = ["denet_conv2d_fprop", "denet_conv2d_dgrad_bnbwd", "denet_conv2d_wgrad", "denet_conv2d_rowfold_fprop",
                    "denet_conv2d_rowfold_wgrad", "denet_wgrad_reduce_multi"]
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -273,11 +273,15 @@ def run_b200(args):
 
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()       # nvidia-smi attaches to the driver for ~10 ms when it starts: keep that out of the timed
-                              # steps (it keeps sampling every 100 ms through both timed regions)
+        sampler.start()       # nvidia-smi stalls the GPU for ~10 ms while it attaches to the driver: run untimed steps
+                              # until its first sample has arrived (it then samples every 100 ms through both regions)
     # ---- region A: inputs resident in HBM (value)
-    for _ in range(3):        # untimed transition steps (input source host batch -> resident batch, sampler start-up)
+    for _ in range(8):        # untimed transition steps (input source host batch -> resident batch, sampler start-up);
+        step_device()         # the same count on every rank (the steps contain collectives)
+    extra = 0
+    while world == 1 and sampler.proc is not None and len(sampler.rows) < 1 and extra < 50:
         step_device()
+        extra += 1
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

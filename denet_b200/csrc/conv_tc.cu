@@ -28,7 +28,9 @@ namespace dn {
 
 constexpr int kBM = 128;      // UMMA M (TMEM lanes)
 constexpr int kBK = 64;       // K elements per pipeline stage (= 128 B of bf16 = one swizzle row)
-constexpr int kThreads = 192; // 6 warps
+constexpr int kThreads = 192; // 6 warps (wgrad kernels): producer, MMA issuer, 4 epilogue warps
+constexpr int kThreadsF = 320; // 10 warps (fprop / dgrad kernels): producer, MMA issuer, 8 epilogue warps
+constexpr int kEpiWarpsF = 8;
 
 // Division by a run-time constant in two instructions (the producer / MMA roles are single threads: every dependent
 // scalar instruction costs ~5 cycles, an integer division by a kernel parameter ~40 of them).
@@ -76,6 +78,18 @@ struct ConvFpropParams {
     const void* residual;    // same layout/dtype as y, or null
     float* stat_sum;         // optional per-channel sum / sum of squares accumulators (fp32 atomics), or null
     float* stat_sqsum;
+    // ---- fused batch-norm backward statistics: this launch is the dgrad whose output dz feeds the backward pass of a
+    // batch-norm(+ReLU) layer.  The epilogue masks dz with the layer's ReLU mask, stores the masked gradient and
+    // accumulates sum(dz') and sum(dz' * xhat) per channel into stat_sum / stat_sqsum (see fprop_epilogue).
+    const void* bnb_x;       // the batch-norm layer's input (layout / dtype of y); null = off
+    const void* bnb_yout;    // its forward output (mask = yout > 0) when the forward added a residual; else the mask is
+                             // recomputed as (x - mean) * (gamma * invstd) + beta > 0
+    const float* bnb_mean;
+    const float* bnb_invstd;
+    const float* bnb_gamma;
+    const float* bnb_beta;
+    int bnb_relu;
+    int bnb_cpad;            // channel pitch of the shared-memory constant table (Cout rounded up to 32)
     // ---- tap-group variant (conv_fprop_halo_kernel): ONE halo'd A box per 64-channel chunk serves all R*S taps
     int a_loads;             // TMA loads per A stage: 1, or 2 = even / odd input rows of a stride-2 row-folded stem
     int a_dw, a_dh;          // start of load 0 relative to the patch origin (w0*stride_w, h0*stride_h), in map coords
@@ -131,8 +145,8 @@ struct SmemLayout {
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
-    static constexpr int kStatOffset = kBarOffset + 256;     // fprop: per-warp running batch-norm sums [4][BN][2] fp32
-    static constexpr int kTotal = kStatOffset + 4 * BN * 8 + 1024;  // + alignment slack
+    static constexpr int kStatOffset = kBarOffset + 256;     // fprop: per-warp running batch-norm sums [8][BN][2] fp32
+    static constexpr int kTotal = kStatOffset + 8 * BN * 8 + 1024;  // + alignment slack (wgrad kernels leave the stat region unused)
 };
 
 __device__ __forceinline__ void store_row_chunk(void* y, int y_fp32, long long elem_off, const float (&v)[32],
@@ -229,17 +243,36 @@ template <int BN>
 __device__ __forceinline__ void fprop_epilogue(const ConvFpropParams& p, float2* stat_smem, uint32_t tmem_base,
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, int warp, int lane) {
     // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarter warp%4)
+    // Eight epilogue warps: warps w and w+4 read the same TMEM lane quarter (w % 4, the hardware's rule) and split the
+    // 32-column chunks of the tile between them (even / odd), which doubles the epilogue throughput of the layers whose
+    // tiles are short (64 / 128 output channels, fused statistics).
+    const int ew = warp - 2;               // 0..7
     const int q = warp & 3;
+    const int half = ew >> 2;              // 0: chunks 0, 2, ..   1: chunks 1, 3, ..
     const int row = q * 32 + lane;
     int it = 0;
     // running per-channel sums of this warp (warp-private shared memory: entry [c][0] = sum, [c][1] = sum of squares)
-    float2* sacc = stat_smem + q * BN;
+    float2* sacc = stat_smem + ew * BN;
     if (p.stat_sum)
         for (int c = lane; c < BN; c += 32) sacc[c] = make_float2(0.f, 0.f);
+    // fused batch-norm backward: per-channel constants [mean | invstd | gamma*invstd | beta] of ALL output channels
+    float* bnb_tab = reinterpret_cast<float*>(stat_smem + kEpiWarpsF * BN);
+    if (p.bnb_x) {
+        const int cp = p.bnb_cpad;
+        for (int c = ew * 32 + lane; c < cp; c += 32 * kEpiWarpsF) {
+            const bool ok = c < p.Cout;
+            const float mu = ok ? p.bnb_mean[c] : 0.f, is = ok ? p.bnb_invstd[c] : 0.f;
+            bnb_tab[c] = mu;
+            bnb_tab[cp + c] = is;
+            bnb_tab[2 * cp + c] = ok ? p.bnb_gamma[c] * is : 0.f;
+            bnb_tab[3 * cp + c] = (ok && p.bnb_beta) ? p.bnb_beta[c] : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");       // the eight epilogue warps only
+    }
     int acc_ct = -1;
     auto flush_stats = [&]() {
         if (p.stat_sum && acc_ct >= 0) {
-            for (int i = lane; i < BN; i += 32) {
+            for (int i = half * 32 + lane; i < BN; i += 64) {      // the chunks this warp owns
                 const int c = acc_ct * BN + i;
                 const float2 a = sacc[i];
                 if (c < p.Cout) {
@@ -278,7 +311,7 @@ __device__ __forceinline__ void fprop_epilogue(const ConvFpropParams& p, float2*
         ptx::tc_fence_after();
         if (stamp) p.timeline[(2 * 64 + it) * 4 + 1] = clock64();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
             uint32_t r[32];
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0;
             ptx::tmem_ld_32x32b_x32(taddr, r);
@@ -309,7 +342,7 @@ __device__ __forceinline__ void fprop_epilogue(const ConvFpropParams& p, float2*
                         for (int i = 0; i < 32; ++i) v[i] += bb[i];
                     }
                 }
-                if (p.stat_sum && !(p.debug & 2)) {
+                if (p.stat_sum && !p.bnb_x && !(p.debug & 2)) {
                     // per-channel batch statistics of the (pre-activation) conv output.  Lane = pixel row, v[] = 32
                     // channels: a halving butterfly (16+8+4+2+1 exchanges per quantity instead of 32 x 5) leaves
                     // lane l with the 32-row sum of channel co + l; it is accumulated in registers across the
@@ -327,7 +360,71 @@ __device__ __forceinline__ void fprop_epilogue(const ConvFpropParams& p, float2*
                     a.y += sq[0];
                     sacc[c0 + lane] = a;
                 }
-                if (row_ok) {
+                if (p.bnb_x) {
+                    // dz = v (+ residual); dz' = dz * [relu mask of the batch-norm layer]; sums of dz' and dz' * xhat.
+                    // Lanes of rows outside the tensor contribute zeros (and store nothing).
+                    const long long off = pix * p.ldy + co;
+                    float xs[32];
+                    if (row_ok) {
+                        if (p.residual) {
+                            float rres[32];
+                            load_row_chunk(p.residual, p.y_fp32, off, rres, nvalid);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += rres[i];
+                        }
+                        load_row_chunk(p.bnb_x, p.y_fp32, off, xs, nvalid);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) xs[i] = 0.f;
+                    }
+                    const int cp = p.bnb_cpad;
+                    const float4* t_mu = reinterpret_cast<const float4*>(bnb_tab + co);
+                    const float4* t_is = reinterpret_cast<const float4*>(bnb_tab + cp + co);
+                    float s[32], sq[32];
+                    if (p.bnb_relu && p.bnb_yout) {
+                        float yo[32];
+                        if (row_ok) {
+                            load_row_chunk(p.bnb_yout, p.y_fp32, off, yo, nvalid);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) yo[i] = 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (!(yo[i] > 0.f)) v[i] = 0.f;
+                    } else if (p.bnb_relu) {
+                        const float4* t_a = reinterpret_cast<const float4*>(bnb_tab + 2 * cp + co);
+                        const float4* t_b = reinterpret_cast<const float4*>(bnb_tab + 3 * cp + co);
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            const float4 mu = t_mu[g4], a = t_a[g4], b = t_b[g4];
+                            // the forward pass's exact expression (bn_apply_kernel): (x - mean) * (gamma*invstd) + beta
+                            if (!((xs[4 * g4 + 0] - mu.x) * a.x + b.x > 0.f)) v[4 * g4 + 0] = 0.f;
+                            if (!((xs[4 * g4 + 1] - mu.y) * a.y + b.y > 0.f)) v[4 * g4 + 1] = 0.f;
+                            if (!((xs[4 * g4 + 2] - mu.z) * a.z + b.z > 0.f)) v[4 * g4 + 2] = 0.f;
+                            if (!((xs[4 * g4 + 3] - mu.w) * a.w + b.w > 0.f)) v[4 * g4 + 3] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 mu = t_mu[g4], is = t_is[g4];
+                        const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, i4[4] = {is.x, is.y, is.z, is.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = 4 * g4 + k;
+                            const float d = row_ok ? v[i] : 0.f;
+                            s[i] = d;
+                            sq[i] = d * ((xs[i] - m4[k]) * i4[k]);
+                        }
+                    }
+                    butterfly_colsum(s, lane);
+                    butterfly_colsum(sq, lane);
+                    float2 a2 = sacc[c0 + lane];
+                    a2.x += s[0];
+                    a2.y += sq[0];
+                    sacc[c0 + lane] = a2;
+                    if (row_ok) store_row_chunk(p.y, p.y_fp32, off, v, nvalid);
+                } else if (row_ok) {
                     const long long off = pix * p.ldy + co;
                     if (p.residual) {
                         float rres[32];
@@ -353,7 +450,7 @@ __device__ __forceinline__ void fprop_epilogue(const ConvFpropParams& p, float2*
 
 // ------------------------------------------------------------------------------------------------ fprop / dgrad
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_constant__ ConvFpropParams p) {
+__global__ void __launch_bounds__(kThreadsF, 1) conv_fprop_kernel(const __grid_constant__ ConvFpropParams p) {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -374,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tfull_bar[s], 1);
-            ptx::mbar_init(&tempty_bar[s], 4);
+            ptx::mbar_init(&tempty_bar[s], kEpiWarpsF);
         }
         ptx::fence_barrier_init();
     }
@@ -515,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
 // 128 x 64 x 16 MMA executes in 32 cycles): every loop-invariant parameter is hoisted into registers, and the only
 // work left per tap is the barrier handshake (streaming filters) and the address adds of the K=16 MMAs.
 template <int BN, int NT, bool RESIDENT, int KM>
-__global__ void __launch_bounds__(kThreads, 1) conv_fprop_halo_kernel(const __grid_constant__ ConvFpropParams p) {
+__global__ void __launch_bounds__(kThreadsF, 1) conv_fprop_halo_kernel(const __grid_constant__ ConvFpropParams p) {
     constexpr int kBBytes = BN * kBK * 2;
     constexpr uint32_t kB16 = kBBytes >> 4;
     extern __shared__ uint8_t smem_raw[];
@@ -546,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_halo_kernel(const __gr
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tfull_bar[s], 1);
-            ptx::mbar_init(&tempty_bar[s], 4);
+            ptx::mbar_init(&tempty_bar[s], kEpiWarpsF);
         }
         ptx::mbar_init(bres_bar, 1);
         ptx::fence_barrier_init();
@@ -1669,9 +1766,10 @@ template <int BN, int STAGES>
 static int launch_fprop(const ConvFpropParams& p, cudaStream_t stream) {
     using L = SmemLayout<BN, STAGES>;
     auto kern = conv_fprop_kernel<BN, STAGES>;
-    DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    const int smem = L::kTotal + (p.bnb_x ? 16 * p.bnb_cpad : 0);     // + batch-norm constant table [4][cpad] fp32
+    DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    kern<<<DN_G(grid), kThreads, L::kTotal, stream>>>(p);
+    kern<<<DN_G(grid), kThreadsF, smem, stream>>>(p);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -1746,11 +1844,12 @@ static long long* g_fprop_timeline = nullptr;
 
 template <int BN, int NT, bool RESIDENT, int KM>
 static int launch_fprop_halo(const ConvFpropParams& p, cudaStream_t stream) {
-    const size_t smem = 1024 + (size_t)p.a_region_bytes + p.b_region_bytes + 512 + 4 * BN * 8;
+    const size_t smem = 1024 + (size_t)p.a_region_bytes + p.b_region_bytes + 512 + 8 * BN * 8 +
+                        (p.bnb_x ? 16 * p.bnb_cpad : 0);
     auto kern = conv_fprop_halo_kernel<BN, NT, RESIDENT, KM>;
     DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    kern<<<DN_G(grid), kThreads, smem, stream>>>(p);
+    kern<<<DN_G(grid), kThreadsF, smem, stream>>>(p);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -1912,12 +2011,56 @@ extern "C" int denet_split_bf16(const float* x, void* hi, void* lo, long long n,
     return 0;
 }
 
+namespace dn {
+struct BnBwdArgs {
+    const void* x;
+    const void* yout;
+    const float* mean;
+    const float* invstd;
+    const float* gamma;
+    const float* beta;
+    int relu;
+};
+}  // namespace dn
+
+static int conv2d_fprop_impl(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin, long long ldx,
+                             const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w,
+                             int stride_h, int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo,
+                             const float* bias, const void* residual, int relu, float* stat_sum, float* stat_sqsum,
+                             const BnBwdArgs* bnb, cudaStream_t stream);
+
 extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin, long long ldx,
                                   const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w,
                                   int stride_h, int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo,
                                   const float* bias,
                                   const void* residual, int relu, float* stat_sum, float* stat_sqsum,
                                   cudaStream_t stream) {
+    return conv2d_fprop_impl(x_hi, x_lo, N, Hi, Wi, Cin, ldx, b_hi, b_lo, Cout, R, S, pad_h, pad_w, stride_h, stride_w, y,
+                             y_dtype, ldy, Ho, Wo, bias, residual, relu, stat_sum, stat_sqsum, nullptr, stream);
+}
+
+extern "C" int denet_conv2d_dgrad_bnbwd(const void* dy_hi, const void* dy_lo, int N, int Hi, int Wi, int Cin,
+                                        long long lddy, const void* b_hi, const void* b_lo, int Cout, int R, int S,
+                                        int pad_h, int pad_w, void* dz, int dz_dtype, long long lddz, int Ho, int Wo,
+                                        const void* residual, const void* bn_x, const void* bn_yout,
+                                        const float* bn_mean, const float* bn_invstd, const float* bn_gamma,
+                                        const float* bn_beta, int bn_relu, float* sum_dz, float* sum_dz_xhat,
+                                        cudaStream_t stream) {
+    DN_REQUIRE(bn_x && bn_mean && bn_invstd && bn_gamma && sum_dz && sum_dz_xhat, "conv2d_dgrad_bnbwd: null pointer");
+    DN_REQUIRE(!bn_relu || bn_yout || bn_beta, "conv2d_dgrad_bnbwd: the relu mask needs the forward output or beta");
+    DN_REQUIRE(Cout <= 512, "conv2d_dgrad_bnbwd: at most 512 channels (shared-memory constant table), got %d", Cout);
+    BnBwdArgs a;
+    a.x = bn_x; a.yout = bn_yout; a.mean = bn_mean; a.invstd = bn_invstd; a.gamma = bn_gamma; a.beta = bn_beta;
+    a.relu = bn_relu;
+    return conv2d_fprop_impl(dy_hi, dy_lo, N, Hi, Wi, Cin, lddy, b_hi, b_lo, Cout, R, S, pad_h, pad_w, 1, 1, dz, dz_dtype,
+                             lddz, Ho, Wo, nullptr, residual, 0, sum_dz, sum_dz_xhat, &a, stream);
+}
+
+static int conv2d_fprop_impl(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin, long long ldx,
+                             const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w,
+                             int stride_h, int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo,
+                             const float* bias, const void* residual, int relu, float* stat_sum, float* stat_sqsum,
+                             const BnBwdArgs* bnb, cudaStream_t stream) {
     DN_REQUIRE(x_hi && b_hi && y, "conv2d_fprop: null pointer");
     DN_REQUIRE((x_lo == nullptr) == (b_lo == nullptr), "conv2d_fprop: x_lo and b_lo must both be given or both null");
     DN_REQUIRE(ldx % 8 == 0, "conv2d_fprop: input pixel pitch must be a multiple of 8 elements (16 B), got %lld", ldx);
@@ -1948,6 +2091,11 @@ extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int
     p.residual = residual;
     p.stat_sum = stat_sum;
     p.stat_sqsum = stat_sqsum;
+    if (bnb) {
+        p.bnb_x = bnb->x; p.bnb_yout = bnb->yout; p.bnb_mean = bnb->mean; p.bnb_invstd = bnb->invstd;
+        p.bnb_gamma = bnb->gamma; p.bnb_beta = bnb->beta; p.bnb_relu = bnb->relu;
+        p.bnb_cpad = (Cout + 31) / 32 * 32;
+    }
 
     int rc;
     // stride-1 multi-tap filters: one halo'd A box per channel chunk serves all taps (conv_fprop_halo_kernel).  The

@@ -349,13 +349,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
                                                                   const float* __restrict__ sum_dy,
                                                                   const float* __restrict__ sum_dy_xhat, int relu,
                                                                   T* __restrict__ dx, T* __restrict__ dres,
-                                                                  const float* __restrict__ beta) {
+                                                                  const float* __restrict__ beta,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                  int accumulate) {
     const int CV = C / VEC;
     const int cvt = CV < kBnThreads ? CV : kBnThreads;
     const int rlanes = kBnThreads / cvt;
     const int cv = blockIdx.y * cvt + threadIdx.x % cvt;
     const int rl = threadIdx.x / cvt;
     if (cv >= CV || rl >= rlanes) return;
+    if (dgamma && blockIdx.x == 0 && rl == 0) {
+        // the sums arrived complete (dgrad epilogue): they ARE the parameter gradients (no finalize launch)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int c = cv * VEC + i;
+            dgamma[c] = accumulate ? dgamma[c] + sum_dy_xhat[c] : sum_dy_xhat[c];
+            dbeta[c] = accumulate ? dbeta[c] + sum_dy[c] : sum_dy[c];
+        }
+    }
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
     const float inv_m = 1.0f / (float)M;
@@ -1012,7 +1023,25 @@ extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x
         const int nslabs2 = ew_slabs(M, C, VEC, &rpb2, &yc2);
         bn_bwd_apply_kernel<T, VEC><<<DN_G(dim3(nslabs2, yc2)), kBnThreads, 0, stream>>>(
             (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb2, mean, invstd, gamma, sums, sums + C, relu,
-            (T*)dx, (T*)dres, beta);
+            (T*)dx, (T*)dres, beta, nullptr, nullptr, 0);
+    });
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int denet_bn_backward_sums(const void* dy, const void* x, int dtype, long long M, int C, long long ld,
+                                      const float* mean, const float* invstd, const float* gamma, const float* sum_dy,
+                                      const float* sum_dy_xhat, void* dx, float* dgamma, float* dbeta, int accumulate,
+                                      cudaStream_t stream) {
+    DN_REQUIRE(dy && x && dx && mean && invstd && gamma && sum_dy && sum_dy_xhat, "bn_backward_sums: null pointer");
+    DN_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "bn_backward_sums: dgamma and dbeta come together");
+    const bool v = vec8_ok(C, ld, dy, x, dx);
+    DN_DISPATCH(dtype, v, {
+        int rpb2, yc2;
+        const int nslabs2 = ew_slabs(M, C, VEC, &rpb2, &yc2);
+        bn_bwd_apply_kernel<T, VEC><<<DN_G(dim3(nslabs2, yc2)), kBnThreads, 0, stream>>>(
+            (const T*)dy, nullptr, (const T*)x, M, C, ld, rpb2, mean, invstd, gamma, sum_dy, sum_dy_xhat, 0, (T*)dx,
+            nullptr, nullptr, dgamma, dbeta, accumulate);
     });
     DN_CHECK_LAUNCH();
     return 0;

@@ -46,6 +46,8 @@ class BatchNormLayer(AbstractLayer):
         self._fused = None          # (sum, sqsum) views into the model's per-step statistics buffer
         self._fused_ready = False
         self._saved = None
+        self._bwd_sums = None       # (sum dz', sum dz' * xhat) views: backward statistics from a dgrad epilogue
+        self._bwd_presummed = False
 
     @staticmethod
     def parse_desc(layers, name, tags, params):
@@ -123,12 +125,32 @@ class BatchNormLayer(AbstractLayer):
         self.output = y
         return y
 
+    MAX_FUSED_BWD_CHANNELS = 512      # the dgrad epilogue keeps the per-channel constants in shared memory
+
+    def bwd_fuse_args(self):
+        """ops.BnBwdFuse for the dgrad that produces this layer's output gradient: its epilogue then applies the ReLU
+        mask and accumulates the two per-channel sums, and backward() below skips its own reduction pass.  None when
+        not applicable (parity mode, statistics buffers not linked, too many channels, no saved forward state)."""
+        if not (self.enabled and self._saved is not None and self._bwd_sums is not None and fuse_bn_stats()):
+            return None
+        x, y, mean, invstd, relu = self._saved
+        if x.shape[-1] > self.MAX_FUSED_BWD_CHANNELS:
+            return None
+        self._bwd_presummed = True
+        return ops.BnBwdFuse(x, y, mean, invstd, self.omega, self.beta, relu, self._bwd_sums[0], self._bwd_sums[1])
+
     def backward(self, dy, want_dres=False):
         """returns dx, or (dx, dres) when want_dres (dres = masked gradient flowing into the fused residual input)"""
         if not self.enabled:
             return (dy, dy) if want_dres else dy
         x, y, mean, invstd, relu = self._saved
         self._saved = None
+        if self._bwd_presummed:
+            # dy arrived masked and the sums are complete (ops.conv2d_fprop(..., bn_bwd=...)): one pass left
+            self._bwd_presummed = False
+            dx = ops.bn_backward_sums(dy, x, mean, invstd, self.omega, self._bwd_sums[0], self._bwd_sums[1],
+                                      self.omega.grad, self.beta.grad)
+            return (dx, dy) if want_dres else dx
         dx, dres = ops.bn_backward(dy, y, x, mean, invstd, self.omega, relu, self.omega.grad, self.beta.grad,
                                    want_dres=want_dres, beta=self.beta)
         return (dx, dres) if want_dres else dx

@@ -236,9 +236,13 @@ class ConvLayer(AbstractLayer):
         self.output = y
         return y
 
-    def backward(self, dy, add_to=None):
+    accepts_bn_next = True
+
+    def backward(self, dy, add_to=None, bn_next=None):
         """dy: gradient wrt the conv output (before any fused residual / relu).  Writes omega.grad (and beta.grad),
-        returns the gradient wrt the input (+ add_to, fused into the dgrad epilogue where possible)."""
+        returns the gradient wrt the input (+ add_to, fused into the dgrad epilogue where possible).
+        bn_next: the batch-norm layer that produced this conv's input and will consume the returned gradient next; where
+        the dgrad runs as one stride-1 correlation its epilogue takes over the first pass of that layer's backward."""
         if not self.enabled:
             return dy if add_to is None else ops.add(dy, add_to)
         _, wop_d = self._operands()
@@ -267,7 +271,7 @@ class ConvLayer(AbstractLayer):
             if not self.is_first:
                 if self.stride == (1, 1):
                     dx = ops.conv2d_fprop(dyop, wop_d, (R - 1 - self.pad[0], S - 1 - self.pad[1]), (h, w), gdt,
-                                          residual=add_to)
+                                          residual=add_to, bn_bwd=bn_next.bwd_fuse_args() if bn_next is not None else None)
                 elif (R, S) == (1, 1) and self.pad == (0, 0):
                     # a 1x1 convolution commutes with the zero insertion: GEMM at the small resolution, then scatter
                     dxc = ops.conv2d_fprop(dyop, wop_d, (0, 0), dy.shape[1:3], gdt)
@@ -280,6 +284,6 @@ class ConvLayer(AbstractLayer):
                     dyd = ops.ActOperand(ops.dilate(dyop.hi, self.stride, (hd, wd)),
                                          None if dyop.lo is None else ops.dilate(dyop.lo, self.stride, (hd, wd)))
                     dx = ops.conv2d_fprop(dyd, wop_d, (R - 1 - self.pad[0], S - 1 - self.pad[1]), (h, w), gdt,
-                                          residual=add_to)
+                                          residual=add_to, bn_bwd=bn_next.bwd_fuse_args() if bn_next is not None else None)
         self._xop = None
         return dx

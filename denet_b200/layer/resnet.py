@@ -153,7 +153,20 @@ class ResnetLayer(AbstractLayer):
             self.output = ops.add(s, h, relu=True)
         return self.output
 
-    def backward(self, dy):
+    @property
+    def accepts_bn_next(self):
+        return not self._preact
+
+    def fusable_last_bn(self):
+        """the batch-norm layer whose backward consumes the gradient wrt this block's output (original version only)"""
+        if self._preact:
+            return None
+        bn = self.layers[self._main_end - 1]
+        return bn if bn.enabled else None
+
+    def backward(self, dy, bn_next=None):
+        """bn_next: batch-norm layer (of the preceding block / layer) that consumes the returned gradient, see
+        ConvLayer.backward"""
         L = self.layers
         if self._preact:
             ds = dy
@@ -177,5 +190,10 @@ class ResnetLayer(AbstractLayer):
             for i in range(len(L) - 1, self._main_end - 1, -1):
                 ds = L[i].backward(ds)
         for i in range(self._main_end - 2, 1, -1):
-            dh = L[i].backward(dh)
-        return L[1].backward(dh, add_to=ds)   # first conv's dgrad epilogue adds the shortcut gradient
+            prev = L[i - 1]
+            if isinstance(L[i], ConvLayer) and isinstance(prev, BatchNormLayer) and prev.enabled and i - 1 > 1:
+                dh = L[i].backward(dh, bn_next=prev)      # dgrad epilogue starts the backward of the BN before it
+            else:
+                dh = L[i].backward(dh)
+        # first conv's dgrad epilogue adds the shortcut gradient (and starts the backward of the preceding block's BN)
+        return L[1].backward(dh, add_to=ds, bn_next=bn_next)

@@ -16,6 +16,7 @@ initialised the gradients are all-reduced over NCCL in buckets that overlap the 
 import ctypes
 import getpass
 import math
+import os
 import random
 import time
 
@@ -92,6 +93,17 @@ def link_fusions(layers):
     return bns
 
 
+def _bn_consumer(prev):
+    """the batch-norm layer whose backward directly consumes the gradient wrt `prev`'s output, or None"""
+    from ..layer.batch_norm import BatchNormLayer
+    from ..layer.resnet import ResnetLayer
+    if isinstance(prev, BatchNormLayer):
+        return prev if prev.enabled else None
+    if isinstance(prev, ResnetLayer):
+        return prev.fusable_last_bn()
+    return None
+
+
 class ModelCNN:
 
     def __init__(self):
@@ -113,6 +125,8 @@ class ModelCNN:
         self.device = None
         self.ddp = None             # denet_b200.multi.GradientAllReduce when running data parallel
         self.defer_wgrad_reduce = True   # one multi-tensor split-K reduction launch instead of one per conv layer
+        # dgrad epilogues take over the reduction pass of the batch-norm backward (DENET_FUSE_BN_BWD=0: A/B switch)
+        self.fuse_bn_backward = os.environ.get("DENET_FUSE_BN_BWD", "1") != "0"
         self._ready = False
         self.last_costs_device = None
         self._image = None          # padded input buffer of a row-folded stem conv
@@ -299,12 +313,18 @@ class ModelCNN:
         self.num_trainable = total
         # per-step batch-norm statistics buffer (conv epilogue -> bn finalize), zeroed once per step
         bns = link_fusions(self.layers)
-        csum = sum(2 * b.input_shape[1] for b in bns)
+        from ..layer.batch_norm import BatchNormLayer
+        all_bns = [l for l in _walk(self.layers) if isinstance(l, BatchNormLayer) and l.enabled]
+        csum = sum(2 * b.input_shape[1] for b in bns) + sum(2 * b.input_shape[1] for b in all_bns)
         self.bn_stat_buffer = torch.zeros((max(csum, 2),), dtype=torch.float32, device=self.device)
         o = 0
         for b in bns:
             c = b.input_shape[1]
             b._fused = (self.bn_stat_buffer[o:o + c], self.bn_stat_buffer[o + c:o + 2 * c])
+            o += 2 * c
+        for b in all_bns:      # backward statistics accumulated by the dgrad epilogue that produces the layer's dy
+            c = b.input_shape[1]
+            b._bwd_sums = (self.bn_stat_buffer[o:o + c], self.bn_stat_buffer[o + c:o + 2 * c])
             o += 2 * c
         layer_mod.bump_param_version()
         self._ready = True
@@ -483,7 +503,12 @@ class ModelCNN:
         layer_mod.set_wgrad_pending(pending)
         try:
             for index in range(len(self.layers) - 1, 0, -1):
-                dy = self.layers[index].backward(dy)
+                layer = self.layers[index]
+                bn_next = _bn_consumer(self.layers[index - 1]) if self.fuse_bn_backward else None
+                if bn_next is not None and getattr(layer, "accepts_bn_next", False):
+                    dy = layer.backward(dy, bn_next=bn_next)
+                else:
+                    dy = layer.backward(dy)
                 if hook is not None:
                     if pending and self.ddp.will_launch(index):
                         ops.wgrad_reduce_pending(pending)

@@ -143,9 +143,21 @@ def act_operand(x):
     return ActOperand(hi[..., :c], lo[..., :c])
 
 
+class BnBwdFuse:
+    """arguments of the batch-norm backward statistics fused into a dgrad epilogue (denet_conv2d_dgrad_bnbwd): the
+    batch-norm layer's saved input x, forward output yout (or None: mask recomputed from x), batch mean / invstd, gamma,
+    beta, relu flag and the two zeroed per-channel accumulators"""
+
+    def __init__(self, x, yout, mean, invstd, gamma, beta, relu, sum_dz, sum_dz_xhat):
+        self.x, self.yout, self.mean, self.invstd, self.gamma, self.beta = x, yout, mean, invstd, gamma, beta
+        self.relu, self.sum_dz, self.sum_dz_xhat = relu, sum_dz, sum_dz_xhat
+
+
 def conv2d_fprop(xop, wop, pad, out_hw, out_dtype, stride=(1, 1), bias=None, residual=None, relu=False, stats=None,
-                 out=None):
-    """Correlation with a prepared operand (see denet_conv2d_fprop). Returns NHWC (N, Ho, Wo, rows)."""
+                 out=None, bn_bwd=None):
+    """Correlation with a prepared operand (see denet_conv2d_fprop). Returns NHWC (N, Ho, Wo, rows).
+    bn_bwd (BnBwdFuse): this call is the dgrad feeding a batch-norm layer's backward; its epilogue masks the gradient
+    and accumulates that layer's two backward sums (denet_conv2d_dgrad_bnbwd)."""
     x = xop.hi
     n, hi_, wi_, cin = x.shape
     assert cin == wop.kin, (cin, wop.kin)
@@ -165,6 +177,16 @@ def conv2d_fprop(xop, wop, pad, out_hw, out_dtype, stride=(1, 1), bias=None, res
     else:
         n_, h_, w_ = n, hi_, wi_
         ho_, wo_ = ho, wo
+    if bn_bwd is not None:
+        assert tuple(stride) == (1, 1) and bias is None and not relu and stats is None
+        b = bn_bwd
+        assert b.x.shape == out.shape and b.x.dtype == out.dtype and _pitch(b.x) == ldy
+        assert b.yout is None or (b.yout.shape == out.shape and b.yout.dtype == out.dtype and _pitch(b.yout) == ldy)
+        call("denet_conv2d_dgrad_bnbwd", x.data_ptr(), _ptr(xop.lo), n_, h_, w_, cin, ldx,
+             wop.hi.data_ptr(), _ptr(wop.lo), cout, wop.R, wop.S, pad[0], pad[1], out.data_ptr(), _dtype_code(out), ldy,
+             ho_, wo_, _ptr(residual), b.x.data_ptr(), _ptr(b.yout), b.mean.data_ptr(), b.invstd.data_ptr(),
+             b.gamma.data_ptr(), _ptr(b.beta), int(b.relu), b.sum_dz.data_ptr(), b.sum_dz_xhat.data_ptr(), _stream())
+        return out
     s0, s1 = (stats if stats is not None else (None, None))
     call("denet_conv2d_fprop", x.data_ptr(), _ptr(xop.lo), n_, h_, w_, cin, ldx,
          wop.hi.data_ptr(), _ptr(wop.lo), cout, wop.R, wop.S, pad[0], pad[1], stride[0], stride[1],
@@ -454,6 +476,19 @@ def bn_backward(dy, yout, x, mean, invstd, gamma, relu, dgamma, dbeta, accumulat
          _ptr(dbeta),
          int(accumulate), ws.data_ptr(), ws.numel() * 4, _stream())
     return dx, dres
+
+
+def bn_backward_sums(dy, x, mean, invstd, gamma, sum_dy, sum_dy_xhat, dgamma, dbeta, accumulate=False, dx=None):
+    """second half of the batch-norm backward from sums the dgrad epilogue accumulated; dy is already masked"""
+    M, C = _rows(x), x.shape[-1]
+    if dx is None:
+        dx = alloc_like(x)
+    ld = _pitch(x)
+    assert _pitch(dy) == ld and _pitch(dx) == ld
+    call("denet_bn_backward_sums", dy.data_ptr(), x.data_ptr(), _dtype_code(x), M, C, ld, mean.data_ptr(),
+         invstd.data_ptr(), gamma.data_ptr(), sum_dy.data_ptr(), sum_dy_xhat.data_ptr(), dx.data_ptr(), _ptr(dgamma),
+         _ptr(dbeta), int(accumulate), _stream())
+    return dx
 
 
 # ---------------------------------------------------------------------------------------------- elementwise

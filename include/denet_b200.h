@@ -77,6 +77,19 @@ int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int Hi, int Wi
                        int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo, const float* bias,
                        const void* residual, int relu, float* stat_sum, float* stat_sqsum, cudaStream_t stream);
 
+/* Data gradient of a stride-1 convolution whose INPUT was produced by a batch-norm(+ReLU) layer, with the first pass of
+ * that layer's backward fused into the epilogue (replaces cuDNN bwd-data followed by the first half of cuDNN BN grad,
+ * denet/layer/convolution.py:83 + batch_norm.py:47-53 / batch_norm_relu.py:50-54).  Arguments up to `residual` as
+ * denet_conv2d_fprop with mode-1 operands (dz = dgrad (+ residual)).  The epilogue masks dz by the layer's ReLU mask
+ * (bn_relu: bn_yout > 0 when given, else recomputed from bn_x with the forward's expression), stores the MASKED
+ * gradient dz' and accumulates sum_dz[c] += sum dz', sum_dz_xhat[c] += sum dz' * (bn_x - mean) * invstd with fp32
+ * atomics (both buffers zeroed by the caller).  denet_bn_backward_sums finishes the layer's backward from them. */
+int denet_conv2d_dgrad_bnbwd(const void* dy_hi, const void* dy_lo, int N, int Hi, int Wi, int Cin, long long lddy,
+                             const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w, void* dz,
+                             int dz_dtype, long long lddz, int Ho, int Wo, const void* residual, const void* bn_x,
+                             const void* bn_yout, const float* bn_mean, const float* bn_invstd, const float* bn_gamma,
+                             const float* bn_beta, int bn_relu, float* sum_dz, float* sum_dz_xhat, cudaStream_t stream);
+
 /* Kernel selection of conv2d_fprop / conv2d_rowfold_fprop (profiling / A-B tests): bit 0 (default on) lets stride-1
  * multi-tap filters and the row-folded stem use the tap-group kernel (one halo'd input box per channel chunk serves
  * all filter taps), bit 1 (default on) keeps filters that fit resident in shared memory; 0 = one box per tap. */
@@ -187,6 +200,12 @@ int denet_bn_backward(const void* dy, const void* yout, const void* x, int dtype
                       void* dx, void* dres,
                       float* dgamma, float* dbeta, int accumulate, float* workspace, size_t workspace_bytes,
                       cudaStream_t stream);
+/* Second half of the batch-norm backward when the producer of dy already masked it and accumulated the two
+ * per-channel sums (denet_conv2d_dgrad_bnbwd): dx = gamma*invstd * (dy - sum_dy/M - xhat * sum_dy_xhat/M);
+ * dgamma (+)= sum_dy_xhat, dbeta (+)= sum_dy (may both be NULL).  One launch. */
+int denet_bn_backward_sums(const void* dy, const void* x, int dtype, long long M, int C, long long ld, const float* mean,
+                           const float* invstd, const float* gamma, const float* sum_dy, const float* sum_dy_xhat,
+                           void* dx, float* dgamma, float* dbeta, int accumulate, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ elementwise
  * relu: tensor.nnet.relu (denet/layer/activation.py:32-34).  add: skip / residual sums (denet/layer/skip.py:78-86,

@@ -150,6 +150,48 @@ def test_conv_rowfold_stem(cuda, case, split):
     assert torch.equal(dw2, dw)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 64, 3, True), (2, 24, 24, 96, 136, 3, False), (3, 12, 20, 200, 72, 1, True),
+                                  (2, 16, 16, 320, 512, 3, False)])
+def test_dgrad_with_fused_bn_backward_statistics(cuda, dtype, case):
+    """conv dgrad whose epilogue masks the gradient and accumulates the batch-norm backward sums
+    (denet_conv2d_dgrad_bnbwd) + denet_bn_backward_sums  ==  plain dgrad + denet_bn_backward, for both ways of
+    getting the ReLU mask (forward output when a residual was added, recomputed from x otherwise)"""
+    ops = _ops()
+    n, h, w, cin, cout, k, with_res = case        # the conv maps cin -> cout; the batch-norm layer has cin channels
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    pad = k // 2
+    split = dtype == torch.float32
+    xbn = (torch.randn(n, cin, h, w, generator=g) * 1.5 + 0.3).to(dtype).float()
+    res = torch.randn(n, cin, h, w, generator=g).to(dtype).float()
+    dy = torch.randn(n, cout, h, w, generator=g).to(dtype).float()
+    add_to = torch.randn(n, cin, h, w, generator=g).to(dtype).float()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cout * k * k)).to(cuda)
+    gamma, beta = (torch.rand(cin, generator=g) + 0.5).to(cuda), torch.randn(cin, generator=g).to(cuda)
+    xd, resd, addd = nhwc(xbn, dtype, cuda), nhwc(res, dtype, cuda), nhwc(add_to, dtype, cuda)
+    dyd = ops.act_operand(nhwc(dy, dtype, cuda)) if split else ops.ActOperand(nhwc(dy, dtype, cuda))
+    mean, invstd = torch.empty(cin, device=cuda), torch.empty(cin, device=cuda)
+    ops.bn_stats(xd, 1e-5, mean, invstd)
+    yout = ops.bn_apply(xd, mean, invstd, gamma, beta, residual=resd if with_res else None, relu=True)
+    wop_d = ops.conv_weight_prep(wt, 1, split)
+    pd = (k - 1 - pad, k - 1 - pad)
+    # reference: plain dgrad (+ add_to), then the two-pass batch-norm backward
+    dz = ops.conv2d_fprop(dyd, wop_d, pd, (h, w), dtype, residual=addd)
+    dg_ref, db_ref = torch.zeros(cin, device=cuda), torch.zeros(cin, device=cuda)
+    dx_ref, dres_ref = ops.bn_backward(dz, yout if with_res else None, xd, mean, invstd, gamma, True, dg_ref, db_ref,
+                                       want_dres=True, beta=beta)
+    # fused
+    s0, s1 = torch.zeros(cin, device=cuda), torch.zeros(cin, device=cuda)
+    fuse = ops.BnBwdFuse(xd, yout if with_res else None, mean, invstd, gamma, beta, True, s0, s1)
+    dzm = ops.conv2d_fprop(dyd, wop_d, pd, (h, w), dtype, residual=addd, bn_bwd=fuse)
+    dg, db = torch.zeros(cin, device=cuda), torch.zeros(cin, device=cuda)
+    dx = ops.bn_backward_sums(dzm, xd, mean, invstd, gamma, s0, s1, dg, db)
+    tol = 2e-5 if split else 1e-2
+    assert relerr(dzm[..., :cin], dres_ref[..., :cin]) < (1e-6 if split else 1e-6), "masked gradient"
+    assert relerr(dg, dg_ref) < tol and relerr(db, db_ref) < tol
+    assert relerr(dx[..., :cin], dx_ref[..., :cin]) < tol
+
+
 def test_conv_epilogue_residual_relu_stats(cuda):
     ops = _ops()
     g = torch.Generator().manual_seed(5)
