@@ -19,7 +19,8 @@ from torch import nn
 # global switches (the reference keeps train flag / epoch / iteration as module-level Theano symbols,
 # denet/layer/__init__.py:5-28)
 _state = {"train": False, "epoch": 0, "iteration": 0, "precision": "bf16", "device": "cuda", "param_version": 0,
-          "fuse_bn_stats": True, "device_targets": True, "gt": None, "wgrad_pending": None}
+          "fuse_bn_stats": True, "device_targets": True, "gt": None, "wgrad_pending": None,
+          "fuse_bn_bwd": False}
 
 
 def get_train():
@@ -38,6 +39,15 @@ def wgrad_pending():
 
 def set_wgrad_pending(v):
     _state["wgrad_pending"] = v
+
+
+def fuse_bn_backward():
+    """let dgrad epilogues take over the reduction pass of the batch-norm backward (throughput mode only)"""
+    return _state["fuse_bn_bwd"] and fuse_bn_stats()
+
+
+def set_fuse_bn_backward(v):
+    _state["fuse_bn_bwd"] = bool(v)
 
 
 def device_targets():

@@ -15,7 +15,7 @@ import numpy
 import torch
 
 from .. import ops
-from . import AbstractLayer, fuse_bn_stats, get_param, get_train, new_param, set_param
+from . import AbstractLayer, fuse_bn_backward, fuse_bn_stats, get_param, get_train, new_param, set_param
 
 
 class BatchNormLayer(AbstractLayer):
@@ -131,7 +131,7 @@ class BatchNormLayer(AbstractLayer):
         """ops.BnBwdFuse for the dgrad that produces this layer's output gradient: its epilogue then applies the ReLU
         mask and accumulates the two per-channel sums, and backward() below skips its own reduction pass.  None when
         not applicable (parity mode, statistics buffers not linked, too many channels, no saved forward state)."""
-        if not (self.enabled and self._saved is not None and self._bwd_sums is not None and fuse_bn_stats()):
+        if not (self.enabled and self._saved is not None and self._bwd_sums is not None and fuse_bn_backward()):
             return None
         x, y, mean, invstd, relu = self._saved
         if x.shape[-1] > self.MAX_FUSED_BWD_CHANNELS:

@@ -125,8 +125,11 @@ class ModelCNN:
         self.device = None
         self.ddp = None             # denet_b200.multi.GradientAllReduce when running data parallel
         self.defer_wgrad_reduce = True   # one multi-tensor split-K reduction launch instead of one per conv layer
-        # dgrad epilogues take over the reduction pass of the batch-norm backward (DENET_FUSE_BN_BWD=0: A/B switch)
-        self.fuse_bn_backward = os.environ.get("DENET_FUSE_BN_BWD", "1") != "0"
+        # dgrad epilogues take over the reduction pass of the batch-norm backward (layer.set_fuse_bn_backward; the
+        # environment variable DENET_FUSE_BN_BWD=0/1 overrides the default for A/B measurements)
+        if os.environ.get("DENET_FUSE_BN_BWD"):
+            layer_mod.set_fuse_bn_backward(os.environ["DENET_FUSE_BN_BWD"] != "0")
+        self.fuse_bn_backward = True
         self._ready = False
         self.last_costs_device = None
         self._image = None          # padded input buffer of a row-folded stem conv
