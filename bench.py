@@ -199,6 +199,11 @@ def run_b200(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference)")
+    # stdout carries exactly ONE line, the JSON result: everything else written to file descriptor 1 (NCCL prints its
+    # version banner there when NCCL_DEBUG is set) is sent to stderr until that line is printed
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, world = ddp.init_process_group()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -371,8 +376,17 @@ def run_b200(args):
     conv_fl = sum(v[1] for v in fam.values())
     n_conv_launch = sum(v[2] for v in fam.values())
     achieved = conv_fl / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+    # DRAM traffic per conv launch: from the committed `ncu` launch list of this same command (dram__bytes_read.sum +
+    # dram__bytes_write.sum summed over the conv kernels of one step / their launch count), see profiles/
+    traffic = None
+    try:
+        traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r1_conv_traffic_final.json")))
+                        ["conv_dram_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "tensor", "kernel": "conv_fprop_halo_kernel / conv_fprop_kernel / conv_wgrad_kernel (+ split-K reduction) (tcgen05 implicit GEMM, bf16)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_unit": "DRAM bytes per conv launch (ncu, profiles/r1_conv_traffic_final.json)",
                 "peak_source": peak_src,
                 "flops_per_launch": conv_fl / max(n_conv_launch, 1), "ms_per_launch": conv_ms / max(n_conv_launch, 1),
                 "launches_per_step": n_conv_launch / args.steps,
@@ -402,6 +416,8 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_run(args.workload, args.cpu_sample_images, args.cpu_sample_steps, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    sys.stdout.flush()
+    os.dup2(json_fd, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
