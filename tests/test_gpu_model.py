@@ -349,3 +349,20 @@ def test_one_launch_operand_preparation_matches_per_layer_kernels(cuda, precisio
                 assert torch.equal(got.lo, want.lo), l.filter_shape
             seen += 1
     assert seen > 20
+
+
+def test_denet101_wide_recipe_trains(cuda):
+    """BASELINE.json configs[4]: the DeNet-101 'wide' recipe (bottleneck ResNet-101, three skip levels, stride-4 corner
+    map, 48 x 48 RoIs per image) builds from its model-desc string and takes training steps at a reduced image size"""
+    from denet_b200.model import recipes
+    desc, _, _, classes, convert, solver = recipes.WORKLOADS["denet101-wide"]
+    model = build(desc, (3, 256, 256), 2, classes, "bf16", convert=convert)
+    model.to_device(precision="bf16")
+    model.build_train_func(solver, [])
+    assert [l.output_shape for l in model.layers if l.type_name == "denet-sparse"] == [(2, 7 * 7 * 128 + 2, 48, 48)]
+    numpy.random.seed(5)
+    x = numpy.random.uniform(0, 1, (2, 3, 256, 256)).astype(numpy.float32)
+    metas = synthetic_metas(2, classes, seed=5, max_boxes=4)
+    costs = [model.train_step(x, metas, 0, it, 0.01, [0.9, 0.9], 1e-4)[0] for it in range(3)]
+    assert all(numpy.isfinite(c) for c in costs), costs
+    assert costs[-1] < costs[0], costs
