@@ -249,7 +249,8 @@ def run_b200(args):
 
     # ---- conv kernel timing (roofline): eager launches of the same steps, every conv entry point bracketed by CUDA
     # events on its stream (events cannot be recorded inside a replayed graph)
-    timed_names = ["denet_conv2d_fprop", "denet_conv2d_dgrad_bnbwd", "denet_conv2d_wgrad", "denet_conv2d_rowfold_fprop",
+    timed_names = ["denet_conv2d_fprop", "denet_conv2d_fprop_scatter", "denet_conv2d_dgrad_bnbwd", "denet_conv2d_wgrad",
+                   "denet_conv2d_rowfold_fprop",
                    "denet_conv2d_rowfold_wgrad", "denet_wgrad_reduce_multi"]
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -366,12 +367,14 @@ def run_b200(args):
                 continue
             kind, layer = tag
             k = "wgrad" if name.endswith("wgrad") else ("fprop" if kind == "fprop" else "dgrad")
+            # a strided data gradient is stride_h * stride_w launches (one per parity class) that share the layer's FLOPs
+            share = 1.0 / (layer.stride[0] * layer.stride[1]) if name.endswith("_scatter") else 1.0
             fam[k][0] += ms
-            fam[k][1] += layer.fprop_flops()
+            fam[k][1] += layer.fprop_flops() * share
             fam[k][2] += 1
             key = (k, layer.filter_shape, layer.input_shape, layer.stride)
             pl = per_layer.setdefault(key, [0.0, 0.0, 0])
-            pl[0] += ms; pl[1] += layer.fprop_flops(); pl[2] += 1
+            pl[0] += ms; pl[1] += layer.fprop_flops() * share; pl[2] += 1
     conv_ms = sum(v[0] for v in fam.values())
     conv_fl = sum(v[1] for v in fam.values())
     n_conv_launch = sum(v[2] for v in fam.values())

@@ -90,6 +90,9 @@ struct ConvFpropParams {
     const float* bnb_beta;
     int bnb_relu;
     int bnb_cpad;            // channel pitch of the shared-memory constant table (Cout rounded up to 32)
+    // ---- scattered output: pixel (n, h, w) of this launch is pixel (n, h*osh + ooh, w*osw + oow) of a tensor with
+    // Hf x Wf pixels per image (one parity class of a strided convolution's data gradient); default 1, 1, 0, 0, Ho, Wo
+    int osh, osw, ooh, oow, Hf, Wf;
     // ---- tap-group variant (conv_fprop_halo_kernel): ONE halo'd A box per 64-channel chunk serves all R*S taps
     int a_loads;             // TMA loads per A stage: 1, or 2 = even / odd input rows of a stride-2 row-folded stem
     int a_dw, a_dh;          // start of load 0 relative to the patch origin (w0*stride_w, h0*stride_h), in map coords
@@ -302,7 +305,7 @@ __device__ __forceinline__ void fprop_epilogue(const ConvFpropParams& p, float2*
         const int h = th * p.TH + rh;
         const int n = tn * p.TN + rn;
         const bool row_ok = (w < p.Wo) && (h < p.Ho) && (n < p.No);
-        const long long pix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;
+        const long long pix = (static_cast<long long>(n) * p.Hf + (h * p.osh + p.ooh)) * p.Wf + (w * p.osw + p.oow);
         const int co0 = ct * BN;
 
         const bool stamp = p.timeline && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 64;
@@ -1630,6 +1633,26 @@ __global__ void __launch_bounds__(256) weight_prep_multi_kernel(const PrepEntry*
         }
         return;
     }
+    if (e.mode == 3) {
+        // parity class of a strided convolution's data gradient: B[ci][(tr, ts)][co] = W[co][ci][r0 + sh*tr][s0 + sw*ts]
+        // Cp packs r0 | s0 << 4 | sh << 8 | sw << 12 | Rc << 16 | Sc << 20 (Rc x Sc taps of this class)
+        const unsigned r0 = e.Cp & 15u, s0 = (e.Cp >> 4) & 15u, sh = (e.Cp >> 8) & 15u, sw = (e.Cp >> 12) & 15u;
+        const unsigned Rc = (e.Cp >> 16) & 15u, Sc = (e.Cp >> 20) & 15u;
+        const unsigned kp = (Cout + 63u) / 64u * 64u;
+        for (unsigned it = start + threadIdx.x; it < end; it += blockDim.x) {
+            const unsigned row = it / kp, k = it - row * kp;        // row = ci, k = co
+            const float* run = e.w + ((size_t)k * Cin + row) * R * S;
+            size_t o = (size_t)row * Rc * Sc * kp + k;
+            for (unsigned tr = 0; tr < Rc; ++tr)
+                for (unsigned ts = 0; ts < Sc; ++ts, o += kp) {
+                    const float v = k < Cout ? run[(r0 + sh * tr) * S + (s0 + sw * ts)] : 0.f;
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                    e.hi[o] = hi;
+                    if (e.lo) e.lo[o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+                }
+        }
+        return;
+    }
     const unsigned ntaps = R * S;
     const unsigned kin = e.mode == 0 ? Cin : Cout;
     const unsigned kp = (kin + 63u) / 64u * 64u;
@@ -2012,6 +2035,9 @@ extern "C" int denet_split_bf16(const float* x, void* hi, void* lo, long long n,
 }
 
 namespace dn {
+struct OutScatter {
+    int Hf, Wf, osh, osw, ooh, oow;
+};
 struct BnBwdArgs {
     const void* x;
     const void* yout;
@@ -2027,7 +2053,7 @@ static int conv2d_fprop_impl(const void* x_hi, const void* x_lo, int N, int Hi, 
                              const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w,
                              int stride_h, int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo,
                              const float* bias, const void* residual, int relu, float* stat_sum, float* stat_sqsum,
-                             const BnBwdArgs* bnb, cudaStream_t stream);
+                             const BnBwdArgs* bnb, const OutScatter* sc, cudaStream_t stream);
 
 extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin, long long ldx,
                                   const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w,
@@ -2036,7 +2062,20 @@ extern "C" int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int
                                   const void* residual, int relu, float* stat_sum, float* stat_sqsum,
                                   cudaStream_t stream) {
     return conv2d_fprop_impl(x_hi, x_lo, N, Hi, Wi, Cin, ldx, b_hi, b_lo, Cout, R, S, pad_h, pad_w, stride_h, stride_w, y,
-                             y_dtype, ldy, Ho, Wo, bias, residual, relu, stat_sum, stat_sqsum, nullptr, stream);
+                             y_dtype, ldy, Ho, Wo, bias, residual, relu, stat_sum, stat_sqsum, nullptr, nullptr, stream);
+}
+
+extern "C" int denet_conv2d_fprop_scatter(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin,
+                                          long long ldx, const void* b_hi, const void* b_lo, int Cout, int R, int S,
+                                          int pad_h, int pad_w, void* y, int y_dtype, long long ldy, int Ho, int Wo,
+                                          int Hf, int Wf, int osh, int osw, int ooh, int oow, const void* residual,
+                                          cudaStream_t stream) {
+    DN_REQUIRE(osh >= 1 && osw >= 1 && ooh >= 0 && oow >= 0 && (Ho - 1) * osh + ooh < Hf && (Wo - 1) * osw + oow < Wf,
+               "conv2d_fprop_scatter: the scattered output does not fit a %d x %d image", Hf, Wf);
+    OutScatter sc;
+    sc.Hf = Hf; sc.Wf = Wf; sc.osh = osh; sc.osw = osw; sc.ooh = ooh; sc.oow = oow;
+    return conv2d_fprop_impl(x_hi, x_lo, N, Hi, Wi, Cin, ldx, b_hi, b_lo, Cout, R, S, pad_h, pad_w, 1, 1, y, y_dtype, ldy,
+                             Ho, Wo, nullptr, residual, 0, nullptr, nullptr, nullptr, &sc, stream);
 }
 
 extern "C" int denet_conv2d_dgrad_bnbwd(const void* dy_hi, const void* dy_lo, int N, int Hi, int Wi, int Cin,
@@ -2053,14 +2092,14 @@ extern "C" int denet_conv2d_dgrad_bnbwd(const void* dy_hi, const void* dy_lo, in
     a.x = bn_x; a.yout = bn_yout; a.mean = bn_mean; a.invstd = bn_invstd; a.gamma = bn_gamma; a.beta = bn_beta;
     a.relu = bn_relu;
     return conv2d_fprop_impl(dy_hi, dy_lo, N, Hi, Wi, Cin, lddy, b_hi, b_lo, Cout, R, S, pad_h, pad_w, 1, 1, dz, dz_dtype,
-                             lddz, Ho, Wo, nullptr, residual, 0, sum_dz, sum_dz_xhat, &a, stream);
+                             lddz, Ho, Wo, nullptr, residual, 0, sum_dz, sum_dz_xhat, &a, nullptr, stream);
 }
 
 static int conv2d_fprop_impl(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin, long long ldx,
                              const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w,
                              int stride_h, int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo,
                              const float* bias, const void* residual, int relu, float* stat_sum, float* stat_sqsum,
-                             const BnBwdArgs* bnb, cudaStream_t stream) {
+                             const BnBwdArgs* bnb, const OutScatter* sc, cudaStream_t stream) {
     DN_REQUIRE(x_hi && b_hi && y, "conv2d_fprop: null pointer");
     DN_REQUIRE((x_lo == nullptr) == (b_lo == nullptr), "conv2d_fprop: x_lo and b_lo must both be given or both null");
     DN_REQUIRE(ldx % 8 == 0, "conv2d_fprop: input pixel pitch must be a multiple of 8 elements (16 B), got %lld", ldx);
@@ -2091,6 +2130,10 @@ static int conv2d_fprop_impl(const void* x_hi, const void* x_lo, int N, int Hi, 
     p.residual = residual;
     p.stat_sum = stat_sum;
     p.stat_sqsum = stat_sqsum;
+    p.osh = p.osw = 1; p.ooh = p.oow = 0; p.Hf = Ho; p.Wf = Wo;
+    if (sc) {
+        p.osh = sc->osh; p.osw = sc->osw; p.ooh = sc->ooh; p.oow = sc->oow; p.Hf = sc->Hf; p.Wf = sc->Wf;
+    }
     if (bnb) {
         p.bnb_x = bnb->x; p.bnb_yout = bnb->yout; p.bnb_mean = bnb->mean; p.bnb_invstd = bnb->invstd;
         p.bnb_gamma = bnb->gamma; p.bnb_beta = bnb->beta; p.bnb_relu = bnb->relu;
@@ -2408,6 +2451,7 @@ extern "C" int denet_conv2d_rowfold_fprop(const void* x_hi, const void* x_lo, in
     p.stride_h = stride_h; p.stride_w = 1;             // the column stride lives in the tensor map
     p.kchunks = 1;
     p.Wo = Wo; p.Ho = Ho; p.No = N;
+    p.osh = p.osw = 1; p.ooh = p.oow = 0; p.Hf = Ho; p.Wf = Wo;
     pick_patch(Wo, Ho, N, 128, p.TW, p.TH, p.TN);
     p.tiles_w = ceil_div(Wo, p.TW);
     p.tiles_h = ceil_div(Ho, p.TH);

@@ -96,6 +96,7 @@ class ConvLayer(AbstractLayer):
         self.stat_consumer = None      # BatchNorm layer fed by this conv's epilogue statistics (set by link pass)
         self._wver = -1
         self._wop_f = self._wop_d = self._w2 = None
+        self._wop_dc = None            # strided multi-tap conv: dgrad operands per parity class {(a, b): ConvOperand}
 
     @staticmethod
     def parse_desc(layers, name, tags, params):
@@ -150,12 +151,38 @@ class ConvLayer(AbstractLayer):
     def use_im2col(self):
         return self.filter_shape[1] <= self.IM2COL_MAX_CIN and self.size != (1, 1) and self.rowfold is None
 
+    def dgrad_classes(self):
+        """parity classes of the strided data gradient (ops.dgrad_parity_classes), or None when this layer's dgrad does
+        not use them (stride 1, 1x1 filters, the image stem, im2col variant, a class without taps)"""
+        if getattr(self, "_dclasses", 0) == 0:
+            cls = None
+            if self.enabled and not self.is_first and self.stride != (1, 1) and self.size != (1, 1) and \
+                    not self.use_im2col and isinstance(self.pad[0], int) and max(self.stride) <= 15 and \
+                    max(self.size) <= 15:
+                cls = ops.dgrad_parity_classes(self.input_shape[2:], self.size, self.stride, self.pad)
+            object.__setattr__(self, "_dclasses", cls)
+        return self._dclasses
+
+    def _class_operands(self, split):
+        """allocate (once) the per-class dgrad operands; returns the prep records [(w, operand, 3, code)]"""
+        cout, cin, R, S = self.filter_shape
+        if self._wop_dc is None or (next(iter(self._wop_dc.values())).lo is not None) != split:
+            self._wop_dc = {}
+            for c in self.dgrad_classes():
+                a, b, r0, s0, rc, sc = c[:6]
+                hi = torch.empty((cin, rc * sc, (cout + 63) // 64 * 64), dtype=torch.bfloat16, device=self.omega.device)
+                self._wop_dc[(a, b)] = ops.ConvOperand(hi, torch.empty_like(hi) if split else None, cin, cout, rc, sc)
+        return [(self.omega, self._wop_dc[(c[0], c[1])], 3, ops.parity_class_code(c, self.stride))
+                for c in self.dgrad_classes()]
+
     def _operands(self):
         """bf16 GEMM operands derived from omega; refreshed when the parameters changed"""
         if self._wver != param_version():
             split = get_precision() == "fp32"
             if self._wop_f is not None and (self._wop_f.lo is not None) != split:
                 self._wop_f = self._wop_d = None
+            if self.dgrad_classes() is not None:
+                ops.conv_weight_prep_records(self._class_operands(split))
             w = self.omega
             if self.rowfold is not None:
                 self._wop_f = ops.conv_weight_prep_rowfold(w, self.rowfold[0], split, self._wop_f)
@@ -192,9 +219,12 @@ class ConvLayer(AbstractLayer):
             self._wop_f = alloc((cout, R * S, (cin + 63) // 64 * 64), cout, cin)
         out = [(self.omega, self._wop_f, 0, 0)]
         if not self.is_first:
-            if self._wop_d is None:
-                self._wop_d = alloc((cin, R * S, (cout + 63) // 64 * 64), cin, cout)
-            out.append((self.omega, self._wop_d, 1, 0))
+            if self.dgrad_classes() is not None:
+                out += self._class_operands(split)       # strided: one small operand per parity class
+            else:
+                if self._wop_d is None:
+                    self._wop_d = alloc((cin, R * S, (cout + 63) // 64 * 64), cin, cout)
+                out.append((self.omega, self._wop_d, 1, 0))
         return out
 
     def mark_operands_current(self):
@@ -278,6 +308,13 @@ class ConvLayer(AbstractLayer):
                     dx = ops.dilate(dxc, self.stride, (h, w))
                     if add_to is not None:
                         dx = ops.add(dx, add_to, out=dx)
+                elif self.dgrad_classes() is not None and self._wop_dc is not None:
+                    # strided conv: one stride-1 correlation per parity class of the input pixel, on the undilated dy,
+                    # each scattering its pixels (and adding add_to there) into dx
+                    dx = ops.alloc_nhwc(n, h, w, ci, gdt, dy.device)
+                    for (a, b, r0, s0, rc, sc, ph, pw, hc, wc) in self.dgrad_classes():
+                        ops.conv2d_fprop(dyop, self._wop_dc[(a, b)], (ph, pw), (hc, wc), gdt, residual=add_to, out=dx,
+                                         scatter=(h, w, self.stride[0], self.stride[1], a, b))
                 else:
                     oh, ow = dy.shape[1:3]
                     hd, wd = (oh - 1) * self.stride[0] + 1, (ow - 1) * self.stride[1] + 1

@@ -460,7 +460,7 @@ class ModelCNN:
                 table[i, 0] = w.data_ptr()
                 table[i, 1] = op.hi.data_ptr()
                 table[i, 2] = op.lo.data_ptr() if op.lo is not None else 0
-                items = op.hi.numel() // (R if mode == 2 else R * S)      # (operand row, K column) pairs
+                items = op.hi.numel() // op.hi.shape[1]      # (operand row, K column) pairs: operands are [rows][taps][K]
                 table[i, 3] = items
                 ints[i, 8:14] = [cout, cin, R, S, mode, cp]
                 for o in range(0, items, chunk):

@@ -116,6 +116,63 @@ def conv_weight_prep(w, mode, split, out=None):
     return out
 
 
+def dgrad_parity_classes(in_hw, size, stride, pad):
+    """Data gradient of a strided convolution as one stride-1 correlation per parity class of the input pixel.
+    With dx[h] = sum_r dyd[h + r - (R-1-pad)] W[r] on the zero-dilated dyd, only the taps r = r0 + s*t with
+    r0 = (R-1-pad - a) mod s reach the pixels h = s*i + a, reading dy[i + o] with o = (a + r - (R-1-pad)) / s.
+    Returns [(a, b, r0, s0, Rc, Sc, pad_h, pad_w, Hc, Wc)] or None when a class has no tap (its pixels are zero)."""
+    out = []
+    per_dim = []
+    for d in range(2):
+        n, k, st, p = in_hw[d], size[d], stride[d], pad[d]
+        dim = []
+        for a in range(st):
+            r0 = (k - 1 - p - a) % st
+            cnt = len(range(r0, k, st))
+            if cnt == 0:
+                return None
+            o_min = (a + r0 - (k - 1 - p)) // st
+            assert (a + r0 - (k - 1 - p)) % st == 0
+            dim.append((a, r0, cnt, -o_min, (n - a + st - 1) // st))
+        per_dim.append(dim)
+    for (a, r0, rc, ph, hc) in per_dim[0]:
+        for (b, s0, sc, pw, wc) in per_dim[1]:
+            out.append((a, b, r0, s0, rc, sc, ph, pw, hc, wc))
+    return out
+
+
+def parity_class_code(cls, stride):
+    a, b, r0, s0, rc, sc = cls[:6]
+    return r0 | (s0 << 4) | (stride[0] << 8) | (stride[1] << 12) | (rc << 16) | (sc << 20)
+
+
+def conv_weight_prep_records(records):
+    """denet_conv_weight_prep_multi for a list of (w, operand, mode, cp) records (table built on the fly: the lazy,
+    per-layer path; ModelCNN.prepare_operands keeps one cached table for the whole model)"""
+    L = lib.load()
+    chunk = L.denet_weight_prep_chunk()
+    assert L.denet_weight_prep_entry_bytes() == 56
+    table = numpy.zeros((len(records), 7), dtype=numpy.int64)
+    ints = table.view(numpy.int32).reshape(len(records), 14)
+    block_entry, block_offset = [], []
+    for i, (w, op, mode, cp) in enumerate(records):
+        cout, cin, R, S = w.shape
+        items = op.hi.numel() // op.hi.shape[1]
+        table[i, 0] = w.data_ptr()
+        table[i, 1] = op.hi.data_ptr()
+        table[i, 2] = op.lo.data_ptr() if op.lo is not None else 0
+        table[i, 3] = items
+        ints[i, 8:14] = [cout, cin, R, S, mode, cp]
+        for o in range(0, items, chunk):
+            block_entry.append(i)
+            block_offset.append(o)
+    dev = records[0][0].device
+    t = (torch.from_numpy(table).to(dev), torch.tensor(block_entry, dtype=torch.int32, device=dev),
+         torch.tensor(block_offset, dtype=torch.int64, device=dev))
+    call("denet_conv_weight_prep_multi", t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), len(block_entry), _stream())
+    return t
+
+
 class ActOperand:
     """bf16 view(s) of an activation: hi only (throughput mode) or hi+lo (fp32 parity mode)."""
 
@@ -154,7 +211,7 @@ class BnBwdFuse:
 
 
 def conv2d_fprop(xop, wop, pad, out_hw, out_dtype, stride=(1, 1), bias=None, residual=None, relu=False, stats=None,
-                 out=None, bn_bwd=None):
+                 out=None, bn_bwd=None, scatter=None):
     """Correlation with a prepared operand (see denet_conv2d_fprop). Returns NHWC (N, Ho, Wo, rows).
     bn_bwd (BnBwdFuse): this call is the dgrad feeding a batch-norm layer's backward; its epilogue masks the gradient
     and accumulates that layer's two backward sums (denet_conv2d_dgrad_bnbwd)."""
@@ -164,6 +221,17 @@ def conv2d_fprop(xop, wop, pad, out_hw, out_dtype, stride=(1, 1), bias=None, res
     assert (xop.lo is None) == (wop.lo is None), "operand split modes differ"
     ho, wo = out_hw
     cout = wop.rows
+    if scatter is not None:
+        # output pixel (h, w) of this launch is pixel (h*osh + ooh, w*osw + oow) of `out` (N, Hf, Wf, cout)
+        hf, wf, osh, osw, ooh, oow = scatter
+        assert out is not None and tuple(out.shape) == (n, hf, wf, cout) and tuple(stride) == (1, 1)
+        assert bias is None and not relu and stats is None and bn_bwd is None
+        assert residual is None or (residual.shape == out.shape and residual.dtype == out.dtype and
+                                    _pitch(residual) == _pitch(out))
+        call("denet_conv2d_fprop_scatter", x.data_ptr(), _ptr(xop.lo), n, hi_, wi_, cin, _pitch(x),
+             wop.hi.data_ptr(), _ptr(wop.lo), cout, wop.R, wop.S, pad[0], pad[1], out.data_ptr(), _dtype_code(out),
+             _pitch(out), ho, wo, hf, wf, osh, osw, ooh, oow, _ptr(residual), _stream())
+        return out
     if out is None:
         out = alloc_nhwc(n, ho, wo, cout, out_dtype, x.device)
     ldx = _pitch(x)

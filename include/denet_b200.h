@@ -55,7 +55,9 @@ int denet_conv_weight_prep(const float* w, int Cout, int Cin, int R, int S, int 
 
 /* The operands of ALL conv layers in one launch.  `entries` is a device array of denet_weight_prep_entry_bytes()-sized
  * records {const float* w; bf16* hi; bf16* lo (or NULL); long long total; int Cout, Cin, R, S, mode, Cp} with mode
- * 0 / 1 as above and 2 = row-folded stem operand (Cp = padded channels); `total` counts work items = operand rows x
+ * 0 / 1 as above, 2 = row-folded stem operand (Cp = padded channels) and 3 = dgrad operand of one parity class of a
+ * strided convolution, [Cin][Rc*Sc][pad64(Cout)] with tap (tr, ts) = filter element (r0 + sh*tr, s0 + sw*ts) and
+ * Cp = r0 | s0<<4 | sh<<8 | sw<<12 | Rc<<16 | Sc<<20; `total` counts work items = operand rows x
  * padded K columns (an item covers that column for all filter taps); block i prepares items
  * [block_offset[i], +denet_weight_prep_chunk()) of operand block_entry[i]. */
 int denet_weight_prep_entry_bytes(void);
@@ -76,6 +78,16 @@ int denet_conv2d_fprop(const void* x_hi, const void* x_lo, int N, int Hi, int Wi
                        const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w, int stride_h,
                        int stride_w, void* y, int y_dtype, long long ldy, int Ho, int Wo, const float* bias,
                        const void* residual, int relu, float* stat_sum, float* stat_sqsum, cudaStream_t stream);
+
+/* denet_conv2d_fprop (stride 1, no bias / relu / statistics) whose output pixel (n, h, w) is written to pixel
+ * (n, h*osh + ooh, w*osw + oow) of a tensor with Hf x Wf pixels per image (`residual`, if given, is read at the same
+ * place).  The data gradient of a convolution with stride s is s*s such launches on the UNDILATED dy, one per parity
+ * class (a, b) of the output pixel, each a small stride-1 correlation over the filter taps r = r0 + s*tr that reach that
+ * class (operand from denet_conv_weight_prep_multi mode 3): no zero-insertion buffer, no multiplications by zero. */
+int denet_conv2d_fprop_scatter(const void* x_hi, const void* x_lo, int N, int Hi, int Wi, int Cin, long long ldx,
+                               const void* b_hi, const void* b_lo, int Cout, int R, int S, int pad_h, int pad_w, void* y,
+                               int y_dtype, long long ldy, int Ho, int Wo, int Hf, int Wf, int osh, int osw, int ooh,
+                               int oow, const void* residual, cudaStream_t stream);
 
 /* Data gradient of a stride-1 convolution whose INPUT was produced by a batch-norm(+ReLU) layer, with the first pass of
  * that layer's backward fused into the epilogue (replaces cuDNN bwd-data followed by the first half of cuDNN BN grad,

@@ -96,6 +96,26 @@ def test_conv_fprop_dgrad_wgrad(cuda, case, split):
                              None if dyd.lo is None else ops.dilate(dyd.lo, (s, s), (hd, wd)))
         dx = ops.conv2d_fprop(dil, wop_d, (k - 1 - pad, k - 1 - pad), (h, w), torch.float32)
     assert relerr(nchw(dx), dxref) < tol
+    if s > 1 and k > 1:
+        # the same data gradient as one stride-1 correlation per parity class on the UNDILATED dy (+ a residual)
+        classes = ops.dgrad_parity_classes((h, w), (k, k), (s, s), (pad, pad))
+        assert classes is not None and len(classes) == s * s
+        records, by_class = [], {}
+        for c in classes:
+            a, b, r0, s0, rc, sc = c[:6]
+            hi = torch.empty((cin, rc * sc, (cout + 63) // 64 * 64), dtype=torch.bfloat16, device=cuda)
+            op = ops.ConvOperand(hi, torch.empty_like(hi) if split else None, cin, cout, rc, sc)
+            by_class[(a, b)] = op
+            records.append((wdev, op, 3, ops.parity_class_code(c, (s, s))))
+        ops.conv_weight_prep_records(records)
+        add_to = torch.randn(n, cin, h, w, generator=g)
+        addd = nhwc(add_to if split else add_to.bfloat16().float(), torch.float32, cuda)
+        dx2 = torch.full_like(addd, 9.0)
+        for (a, b, r0, s0, rc, sc, ph, pw, hc, wc) in classes:
+            ops.conv2d_fprop(dyd, by_class[(a, b)], (ph, pw), (hc, wc), torch.float32, residual=addd, out=dx2,
+                             scatter=(h, w, s, s, a, b))
+        want = dxref + (add_to if split else add_to.bfloat16().float()).double()
+        assert relerr(nchw(dx2), want) < tol
 
 
 ROWFOLD_CASES = [

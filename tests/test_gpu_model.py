@@ -340,7 +340,18 @@ def test_one_launch_operand_preparation_matches_per_layer_kernels(cuda, precisio
             ref = [(l._wop_f, ops.conv_weight_prep_rowfold(l.omega, l.rowfold[0], split))]
         else:
             ref = [(l._wop_f, ops.conv_weight_prep(l.omega, 0, split))]
-            if not l.is_first:
+            if not l.is_first and l.dgrad_classes() is not None:
+                # strided conv: one dgrad operand per parity class, B[ci][(tr,ts)][co] = W[co][ci][r0+sh*tr][s0+sw*ts]
+                cout, cin = l.filter_shape[:2]
+                for (a, b, r0, s0, rc, sc) in [c[:6] for c in l.dgrad_classes()]:
+                    sub = l.omega.detach()[:, :, r0::l.stride[0], s0::l.stride[1]]
+                    assert tuple(sub.shape[2:]) == (rc, sc)
+                    want = torch.zeros((cin, rc * sc, (cout + 63) // 64 * 64), device=sub.device)
+                    want[:, :, :cout] = sub.permute(1, 2, 3, 0).reshape(cin, rc * sc, cout)
+                    hi = want.bfloat16()
+                    lo = (want - hi.float()).bfloat16() if split else None
+                    ref.append((l._wop_dc[(a, b)], ops.ConvOperand(hi, lo, cin, cout, rc, sc)))
+            elif not l.is_first:
                 ref.append((l._wop_d, ops.conv_weight_prep(l.omega, 1, split)))
         for got, want in ref:
             assert torch.equal(got.hi, want.hi), l.filter_shape

@@ -23,9 +23,10 @@ def build(desc, shape, batch, classes, convert=False, seed=1):
 
 
 def test_recipes_shapes_and_flops():
-    """the three BASELINE.json workloads parse through parse_desc; conv FLOPs match SURVEY.md §8d"""
+    """the BASELINE.json workloads (cfg1, cfg2, cfg3/4, cfg5) parse through parse_desc; conv FLOPs match SURVEY.md §8d"""
     from denet_b200.model import model_cnn, recipes
-    want = {"cifar-cnn": ((32, 10), 0.920e9), "resnet34": ((256, 1000), 21.74e9), "denet34-skip": (None, 163.05e9)}
+    want = {"cifar-cnn": ((32, 10), 0.920e9), "resnet34": ((256, 1000), 21.74e9), "denet34-skip": (None, 163.05e9),
+            "denet101-wide": (None, 841.85e9)}
     for name, (desc, shape, batch, classes, convert, _) in recipes.WORKLOADS.items():
         b = 2 if name != "cifar-cnn" else batch
         m = build(desc, shape, b, classes, convert)
@@ -40,6 +41,11 @@ def test_recipes_shapes_and_flops():
             dnc = [l for l in m.layers if l.type_name == "denet-corner"][0]
             assert dnc.corner_shape == (b, 2, 4, 64, 64)
             assert m.get_parameter_num() > 32e6
+        elif name == "denet101-wide":
+            dns = [l for l in m.layers if l.type_name == "denet-sparse"][0]
+            assert dns.output_shape == (b, 7 * 7 * 128 + 2, 48, 48)
+            dnc = [l for l in m.layers if l.type_name == "denet-corner"][0]
+            assert dnc.corner_shape == (b, 2, 4, 128, 128)
         else:
             assert tuple(m.get_output_shape()) == (b, classes) or tuple(m.get_output_shape())[:2] == (b, classes)
 
