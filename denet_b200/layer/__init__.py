@@ -20,7 +20,7 @@ from torch import nn
 # denet/layer/__init__.py:5-28)
 _state = {"train": False, "epoch": 0, "iteration": 0, "precision": "bf16", "device": "cuda", "param_version": 0,
           "fuse_bn_stats": True, "device_targets": True, "gt": None, "wgrad_pending": None,
-          "fuse_bn_bwd": False}
+          "fuse_bn_bwd": False, "wgrad_side": None}
 
 
 def get_train():
@@ -39,6 +39,15 @@ def wgrad_pending():
 
 def set_wgrad_pending(v):
     _state["wgrad_pending"] = v
+
+
+def wgrad_side():
+    """(side stream, keep-alive list) while ModelCNN.backward runs the filter gradients on a second stream, else None"""
+    return _state["wgrad_side"]
+
+
+def set_wgrad_side(v):
+    _state["wgrad_side"] = v
 
 
 def fuse_bn_backward():

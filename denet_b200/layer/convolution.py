@@ -12,7 +12,7 @@ import torch
 
 from .. import lib, ops
 from . import (AbstractLayer, act_dtype, get_param, get_precision, new_param, param_version, set_param,
-               wgrad_pending)
+               wgrad_pending, wgrad_side)
 
 
 def conv_output_hw(in_hw, size, stride, border_mode):
@@ -160,6 +160,12 @@ class ConvLayer(AbstractLayer):
                     not self.use_im2col and isinstance(self.pad[0], int) and max(self.stride) <= 15 and \
                     max(self.size) <= 15:
                 cls = ops.dgrad_parity_classes(self.input_shape[2:], self.size, self.stride, self.pad)
+                if cls is not None:
+                    # each class is its own launch of 8 x 16-pixel tiles: worth it only while a class fills the GPU
+                    # (measured: 64 tiles per class lose to one launch on the zero-dilated gradient)
+                    hc, wc = cls[0][8], cls[0][9]
+                    if self.input_shape[0] * ((hc + 15) // 16) * ((wc + 7) // 8) < 148:
+                        cls = None
             object.__setattr__(self, "_dclasses", cls)
         return self._dclasses
 
@@ -297,7 +303,19 @@ class ConvLayer(AbstractLayer):
                 if add_to is not None:
                     dx = ops.add(dx, add_to, out=dx)
         else:
-            ops.conv2d_wgrad(dyop, self._xop, R, S, self.pad, self.stride, dw=self.omega.grad, defer=defer)
+            side = wgrad_side() if defer is not None else None
+            if side is not None:
+                # the filter gradient only feeds the (deferred) reduction at the end of the pass: run it on the side
+                # stream, next to the data-gradient / batch-norm chain of the layers below
+                stream, keep = side
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream())
+                stream.wait_event(ready)
+                with ops.on_stream(stream):
+                    ops.conv2d_wgrad(dyop, self._xop, R, S, self.pad, self.stride, dw=self.omega.grad, defer=defer)
+                keep.append((dyop, self._xop, dy))       # both operands must outlive the side stream's kernel
+            else:
+                ops.conv2d_wgrad(dyop, self._xop, R, S, self.pad, self.stride, dw=self.omega.grad, defer=defer)
             if not self.is_first:
                 if self.stride == (1, 1):
                     dx = ops.conv2d_fprop(dyop, wop_d, (R - 1 - self.pad[0], S - 1 - self.pad[1]), (h, w), gdt,

@@ -114,6 +114,10 @@ def stop_timing():
     return out
 
 
+def timing_active():
+    return _timed is not None
+
+
 _tag = None
 
 

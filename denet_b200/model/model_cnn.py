@@ -130,6 +130,9 @@ class ModelCNN:
         if os.environ.get("DENET_FUSE_BN_BWD"):
             layer_mod.set_fuse_bn_backward(os.environ["DENET_FUSE_BN_BWD"] != "0")
         self.fuse_bn_backward = True
+        # filter gradients on a second stream, concurrent with the data-gradient / batch-norm chain (A/B: DENET_OVERLAP_WGRAD)
+        self.overlap_wgrad = os.environ.get("DENET_OVERLAP_WGRAD", "0") != "0"
+        self._wgrad_stream = None
         self._ready = False
         self.last_costs_device = None
         self._image = None          # padded input buffer of a row-folded stem conv
@@ -504,6 +507,19 @@ class ModelCNN:
         hook = self.ddp.layer_done if self.ddp is not None else None
         pending = [] if self.defer_wgrad_reduce else None
         layer_mod.set_wgrad_pending(pending)
+        side = keep = None
+        if self.overlap_wgrad and pending is not None and not lib.timing_active():
+            if self._wgrad_stream is None:
+                self._wgrad_stream = torch.cuda.Stream()
+            side, keep = self._wgrad_stream, []
+            layer_mod.set_wgrad_side((side, keep))
+
+        def join_side():
+            # the reductions (and anything that reads the gradients) wait for the filter gradients of the side stream
+            if side is not None:
+                done = torch.cuda.Event()
+                done.record(side)
+                torch.cuda.current_stream().wait_event(done)
         try:
             for index in range(len(self.layers) - 1, 0, -1):
                 layer = self.layers[index]
@@ -514,12 +530,15 @@ class ModelCNN:
                     dy = layer.backward(dy)
                 if hook is not None:
                     if pending and self.ddp.will_launch(index):
+                        join_side()
                         ops.wgrad_reduce_pending(pending)
                     hook(index)
+            join_side()
             if pending:
                 ops.wgrad_reduce_pending(pending)
         finally:
             layer_mod.set_wgrad_pending(None)
+            layer_mod.set_wgrad_side(None)
         return dy
 
     def solver_step(self, learning_rate, momentum, decay, iteration, grad_scale=1.0, hp_dev=None):

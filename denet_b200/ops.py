@@ -28,6 +28,22 @@ def pin_stream(on=True):
     _stream_handle = torch.cuda.current_stream().cuda_stream if on else None
 
 
+class on_stream:
+    """context manager: the ops inside are enqueued on `stream` (a torch.cuda.Stream) instead of the pinned one"""
+
+    def __init__(self, stream):
+        self.handle = stream.cuda_stream
+
+    def __enter__(self):
+        global _stream_handle
+        self.prev = _stream_handle
+        _stream_handle = self.handle
+
+    def __exit__(self, *exc):
+        global _stream_handle
+        _stream_handle = self.prev
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
