@@ -178,3 +178,35 @@ def test_native_pyrandom_matches_the_interpreter():
     lib.call("denet_pyrandom_random", mt.ctypes.data, ctypes.addressof(pos), 1500, out.ctypes.data)
     mt_import(mt, pos, version, gauss)
     assert list(out) == want and random.random() == [random.seed(9), [random.random() for _ in range(1501)]][1][-1]
+
+
+def test_strided_dgrad_parity_classes_restate_the_data_gradient():
+    """ops.dgrad_parity_classes: the data gradient of a strided (true) convolution equals one stride-1 correlation per
+    parity class of the input pixel on the UNDILATED dy, with the class's taps r0 + s*t and leading pad - checked on the
+    CPU against autograd of the oracle convolution (the CUDA path uses exactly these class parameters)"""
+    import torch
+    import torch.nn.functional as F
+    from denet_b200 import ops
+    from oracle import ref_ops as R
+    g = torch.Generator().manual_seed(7)
+    for (h, w, k, s, pad) in [(16, 16, 3, 2, 1), (15, 18, 3, 2, 1), (20, 20, 5, 2, 2), (21, 17, 7, 2, 3), (18, 18, 3, 3, 1),
+                              (16, 16, 4, 2, 1)]:
+        cin, cout, n = 3, 4, 2
+        x = torch.randn(n, cin, h, w, generator=g, dtype=torch.float64, requires_grad=True)
+        wt = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64)
+        y = R.conv2d(x, wt, (s, s), pad, None)
+        dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+        (dx_ref,) = torch.autograd.grad(y, x, dy)
+        classes = ops.dgrad_parity_classes((h, w), (k, k), (s, s), (pad, pad))
+        assert classes is not None and len(classes) == s * s
+        dx = torch.zeros_like(dx_ref)
+        for (a, b, r0, s0, rc, sc, ph, pw, hc, wc) in classes:
+            sub = wt[:, :, r0::s, s0::s]                       # (cout, cin, rc, sc): taps of this class
+            assert tuple(sub.shape[2:]) == (rc, sc)
+            kern = sub.permute(1, 0, 2, 3)                      # correlation dy (cout channels) -> dx (cin channels)
+            need_h, need_w = hc + rc - 1, wc + sc - 1           # out[i] = sum_t in[i + t - ph] K[t], i < hc
+            dyp = F.pad(dy, (pw, max(0, need_w - pw - dy.shape[3]), ph, max(0, need_h - ph - dy.shape[2])))
+            out = F.conv2d(dyp[:, :, :need_h, :need_w], kern)
+            assert tuple(out.shape[2:]) == (hc, wc)
+            dx[:, :, a::s, b::s] = out
+        assert float((dx - dx_ref).abs().max()) < 1e-10, (h, w, k, s, pad)
