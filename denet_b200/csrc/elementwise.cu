@@ -663,6 +663,71 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
     }
 }
 
+// 3x3 / stride 2 / pad 1 max-pool backward (the ResNet stem pool), bf16 x 8 channels: one thread per 2x2 quad of input
+// pixels.  The quad (2i..2i+1, 2j..2j+1) is covered by exactly the windows (i..i+1, j..j+1): 4 tap words + 4 dy packs
+// are loaded once and serve the 9 (window, pixel) pairs of the quad, and the index arithmetic is done once per quad
+// (the per-pixel kernel was instruction-bound: ~250 instructions per 16-byte store).  Same sums in the same order as
+// maxpool_bwd_kernel (windows in decreasing ho, then decreasing wo).
+__global__ void __launch_bounds__(256) maxpool_bwd_3x3s2_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                 const uint8_t* __restrict__ argmax, int N, int H, int W,
+                                                                 int C, long long ldx, int Ho, int Wo, long long ldy,
+                                                                 __nv_bfloat16* __restrict__ dx) {
+    const int CV = C / 8;
+    const int QH = (H + 1) / 2, QW = (W + 1) / 2;
+    const unsigned total = (unsigned)N * QH * QW * CV;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        unsigned u = idx;
+        const int cv = (int)(u % (unsigned)CV); u /= (unsigned)CV;
+        const int j = (int)(u % (unsigned)QW); u /= (unsigned)QW;
+        const int i = (int)(u % (unsigned)QH);
+        const int n = (int)(u / (unsigned)QH);
+        uint2 am[4];
+        Raw<__nv_bfloat16, 8> g[4];
+        bool ok[4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int q = 2 * a + b;
+                const int ho = i + a, wo = j + b;
+                ok[q] = ho < Ho && wo < Wo;
+                const long long opix = ((long long)n * Ho + (ok[q] ? ho : 0)) * Wo + (ok[q] ? wo : 0);
+                am[q] = ok[q] ? *reinterpret_cast<const uint2*>(argmax + opix * C + cv * 8) : make_uint2(~0u, ~0u);
+                g[q].load(dy + opix * ldy + (long long)cv * 8);
+            }
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                const int h = 2 * i + py, w = 2 * j + px;
+                if (h >= H || w >= W) continue;
+                float acc[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+                // windows of pixel (py, px): a in {0} (py == 0) or {1, 0} (py == 1), likewise b; tap = r*3 + s with
+                // r = py + 1 - 2a, s = px + 1 - 2b
+#pragma unroll
+                for (int a = 1; a >= 0; --a)
+#pragma unroll
+                    for (int b = 1; b >= 0; --b) {
+                        const int r = py + 1 - 2 * a, sx = px + 1 - 2 * b;
+                        if (r < 0 || sx < 0) continue;                 // compile-time after unrolling
+                        const int q = 2 * a + b;
+                        const uint32_t tapw = (uint32_t)(r * 3 + sx) * 0x01010101u;
+                        const uint32_t m0 = __vcmpeq4(am[q].x, tapw), m1 = __vcmpeq4(am[q].y, tapw);
+                        if ((m0 | m1) == 0) continue;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (((c < 4 ? m0 : m1) >> (8 * (c & 3))) & 1u) acc[c] += g[q].get(c);
+                    }
+                Pack<__nv_bfloat16, 8> o;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o.v[c] = acc[c];
+                o.store(dx + (((long long)n * H + h) * W + w) * ldx + (long long)cv * 8);
+            }
+    }
+}
+
 // average_inc_pad: divisor is always kh*kw
 template <typename T, int VEC>
 __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, long long ldx, int kh, int kw,
@@ -1134,6 +1199,14 @@ extern "C" int denet_pool_bwd(const void* dy, int dtype, int N, int H, int W, in
     DN_REQUIRE(dy && dx, "pool_bwd: null pointer");
     DN_REQUIRE(mode == 1 || argmax, "pool_bwd: max pooling needs the argmax buffer of the forward pass");
     const bool v = vec8_ok(C, ldx, dx) && vec8_ok(C, ldy, dy);
+    if (mode == 0 && v && dtype == DENET_BF16 && kh == 3 && kw == 3 && sh == 2 && sw == 2 && ph == 1 && pw == 1 &&
+        (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8) < 0x7fffffffLL) {
+        const int grid = ew_grid((long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8), 256);
+        maxpool_bwd_3x3s2_kernel<<<DN_G(grid), 256, 0, stream>>>((const __nv_bfloat16*)dy, argmax, N, H, W, C, ldx, Ho, Wo,
+                                                                  ldy, (__nv_bfloat16*)dx);
+        DN_CHECK_LAUNCH();
+        return 0;
+    }
     DN_DISPATCH(dtype, v, {
         const int grid = ew_grid((long long)N * H * W * (C / VEC), 256);
         if (mode == 0)

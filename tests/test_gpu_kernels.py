@@ -400,6 +400,27 @@ def test_pool(cuda, mode, size, stride, pad):
     assert relerr(nchw(dx), dxr) < 1e-6
 
 
+@pytest.mark.parametrize("hw", [(14, 14), (13, 17), (32, 30)])
+def test_maxpool_3x3s2_bf16_quad_backward(cuda, hw):
+    """the bf16 3x3/stride-2/pad-1 max-pool backward (one thread per 2x2 input quad) gives exactly the fp32 gather
+    kernel's result rounded to bf16 (same windows, same summation order), for even and odd extents"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(sum(hw))
+    h, w = hw
+    x = torch.randn(3, 64, h, w, generator=g).bfloat16().float()
+    oh, ow = R.pool_out_hw((h, w), (3, 3), (2, 2), (1, 1))
+    dy = torch.randn(3, 64, oh, ow, generator=g).bfloat16().float()
+    x32, dy32 = nhwc(x, torch.float32, cuda), nhwc(dy, torch.float32, cuda)
+    y32, arg32 = ops.pool_fwd(x32, 0, (3, 3), (2, 2), (1, 1), (oh, ow))
+    dx32 = ops.pool_bwd(dy32, 0, (3, 3), (2, 2), (1, 1), tuple(x32.shape), arg32)
+    xb, dyb = nhwc(x, torch.bfloat16, cuda), nhwc(dy, torch.bfloat16, cuda)
+    yb, argb = ops.pool_fwd(xb, 0, (3, 3), (2, 2), (1, 1), (oh, ow))
+    assert torch.equal(argb, arg32) and torch.equal(yb.float(), y32)
+    dxb = ops.pool_bwd(dyb, 0, (3, 3), (2, 2), (1, 1), tuple(xb.shape), argb)
+    assert dxb.dtype == torch.bfloat16
+    assert torch.equal(dxb[..., :64], dx32[..., :64].bfloat16())
+
+
 def test_pool_inv_matches_reference_kernels(cuda):
     """recipe of the reference's own A/B block (pool_inv.py:43-88): (4,64,4,4), 2x2, seed 1"""
     ops = _ops()
