@@ -1944,6 +1944,7 @@ int halo_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStre
 // where t_kblock is the larger of the MMA time and the L2 -> shared-memory time of one k-block on one SM and t_reduce
 // the workspace write + read of one split (the fixed-order reduction pass).  Ties go to fewer splits.
 static int g_wgrad_legacy_splits = 0;
+static int g_wgrad_rows_max_cin = 64;     // widest layer (input channels) that takes the row-shared wgrad kernel
 int wgrad_splits(int total_kblocks, int base_tiles, int bn_cols, int stage_bytes, long long out_elems) {
     const int sms = num_sms();
     if (g_wgrad_legacy_splits) {
@@ -2199,7 +2200,7 @@ static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cout, int Cin, int R, int
     // measured on B200 (scripts/bench_wgrad.py): the row-shared kernel wins for Cin <= 64 (266 vs 181 TFLOP/s at
     // 64->64 3x3 128^2); from 128 channels on, its smaller Cin tile and single accumulator set lose to one tap per tile
     pl.rows_path = want_rows && stride_h == 1 && stride_w == 1 && S > 1 && S <= 8 && pl.TW >= 8 && pl.xrows <= 80 &&
-                   Cin <= 64;
+                   Cin <= g_wgrad_rows_max_cin;
     if (pl.rows_path)
         while (S * pl.BN > 512) pl.BN /= 2;
     pl.co_tiles = ceil_div(Cout, 128);
@@ -2225,6 +2226,7 @@ extern "C" int denet_conv2d_wgrad_set_mode(int row_shared) {
     g_wgrad_debug = ((row_shared >> 1) & 7) | (((row_shared >> 5) & 1) << 3);   // undocumented profiling knobs (bit1: no
                                                   // MMA, bit2: no TMA, bit3: no store; bit5: per-tap MMAs in the rows kernel)
     g_wgrad_legacy_splits = (row_shared >> 4) & 1;   // bit4: the former split-K rule (A/B measurements)
+    g_wgrad_rows_max_cin = ((row_shared >> 6) & 1) ? 4096 : 64;   // bit6: row-shared kernel for every channel count
     return 0;
 }
 

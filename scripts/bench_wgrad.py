@@ -7,22 +7,22 @@ import torch
 from denet_b200 import ops, lib
 L = lib.load()
 cuda = torch.device("cuda:0")
-for (n, h, w, cin, cout, k) in [(32, 128, 128, 64, 64, 3), (32, 64, 64, 128, 128, 3), (32, 32, 32, 256, 256, 3)]:
+for (n, h, w, cin, cout, k) in [(32, 128, 128, 64, 64, 3), (32, 64, 64, 128, 128, 3), (32, 32, 32, 256, 256, 3), (32, 16, 16, 512, 512, 3)]:
     x = ops.ActOperand(torch.randn(n, h, w, cin, device=cuda).bfloat16())
     dy = ops.ActOperand(torch.randn(n, h, w, cout, device=cuda).bfloat16())
     dw = torch.empty(cout, cin, k, k, device=cuda)
     flops = 2.0 * n * h * w * cin * cout * k * k
     ref = None
-    for mode in [1, 33, 0, 3, 5, 9]:
+    for mode in [1, 65, 0]:
         L.denet_conv2d_wgrad_set_mode(mode)
         for _ in range(3):
             ops.conv2d_wgrad(dy, x, k, k, (1, 1), (1, 1), dw=dw)
-        if mode in (1, 33, 0):
+        if mode in (1, 65, 0):
             if ref is None:
                 ref = dw.clone()
             else:
                 err = ((dw - ref).norm() / ref.norm()).item()
-                assert err < 1e-5, (mode, err)
+                assert err < 1e-4, (mode, err)
         evs = []
         for _ in range(10):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
