@@ -80,7 +80,12 @@ def _rows(t):
 def alloc_nhwc(n, h, w, c, dtype, device="cuda", zero=False):
     """NHWC tensor whose pixel pitch is padded to a multiple of 8 elements."""
     ld = (c + 7) // 8 * 8
-    buf = (torch.zeros if zero or ld != c else torch.empty)((n, h, w, ld), dtype=dtype, device=device)
+    if zero:
+        buf = torch.zeros((n, h, w, ld), dtype=dtype, device=device)
+    else:
+        buf = torch.empty((n, h, w, ld), dtype=dtype, device=device)
+        if ld != c:
+            buf[..., c:].zero_()       # only the pad columns (the 4706-channel RoI tensor has 6 of them, not 174 MB)
     return buf[..., :c] if ld != c else buf
 
 
