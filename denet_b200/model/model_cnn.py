@@ -346,6 +346,18 @@ class ModelCNN:
         if average_bn_stats:
             for l in _walk(self.layers):
                 extra += [t for t, _ in l.updates()] if not len(l.layers) else []
+            if extra and all(t.is_cuda and t.dtype == torch.float32 for t in extra):
+                # move the running statistics of all batch-norm layers into ONE flat buffer (the parameters become
+                # views of it): their per-step average is then a single in-place all-reduce
+                flat = torch.empty((sum(t.numel() for t in extra),), dtype=torch.float32, device=extra[0].device)
+                o = 0
+                for t in extra:
+                    n = t.numel()
+                    flat[o:o + n].copy_(t.detach().reshape(-1))
+                    t.data = flat[o:o + n].view(t.shape)
+                    o += n
+                self._bn_running_flat = flat
+                extra = [flat]
         self.ddp = GradientAllReduce(self.flat_grad, ranges, bucket_bytes, extra, group)
         return self.ddp
 

@@ -107,7 +107,10 @@ class GradientAllReduce:
             self._launch(start, end)
             self._next += 1
         if self.extra:
-            flat = torch.cat([t.reshape(-1) for t in self.extra])
+            # one contiguous tensor (ModelCNN keeps the running statistics of all batch-norm layers in one flat buffer):
+            # reduce and scale it in place - no gather / scatter kernels per tensor
+            inplace = len(self.extra) == 1 and self.extra[0].is_contiguous()
+            flat = self.extra[0].view(-1) if inplace else torch.cat([t.reshape(-1) for t in self.extra])
             if self.cuda:
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream())
@@ -123,8 +126,9 @@ class GradientAllReduce:
                 w.wait()
         if self.extra:
             flat.mul_(1.0 / self.world)
-            o = 0
-            for t in self.extra:
-                t.copy_(flat[o:o + t.numel()].view(t.shape))
-                o += t.numel()
+            if not inplace:
+                o = 0
+                for t in self.extra:
+                    t.copy_(flat[o:o + t.numel()].view(t.shape))
+                    o += t.numel()
         return 1.0 / self.world
