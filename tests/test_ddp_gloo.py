@@ -44,6 +44,22 @@ def _worker(rank, world, port, out):
     for layer in range(9, 0, -1):                         # the backward pass retires layers in descending order
         red.layer_done(layer)
     scale = red.finish_step()
+    # several extra tensors (gathered, reduced, scattered back) and the will_launch() contract the deferred split-K
+    # reduction relies on: it announces exactly the layer_done() calls that start an all-reduce
+    flat2 = torch.from_numpy(rs.randn(5000).astype(numpy.float32))
+    ea, eb = torch.full((3,), float(rank)), torch.full((2, 2), 10.0 * (rank + 1))
+    red2 = ddp.GradientAllReduce(flat2, ranges, bucket_bytes=4000, extra_mean_tensors=[ea, eb])
+    red2.begin_step()
+    announced = []
+    for layer in range(9, 0, -1):
+        before = red2._next
+        will = red2.will_launch(layer)
+        red2.layer_done(layer)
+        assert will == (red2._next > before), layer
+        announced.append(will)
+    red2.finish_step()
+    assert any(announced)
+    assert torch.allclose(ea, torch.full((3,), 0.5)) and torch.allclose(eb, torch.full((2, 2), 15.0))
     out.put((rank, mine.numpy(), flat.numpy().copy(), scale, bn_stat.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
