@@ -52,3 +52,26 @@ def test_product_has_no_oracle_import():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_wgrad_split_plan_fills_whole_waves():
+    """the split-K factor of the filter gradient (plan query of the C-ABI, no GPU needed: 148 SMs assumed) puts the
+    DeNet-34 layers on whole waves of the persistent grid - the former rule ceil(2*SMs / tiles) left 297..306 tiles on
+    148 SMs, i.e. three rounds for two waves of work"""
+    from denet_b200 import lib
+    L = lib.load()
+    sms = 148
+    # (N, Ho, Wo, Cout, Cin, k): the stride-1 3x3 layers of the ResNet-34 stages at 512 x 512 input, batch 32
+    for (n, ho, wo, cout, cin, k) in [(32, 128, 128, 64, 64, 3), (32, 64, 64, 128, 128, 3), (32, 32, 32, 256, 256, 3),
+                                      (32, 16, 16, 512, 512, 3)]:
+        splits = L.denet_conv2d_wgrad_splits(n, ho, wo, cout, cin, k, k, 1, 1)
+        bn = 64 if cin <= 64 else (128 if cin <= 128 else 256)
+        rows_kernel = cin <= 64                                  # one tile per filter ROW, else one per tap
+        base = -(-cout // 128) * -(-cin // bn) * (k if rows_kernel else k * k)
+        tiles = base * splits
+        rounds = -(-tiles // sms)
+        assert tiles / (rounds * sms) >= 0.95, (cout, cin, splits, tiles)
+        ws = L.denet_conv2d_wgrad_workspace(n, ho, wo, cout, cin, k, k)
+        assert ws >= splits * cout * cin * k * k * 4
+    # the row-folded stem: every filter row in one tile -> splits = persistent CTAs
+    assert L.denet_conv2d_rowfold_wgrad_splits(32, 256, 256, 64, 7, 2) == sms
