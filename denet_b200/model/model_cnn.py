@@ -578,6 +578,7 @@ class ModelCNN:
         """forward + backward + update on the device; returns the device tensor [total, cost_0, cost_1, ...]"""
         layer_mod.set_epoch(epoch)
         layer_mod.set_iteration(it)
+        self._host_costs = None        # set again by a graphed step that fetched its costs early (see train_step)
         ops.pin_stream(True)
         try:
             with torch.no_grad():
