@@ -83,3 +83,16 @@ def get_params_dict(params):
         pv = item.split("=")
         out[pv[0]] = True if len(pv) == 1 else convert_num(pv[1])
     return out
+
+
+def import_c(fname):
+    """reference common.import_c (common/__init__.py:171-195) JIT-compiles a CPython extension from a .cc file next to
+    the layer; here the same call returns the GPU-backed module with the extension's functions and signatures
+    (denet_sparse.cc -> denet_b200.layer.denet_sparse_c)"""
+    import importlib
+    import os
+    base = os.path.splitext(os.path.basename(fname))[0]
+    table = {"denet_sparse": "denet_b200.layer.denet_sparse_c", "denet_detect": "denet_b200.layer.denet_detect_c"}
+    if base not in table:
+        raise ImportError("import_c: no B200 replacement for %s" % fname)
+    return importlib.import_module(table[base])

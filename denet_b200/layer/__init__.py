@@ -11,6 +11,8 @@ hand-written sm_100a kernels (denet_b200.ops -> C-ABI) on the current CUDA strea
 tensors (bf16 in throughput mode, fp32 in parity mode); `output` holds the tensor of the last forward pass instead of
 a symbolic variable.  There is no autograd graph and no CPU fallback.
 """
+import itertools
+
 import numpy
 import torch
 from torch import nn
@@ -168,6 +170,36 @@ transfer_bytes = {"h2d": 0, "d2h": 0}
 
 
 _slots = {}     # slot name -> (pinned host tensor, device tensor, copy-done event)
+_slot_uid = itertools.count(1)
+_frozen_ns = set()
+
+
+def new_slot_namespace():
+    """suffix that makes the slot names of one model / layer INSTANCE unique: two models (or two sparse layers) with
+    equal shapes must not alias each other's staging buffers"""
+    return "#%d" % next(_slot_uid)
+
+
+def freeze_slots(ns, on=True):
+    """after a CUDA-graph capture the device tensors of the namespace's slots are baked into the graphs: a shape change
+    must not silently re-allocate them (the graphs would keep reading the old tensor)"""
+    (_frozen_ns.add if on else _frozen_ns.discard)(ns)
+
+
+class SlotFrozenError(RuntimeError):
+    pass
+
+
+def _slot_entry(slot, t, dev):
+    ent = _slots.get(slot)
+    if ent is None or ent[1].shape != t.shape or ent[1].dtype != t.dtype:
+        if ent is not None and "#" in slot and slot[slot.rindex("#"):] in _frozen_ns:
+            raise SlotFrozenError("slot %s is an input of captured CUDA graphs: shape %s -> %s is not allowed (disable "
+                                  "the graphs or keep the batch shape)" % (slot, tuple(ent[1].shape), tuple(t.shape)))
+        ent = (torch.empty(t.shape, dtype=t.dtype).pin_memory(), torch.empty(t.shape, dtype=t.dtype, device=dev),
+               torch.cuda.Event())
+        _slots[slot] = ent
+    return ent
 
 
 def h2d(array, device=None, slot=None):
@@ -185,12 +217,7 @@ def h2d(array, device=None, slot=None):
         if not t.is_pinned():
             t = t.pin_memory()
         return t.to(dev, non_blocking=True)
-    ent = _slots.get(slot)
-    if ent is None or ent[1].shape != t.shape or ent[1].dtype != t.dtype:
-        ent = (torch.empty(t.shape, dtype=t.dtype).pin_memory(), torch.empty(t.shape, dtype=t.dtype, device=dev),
-               torch.cuda.Event())
-        _slots[slot] = ent
-    pinned, dst, done = ent
+    pinned, dst, done = _slot_entry(slot, t, dev)
     if t.is_cuda:
         if t.data_ptr() != dst.data_ptr():
             dst.copy_(t, non_blocking=True)
@@ -212,12 +239,7 @@ def h2d_on_stream(array, device, slot, stream, after=None):
     (device tensor, event that fires when the data has landed); the consumer's stream must wait on that event."""
     t = array if torch.is_tensor(array) else torch.from_numpy(numpy.ascontiguousarray(array))
     assert not t.is_cuda
-    ent = _slots.get(slot)
-    if ent is None or ent[1].shape != t.shape or ent[1].dtype != t.dtype:
-        ent = (torch.empty(t.shape, dtype=t.dtype).pin_memory(), torch.empty(t.shape, dtype=t.dtype, device=device),
-               torch.cuda.Event())
-        _slots[slot] = ent
-    pinned, dst, done = ent
+    pinned, dst, done = _slot_entry(slot, t, device)
     transfer_bytes["h2d"] += t.numel() * t.element_size()
     ready = torch.cuda.Event()
     with torch.cuda.stream(stream):
@@ -282,6 +304,7 @@ class AbstractLayer(nn.Module):
         self.has_split = has_split
         self.layers = nn.ModuleList()
         self.layer_index = layer_index
+        object.__setattr__(self, "_slot_ns", new_slot_namespace())      # per-instance staging-buffer names
 
     def __str__(self):
         groups = {"int": [], "str": [], "float": [], "bool": [], "tuple": []}

@@ -130,7 +130,7 @@ class DeNetSparseLayer(AbstractLayer):
     def collect_samples(self):
         """device -> host copy of the packed sampler output (one small synchronising copy):
         pr (B,K) f32, bbox (B,K,4) f32, count (B)"""
-        packed = d2h(self._packed_dev, slot="denet-sparse/samples")
+        packed = d2h(self._packed_dev, slot="denet-sparse/samples" + self._slot_ns)
         b, k = self.batch_size, self.sample_count
         return (packed[:b * k].reshape(b, k), packed[b * k:5 * b * k].reshape(b, k, 4),
                 packed[5 * b * k:].astype(numpy.int64))
@@ -160,9 +160,9 @@ class DeNetSparseLayer(AbstractLayer):
         self._sample_bbox_list = None
         arr = numpy.ascontiguousarray(bbox.astype(numpy.float32).reshape(self.batch_size, self.sample_num,
                                                                          self.sample_num, 4))
-        self.sample_bbox = h2d(arr, slot="denet-sparse/bbox32")
+        self.sample_bbox = h2d(arr, slot="denet-sparse/bbox32" + self._slot_ns)
         # the doubles feed the device-side detection targets (python floats in the reference, denet_detect.py:200-212)
-        self.sample_bbox64 = h2d(numpy.ascontiguousarray(bbox, dtype=numpy.float64), slot="denet-sparse/bbox64")
+        self.sample_bbox64 = h2d(numpy.ascontiguousarray(bbox, dtype=numpy.float64), slot="denet-sparse/bbox64" + self._slot_ns)
         return arr
 
     def set_samples(self, sample_bboxs):
@@ -200,6 +200,11 @@ class DeNetSparseLayer(AbstractLayer):
         mt_import(mt, pos, version, gauss)
         if self.sample_gt:
             for b, meta in enumerate(metas):
+                if len(meta["bbox"]) > k:
+                    # the reference's list assignment raises here too (denet_sparse.py:199-201); numpy would wrap the
+                    # negative index and let ground-truth entries overwrite each other
+                    raise IndexError("denet-sparse: image %d has %d ground-truth boxes but only %d samples"
+                                     % (b, len(meta["bbox"]), k))
                 for index, gt in enumerate(meta["bbox"]):       # the LAST len(GT) slots become the ground truth
                     pr[b, k - (index + 1)] = 1.0
                     bbox[b, k - (index + 1)] = gt

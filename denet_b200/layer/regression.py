@@ -61,7 +61,7 @@ class RegressionLayer(AbstractLayer):
     def set_target(self, yt_index, yt_value):
         classes = self.output_shape[1]
         label = (numpy.asarray(yt_index, dtype=numpy.int64) % classes).astype(numpy.int32)
-        self._label = h2d(label, slot="regression/label")
+        self._label = h2d(label, slot="regression/label" + self._slot_ns)
 
     def forward(self, x):
         self.input = x

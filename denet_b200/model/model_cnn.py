@@ -148,6 +148,7 @@ class ModelCNN:
         self._img_consumed_valid = False
         self._costs_pinned = None
         self._host_costs = None
+        self._slot_ns = layer_mod.new_slot_namespace()     # staging buffers (image, ground truth, scalars) of THIS model
 
     # ---------------------------------------------------------------------------------------------- shapes
     def get_input_shape(self):
@@ -359,7 +360,33 @@ class ModelCNN:
                 self._bn_running_flat = flat
                 extra = [flat]
         self.ddp = GradientAllReduce(self.flat_grad, ranges, bucket_bytes, extra, group)
+        # every replica must start from ONE model (the reference's workers all load the shared model,
+        # multi/worker.py:85-122): fresh models draw their weights from the unseeded global numpy.random, so without
+        # this the ranks would apply an averaged gradient to different weights and never converge
+        self.sync_state_from_rank0(group)
         return self.ddp
+
+    def state_tensors(self):
+        """every tensor that defines the training state of this replica: parameters + batch-norm running statistics
+        (layer.params()), and the solver momenta once build_train_func() has created them"""
+        out = []
+        for l in _walk(self.layers):
+            if not len(l.layers):
+                out += list(l.params())
+        seen, uniq = set(), []
+        for t in out + list(getattr(self, "momenta", None) or []) + list(getattr(self, "momenta2", None) or []):
+            if id(t) not in seen:
+                seen.add(id(t))
+                uniq.append(t)
+        return uniq
+
+    def sync_state_from_rank0(self, group=None):
+        """broadcast parameters, running statistics and momenta from rank 0 (no-op without torch.distributed)"""
+        from ..multi import ddp as ddp_mod
+        n = ddp_mod.broadcast_state(self.state_tensors(), src=0, group=group)
+        if n:
+            layer_mod.bump_param_version()
+        return n
 
     def _build_solver_tables(self):
         chunk = lib.load().denet_solver_chunk()
@@ -384,6 +411,8 @@ class ModelCNN:
         self._solver_block_tensor = torch.tensor(block_tensor, dtype=torch.int32, device=self.device)
         self._solver_block_offset = torch.tensor(block_offset, dtype=torch.int64, device=self.device)
         self._solver_nblocks = len(block_tensor)
+        if self.ddp is not None:
+            self.sync_state_from_rank0(self.ddp.group)
 
     def build_train_func(self, solver_mode="sgd", cost_factors=[], use_acc_mode=False, skip_build=False):
         """collect the cost layers and prepare the solver (model_cnn.py:205-405)"""
@@ -414,7 +443,7 @@ class ModelCNN:
         """host NCHW fp32 batch (numpy or pinned tensor) -> NHWC device activation"""
         if isinstance(data_x, numpy.ndarray):
             data_x = numpy.ascontiguousarray(data_x, dtype=numpy.float32)
-        t = layer_mod.h2d(data_x, self.device, slot="model/image" if self._static_inputs else None).contiguous()
+        t = layer_mod.h2d(data_x, self.device, slot="model/image" + self._slot_ns if self._static_inputs else None).contiguous()
         first = self.layers[1] if len(self.layers) > 1 else None
         geom = getattr(first, "rowfold", None)
         if geom is not None:
@@ -446,8 +475,8 @@ class ModelCNN:
             if n:
                 box[i, :n] = numpy.asarray(m["bbox"], dtype=numpy.float64)
                 cls[i, :n] = numpy.asarray(m["class"], dtype=numpy.int32)
-        return (layer_mod.h2d(box, self.device, slot="model/gt_bbox"), layer_mod.h2d(cls, self.device, slot="model/gt_class"),
-                layer_mod.h2d(cnt, self.device, slot="model/gt_count"))
+        return (layer_mod.h2d(box, self.device, slot="model/gt_bbox" + self._slot_ns), layer_mod.h2d(cls, self.device, slot="model/gt_class" + self._slot_ns),
+                layer_mod.h2d(cnt, self.device, slot="model/gt_count" + self._slot_ns))
 
     def prepare_operands(self):
         """bf16 GEMM operands of every conv layer from the fp32 master weights in ONE kernel launch (after each
@@ -578,6 +607,14 @@ class ModelCNN:
         """forward + backward + update on the device; returns the device tensor [total, cost_0, cost_1, ...]"""
         layer_mod.set_epoch(epoch)
         layer_mod.set_iteration(it)
+        if tuple(data_x.shape) != self.get_input_shape():
+            # layer shapes (and captured graphs) are static; the reference's Dataset.export pads the last batch to a
+            # full one (dataset/__init__.py:349-366), so a short batch is a caller error
+            raise ValueError("train_step: batch shape %s does not match the model input %s" %
+                             (tuple(data_x.shape), self.get_input_shape()))
+        if self.gradient_clip > 0:
+            raise NotImplementedError("gradient_clip > 0 (reference model_cnn.py grad_clip) is not implemented on the "
+                                      "B200 path; refusing to train without it")
         self._host_costs = None        # set again by a graphed step that fetched its costs early (see train_step)
         ops.pin_stream(True)
         try:
@@ -625,14 +662,14 @@ class ModelCNN:
         mom = list(momentum) + [0.0, 0.0]
         world = self.ddp.world if self.ddp is not None else 1
         hp = numpy.array([learning_rate, mom[0], mom[1], decay, float(it), 1.0 / world], dtype=numpy.float32)
-        return layer_mod.h2d(hp, self.device, slot="model/hp")
+        return layer_mod.h2d(hp, self.device, slot="model/hp" + self._slot_ns)
 
     def _segment_a(self, si):
         """image -> ... -> corner layer (+ device targets, corner cost) -> device sampler"""
         self.bn_stat_buffer.zero_()
         self._prep_version = -1                  # the operand preparation is part of the captured graph
         self.prepare_operands()
-        x = self.upload(layer_mod.slot_tensor("model/image"))
+        x = self.upload(layer_mod.slot_tensor("model/image" + self._slot_ns))
         self.layers[0].output = x
         end = si if si is not None else len(self.layers)
         x = self.forward_layers(x, 1, end, train=True, with_targets=False)
@@ -667,6 +704,12 @@ class ModelCNN:
             self._host_costs = None
             return self._train_step_eager(data_x, data_m, it, learning_rate, momentum, decay)
         si = self._sparse_index()
+        if si is not None and data_m and max(len(m.get("bbox", [])) for m in data_m) > ops.MAX_GT:
+            # the captured corner / detection target kernels read the persistent ground-truth slots, which hold at
+            # most MAX_GT boxes per image: this batch takes the eager step with the host target builders instead
+            # (replaying the graphs would silently train on the previous batch's targets)
+            self._host_costs = None
+            return self._train_step_eager(data_x, data_m, it, learning_rate, momentum, decay)
         layer_mod.set_train(True)
         cur = torch.cuda.current_stream()
         # refresh the static inputs of this step
@@ -680,10 +723,10 @@ class ModelCNN:
         if host_image:
             if isinstance(data_x, numpy.ndarray):
                 data_x = numpy.ascontiguousarray(data_x, dtype=numpy.float32)
-            _, img_ready = layer_mod.h2d_on_stream(data_x, self.device, "model/image", self._copy_stream,
+            _, img_ready = layer_mod.h2d_on_stream(data_x, self.device, "model/image" + self._slot_ns, self._copy_stream,
                                                    self._img_consumed if self._img_consumed_valid else None)
         else:
-            layer_mod.h2d(data_x, self.device, slot="model/image")
+            layer_mod.h2d(data_x, self.device, slot="model/image" + self._slot_ns)
         gt = self.upload_metas(data_m)
         layer_mod.set_ground_truth(gt)
         for l in self.layers[1:]:
@@ -748,6 +791,10 @@ class ModelCNN:
             self._segment_b2(hp_dev)
         ops.pin_stream(True)
         self._graphs = (ga, gb1, gb2)
+        # the staging tensors are baked into the graphs now: a later shape change must fail loudly, not re-allocate
+        layer_mod.freeze_slots(self._slot_ns)
+        for l in _walk(self.layers):
+            layer_mod.freeze_slots(l._slot_ns)
 
     def train_step(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):
         """reference contract (model_cnn.py:407-445): returns (cost, [layer costs]) as python floats"""

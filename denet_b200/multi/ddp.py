@@ -31,6 +31,35 @@ def shard_batch(global_count, rank, world):
     return rank * per, (rank + 1) * per
 
 
+def broadcast_state(tensors, src=0, group=None):
+    """make every rank's copy of `tensors` equal to rank `src`'s: one flat broadcast per dtype (the tensors are small
+    and many: per-tensor broadcasts would be ~hundreds of collectives).  Returns the number of tensors synchronised
+    (0 when torch.distributed is not initialised or the world is a single rank)."""
+    if not dist.is_initialized() or dist.get_world_size(group) <= 1 or not tensors:
+        return 0
+    by_kind = {}
+    for t in tensors:
+        by_kind.setdefault((t.dtype, t.device), []).append(t)
+    with torch.no_grad():
+        for (_, _), ts in by_kind.items():
+            flat = torch.cat([t.detach().reshape(-1) for t in ts])
+            dist.broadcast(flat, src=src, group=group)
+            o = 0
+            for t in ts:
+                n = t.numel()
+                t.detach().copy_(flat[o:o + n].view(t.shape))
+                o += n
+    return len(tensors)
+
+
+def state_checksum(tensors):
+    """order-sensitive fp64 checksum of a tensor list (used to assert that replicas hold the same state)"""
+    acc = 0.0
+    for i, t in enumerate(tensors):
+        acc += float(t.detach().double().sum().item()) * (1.0 + 1e-3 * (i % 97))
+    return acc
+
+
 def plan_buckets(layer_ranges, bucket_elems):
     """layer_ranges: [(layer_index, start, end)] element ranges of a flat gradient buffer, ascending in layer order.
     Gradients become final in DESCENDING layer order during backward; returns [(ready_after_layer, start, end)]:

@@ -708,9 +708,11 @@ def sparse_sample_index(bbox, gs, H, W):
     return ys, xs
 
 
-def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, local_max=0):
+def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, local_max=0, cluster_threshold=1.0):
     """corner_pr (B,2,4,H,W) fp32 device.  Returns (pr (B,K), bbox (B,K,4), ibox (B,K,4) int32, count (B), ncand (B))"""
     assert corner_pr.dtype == torch.float32 and corner_pr.is_contiguous() and corner_pr.shape[1:3] == (2, 4)
+    if cluster_threshold < 1.0:
+        raise NotImplementedError("build_samples: corner clustering (cluster_threshold < 1, denet_sparse.cc:165-242)")
     b, _, _, h, w = corner_pr.shape
     k = sample_num * sample_num
     dev = corner_pr.device

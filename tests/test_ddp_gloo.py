@@ -83,3 +83,45 @@ def test_gradient_allreduce_world2_gloo():
         assert numpy.allclose(reduced, total, rtol=1e-6, atol=1e-6)      # sum over ranks in every bucket
         assert scale == 0.5                                              # the solver applies 1/world
         assert numpy.allclose(bn, 1.5)                                   # running statistics are averaged
+
+
+def _worker_sync(rank, world, port, out):
+    """replicas built from different numpy seeds must be made identical by the data-parallel setup"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    ddp.init_process_group("gloo")
+    from denet_b200.model import model_cnn
+    numpy.random.seed(1000 + rank)                        # what an unseeded torchrun launch amounts to
+    model = model_cnn.ModelCNN()
+    model.batch_size, model.class_num = 2, 10
+    model.build("C[8,3] BN A P[2] C.B[16,3] BN A P.A R".split(), (3, 8, 8), "relu", "half", ["he-backward"])
+    tensors = model.state_tensors()
+    for t in tensors[-2:]:
+        t.data.add_(float(rank))                          # running statistics differ too
+    before = ddp.state_checksum(tensors)
+    n = model.sync_state_from_rank0()
+    after = ddp.state_checksum(tensors)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (before, after, n, len(tensors)))
+    out.put((rank, gathered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replicas_built_with_different_seeds_are_synchronised_world2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_sync, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (b0, a0, n0, k0), (b1, a1, n1, k1) = res[0][1]
+    assert b0 != b1                     # the replicas really started from different weights
+    assert a0 == a1 == b0               # ... and both hold rank 0's state afterwards
+    assert n0 == n1 == k0 == k1 and k0 >= 8
