@@ -10,7 +10,7 @@ cuda = torch.device("cuda:0")
 cases = [(32, 128, 128, 64, 64, 3), (32, 64, 64, 128, 128, 3), (32, 32, 32, 256, 256, 3), (32, 16, 16, 512, 512, 3)]
 if len(sys.argv) > 1:
     cases = cases[:int(sys.argv[1])]
-knob_sets = [0, 1, 2, 4, 8, 5, 9, 13]
+knob_sets = [1, 4, 8, 5, 9, 13]
 
 
 def timeit(fn, reps=10):
@@ -32,8 +32,8 @@ for (n, h, w, cin, cout, k) in cases:
     out = ops.alloc_nhwc(n, h, w, cout, torch.bfloat16, cuda)
     s0, s1 = torch.zeros(cout, device=cuda), torch.zeros(cout, device=cuda)
     flops = 2.0 * n * h * w * cin * cout * k * k
-    for stats in (True, False):
-        for variant in (0, 1, 3):
+    for stats in (True,):
+        for variant in (3, 7):
             row = []
             for kn in knob_sets:
                 L.denet_conv2d_fprop_set_mode(variant | (kn << 4))
@@ -45,6 +45,8 @@ for (n, h, w, cin, cout, k) in cases:
                                                  stats=(s0, s1) if stats else None, out=out))
             print("%s stats=%d variant=%d: %.3f ms %.0f TFLOP/s | %s" % ((n, h, w, cin, cout, k), stats, variant, ms,
                                                                        flops / ms / 1e9, " ".join(row)), flush=True)
+L.denet_conv2d_fprop_set_mode(7)
+sys.exit(0)
 # stem
 n, h, w, cin, cout, k, s, pad = 32, 512, 512, 3, 64, 7, 2, 3
 oh = ow = 256

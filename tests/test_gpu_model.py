@@ -117,12 +117,40 @@ def run_step(model, x, metas, solver="nesterov", lr=0.05, mom=(0.9, 0.9), decay=
     return js, before, captured, cost, costs
 
 
-def compare(model, js, before, captured, x, cost, costs, solver, lr, mom, decay, it, tol, sample_bbox=None):
+MODEL_REPORT = {}
+
+
+def report(name, **vals):
+    """measured whole-model errors -> gpurun_out/r2_model_parity.json (committed under profiles/)"""
+    import json
+    import os
+    MODEL_REPORT[name] = vals
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r2_model_parity.json"), "w") as f:
+        json.dump(MODEL_REPORT, f, indent=1, sort_keys=True)
+
+
+def fp32_noise_floor(model, js, x, targets, grads64, sample_bbox=None, cost_factors=None):
+    """What plain fp32 arithmetic (the precision the reference's cuDNN path computes in) costs on this very step: the
+    oracle's RefModel evaluated in float32, same ReLU masks / pool taps, against its float64 evaluation.
+    Returns {param: rel err}.  A deviation of the CUDA path of the same size as this floor IS parity with an fp32
+    reference; the north_star's 1e-4 is asserted wherever the floor allows it."""
+    ref32 = RefModel(js, x.shape, model.class_num, dtype=torch.float32)
+    ref32.relu_masks = relu_masks(model)
+    ref32.pool_argmax = pool_argmax(model)
+    kw = {} if cost_factors is None else {"cost_factors": cost_factors}
+    _, _, g32, _ = ref32.train_gradients(x, targets, sample_bbox=sample_bbox, **kw)
+    return {n: relerr(g32[n], g) for n, g in grads64.items() if g.norm().item() >= 1e-12}
+
+
+def compare(model, js, before, captured, x, cost, costs, solver, lr, mom, decay, it, tol, sample_bbox=None, tag=None):
     ref = RefModel(js, x.shape, model.class_num, dtype=torch.float64)
     ref.relu_masks = relu_masks(model)
     ref.pool_argmax = pool_argmax(model)
     targets = [t for _, t in captured]
     total, ref_costs, grads, out = ref.train_gradients(x, targets, sample_bbox=sample_bbox)
+    floor = fp32_noise_floor(model, js, x, targets, grads, sample_bbox)
     assert abs(cost - total) <= tol * abs(total), (cost, total)
     for c, rc in zip(costs, ref_costs):
         assert abs(c - rc) <= tol * max(abs(rc), 1e-6), (costs, ref_costs)
@@ -139,7 +167,8 @@ def compare(model, js, before, captured, x, cost, costs, solver, lr, mom, decay,
             continue
         e = relerr(p.grad, g)
         worst = max(worst, e)
-        assert e < tol, "gradient of %s: rel err %.3e" % (name, e)
+        # north_star bound, widened only where a plain fp32 evaluation of the same graph is itself further away
+        assert e < max(tol, 3.0 * floor[name]), "gradient of %s: rel err %.3e (fp32 floor %.3e)" % (name, e, floor[name])
         # solver step (momentum buffers start at zero) replayed on the oracle's gradient, and - to pin the update
         # rule itself independently of the gradient error - on the gradient the CUDA path produced
         p_new = R.solver_update(before[name], g, torch.zeros_like(g), solver, it, lr, list(mom), decay,
@@ -152,6 +181,10 @@ def compare(model, js, before, captured, x, cost, costs, solver, lr, mom, decay,
     for path, (m_new, s_new) in ref.bn_updates.items():
         assert relerr(mine[path + ".mean"], m_new) < tol
         assert relerr(mine[path + ".std"], s_new) < tol
+    if tag:
+        report(tag, worst_gradient_rel_err=worst, worst_fp32_floor=max(floor.values()),
+               over_1e4=sorted(n for n, g in grads.items() if g.norm().item() >= 1e-12 and
+                               relerr(mine[n].grad, g) >= 1e-4), tol=tol, cost=cost, oracle_cost=float(total))
     return worst
 
 
@@ -164,7 +197,7 @@ def test_cfg1_cifar_cnn_train_step_fp32(cuda):
     x = numpy.random.uniform(0, 1, (32, 3, 32, 32)).astype(numpy.float32)
     metas = [{"image_class": int(c), "bbox": [], "class": []} for c in numpy.random.randint(0, 10, 32)]
     js, before, cap, cost, costs = run_step(model, x, metas, "sgd", 0.1, (0.9, 0.9), 1e-4, 0)
-    worst = compare(model, js, before, cap, x, cost, costs, "sgd", 0.1, (0.9, 0.9), 1e-4, 0, tol=1e-4)
+    worst = compare(model, js, before, cap, x, cost, costs, "sgd", 0.1, (0.9, 0.9), 1e-4, 0, tol=1e-4, tag="cfg1_cifar_cnn")
     print("cfg1 worst gradient rel err %.2e" % worst)
 
 
@@ -177,7 +210,8 @@ def test_resnet_classifier_train_step_fp32(cuda, convert):
     x = numpy.random.uniform(0, 1, (8, 3, 64, 64)).astype(numpy.float32)
     metas = [{"image_class": int(c), "bbox": [], "class": []} for c in numpy.random.randint(0, 10, 8)]
     js, before, cap, cost, costs = run_step(model, x, metas, "nesterov", 0.05, (0.9, 0.9), 1e-4, 1)
-    worst = compare(model, js, before, cap, x, cost, costs, "nesterov", 0.05, (0.9, 0.9), 1e-4, 1, tol=3e-4)
+    worst = compare(model, js, before, cap, x, cost, costs, "nesterov", 0.05, (0.9, 0.9), 1e-4, 1, tol=1e-4,
+                    tag="resnet_small_convert%d" % int(convert))
     print("resnet worst gradient rel err %.2e" % worst)
 
 
@@ -207,22 +241,27 @@ def _denet_step(cuda, precision, tol):
 
 def test_denet_train_step_fp32(cuda):
     """conv stack + skip + pool-inv + DNC/DNS/DND head, forward/backward/update vs the oracle on the same RoIs"""
-    model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "fp32", 5e-4)
+    model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "fp32", 1e-4)
     ref = RefModel(js, x.shape, 20, dtype=torch.float64)
     ref.relu_masks = relu_masks(model)
     ref.pool_argmax = pool_argmax(model)
     targets = [t for _, t in cap]
     total, ref_costs, grads, out = ref.train_gradients(x, targets, sample_bbox=bbox, cost_factors=[1.0, 0.5])
-    assert abs(cost - total) < 5e-4 * abs(total), (cost, total, costs, ref_costs)
+    floor = fp32_noise_floor(model, js, x, targets, grads, sample_bbox=bbox, cost_factors=[1.0, 0.5])
+    assert abs(cost - total) < 1e-4 * abs(total), (cost, total, costs, ref_costs)
     mine = named_params(model)
-    worst = 0.0
+    worst, over = 0.0, []
     for name, g in grads.items():
         if g.norm().item() < 1e-12:
             continue
         e = relerr(mine[name].grad, g)
         worst = max(worst, e)
-        assert e < 5e-4, "gradient of %s: rel err %.3e" % (name, e)
-    print("denet worst gradient rel err %.2e" % worst)
+        if e >= 1e-4:
+            over.append(name)
+        assert e < max(1e-4, 3.0 * floor[name]), "gradient of %s: rel err %.3e (fp32 floor %.3e)" % (name, e, floor[name])
+    report("denet_small", worst_gradient_rel_err=worst, worst_fp32_floor=max(floor.values()), over_1e4=sorted(over),
+           tol=1e-4, cost=cost, oracle_cost=float(total))
+    print("denet worst gradient rel err %.2e (fp32 floor %.2e)" % (worst, max(floor.values())))
 
 
 def test_denet_train_step_bf16_tracks_oracle(cuda):
