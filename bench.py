@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-steps", type=int, default=4)
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--detail", action="store_true", help="also print a per-layer conv timing table to stderr")
+    ap.add_argument("--no-parity-mode", action="store_true",
+                    help="skip the fp32-parity-mode measurement (a second model, bf16x3 MMA) reported beside the bf16 line")
+    ap.add_argument("--parity-steps", type=int, default=5)
     return ap.parse_args()
 
 
@@ -173,7 +176,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, args.batch or wb, args.gpus, data_shape, classes, solver),
+            # the CPU arm runs a bounded SAMPLE of the workload: `images` images per step, stated as such (the full
+            # per-GPU batch of the GPU arm would take minutes per step on the host cores)
+            "config": dict(workload_config(args.workload, images, 1, data_shape, classes, solver),
+                           sample_of="per-GPU batch %d of the GPU arm" % (args.batch or wb)),
             "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                              "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -187,6 +193,55 @@ def workload_config(workload, batch, gpus, data_shape, classes, solver):
             "per_gpu_batch": batch, "global_batch": batch * gpus, "solver": solver,
             "parallelism": "dp%d (batch sharded over ranks, NCCL gradient all-reduce)" % gpus if gpus > 1 else "single GPU",
             "l2": "working set per step (activations + gradients, several GB) far exceeds the 126 MB L2; no flush needed"}
+
+
+def measure_parity_mode(args, dev, x_dev, metas, peak):
+    """images/s, ms/step and conv TFLOP/s of the fp32-parity mode (bf16x3 MMA: a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with
+    fp32 accumulation).  Its conv FLOP figure counts the ALGORITHMIC FLOPs once (the tensor pipe executes 3x as many)."""
+    import torch
+    from denet_b200 import lib
+    model, data_shape, batch, classes, solver = build_model(args.workload, args.batch, seed=1)
+    model.to_device(dev, precision="fp32")
+    model.build_train_func(solver, [])
+    random.seed(1)
+    hp = SOLVER_HP
+    fwd_flops, train_flops, _ = conv_flops(model)
+    it = 0
+
+    def step():
+        nonlocal it
+        model._train_step_device(x_dev, metas, 0, it, hp["lr"], hp["momentum"], hp["decay"])
+        it += 1
+    names = ["denet_conv2d_fprop", "denet_conv2d_fprop_scatter", "denet_conv2d_dgrad_bnbwd", "denet_conv2d_wgrad",
+             "denet_conv2d_rowfold_fprop", "denet_conv2d_rowfold_wgrad", "denet_wgrad_reduce_multi"]
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    lib.start_timing(names)
+    for _ in range(args.parity_steps):
+        step()
+    torch.cuda.synchronize()
+    timings = lib.stop_timing()
+    conv_ms = sum(ms for evs in timings.values() for ms, _ in evs) / args.parity_steps
+    model.enable_cuda_graphs(True)
+    for _ in range(6):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.parity_steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.parity_steps
+    tf = train_flops / (conv_ms / 1000.0) / 1e12
+    out = {"precision": "fp32 activations, bf16x3 tcgen05 MMA (kind::f16, three terms, fp32 accumulate)",
+           "value": batch / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "steps": args.parity_steps,
+           "conv_ms_per_step": conv_ms, "conv_tflops_algorithmic": tf, "conv_frac_of_bf16_peak": tf / peak,
+           "conv_tflops_executed": 3 * tf,
+           "note": "the mode the 1e-4 parity tests (tests/test_gpu_fullsize.py, test_gpu_model.py) run in"}
+    del model
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -379,17 +434,22 @@ def run_b200(args):
     conv_fl = sum(v[1] for v in fam.values())
     n_conv_launch = sum(v[2] for v in fam.values())
     achieved = conv_fl / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-    # DRAM traffic per conv launch: from the committed `ncu` launch list of this same command (dram__bytes_read.sum +
-    # dram__bytes_write.sum summed over the conv kernels of one step / their launch count), see profiles/
-    traffic = None
-    try:
-        traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r1_conv_traffic_final.json")))
-                        ["conv_dram_bytes_per_launch"])
-    except (OSError, ValueError, KeyError):
-        pass
+    # DRAM traffic per conv launch (dram__bytes_read.sum + dram__bytes_write.sum summed over the conv kernels of one
+    # step / their launch count).  Hardware counters cannot be read inside a timed run: the figure comes from the `ncu`
+    # launch list of this same command committed under profiles/ (newest round first) and is labelled with its source;
+    # null when no such file exists.
+    traffic, traffic_src = None, None
+    for name in ("r2_conv_traffic.json", "r1_conv_traffic_final.json"):
+        try:
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", name)))["conv_dram_bytes_per_launch"])
+            traffic_src = "profiles/" + name
+            break
+        except (OSError, ValueError, KeyError):
+            continue
     roofline = {"bound": "tensor", "kernel": "conv_fprop_halo_kernel / conv_fprop_kernel / conv_wgrad_kernel (+ split-K reduction) (tcgen05 implicit GEMM, bf16)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_unit": "DRAM bytes per conv launch (ncu, profiles/r1_conv_traffic_final.json)",
+                "traffic_unit": "DRAM bytes per conv launch; NOT measured in this run: ncu launch list of the same "
+                                "command, %s" % traffic_src,
                 "peak_source": peak_src,
                 "flops_per_launch": conv_fl / max(n_conv_launch, 1), "ms_per_launch": conv_ms / max(n_conv_launch, 1),
                 "launches_per_step": n_conv_launch / args.steps,
@@ -416,6 +476,12 @@ def run_b200(args):
                     "h2d_bytes_per_step": (tb1["h2d"] - tb0["h2d"]) // args.steps,
                     "d2h_bytes_per_step": (tb1["d2h"] - tb0["d2h"]) // args.steps},
             "gpu_launches": launches, "roofline": roofline, "last_cost": cost}
+    if world == 1 and args.precision == "bf16" and not args.no_parity_mode:
+        # SURVEY.md §7 / BASELINE.md §2 "report both": the same step in fp32-parity mode (fp32 activations, every conv
+        # operand split into bf16 hi + lo, three MMA terms - the arithmetic the 1e-4 parity tests run in)
+        del model
+        torch.cuda.empty_cache()
+        line["parity_mode"] = measure_parity_mode(args, dev, x_dev, metas, peak)
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_run(args.workload, args.cpu_sample_images, args.cpu_sample_steps, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -419,6 +419,206 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
     }
 }
 
+// ---- batch-norm backward as ONE launch (the three kernels above cost two launch gaps and a 10 us finalize per layer:
+// 84 extra launches per DeNet-34 step).  All blocks are co-resident (grid sized from the occupancy of this kernel), so
+// the two reductions are separated by grid-wide barriers on module-scope counters instead of kernel boundaries:
+//   phase 1  per-slab partial sums of dy' and dy' * xhat            (same arithmetic as bn_bwd_partial_kernel)
+//   barrier  -> the first ceil(C/32) blocks add the slabs in a FIXED order, in double (reduce_slabs' order: 8 slab
+//            lanes, then lanes in order): deterministic, independent of which block runs when
+//   barrier  -> phase 2: dx (and the residual gradient) over the SAME rows the block has just read (L2 / L1 hits)
+// The counters live in a module-scope array (zero at load); the last block to finish resets its slot, so a slot is zero
+// again before the stream can launch the next kernel that uses it.
+constexpr int kBnSyncSlots = 64;
+__device__ unsigned int g_bn_sync[kBnSyncSlots][4];
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned int*>(counter) < expected) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <typename T, int VEC, int U>
+__global__ void __launch_bounds__(kBnThreads, 2)
+    bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ yout, const T* __restrict__ x, long long M, int C,
+                        long long ld, int rows_per_block, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, int relu, T* __restrict__ dx, T* __restrict__ dres,
+                        float* __restrict__ partial, float* __restrict__ sums, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, int accumulate, int sync_slot) {
+    const int CV = C / VEC;
+    const int cvt = CV < kBnThreads ? CV : kBnThreads;
+    const int rlanes = kBnThreads / cvt;
+    const int cv = blockIdx.y * cvt + threadIdx.x % cvt;
+    const int rl = threadIdx.x / cvt;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    const int nslabs = gridDim.x;
+    const unsigned int nblocks = gridDim.x * gridDim.y;
+    const unsigned int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    unsigned int* sync = g_bn_sync[sync_slot];
+    __shared__ float red[2 * kBnThreads * (VEC == 8 ? 8 : 1)];
+    __shared__ double fin[2][8][33];
+    const bool active = (cv < CV) && (rl < rlanes);
+    const bool mask_from_x = relu && (yout == nullptr);
+    const long long coff = (long long)cv * VEC;
+    float mu[VEC], is[VEC], k1[VEC], fb[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = cv * VEC + i;
+        mu[i] = active ? mean[c] : 0.f;
+        is[i] = active ? invstd[c] : 0.f;
+        k1[i] = active ? gamma[c] * is[i] : 0.f;                      // the forward pass's gamma * invstd
+        fb[i] = (active && mask_from_x) ? beta[c] : 0.f;
+    }
+    // ---------------------------------------------------------------- phase 1
+    {
+        float s[VEC], s2[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) s[i] = s2[i] = 0.f;
+        if (active) {
+            for (long long r = r0 + rl; r < r1; r += (long long)rlanes * U) {
+                Raw<T, VEC> g[U], xv[U], yo[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const long long rr = r + (long long)u * rlanes;
+                    if (rr < r1) {
+                        g[u].load(dy + rr * ld + coff);
+                        xv[u].load(x + rr * ld + coff);
+                        if (relu && !mask_from_x) yo[u].load(yout + rr * ld + coff);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const long long rr = r + (long long)u * rlanes;
+                    if (rr < r1) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            float d = g[u].get(i);
+                            const float xc = xv[u].get(i) - mu[i];
+                            if (mask_from_x) {
+                                if (!(xc * k1[i] + fb[i] > 0.f)) d = 0.f;
+                            } else if (relu && !(yo[u].get(i) > 0.f)) {
+                                d = 0.f;
+                            }
+                            s[i] += d;
+                            s2[i] += d * (xc * is[i]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            red[(threadIdx.x * VEC + i) * 2 + 0] = s[i];
+            red[(threadIdx.x * VEC + i) * 2 + 1] = s2[i];
+        }
+        __syncthreads();
+        if (active && rl == 0) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float a = 0.f, b = 0.f;
+                for (int l = 0; l < rlanes; ++l) {
+                    const int t = l * cvt + threadIdx.x;
+                    a += red[(t * VEC + i) * 2 + 0];
+                    b += red[(t * VEC + i) * 2 + 1];
+                }
+                const int c = cv * VEC + i;
+                partial[((long long)blockIdx.x * 2 + 0) * C + c] = a;
+                partial[((long long)blockIdx.x * 2 + 1) * C + c] = b;
+            }
+        }
+    }
+    grid_barrier(&sync[0], nblocks);
+    // ---------------------------------------------------------------- slab totals (fixed order, double)
+    for (unsigned int cb = bid; cb * 32u < (unsigned int)C; cb += nblocks) {
+        const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+        const int c = cb * 32 + cl;
+        double a0 = 0.0, a1 = 0.0;
+        if (c < C)
+            for (int sb = sl; sb < nslabs; sb += 8) {
+                a0 += (double)partial[((long long)sb * 2 + 0) * C + c];
+                a1 += (double)partial[((long long)sb * 2 + 1) * C + c];
+            }
+        fin[0][sl][cl] = a0;
+        fin[1][sl][cl] = a1;
+        __syncthreads();
+        if (sl == 0 && c < C) {
+            double t0 = 0.0, t1 = 0.0;
+            for (int j = 0; j < 8; ++j) {
+                t0 += fin[0][j][cl];
+                t1 += fin[1][j][cl];
+            }
+            sums[c] = (float)t0;
+            sums[C + c] = (float)t1;
+            if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)t0 : (float)t0;
+            if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)t1 : (float)t1;
+        }
+        __syncthreads();
+    }
+    grid_barrier(&sync[1], nblocks);
+    // ---------------------------------------------------------------- phase 2
+    if (active) {
+        const float inv_m = 1.0f / (float)M;
+        float c1[VEC], c2[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int c = cv * VEC + i;
+            c1[i] = __ldcg(sums + c) * inv_m;            // written by another block after kernel start: bypass L1
+            c2[i] = __ldcg(sums + C + c) * inv_m;
+        }
+        for (long long r = r0 + rl; r < r1; r += (long long)rlanes * U) {
+            Raw<T, VEC> g[U], xv[U], yo[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long rr = r + (long long)u * rlanes;
+                if (rr < r1) {
+                    g[u].load(dy + rr * ld + coff);
+                    xv[u].load(x + rr * ld + coff);
+                    if (relu && !mask_from_x) yo[u].load(yout + rr * ld + coff);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long rr = r + (long long)u * rlanes;
+                if (rr < r1) {
+                    Pack<T, VEC> o, gm;
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        float d = g[u].get(i);
+                        const float xc = xv[u].get(i) - mu[i];
+                        if (mask_from_x) {
+                            if (!(xc * k1[i] + fb[i] > 0.f)) d = 0.f;
+                        } else if (relu && !(yo[u].get(i) > 0.f)) {
+                            d = 0.f;
+                        }
+                        gm.v[i] = d;
+                        const float xh = xc * is[i];
+                        o.v[i] = k1[i] * (d - c1[i] - xh * c2[i]);
+                    }
+                    o.store(dx + rr * ld + coff);
+                    if (dres) gm.store(dres + rr * ld + coff);
+                }
+            }
+        }
+    }
+    // the last block out re-arms the slot
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&sync[2], 1u);
+        if (ticket == nblocks - 1) {
+            sync[0] = 0;
+            sync[1] = 0;
+            sync[2] = 0;
+            __threadfence();
+        }
+    }
+}
+
 __global__ void bn_inference_invstd_kernel(const float* __restrict__ run_stdinv, float eps, float* __restrict__ out,
                                            int C) {
     // batch_norm.py:50-52: var = (1/stdinv)^2 is handed to cuDNN inference, which adds eps again
@@ -968,6 +1168,22 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int ns
     out[c] = accumulate ? out[c] + (float)a : (float)a;
 }
 
+static int g_bn_fused_bwd = 1;     // batch-norm backward as one launch with grid barriers (A/B: denet_bn_set_mode)
+
+// slabs for a grid of at most `max_blocks` co-resident blocks (rows split as evenly as the row-lane quantum allows)
+static int bn_slabs_for(long long M, int C, int vec, int max_blocks, int* rows_per_block, int* ychunks) {
+    const int CV = C / vec;
+    const int cvt = CV < kBnThreads ? CV : kBnThreads;
+    *ychunks = ceil_div(CV, cvt);
+    const int rlanes = kBnThreads / cvt;
+    long long target = max_blocks / *ychunks;
+    if (target < 1) target = 1;
+    long long rpb = ceil_div_ll(M, target);
+    if (rpb < rlanes * 4) rpb = rlanes * 4;
+    *rows_per_block = (int)std::min<long long>(rpb, 1 << 30);
+    return (int)ceil_div_ll(M, *rows_per_block);
+}
+
 static int bn_slabs(long long M, int C, int vec, int* rows_per_block, int* ychunks) {
     const int CV = C / vec;
     const int cvt = CV < kBnThreads ? CV : kBnThreads;
@@ -1061,6 +1277,11 @@ extern "C" int denet_bn_apply_sums(const void* x, int dtype, long long M, int C,
     return 0;
 }
 
+extern "C" int denet_bn_set_mode(int mode) {
+    g_bn_fused_bwd = mode & 1;       // bit0: one-launch backward (grid barriers); 0 = partial / finalize / apply kernels
+    return 0;
+}
+
 extern "C" int denet_bn_inference_invstd(const float* run_stdinv, float eps, float* out, int C, cudaStream_t stream) {
     DN_REQUIRE(run_stdinv && out, "bn_inference_invstd: null pointer");
     bn_inference_invstd_kernel<<<DN_G(ceil_div(C, 128)), 128, 0, stream>>>(run_stdinv, eps, out, C);
@@ -1079,6 +1300,23 @@ extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x
     int rpb, yc;
     const int nslabs = bn_slabs(M, C, v ? 8 : 1, &rpb, &yc);
     float* sums = workspace + (size_t)nslabs * 2 * C;
+    if (g_bn_fused_bwd) {
+        // one launch: co-resident grid (2 blocks per SM at <= 128 registers), slabs sized for it
+        int rpbf, ycf;
+        const int nsf = bn_slabs_for(M, C, v ? 8 : 1, 2 * num_sms(), &rpbf, &ycf);
+        if (nsf * ycf <= 2 * num_sms()) {
+            static int slot_counter = 0;
+            const int slot = (slot_counter++) % kBnSyncSlots;
+            DN_DISPATCH(dtype, v, {
+                constexpr int U = sizeof(T) == 4 ? 2 : 4;
+                bn_bwd_fused_kernel<T, VEC, U><<<DN_G(dim3(nsf, ycf)), kBnThreads, 0, stream>>>(
+                    (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpbf, mean, invstd, gamma, beta, relu, (T*)dx,
+                    (T*)dres, workspace, sums, dgamma, dbeta, accumulate, slot);
+            });
+            DN_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     DN_DISPATCH(dtype, v, {
         bn_bwd_partial_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>(
             (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpb, mean, invstd, relu, workspace, gamma, beta);

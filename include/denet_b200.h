@@ -207,6 +207,9 @@ int denet_bn_apply_sums(const void* x, int dtype, long long M, int C, long long 
                         int relu, void* y, float* mean, float* invstd, float* run_mean, float* run_stdinv,
                         float momentum, cudaStream_t stream);
 int denet_bn_inference_invstd(const float* run_stdinv, float eps, float* out, int C, cudaStream_t stream);
+/* A/B switch for measurements: bit0 = denet_bn_backward as ONE launch (two grid-wide barriers between the reductions and
+ * the apply pass; default) instead of three kernels.  Results are identical (same fixed summation order per mode). */
+int denet_bn_set_mode(int mode);
 int denet_bn_backward(const void* dy, const void* yout, const void* x, int dtype, long long M, int C, long long ld,
                       const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
                       void* dx, void* dres,
