@@ -4,8 +4,8 @@
 A zero-initialised 1x1 convolution with bias classifies every RoI into classNum+1 classes (+4 box regression
 outputs when bbox_factor > 0).  get_target assigns classes / box targets by IoU against the ground truth
 (:147-235); the cost is -sum(t*logp)/ln(s0) per RoI summed / batch * cost_factor, plus the Fast R-CNN smooth-L1 box
-loss (:238-313, bbox_factor applied in :295 and again in :310).  Joint / independent fitness, bounded IoU and the
-predict-time get_detections + NMS are outside the hot path.
+loss (:238-313, bbox_factor applied in :295 and again in :310).  get_detections (:316-424) is the inference tail:
+one test-mode forward, device sampler, head, per-class NMS on the GPU (csrc/detect_nms.cu).
 """
 import numpy
 import torch
@@ -205,3 +205,34 @@ class DeNetDetectLayer(AbstractLayer):
         dx = self.layers[0].backward(self._dout)
         self._dout = None
         return dx if dy is None else ops.add(dx, dy)
+
+    # ---------------------------------------------------------------------------------------------- inference
+    def get_detections(self, model, data_x, data_m, params):
+        """reference get_detections (denet_detect.py:316-424): most likely (class, box) instances of every image.
+
+        params: prThreshold (0.01), nmsThreshold (0.5), cornerThreshold (the sparse layer's), cornerMax (1024),
+        useSoftNMS (0).  Returns [{"detections": [(pr, cls, (x0, y0, x1, y1)), ...], "meta": data_m[i]}].
+
+        The reference compiles two Theano functions (corner maps, then the head on cached features); here ONE
+        test-mode forward pass pauses at the sparse layer: the device sampler ranks the RoIs from the corner maps of
+        that pass, the head classifies them, denet_detect_outputs produces log-probabilities + decoded boxes and
+        denet_detections_nms runs the per-class NMS - only the final detection lists leave the GPU."""
+        from . import denet_detect_c
+        pr_threshold = params.get("prThreshold", 0.01)
+        nms_threshold = params.get("nmsThreshold", 0.5)
+        sp = self.sparse_layer
+        corner_threshold = params.get("cornerThreshold", sp.corner_threshold)
+        corner_max = params.get("cornerMax", 1024)
+        use_soft_nms = params.get("useSoftNMS", 0) == 1
+        det_pr, fitness, bboxs, counts = model.detect_forward(data_x, self, corner_threshold, corner_max)
+        detlists = denet_detect_c.build_detections_nms(pr_threshold, nms_threshold, int(use_soft_nms), det_pr, fitness,
+                                                       bboxs, counts)
+        data_m = data_m if data_m is not None else [None] * len(detlists)
+        return [{"detections": detlist, "meta": data_m[i]} for i, detlist in enumerate(detlists)]
+
+    def detect_outputs(self):
+        """(det_pr (B,s0,sn,sn), fitness, bbox (B,sn,sn,4)) device tensors of the last test-mode forward
+        (the outputs of the reference's detect_func, denet_detect.py:330-362; fitness = det_pr without joint fitness)"""
+        det_pr, bbox = ops.detect_outputs(self.logits, self.sample_num, self.det_shape[1], self.use_bbox_reg,
+                                          self.sparse_layer.sample_bbox)
+        return det_pr, det_pr, bbox

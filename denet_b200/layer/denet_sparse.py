@@ -176,6 +176,20 @@ class DeNetSparseLayer(AbstractLayer):
                 bbox[b, i] = bb
         return self.set_samples_arrays(pr, bbox)
 
+    def sample_for_inference(self):
+        """test-time sampling entirely on the device: the ranked RoIs of the corner maps of this pass become the sample
+        boxes (slots past the per-image count are zero boxes, like the reference's zero-initialised bbox array,
+        denet_sparse.py:151-157); returns the per-image counts (B) int32 on the device"""
+        pr, bbox, _, count, _ = ops.build_samples(self.corner_layer.corner_pr, self.corner_threshold, self.sample_num,
+                                                  self.corner_max, self.local_max)
+        b, k = self.batch_size, self.sample_count
+        valid = (torch.arange(k, device=bbox.device)[None, :] < count[:, None]).unsqueeze(-1)
+        self.sample_bbox = torch.where(valid, bbox, torch.zeros_like(bbox)).reshape(b, self.sample_num, self.sample_num,
+                                                                                   4).contiguous()
+        self.sample_bbox64 = None
+        self.sample_bbox_host = self.sample_pr_host = self._sample_bbox_list = None
+        return count
+
     def get_target(self, model, data_x, metas):
         """denet_sparse.py:164-206, vectorised; consumes python's `random` stream exactly like the reference loops"""
         return self.finish_target(metas, *self.get_samples_arrays())

@@ -827,6 +827,39 @@ class ModelCNN:
         return total_cost
 
     # ---------------------------------------------------------------------------------------------- prediction
+    def detect_forward(self, data_x, detect_layer, corner_threshold=None, corner_max=None):
+        """test-mode forward of a DSS detector for DeNetDetectLayer.get_detections: backbone -> corner maps -> device
+        RoI sampler (no random / ground-truth boxes at test time, denet_sparse.py:117-145 with train=False) -> sparse
+        gather -> head.  Returns (det_pr, fitness, bbox, sample counts) as device tensors."""
+        if not self._ready:
+            self.to_device()
+        si = self._sparse_index()
+        assert si is not None, "detect_forward: the model has no denet-sparse layer"
+        sp = self.layers[si]
+        ops.pin_stream(True)
+        try:
+            with torch.no_grad():
+                layer_mod.set_train(False)
+                layer_mod.set_ground_truth(None)
+                self.prepare_operands()
+                x = self.upload(data_x)
+                self.layers[0].output = x
+                x = self.forward_layers(x, 1, si, train=False)
+                saved = (sp.corner_threshold, sp.corner_max)
+                try:
+                    if corner_threshold is not None:
+                        sp.corner_threshold = corner_threshold
+                    if corner_max is not None:
+                        sp.corner_max = corner_max
+                    counts = sp.sample_for_inference()
+                finally:
+                    sp.corner_threshold, sp.corner_max = saved
+                self.forward_layers(x, si, len(self.layers), train=False)
+                det_pr, fitness, bbox = detect_layer.detect_outputs()
+        finally:
+            ops.pin_stream(False)
+        return det_pr, fitness, bbox, counts
+
     def predict_output_step(self, data_x):
         if not self._ready:
             self.to_device()

@@ -787,3 +787,31 @@ def softmax_nll(o, classes, label, grad_factor, dout, logp, cost):
     ws = _loss_ws(o.device)
     call("denet_softmax_nll", o.data_ptr(), _dtype_code(o), _pitch(o), b, classes, label.data_ptr(), grad_factor,
          _ptr(dout), _ptr(logp), cost.data_ptr(), ws.data_ptr(), _stream())
+
+
+# ---------------------------------------------------------------------------------------------- inference tail
+def detect_outputs(logits, sn, s0, use_bbox, sample_bbox):
+    """detect-layer logits (B,sn,sn,>=s0[+4]) fp32 -> (det_pr (B,s0,sn,sn) log-probabilities, bbox (B,sn,sn,4))"""
+    assert logits.dtype == torch.float32
+    b = logits.shape[0]
+    det_pr = torch.empty((b, s0, sn, sn), dtype=torch.float32, device=logits.device)
+    bbox = torch.empty((b, sn, sn, 4), dtype=torch.float32, device=logits.device)
+    call("denet_detect_outputs", logits.data_ptr(), _pitch(logits), b, sn, s0, int(use_bbox), sample_bbox.data_ptr(),
+         det_pr.data_ptr(), bbox.data_ptr(), _stream())
+    return det_pr, bbox
+
+
+def detections_nms(det_pr, fitness, bbox, bbox_num, pr_threshold, nms_threshold, use_soft_nms):
+    """det_pr / fitness (B, classes+1, sn, sn) fp32 device, bbox (B,sn,sn,4) fp32 device, bbox_num (B) int32 device.
+    Returns (score (B,classes,K), index (B,classes,K) int32, count (B,classes) int32) device tensors."""
+    assert det_pr.dtype == torch.float32 and det_pr.is_contiguous() and fitness.is_contiguous()
+    b, c1, sn, _ = det_pr.shape
+    k, classes = sn * sn, c1 - 1
+    dev = det_pr.device
+    score = torch.empty((b, classes, k), dtype=torch.float32, device=dev)
+    index = torch.empty((b, classes, k), dtype=torch.int32, device=dev)
+    count = torch.empty((b, classes), dtype=torch.int32, device=dev)
+    call("denet_detections_nms", det_pr.data_ptr(), fitness.data_ptr(), c1 * k, k, 1, bbox.data_ptr(), bbox_num.data_ptr(),
+         b, classes, k, float(pr_threshold), float(nms_threshold), int(use_soft_nms), score.data_ptr(), index.data_ptr(),
+         count.data_ptr(), _stream())
+    return score, index, count

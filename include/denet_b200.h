@@ -345,6 +345,26 @@ int denet_solver_update(const void* entries, const int* block_tensor, const long
 int denet_solver_update_dev(const void* entries, const int* block_tensor, const long long* block_offset, int nblocks,
                             int solver, const float* hp, int bias_decay, cudaStream_t stream);
 
+/* ---- inference tail: detect-layer outputs and per-class NMS --------------------------------------
+ * detect_outputs: what DeNetDetectLayer.get_detections' compiled Theano function returns
+ *   (denet/layer/denet_detect.py:60-107,330-362): det_pr (B, s0, sn, sn) = log_softmax over the s0 class channels of
+ *   the layer's logits (rows = RoIs in (b, j, i) order, pitch ld floats) and, when bbox_out != NULL, the boxes
+ *   (B, sn, sn, 4): the Fast R-CNN decode of channels [s0, s0+4) against sample_bbox (use_bbox = 1) or the sample boxes
+ *   themselves (use_bbox = 0).
+ * detections_nms: replaces the reference's CPython extension function build_detections_nms
+ *   (denet/layer/denet_detect.cc:101-173; hard NMS :74-99, Gaussian soft-NMS :35-72).  det_pr / fitness element
+ *   (b, cls, k = j*sn + i) lives at b*stride_b + cls*stride_c + k*stride_k (elements), so both the reference's
+ *   (B, classes+1, sn, sn) arrays and NHWC log-probabilities are accepted; bbox (B, K, 4) fp32; bbox_num (B) = samples
+ *   of each image that are real (the rest is padding).  Per (image, class) the surviving instances are written in the
+ *   reference's output order (sample order for hard NMS, pick order for soft-NMS): out_score = exp(fitness) with libm
+ *   expf's bits, out_index = sample index k; out_count (B, class_num).  Results are bit-identical to the reference. */
+int denet_detect_outputs(const float* logits, long long ld, int B, int sn, int s0, int use_bbox,
+                         const float* sample_bbox, float* det_pr, float* bbox_out, cudaStream_t stream);
+int denet_detections_nms(const float* det_pr, const float* fitness, long long stride_b, long long stride_c,
+                         long long stride_k, const float* bbox, const int* bbox_num, int B, int class_num, int K,
+                         float pr_threshold, float nms_threshold, int use_soft_nms, float* out_score, int* out_index,
+                         int* out_count, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,6 +142,23 @@ def reference_cc():
     return _ref_cc
 
 
+_ref_detect_cc = None
+
+
+def reference_detect_cc():
+    """the reference's own denet_detect C++ extension (NMS) compiled unmodified (oracle/_ref), or None if not built"""
+    global _ref_detect_cc
+    if _ref_detect_cc is None:
+        hits = sorted(glob.glob(os.path.join(REF_DIR, "denet_detect*.so")))
+        if not hits:
+            return None
+        spec = importlib.util.spec_from_file_location("denet_detect", hits[0])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _ref_detect_cc = mod
+    return _ref_detect_cc
+
+
 def reference_cuda():
     """the reference's inline CUDA kernels compiled for the GPU box (oracle/_ref), or None if not built"""
     global _ref_cuda

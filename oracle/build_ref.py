@@ -54,10 +54,11 @@ def build_restatement():
     return out
 
 
-def build_reference_cc():
-    """the reference's own C++ sampling extension, compiled from /root/reference unmodified"""
+def build_reference_cc(name="denet_sparse"):
+    """one of the reference's own CPython extensions (denet_sparse: RoI sampling, denet_detect: NMS), compiled from
+    /root/reference unmodified"""
     import numpy
-    src = os.path.join(REF_ROOT, "denet", "layer", "denet_sparse.cc")
+    src = os.path.join(REF_ROOT, "denet", "layer", name + ".cc")
     if not os.path.exists(src):
         return None
     os.makedirs(os.path.join(REF_OUT, "stub"), exist_ok=True)
@@ -65,7 +66,7 @@ def build_reference_cc():
     with open(stub, "w") as f:
         f.write(STUB_HEADER)
     ext = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
-    out = os.path.join(REF_OUT, "denet_sparse" + ext)
+    out = os.path.join(REF_OUT, name + ext)
     if not newer(out, src):
         # flags = the reference's common.import_c (denet/common/__init__.py:182); the two -D map numpy-1 aliases
         # removed in numpy 2 (used at denet_sparse.cc:573,677)
@@ -178,7 +179,8 @@ def build_reference_cuda():
 def build_all(verbose=True):
     built = {"restatement": build_restatement()}
     if os.path.isdir(REF_ROOT):
-        built["reference_cc"] = build_reference_cc()
+        built["reference_cc"] = build_reference_cc("denet_sparse")
+        built["reference_detect_cc"] = build_reference_cc("denet_detect")
         try:
             built["reference_cuda"] = build_reference_cuda()
         except Exception as e:  # the CUDA harness is a bonus pin; never block the build on it

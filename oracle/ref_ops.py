@@ -347,3 +347,82 @@ def solver_update(p, g, m, solver, iteration, lr, momentum, decay, is_weight, v=
         return p - lr * m_hat / (v_hat ** 0.5 + eps), m_new, v_new
     m_new = rho * m + (1.0 - rho) * g
     return p - lr * m_new, m_new
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# inference tail (test infrastructure like everything here): restatement of denet/layer/denet_detect.cc
+
+
+def _libm_logf(x):
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.logf.restype, libm.logf.argtypes = ctypes.c_float, [ctypes.c_float]
+    return np.float32(libm.logf(ctypes.c_float(x)))
+
+
+def libm_expf(x):
+    """std::exp(float) as the reference's extension evaluates it"""
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.expf.restype, libm.expf.argtypes = ctypes.c_float, [ctypes.c_float]
+    return np.float32(libm.expf(ctypes.c_float(float(x))))
+
+
+def _iou_f32(a, b):
+    """denet_detect.cc:12-31 in float32, operation for operation"""
+    f = np.float32
+    dx = max(f(0.0), f(min(a[2], b[2]) - max(a[0], b[0])))
+    dy = max(f(0.0), f(min(a[3], b[3]) - max(a[1], b[1])))
+    ai = f(dx * dy)
+    aa = f(f(a[2] - a[0]) * f(a[3] - a[1]))
+    ab = f(f(b[2] - b[0]) * f(b[3] - b[1]))
+    au = f(f(aa + ab) - ai)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return f(ai / au)
+
+
+def build_detections_nms(pr_threshold, nms_threshold, use_soft_nms, det_pr, fitness, bbox, bbox_num):
+    """denet_detect.cc:101-173 (+ perform_nms :74-99, perform_soft_nms :35-72).  det_pr / fitness (B,C+1,sn,sn) fp32,
+    bbox (B,sn,sn,4) fp32.  Returns list[B] of [(fitness score in LOG basis as float32, cls, sample index k)] in the
+    reference's output order; the caller applies exp (the reference's std::exp(float) is libm expf)."""
+    f = np.float32
+    det_pr, fitness, bbox = np.asarray(det_pr, f), np.asarray(fitness, f), np.asarray(bbox, f)
+    log_thr = _libm_logf(pr_threshold)           # std::log(float) of the reference = libm logf
+    B, C1, sn, _ = det_pr.shape
+    out = []
+    for b in range(B):
+        dets = []
+        nb = int(bbox_num[b])
+        for cls in range(C1 - 1):
+            inst = []
+            for k in range(min(nb, sn * sn)):
+                j, i = divmod(k, sn)
+                if det_pr[b, cls, j, i] >= log_thr:
+                    inst.append([f(fitness[b, cls, j, i]), bbox[b, j, i], k])
+            if not (0.0 < nms_threshold < 1.0) or not inst:
+                keep = inst
+            elif use_soft_nms:
+                keep, rest = [], list(inst)
+                thr, discard = f(nms_threshold), f(-6.9)
+                while rest:
+                    m = 0
+                    for t in range(1, len(rest)):
+                        if rest[t][0] > rest[m][0]:
+                            m = t
+                    M = rest.pop(m)
+                    keep.append(M)
+                    for r in rest:
+                        iou = _iou_f32(M[1], r[1])
+                        r[0] = f(r[0] - f(f(iou * iou) / thr))
+                    rest = [r for r in rest if not (r[0] < discard)]
+            else:
+                thr = f(nms_threshold)
+                keep = []
+                for a in inst:
+                    if not any((a[0] < o[0]) and (_iou_f32(a[1], o[1]) > thr) for o in inst):
+                        keep.append(a)
+            dets += [(s, cls, k) for s, _, k in keep]
+        out.append(dets)
+    return out

@@ -169,3 +169,26 @@ def test_reference_train_step_runs_and_learns():
     metas = synthetic_metas(2, 5, 2, max_boxes=3)
     costs = [tr.train_step(x, metas, it, 0.02, [0.9, 0.9], 1e-4)[0] for it in range(6)]
     assert all(math.isfinite(c) for c in costs) and costs[-1] < costs[0]
+
+
+@pytest.mark.parametrize("soft", [0, 1])
+def test_nms_restatement_matches_compiled_reference(soft):
+    """oracle.ref_ops.build_detections_nms (python restatement of denet_detect.cc) is pinned to the reference's own
+    extension compiled unmodified (oracle/_ref): identical lists, scores and boxes bit for bit"""
+    import oracle
+    cc = oracle.reference_detect_cc()
+    if cc is None:
+        pytest.skip("oracle/_ref/denet_detect*.so not built")
+    from util import nms_inputs
+    det_pr, bbox, num = nms_inputs(2, 5, 6, seed=3 + soft)
+    fitness = det_pr.copy()
+    for pr_thr, nms_thr in [(0.05, 0.5), (0.2, 0.3), (0.01, 1.0)]:
+        ref = cc.build_detections_nms(pr_thr, nms_thr, soft, det_pr, fitness, bbox, num)
+        mine = R.build_detections_nms(pr_thr, nms_thr, soft, det_pr, fitness, bbox, num)
+        assert len(ref) == len(mine) == 2
+        for b in range(2):
+            assert len(ref[b]) == len(mine[b]) and len(ref[b]) > 0
+            for (pr, cls, bb), (logs, mcls, k) in zip(ref[b], mine[b]):
+                assert cls == mcls
+                assert numpy.float32(pr) == R.libm_expf(logs)
+                assert tuple(numpy.float32(v) for v in bb) == tuple(bbox[b].reshape(-1, 4)[k])

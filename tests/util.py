@@ -59,3 +59,20 @@ def nhwc(x_nchw, dtype, device):
 
 def nchw(x_nhwc):
     return x_nhwc.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def nms_inputs(B, classes, sn, seed, crowd=True):
+    """random detect-layer outputs: log-softmax class scores, boxes clustered around a few centres so that NMS bites"""
+    rs = numpy.random.RandomState(seed)
+    z = rs.randn(B, classes + 1, sn, sn).astype(numpy.float32) * 2
+    z[:, classes] += 1.0
+    m = z.max(axis=1, keepdims=True)
+    det_pr = ((z - m) - numpy.log(numpy.exp(z - m).sum(axis=1, keepdims=True))).astype(numpy.float32)
+    cx, cy = rs.uniform(0.2, 0.8, (B, 6)), rs.uniform(0.2, 0.8, (B, 6))
+    which = rs.randint(0, 6, (B, sn, sn))
+    bx = numpy.take_along_axis(cx, which.reshape(B, -1), 1).reshape(B, sn, sn) + rs.randn(B, sn, sn) * (0.03 if crowd else 0.3)
+    by = numpy.take_along_axis(cy, which.reshape(B, -1), 1).reshape(B, sn, sn) + rs.randn(B, sn, sn) * (0.03 if crowd else 0.3)
+    w, h = rs.uniform(0.05, 0.3, (B, sn, sn)), rs.uniform(0.05, 0.3, (B, sn, sn))
+    bbox = numpy.stack([bx - w / 2, by - h / 2, bx + w / 2, by + h / 2], axis=-1).astype(numpy.float32)
+    num = [int(v) for v in rs.randint(sn * sn // 2, sn * sn + 1, B)]
+    return det_pr, bbox, num
