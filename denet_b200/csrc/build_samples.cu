@@ -81,19 +81,19 @@ __device__ __forceinline__ bool is_corner(const float* __restrict__ map, int H, 
     return true;
 }
 
-// corners: [B][4][max_corners] packed (y << 16 | x); counts: [B][4]
-__global__ void __launch_bounds__(kBsThreads) corner_select_kernel(const float* __restrict__ corner_pr, int H, int W,
-                                                                    float thr, int max_corners, int local_max,
+// corners: [B][CN][max_corners] packed (y << 16 | x); counts: [B][CN]
+__global__ void __launch_bounds__(kBsThreads) corner_select_kernel(const float* __restrict__ corner_pr, int CN, int H,
+                                                                    int W, float thr, int max_corners, int local_max,
                                                                     uint32_t* __restrict__ corners,
                                                                     int* __restrict__ counts) {
     __shared__ int warp_sums[33];
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix;
     __shared__ int s_need;
-    const int b = blockIdx.x >> 2, ci = blockIdx.x & 3;
+    const int b = blockIdx.x / CN, ci = blockIdx.x % CN;      // CN = 4 corner types, 5 with the centre map (DNC.C)
     const int HW = H * W;
-    const float* map = corner_pr + (((long long)b * 2 + 1) * 4 + ci) * HW;
-    uint32_t* out = corners + ((long long)b * 4 + ci) * max_corners;
+    const float* map = corner_pr + (((long long)b * 2 + 1) * CN + ci) * HW;
+    uint32_t* out = corners + ((long long)b * CN + ci) * max_corners;
 
     // pass 0: count
     int mine = 0;
@@ -162,25 +162,62 @@ __global__ void __launch_bounds__(kBsThreads) corner_select_kernel(const float* 
         base += n;
         tie_base += ntie;
     }
-    if (threadIdx.x == 0) counts[b * 4 + ci] = base;
+    if (threadIdx.x == 0) counts[b * CN + ci] = base;
 }
 
 struct PairCtx {
-    const float* cp;  // corner_pr[b] = (2,4,H,W)
-    int H, W, HW;
+    const float* cp;  // corner_pr[b] = (2,CN,H,W)
+    int CN, H, W, HW;
     const uint32_t* c0;  // TL
     const uint32_t* c1;  // TR
     const uint32_t* c2;  // BL
     const uint32_t* c3;  // BR
-    int n0, n1, n2, n3;
+    const uint32_t* c4;  // centres (CN == 5)
+    int n0, n1, n2, n3, n4;
     const uint32_t* bm_tl;
     const uint32_t* bm_br;
+    const uint32_t* bm_tr;   // CN == 5 only
+    const uint32_t* bm_bl;
 };
 
+__device__ __forceinline__ bool bm_test(const uint32_t* bm, int p) { return (bm[p >> 5] >> (p & 31)) & 1u; }
+
 // candidate idx -> unique 64-bit rank key (d bits << 32 | box); false if the pair is not a sample
-__device__ __forceinline__ bool pair_key(const PairCtx& c, long long idx, long long nA, uint64_t* key) {
+// Centre phase (:377-468, CN == 5): candidate = (centre m, corner type, corner a), centre-major like the reference's
+// loops.  The box is the corner reflected through the centre, so a box has exactly ONE possible centre
+// ((x0+x1)/2, (y0+y1)/2 with even extents): the reference's hash set can only have seen it before through the TL x BR
+// search, the TR x BL search, or an EARLIER corner type of the same centre - three questions the four position bitmaps
+// answer without a hash table.
+__device__ __forceinline__ bool centre_box(const PairCtx& c, long long j, int* bx0, int* by0, int* bx1, int* by1) {
+    const int nsum = c.n0 + c.n1 + c.n2 + c.n3;
+    const int m = (int)(j / nsum);
+    int a = (int)(j % nsum);
+    const uint32_t ctr = c.c4[m];
+    const int cx = ctr & 0xffff, cy = ctr >> 16;
+    int type = 0;
+    if (a >= c.n0) { a -= c.n0; type = 1; if (a >= c.n1) { a -= c.n1; type = 2; if (a >= c.n2) { a -= c.n2; type = 3; } } }
+    const uint32_t v = type == 0 ? c.c0[a] : (type == 1 ? c.c1[a] : (type == 2 ? c.c2[a] : c.c3[a]));
+    const int px = v & 0xffff, py = v >> 16;
     int x0, y0, x1, y1;
-    if (idx < nA) {  // top-left x bottom-right (:337-353)
+    if (type == 0) { x0 = px; y0 = py; x1 = x0 + 2 * (cx - x0); y1 = y0 + 2 * (cy - y0); }
+    else if (type == 1) { x1 = px; y0 = py; x0 = x1 - 2 * (x1 - cx); y1 = y0 + 2 * (cy - y0); }
+    else if (type == 2) { x0 = px; y1 = py; x1 = x0 + 2 * (cx - x0); y0 = y1 - 2 * (y1 - cy); }
+    else { x1 = px; y1 = py; x0 = x1 - 2 * (x1 - cx); y0 = y1 - 2 * (y1 - cy); }
+    if (x0 < 0 || y0 < 0 || x1 >= c.W || y1 >= c.H || x1 <= x0 || y1 <= y0) return false;
+    const int p00 = y0 * c.W + x0, p01 = y0 * c.W + x1, p10 = y1 * c.W + x0, p11 = y1 * c.W + x1;
+    const bool tl = bm_test(c.bm_tl, p00), tr = bm_test(c.bm_tr, p01), bl = bm_test(c.bm_bl, p10),
+               br = bm_test(c.bm_br, p11);
+    if ((tl && br) || (tr && bl)) return false;                         // found by the corner-pair searches
+    if ((type >= 1 && tl) || (type >= 2 && tr) || (type >= 3 && bl)) return false;   // earlier type, same centre
+    *bx0 = x0; *by0 = y0; *bx1 = x1; *by1 = y1;
+    return true;
+}
+
+__device__ __forceinline__ bool pair_key(const PairCtx& c, long long idx, long long nA, long long nB, uint64_t* key) {
+    int x0, y0, x1, y1;
+    if (idx >= nB) {
+        if (!centre_box(c, idx - nB, &x0, &y0, &x1, &y1)) return false;
+    } else if (idx < nA) {  // top-left x bottom-right (:337-353)
         const uint32_t tl = c.c0[idx / c.n3], br = c.c3[idx % c.n3];
         x0 = tl & 0xffff; y0 = tl >> 16; x1 = br & 0xffff; y1 = br >> 16;
         if (x1 <= x0 || y1 <= y0) return false;
@@ -190,11 +227,11 @@ __device__ __forceinline__ bool pair_key(const PairCtx& c, long long idx, long l
         x1 = tr & 0xffff; y0 = tr >> 16; x0 = bl & 0xffff; y1 = bl >> 16;
         if (x1 <= x0 || y1 <= y0) return false;
         const int p00 = y0 * c.W + x0, p11 = y1 * c.W + x1;
-        if (((c.bm_tl[p00 >> 5] >> (p00 & 31)) & 1u) && ((c.bm_br[p11 >> 5] >> (p11 & 31)) & 1u)) return false;
+        if (bm_test(c.bm_tl, p00) && bm_test(c.bm_br, p11)) return false;
     }
     // get_sample (:280-294): fp32 sums in the reference's order, starting from 0
     const float* f = c.cp;
-    const float* t = c.cp + 4 * c.HW;
+    const float* t = c.cp + c.CN * c.HW;
     const int p00 = y0 * c.W + x0, p01 = y0 * c.W + x1, p10 = y1 * c.W + x0, p11 = y1 * c.W + x1;
     float pr_f = __fadd_rn(0.f, f[p00]);
     pr_f = __fadd_rn(pr_f, f[c.HW + p01]);
@@ -204,14 +241,19 @@ __device__ __forceinline__ bool pair_key(const PairCtx& c, long long idx, long l
     pr_t = __fadd_rn(pr_t, t[c.HW + p01]);
     pr_t = __fadd_rn(pr_t, t[2 * c.HW + p10]);
     pr_t = __fadd_rn(pr_t, t[3 * c.HW + p11]);
+    if (c.CN == 5) {     // :296-303 centre map at the box centre (integer division)
+        const int pc = ((y0 + y1) / 2) * c.W + (x0 + x1) / 2;
+        pr_f = __fadd_rn(pr_f, f[4 * c.HW + pc]);
+        pr_t = __fadd_rn(pr_t, t[4 * c.HW + pc]);
+    }
     const float d = fabsf(__fsub_rn(pr_f, pr_t));
     const uint32_t box = ((uint32_t)x0 << 24) | ((uint32_t)y0 << 16) | ((uint32_t)x1 << 8) | (uint32_t)y1;
     *key = ((uint64_t)__float_as_uint(d) << 32) | box;  // d >= 0 (or NaN, which sorts last like the reference's pr=NaN)
     return true;
 }
 
-__global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __restrict__ corner_pr, int H, int W,
-                                                                  int max_corners, int K,
+__global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __restrict__ corner_pr, int CN, int H,
+                                                                  int W, int max_corners, int K,
                                                                   const uint32_t* __restrict__ corners,
                                                                   const int* __restrict__ counts,
                                                                   float* __restrict__ out_pr,
@@ -224,50 +266,56 @@ __global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __
     const int HW = H * W;
     const int bm_words = (HW + 31) / 32;
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(bs_smem);                   // kSortCap
-    uint32_t* s_c = reinterpret_cast<uint32_t*>(s_keys + kSortCap);            // 4 * max_corners
-    uint32_t* s_bm_tl = s_c + 4 * max_corners;                                 // bm_words
-    uint32_t* s_bm_br = s_bm_tl + bm_words;                                    // bm_words
-    int* s_hist = reinterpret_cast<int*>(s_bm_br + bm_words);                  // kRadixBins
+    uint32_t* s_c = reinterpret_cast<uint32_t*>(s_keys + kSortCap);            // CN * max_corners
+    uint32_t* s_bm_tl = s_c + CN * max_corners;                                // bm_words each
+    uint32_t* s_bm_br = s_bm_tl + bm_words;
+    uint32_t* s_bm_tr = s_bm_br + bm_words;                                    // (used when CN == 5)
+    uint32_t* s_bm_bl = s_bm_tr + bm_words;
+    int* s_hist = reinterpret_cast<int*>(s_bm_bl + bm_words);                  // kRadixBins
     __shared__ int s_cnt;
     __shared__ unsigned long long s_prefix;
     __shared__ int s_need, s_below, s_done;
 
     PairCtx c;
-    c.cp = corner_pr + (long long)b * 8 * HW;
-    c.H = H; c.W = W; c.HW = HW;
-    c.n0 = counts[b * 4 + 0]; c.n1 = counts[b * 4 + 1]; c.n2 = counts[b * 4 + 2]; c.n3 = counts[b * 4 + 3];
+    c.cp = corner_pr + (long long)b * 2 * CN * HW;
+    c.CN = CN; c.H = H; c.W = W; c.HW = HW;
+    c.n0 = counts[b * CN + 0]; c.n1 = counts[b * CN + 1]; c.n2 = counts[b * CN + 2]; c.n3 = counts[b * CN + 3];
+    c.n4 = CN == 5 ? counts[b * CN + 4] : 0;
     c.c0 = s_c; c.c1 = s_c + max_corners; c.c2 = s_c + 2 * max_corners; c.c3 = s_c + 3 * max_corners;
-    c.bm_tl = s_bm_tl; c.bm_br = s_bm_br;
+    c.c4 = s_c + 4 * max_corners;
+    c.bm_tl = s_bm_tl; c.bm_br = s_bm_br; c.bm_tr = s_bm_tr; c.bm_bl = s_bm_bl;
 
-    const uint32_t* gc = corners + (long long)b * 4 * max_corners;
-    for (int i = threadIdx.x; i < 4 * max_corners; i += kBsThreads) {
+    const uint32_t* gc = corners + (long long)b * CN * max_corners;
+    for (int i = threadIdx.x; i < CN * max_corners; i += kBsThreads) {
         const int ci = i / max_corners, j = i % max_corners;
-        const int n = ci == 0 ? c.n0 : (ci == 1 ? c.n1 : (ci == 2 ? c.n2 : c.n3));
+        const int n = counts[b * CN + ci];
         s_c[i] = j < n ? gc[i] : 0u;
     }
-    for (int i = threadIdx.x; i < 2 * bm_words; i += kBsThreads) s_bm_tl[i] = 0u;
+    for (int i = threadIdx.x; i < 4 * bm_words; i += kBsThreads) s_bm_tl[i] = 0u;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < c.n0; i += kBsThreads) {
-        const int p = (int)(s_c[i] >> 16) * W + (int)(s_c[i] & 0xffff);
-        atomicOr(&s_bm_tl[p >> 5], 1u << (p & 31));
-    }
-    for (int i = threadIdx.x; i < c.n3; i += kBsThreads) {
-        const uint32_t v = s_c[3 * max_corners + i];
-        const int p = (int)(v >> 16) * W + (int)(v & 0xffff);
-        atomicOr(&s_bm_br[p >> 5], 1u << (p & 31));
+    for (int ci = 0; ci < 4; ++ci) {
+        if (CN != 5 && (ci == 1 || ci == 2)) continue;          // TR / BL bitmaps serve the centre phase only
+        const int n = ci == 0 ? c.n0 : (ci == 1 ? c.n1 : (ci == 2 ? c.n2 : c.n3));
+        uint32_t* bm = ci == 0 ? s_bm_tl : (ci == 1 ? s_bm_tr : (ci == 2 ? s_bm_bl : s_bm_br));
+        for (int i = threadIdx.x; i < n; i += kBsThreads) {
+            const uint32_t v = s_c[ci * max_corners + i];
+            const int p = (int)(v >> 16) * W + (int)(v & 0xffff);
+            atomicOr(&bm[p >> 5], 1u << (p & 31));
+        }
     }
     __syncthreads();
 
     const long long nA = (long long)c.n0 * c.n3;
-    const long long nP = nA + (long long)c.n1 * c.n2;
+    const long long nB = nA + (long long)c.n1 * c.n2;
+    const long long nP = nB + (long long)c.n4 * ((long long)c.n0 + c.n1 + c.n2 + c.n3);
 
     // total number of samples (unique valid boxes)
     {
         int mine = 0;
         for (long long idx = threadIdx.x; idx < nP; idx += kBsThreads) {
             uint64_t key;
-            mine += pair_key(c, idx, nA, &key) ? 1 : 0;
+            mine += pair_key(c, idx, nA, nB, &key) ? 1 : 0;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
@@ -298,7 +346,7 @@ __global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __
             const unsigned long long pfx = s_prefix;
             for (long long idx = threadIdx.x; idx < nP; idx += kBsThreads) {
                 uint64_t key;
-                if (pair_key(c, idx, nA, &key)) {
+                if (pair_key(c, idx, nA, nB, &key)) {
                     if (shift == 64 || (key >> shift) == pfx) atomicAdd(&s_hist[(key >> nshift) & ((1u << bits) - 1)], 1);
                 }
             }
@@ -327,7 +375,7 @@ __global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __
     // collect survivors
     for (long long idx = threadIdx.x; idx < nP; idx += kBsThreads) {
         uint64_t key;
-        if (pair_key(c, idx, nA, &key)) {
+        if (pair_key(c, idx, nA, nB, &key)) {
             if (shift == 64 || (key >> shift) <= prefix) {
                 const int slot = atomicAdd(&s_cnt, 1);
                 if (slot < kSortCap) s_keys[slot] = key;
@@ -386,9 +434,9 @@ __global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __
     }
 }
 
-static size_t pair_smem_bytes(int H, int W, int max_corners) {
+static size_t pair_smem_bytes(int CN, int H, int W, int max_corners) {
     const size_t bm_words = ((size_t)H * W + 31) / 32;
-    return sizeof(uint64_t) * kSortCap + sizeof(uint32_t) * 4 * max_corners + sizeof(uint32_t) * 2 * bm_words +
+    return sizeof(uint64_t) * kSortCap + sizeof(uint32_t) * CN * max_corners + sizeof(uint32_t) * 4 * bm_words +
            sizeof(int) * kRadixBins;
 }
 
@@ -397,14 +445,24 @@ static size_t pair_smem_bytes(int H, int W, int max_corners) {
 using namespace dn;
 
 extern "C" size_t denet_build_samples_workspace(int B, int H, int W, int max_corners) {
-    (void)H; (void)W;
-    return (size_t)B * 4 * max_corners * sizeof(uint32_t) + (size_t)B * 4 * sizeof(int);
+    (void)H; (void)W;          // sized for 5 corner types (DNC.C); 4 need less
+    return (size_t)B * 5 * max_corners * sizeof(uint32_t) + (size_t)B * 5 * sizeof(int);
 }
 
 extern "C" int denet_build_samples(const float* corner_pr, int B, int H, int W, float corner_threshold, int sample_num,
                                    int max_corners, int local_max, float* out_pr, float* out_bbox, int* out_ibox,
                                    int* out_count, int* out_ncand, void* workspace, size_t workspace_bytes,
                                    cudaStream_t stream) {
+    return denet_build_samples_cn(corner_pr, B, 4, H, W, corner_threshold, sample_num, max_corners, local_max, out_pr,
+                                  out_bbox, out_ibox, out_count, out_ncand, workspace, workspace_bytes, stream);
+}
+
+extern "C" int denet_build_samples_cn(const float* corner_pr, int B, int corner_num, int H, int W,
+                                      float corner_threshold, int sample_num, int max_corners, int local_max,
+                                      float* out_pr, float* out_bbox, int* out_ibox, int* out_count, int* out_ncand,
+                                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const int CN = corner_num;
+    DN_REQUIRE(CN == 4 || CN == 5, "build_samples: corner_num must be 4 or 5 (centre map), got %d", CN);
     DN_REQUIRE(corner_pr && out_pr && out_bbox && out_ibox && out_count && workspace, "build_samples: null pointer");
     DN_REQUIRE(B > 0 && H > 0 && W > 0 && H <= 256 && W <= 256, "build_samples: map size must be in [1,256]");
     DN_REQUIRE(sample_num > 0 && sample_num * sample_num <= kSortCap, "build_samples: sample_num^2 must be <= %d",
@@ -413,15 +471,17 @@ extern "C" int denet_build_samples(const float* corner_pr, int B, int H, int W, 
     DN_REQUIRE(workspace_bytes >= denet_build_samples_workspace(B, H, W, max_corners),
                "build_samples: workspace too small");
     uint32_t* corners = reinterpret_cast<uint32_t*>(workspace);
-    int* counts = reinterpret_cast<int*>(corners + (size_t)B * 4 * max_corners);
+    int* counts = reinterpret_cast<int*>(corners + (size_t)B * CN * max_corners);
     const float thr = logf(corner_threshold);  // std::log(float), denet_sparse.cc:504
-    corner_select_kernel<<<DN_G(B * 4), kBsThreads, 0, stream>>>(corner_pr, H, W, thr, max_corners, local_max, corners, counts);
+    corner_select_kernel<<<DN_G(B * CN), kBsThreads, 0, stream>>>(corner_pr, CN, H, W, thr, max_corners, local_max, corners,
+                                                                  counts);
     DN_CHECK_LAUNCH();
-    const size_t smem = pair_smem_bytes(H, W, max_corners);
+    const size_t smem = pair_smem_bytes(CN, H, W, max_corners);
     DN_REQUIRE(smem <= 200 * 1024, "build_samples: shared memory budget exceeded");
     DN_CHECK_CUDA(cudaFuncSetAttribute(pair_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pair_select_kernel<<<DN_G(B), kBsThreads, smem, stream>>>(corner_pr, H, W, max_corners, sample_num * sample_num, corners,
-                                                        counts, out_pr, out_bbox, out_ibox, out_count, out_ncand);
+    pair_select_kernel<<<DN_G(B), kBsThreads, smem, stream>>>(corner_pr, CN, H, W, max_corners, sample_num * sample_num,
+                                                              corners, counts, out_pr, out_bbox, out_ibox, out_count,
+                                                              out_ncand);
     DN_CHECK_LAUNCH();
     return 0;
 }

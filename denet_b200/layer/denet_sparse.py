@@ -82,9 +82,7 @@ class DeNetSparseLayer(AbstractLayer):
         self.thread_num = self.batch_size
         self.sample_count = self.sample_num * self.sample_num
 
-        corner_layer = common.find_layers(layers, "denet-corner", True)
-        if corner_layer.corner_num != 4:
-            raise Exception("denet-sparse: centre corners (DNC.C) are not on the B200 hot path")
+        corner_layer = common.find_layers(layers, "denet-corner", True)     # 4 corner maps, 5 with centres (DNC.C)
         object.__setattr__(self, "corner_layer", corner_layer)
 
         self.sample_bbox = None           # (B,sn,sn,4) fp32 device tensor consumed by the gather kernel

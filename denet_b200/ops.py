@@ -709,11 +709,13 @@ def sparse_sample_index(bbox, gs, H, W):
 
 
 def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, local_max=0, cluster_threshold=1.0):
-    """corner_pr (B,2,4,H,W) fp32 device.  Returns (pr (B,K), bbox (B,K,4), ibox (B,K,4) int32, count (B), ncand (B))"""
-    assert corner_pr.dtype == torch.float32 and corner_pr.is_contiguous() and corner_pr.shape[1:3] == (2, 4)
+    """corner_pr (B,2,4|5,H,W) fp32 device (5 = with the centre map of DNC.C).
+    Returns (pr (B,K), bbox (B,K,4), ibox (B,K,4) int32, count (B), ncand (B))"""
+    assert corner_pr.dtype == torch.float32 and corner_pr.is_contiguous() and corner_pr.shape[1] == 2 and \
+        corner_pr.shape[2] in (4, 5)
     if cluster_threshold < 1.0:
         raise NotImplementedError("build_samples: corner clustering (cluster_threshold < 1, denet_sparse.cc:165-242)")
-    b, _, _, h, w = corner_pr.shape
+    b, _, cn, h, w = corner_pr.shape
     k = sample_num * sample_num
     dev = corner_pr.device
     pr = torch.empty((b, k), dtype=torch.float32, device=dev)
@@ -723,8 +725,8 @@ def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, loc
     ncand = torch.empty((b,), dtype=torch.int32, device=dev)
     nbytes = lib.load().denet_build_samples_workspace(b, h, w, max_corners)
     ws = workspace(nbytes, dev, "samples")
-    call("denet_build_samples", corner_pr.data_ptr(), b, h, w, corner_threshold, sample_num, max_corners, local_max,
-         pr.data_ptr(), bbox.data_ptr(), ibox.data_ptr(), count.data_ptr(), ncand.data_ptr(), ws.data_ptr(),
+    call("denet_build_samples_cn", corner_pr.data_ptr(), b, cn, h, w, corner_threshold, sample_num, max_corners,
+         local_max, pr.data_ptr(), bbox.data_ptr(), ibox.data_ptr(), count.data_ptr(), ncand.data_ptr(), ws.data_ptr(),
          ws.numel() * 4, _stream())
     return pr, bbox, ibox, count, ncand
 

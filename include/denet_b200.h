@@ -281,6 +281,14 @@ size_t denet_build_samples_workspace(int B, int H, int W, int max_corners);
 int denet_build_samples(const float* corner_pr, int B, int H, int W, float corner_threshold, int sample_num,
                         int max_corners, int local_max, float* out_pr, float* out_bbox, int* out_ibox, int* out_count,
                         int* out_ncand, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* the same with `corner_num` maps per image: 4 corner types, or 5 when the corner layer also predicts box centres
+ * (model token DNC.C, denet/layer/denet_corner.py:34-37): centres pair with every corner type
+ * (denet_sparse.cc:377-468) and the centre probability joins every box score (:296-303).
+ * corner_pr is (B, 2, corner_num, H, W). */
+int denet_build_samples_cn(const float* corner_pr, int B, int corner_num, int H, int W, float corner_threshold,
+                           int sample_num, int max_corners, int local_max, float* out_pr, float* out_bbox,
+                           int* out_ibox, int* out_count, int* out_ncand, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ costs
  * corner_logprob: DeNetCornerLayer.corner_pr (denet/layer/denet_corner.py:50-53 + common/theano_util.py:27-29):

@@ -116,3 +116,50 @@ def test_get_detections_end_to_end(cuda):
     sb = sp.sample_bbox.cpu().numpy().reshape(4, -1, 4)
     for i in range(4):
         assert (sb[i, counts[i]:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ golden fixtures
+import glob
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NMS_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "nms_*.npz")))
+SAMPLE_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "build_samples_*.npz")))
+
+
+@pytest.mark.parametrize("path", NMS_FIXTURES, ids=[os.path.basename(p)[:-4] for p in NMS_FIXTURES])
+def test_detections_nms_vs_reference_golden(cuda, path):
+    """the CUDA NMS against detection lists the reference's own compiled extension produced (tests/golden/make_golden.py)"""
+    from denet_b200 import common
+    g = numpy.load(path)
+    got = common.import_c("denet_detect.cc").build_detections_nms(
+        float(g["pr_threshold"]), float(g["nms_threshold"]), int(g["use_soft_nms"]), g["det_pr"], g["fitness"], g["bbox"],
+        [int(v) for v in g["bbox_num"]])
+    for b, dets in enumerate(got):
+        n = int(g["count"][b])
+        assert len(dets) == n
+        for i, (pr, cls, bb) in enumerate(dets):
+            assert cls == g["cls"][b, i] and numpy.float32(pr) == g["score"][b, i]
+            assert tuple(numpy.float32(v) for v in bb) == tuple(g["box"][b, i])
+
+
+@pytest.mark.parametrize("path", SAMPLE_FIXTURES, ids=[os.path.basename(p)[:-4] for p in SAMPLE_FIXTURES])
+def test_build_samples_vs_reference_golden(cuda, path):
+    """the CUDA sampler (4 and 5 corner maps) against the outputs of the reference's compiled build_samples"""
+    from denet_b200 import ops
+    g = numpy.load(path)
+    sn = int(g["sample_num"])
+    K = sn * sn
+    pr, bbox, ibox, count, ncand = [t.cpu().numpy() for t in ops.build_samples(
+        torch.from_numpy(g["corner_pr"]).cuda(), float(g["threshold"]), sn, int(g["max_corners"]), int(g["local_max"]))]
+    for b in range(g["corner_pr"].shape[0]):
+        n = int(g["count"][b])
+        assert count[b] == n
+        assert numpy.array_equal(pr[b, :n], g["pr"][b, :n])          # the score sequence is bit-exact
+        got = {tuple(bbox[b, i]): pr[b, i] for i in range(n)}
+        want = {tuple(g["bbox"][b, i]): g["pr"][b, i] for i in range(n)}
+        if ncand[b] <= K:
+            assert got == want
+        else:
+            cut = g["pr"][b, n - 1]                                   # ties at the K-th score may permute boxes
+            assert {k: v for k, v in got.items() if v > cut} == {k: v for k, v in want.items() if v > cut}

@@ -563,6 +563,27 @@ def test_build_samples_vs_oracle(cuda, k, H, sn):
     assert ncand.max() > 0
 
 
+@pytest.mark.parametrize("k,H,sn", [(6, 32, 8), (20, 64, 24), (48, 64, 24)])
+def test_build_samples_centre_corners(cuda, k, H, sn):
+    """DNC.C: five maps per image - centres pair with every corner type (denet_sparse.cc:377-468) and the centre
+    probability joins every score (:296-303); vs the C restatement and the reference's compiled extension"""
+    cp = busy_corner_map(3, H, H, k, seed=100 + k, corner_num=5)
+    count, ncand = _check_samples(cp, sn)
+    assert ncand.max() > 0
+    ref_cc = oracle.reference_cc()
+    if ref_cc is not None:
+        ops = _ops()
+        pr, bbox, ibox, cnt, nc = [t.cpu().numpy() for t in ops.build_samples(torch.from_numpy(cp).cuda(), 0.01, sn)]
+        ref = ref_cc.build_samples(3, cp, 0.01, sn, 1024, 0, 1.0)
+        for b in range(3):
+            assert cnt[b] == len(ref[b])
+            want = {tuple(numpy.float32(v) for v in bb): numpy.float32(p) for p, bb in ref[b]}
+            cut = min(want.values()) if want else 0
+            for i in range(cnt[b]):
+                if pr[b, i] > cut or nc[b] <= sn * sn:
+                    assert want[tuple(bbox[b, i])] == pr[b, i]
+
+
 def test_build_samples_edge_cases(cuda):
     # untrained net: bias 5 everywhere (denet_corner.py:42-47) -> no corner passes the threshold -> zero samples
     from util import log_softmax_corner

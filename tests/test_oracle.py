@@ -51,6 +51,24 @@ def test_build_samples_restatement_vs_reference_golden(path):
     assert numpy.array_equal(R.bbox_array(samples, len(res), sn), g["bbox_array"])
 
 
+NMS_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "nms_*.npz")))
+
+
+@pytest.mark.parametrize("path", NMS_FIXTURES, ids=[os.path.basename(p)[:-4] for p in NMS_FIXTURES])
+def test_nms_restatement_vs_reference_golden(path):
+    """oracle.ref_ops.build_detections_nms == the detection lists the reference's compiled denet_detect.cc produced"""
+    g = numpy.load(path)
+    got = R.build_detections_nms(float(g["pr_threshold"]), float(g["nms_threshold"]), int(g["use_soft_nms"]),
+                                 g["det_pr"], g["fitness"], g["bbox"], g["bbox_num"])
+    flat = g["bbox"].reshape(g["bbox"].shape[0], -1, 4)
+    for b, dets in enumerate(got):
+        n = int(g["count"][b])
+        assert len(dets) == n
+        for i, (logs, cls, k) in enumerate(dets):
+            assert cls == g["cls"][b, i] and R.libm_expf(logs) == g["score"][b, i]
+            assert numpy.array_equal(flat[b, k], g["box"][b, i])
+
+
 def test_build_samples_restatement_vs_live_reference():
     """same check against the compiled reference itself when oracle/_ref is present (it is in the build container)"""
     ref = oracle.reference_cc()

@@ -14,12 +14,13 @@ def log_softmax_corner(z):
     return (d - numpy.log(numpy.exp(d).sum(axis=1, keepdims=True, dtype=numpy.float32))).astype(numpy.float32)
 
 
-def busy_corner_map(B, H, W, k, seed, quantize=None):
-    """SURVEY.md §8d 'busy' corner map: logits 5+N(0,1) (not a corner) with k strong corners per type"""
+def busy_corner_map(B, H, W, k, seed, quantize=None, corner_num=4):
+    """SURVEY.md §8d 'busy' corner map: logits 5+N(0,1) (not a corner) with k strong corners per type
+    (corner_num = 5 adds the centre map of DNC.C)"""
     rng = numpy.random.RandomState(seed)
-    z = 5.0 + rng.randn(B, 4, H, W).astype(numpy.float32)
+    z = 5.0 + rng.randn(B, corner_num, H, W).astype(numpy.float32)
     for b in range(B):
-        for c in range(4):
+        for c in range(corner_num):
             for _ in range(k):
                 z[b, c, rng.randint(H), rng.randint(W)] = -1.0 - 4.0 * rng.rand()
     if quantize:
