@@ -110,6 +110,12 @@ struct ConvFpropParams {
     int debug;               // profiling knobs (results are garbage): bit0 epilogue = TMEM read only, bit1 no statistics,
                              // bit2 no MMAs, bit3 no A / B loads
     long long* timeline;     // profiling: CTA 0 records clock64() stamps [role][tile][4] (roles: producer, MMA, epilogue)
+    // ---- staged epilogue (fprop_epilogue_tma): the bf16 output tile goes through shared memory and leaves with TMA
+    // stores; batch-norm statistics are summed from the staged tile
+    CUtensorMap tmY;         // output (Cout, Wo, Ho, N) bf16, box 64 x TW x TH x TN, 128B swizzle
+    int epi_tma;             // 1 = staged epilogue
+    uint32_t stage_off;      // staging tile [BN/64][128 rows][128 B] relative to the 1024-aligned shared-memory base
+    uint32_t smem_total;     // dynamic shared memory of the launch (host side only)
 };
 
 struct ConvWgradParams {
@@ -459,6 +465,182 @@ __device__ __forceinline__ void fprop_epilogue(const ConvFpropParams& p, float2*
         if (stamp) p.timeline[(2 * 64 + it) * 4 + 2] = clock64();
     }
     flush_stats();
+}
+
+// ------------------------------------------------------------------------------------------------ staged epilogue
+// bf16 outputs without scatter / fused batch-norm backward.  fprop_epilogue above costs ~2500 cycles per 128 x 64 tile
+// (two 31-shuffle butterflies per 32-column chunk for the statistics, 16-byte global stores scattered over 128 pixel
+// rows) - MORE than the 36 MMAs of a 64-channel 3x3 tile, so the short-tile layers were epilogue-bound.  Here:
+//   TMEM -> registers -> (bias / residual / ReLU) -> bf16 -> st.shared.v4 into a staging tile laid out exactly as a
+//   TMA box with 128B swizzle (row = pixel of the patch, 64-channel sub-tiles 16 KB apart; 4 lanes per bank group is the
+//   512-byte-per-instruction floor), the accumulator is released right after the TMEM reads, ONE thread issues the
+//   TMA stores (UTMASTG, clipped at the tensor edge) and meanwhile all 256 epilogue threads sum the statistics from the
+//   staged tile: thread = (column pair, row group), 4-byte conflict-free reads, running sums in 4 registers across the
+//   tiles of the CTA - no shuffles, no per-tile atomics.  The statistics are those of the bf16-ROUNDED outputs, i.e. of
+//   exactly the values the batch-norm apply pass normalises.
+template <int BN, bool PAIR>
+__device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uint8_t* stage, float* stat_red,
+                                                   uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                   int warp, int lane) {
+    const int ew = warp - 2;               // 0..7
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int row = q * 32 + lane;
+    const int et = static_cast<int>(threadIdx.x) - 64;     // 0..255
+    constexpr int kPairs = BN / 2;               // column pairs of the tile
+    constexpr int kGroups = 256 / kPairs;        // row groups summed by different threads
+    constexpr int kRowsPerGroup = 128 / kGroups;
+    const int cpair = et % kPairs, grp = et / kPairs;
+    const uint32_t stage_u32 = ptx::smem_u32(stage);
+    // staged word of (row r, column pair cpair): sub-tile cpair / 32, 16-byte chunk (cpair % 32) / 4 swizzled by r & 7
+    const uint32_t stat_base = stage_u32 + static_cast<uint32_t>(cpair >> 5) * 16384u + static_cast<uint32_t>(cpair & 3) * 4u;
+    const uint32_t stat_chunk = static_cast<uint32_t>((cpair & 31) >> 2);
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    int acc_ct = -1;
+    const bool want_stats = p.stat_sum != nullptr;
+    auto flush_stats = [&]() {
+        if (!want_stats || acc_ct < 0) return;
+        // combine the row groups in a fixed order, then one atomic per channel per CTA
+        float* red = stat_red + (grp * BN + 2 * cpair) * 2;
+        red[0] = s0; red[1] = q0; red[2] = s1; red[3] = q1;
+        ptx::named_bar_sync(3, 256);
+        if (et < BN) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int g2 = 0; g2 < kGroups; ++g2) {
+                a += stat_red[(g2 * BN + et) * 2 + 0];
+                b += stat_red[(g2 * BN + et) * 2 + 1];
+            }
+            const int c = acc_ct * BN + et;
+            if (c < p.Cout) {
+                atomicAdd(p.stat_sum + c, a);
+                atomicAdd(p.stat_sqsum + c, b);
+            }
+        }
+        ptx::named_bar_sync(3, 256);
+        s0 = s1 = q0 = q1 = 0.f;
+    };
+    const uint32_t pair_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+    const int tile0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x, tile_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
+    int it = 0;
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        uint32_t uct, mt, tw, th, tn;
+        p.fd_co.divmod(tile, mt, uct);
+        if (PAIR) mt = 2 * mt + pair_rank;
+        const int ct = static_cast<int>(uct);
+        if (ct != acc_ct) {
+            flush_stats();
+            acc_ct = ct;
+        }
+        p.fd_w.divmod(mt, mt, tw);
+        p.fd_h.divmod(mt, tn, th);
+        uint32_t rq, rw, rn, rh;
+        p.fd_tw.divmod(row, rq, rw);
+        p.fd_th.divmod(rq, rn, rh);
+        const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+        const int w = w0 + rw, h = h0 + rh, n = n0 + rn;
+        const bool row_ok = (w < p.Wo) && (h < p.Ho) && (n < p.No);
+        const long long pix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;
+        const int co0 = ct * BN;
+
+        ptx::mbar_wait(&tfull_bar[as], aphase);
+        ptx::tc_fence_after();
+        // the staging tile is free once the previous tile's TMA stores have read it and every thread has finished
+        // summing its statistics from it
+        if (et == 0 && it > 0) ptx::bulk_wait_read0();
+        ptx::named_bar_sync(1, 256);
+        const uint32_t srow = stage_u32 + static_cast<uint32_t>(row) * 128u;
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0;
+            ptx::tmem_ld_32x32b_x32(taddr, r);
+            ptx::tmem_ld_wait();
+            const int co = co0 + c0;
+            int nvalid = p.Cout - co;
+            nvalid = nvalid > 32 ? 32 : nvalid;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (nvalid > 0 && row_ok) {
+                if (p.bias) {
+                    const float* bp = p.bias + co;
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+                        float4 b4[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bp) + i);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            v[4 * i] += b4[i].x; v[4 * i + 1] += b4[i].y; v[4 * i + 2] += b4[i].z; v[4 * i + 3] += b4[i].w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += (i < nvalid) ? __ldg(bp + i) : 0.f;
+                    }
+                }
+                if (p.residual) {
+                    float rres[32];
+                    load_row_chunk(p.residual, 0, pix * p.ldy + co, rres, nvalid);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += rres[i];
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i >= nvalid) v[i] = 0.f;
+            } else {
+                // rows outside the tensor / channels past Cout: zeros (clipped by the store, neutral for the sums)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            uint32_t w16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w16[i] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+            const uint32_t sub = static_cast<uint32_t>(c0 >> 6) * 16384u;
+            const uint32_t cbase = static_cast<uint32_t>((c0 & 63) >> 3);       // first 16-byte chunk of this 32-column run
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                ptx::st_shared_v4(srow + sub + (((cbase + j) ^ static_cast<uint32_t>(row & 7)) << 4), w16[4 * j],
+                                  w16[4 * j + 1], w16[4 * j + 2], w16[4 * j + 3]);
+        }
+        // accumulator buffer read completely: hand it back to the MMA issuer before the stores / statistics
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            if (PAIR)
+                ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty_bar[as]), 0));
+            else
+                ptx::mbar_arrive(&tempty_bar[as]);
+        }
+        ptx::fence_proxy_async();              // generic-proxy writes of the staging tile -> visible to the TMA engine
+        ptx::named_bar_sync(2, 256);
+        if (et == 0) {
+#pragma unroll
+            for (int sb = 0; sb < BN / 64; ++sb)
+                if (co0 + sb * 64 < p.Cout) ptx::tma_store_4d(&p.tmY, stage + sb * 16384, co0 + sb * 64, w0, h0, n0);
+            ptx::bulk_commit_group();
+        }
+        if (want_stats) {
+#pragma unroll 4
+            for (int rr = 0; rr < kRowsPerGroup; ++rr) {
+                const uint32_t r2 = static_cast<uint32_t>(grp * kRowsPerGroup + rr);
+                const uint32_t wv = ptx::ld_shared_u32(stat_base + r2 * 128u + ((stat_chunk ^ (r2 & 7u)) << 4));
+                const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
+                s0 += f0; q0 = fmaf(f0, f0, q0);
+                s1 += f1; q1 = fmaf(f1, f1, q1);
+            }
+        }
+    }
+    flush_stats();
+    if (et == 0) ptx::bulk_wait0();            // the last stores have completed before the CTA (and its smem) goes away
 }
 
 // ------------------------------------------------------------------------------------------------ fprop / dgrad
@@ -876,6 +1058,9 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_fprop_halo_kernel(const __g
             __syncwarp();
             if (stamp) p.timeline[(1 * 64 + it) * 4 + 3] = clock64();
         }
+    } else if (p.epi_tma) {
+        fprop_epilogue_tma<BN, false>(p, smem + p.stage_off, reinterpret_cast<float*>(stat_smem), tmem_base, tfull_bar,
+                                      tempty_bar, warp, lane);
     } else {
         fprop_epilogue<BN>(p, stat_smem, tmem_base, tfull_bar, tempty_bar, warp, lane);
     }
@@ -1114,7 +1299,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
             __syncwarp();
         }
     } else if (warp >= 2) {
-        fprop_epilogue<BN, true>(p, stat_smem, tmem_base, tfull_bar, tempty_bar, warp, lane);
+        if (p.epi_tma)
+            fprop_epilogue_tma<BN, true>(p, smem + p.stage_off, reinterpret_cast<float*>(stat_smem), tmem_base, tfull_bar,
+                                         tempty_bar, warp, lane);
+        else
+            fprop_epilogue<BN, true>(p, stat_smem, tmem_base, tfull_bar, tempty_bar, warp, lane);
     }
 
     // the peer's shared memory and barriers must outlive every MMA read / remote arrive of the pair
@@ -2122,14 +2311,14 @@ int fprop_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStr
 // ---- tap-group (halo) fprop: ring sizing, weight map, dispatch.  The caller has filled the A map(s), the patch
 // geometry (TW/TH/TN, tiles_w/h/n) and the a_* / tap-offset fields.  Returns 1 when the layer does not fit (caller falls
 // back to conv_fprop_kernel), 0 on success, < 0 on error.
-static int g_fprop_mode = 7;      // bit0: use the tap-group kernel where eligible, bit1: resident filters, bit2: CTA pairs
+static int g_fprop_mode = 15;     // bit0: tap-group kernel where eligible, bit1: resident filters, bit2: CTA pairs,
+                                  // bit3: staged epilogue (TMA stores, statistics from the staged tile)
 static int g_fprop_debug = 0;     // ConvFpropParams::debug
 static long long* g_fprop_timeline = nullptr;
 
 template <int BN, int NT, bool RESIDENT, int KM>
 static int launch_fprop_halo(const ConvFpropParams& p, cudaStream_t stream) {
-    const size_t smem = 1024 + (size_t)p.a_region_bytes + p.b_region_bytes + 512 + 8 * BN * 8 +
-                        (p.bnb_x ? 16 * p.bnb_cpad : 0);
+    const size_t smem = p.smem_total;
     auto kern = conv_fprop_halo_kernel<BN, NT, RESIDENT, KM>;
     DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
@@ -2154,10 +2343,36 @@ static int dispatch_fprop_halo(const ConvFpropParams& p, cudaStream_t stream) {
     return launch_fprop_halo<BN, 0, false, 0>(p, stream);
 }
 
+// staged (TMA store) epilogue: applicable to bf16 outputs written in place (no scatter, no fused batch-norm backward).
+// Fills tmY / epi_tma; returns the bytes of the staging tile (0 = not applicable).  The caller places it with
+// place_stage() once the A / B regions are sized.
+static uint32_t staged_epilogue_bytes(ConvFpropParams& p, int BN, int* rc) {
+    *rc = 0;
+    p.epi_tma = 0;
+    // (the statistics are those of the conv output BEFORE a fused residual / ReLU: the staged tile holds the final
+    // values, so that combination - which no layer of the model uses - keeps the register epilogue)
+    const bool ok = (g_fprop_mode & 8) && !p.y_fp32 && !p.bnb_x && p.osh == 1 && p.osw == 1 && p.ooh == 0 && p.oow == 0 &&
+                    p.Hf == p.Ho && p.Wf == p.Wo && p.TW <= 256 && p.TH <= 256 && p.TN <= 256 &&
+                    !(p.stat_sum && (p.residual || p.relu));
+    if (!ok) return 0;
+    uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.No};
+    uint64_t strides[3] = {(uint64_t)p.ldy * 2, (uint64_t)p.ldy * 2 * p.Wo, (uint64_t)p.ldy * 2 * p.Wo * p.Ho};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+    if ((*rc = encode_tmap_bf16(&p.tmY, p.y, 4, dims, strides, box, nullptr))) return 0;
+    p.epi_tma = 1;
+    return (uint32_t)(128 * BN * 2);
+}
+
+static size_t place_stage(ConvFpropParams& p, int BN, uint32_t stage_bytes) {
+    const size_t front = (size_t)p.a_region_bytes + p.b_region_bytes + 512 + 8 * (size_t)BN * 8;
+    if (!p.epi_tma) return 1024 + front + (p.bnb_x ? 16 * p.bnb_cpad : 0);
+    p.stage_off = (uint32_t)((front + 1023) / 1024 * 1024);
+    return 1024 + (size_t)p.stage_off + stage_bytes;
+}
+
 template <int BN, int NT, bool RESIDENT, int KM>
 static int launch_fprop_halo2(const ConvFpropParams& p, cudaStream_t stream) {
-    const size_t smem = 1024 + (size_t)p.a_region_bytes + p.b_region_bytes + 512 + 8 * BN * 8 +
-                        (p.bnb_x ? 16 * p.bnb_cpad : 0);
+    const size_t smem = p.smem_total;
     auto kern = conv_fprop_halo2_kernel<BN, NT, RESIDENT, KM>;
     DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int pairs = p.num_tiles < num_sms() / 2 ? p.num_tiles : num_sms() / 2;
@@ -2175,7 +2390,10 @@ static int halo2_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, 
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     if (m_tiles < 2) return 1;
     const uint32_t bh_bytes = (BN / 2) * 128;
-    const uint32_t budget = 200 * 1024;
+    int rc;
+    const uint32_t stage_bytes = staged_epilogue_bytes(p, BN, &rc);
+    if (rc) return rc;
+    const uint32_t budget = 200 * 1024 - stage_bytes;
     p.a_stage_bytes = p.a_loads * p.a_load_stride;
     p.b_resident = (g_fprop_mode & 2) && p.nterms == 1 && BN == 64 && Cout <= BN &&
                    (uint32_t)(ntaps * p.kchunks) * bh_bytes <= 80 * 1024;
@@ -2185,13 +2403,14 @@ static int halo2_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, 
         p.a_stages = (int)((budget - p.b_region_bytes) / p.a_stage_bytes);
         if (p.a_stages > 6) p.a_stages = 6;
     } else {
-        p.b_stages = BN == 256 ? 8 : 12;
+        p.b_stages = BN == 256 ? (stage_bytes ? 4 : 8) : 12;
         p.b_region_bytes = p.b_stages * bh_bytes;
         p.a_stages = (int)((budget - p.b_region_bytes) / p.a_stage_bytes);
         if (p.a_stages > 4) p.a_stages = 4;
     }
     if (p.a_stages < 2) return 1;
     p.a_region_bytes = p.a_stages * p.a_stage_bytes;
+    p.smem_total = (uint32_t)place_stage(p, BN, stage_bytes);
     p.tiles_co = ceil_div(Cout, BN);
     p.num_tiles = ceil_div(m_tiles, 2) * p.tiles_co;          // PAIR tiles
     p.fd_co = make_fastdiv(p.tiles_co);
@@ -2199,7 +2418,6 @@ static int halo2_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, 
     p.fd_h = make_fastdiv(p.tiles_h);
     p.fd_tw = make_fastdiv(p.TW);
     p.fd_th = make_fastdiv(p.TH);
-    int rc;
     const uint64_t ktot = (uint64_t)ntaps * p.kchunks * 64;
     uint64_t dims[2] = {ktot, (uint64_t)Cout};
     uint64_t strides[1] = {ktot * 2};
@@ -2224,7 +2442,14 @@ int halo_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStre
     const int Cout = p.Cout;
     const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
     const uint32_t b_bytes = BN * 128;
-    const uint32_t budget = 200 * 1024;
+    int rc;
+    uint32_t stage_bytes = 0;
+    p.epi_tma = 0;
+    if (BN <= 128) {                    // (a 256-wide staging tile does not fit next to four 32 KB filter stages)
+        stage_bytes = staged_epilogue_bytes(p, BN, &rc);
+        if (rc) return rc;
+    }
+    const uint32_t budget = 200 * 1024 - stage_bytes;
     const int ntaps = p.R * p.S;
     p.a_stage_bytes = p.a_loads * p.a_load_stride;
     p.b_resident = (g_fprop_mode & 2) && p.nterms == 1 && BN <= 128 && Cout <= BN &&
@@ -2242,6 +2467,7 @@ int halo_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStre
     }
     if (p.a_stages < 2) return 1;
     p.a_region_bytes = p.a_stages * p.a_stage_bytes;
+    p.smem_total = (uint32_t)place_stage(p, BN, stage_bytes);
     p.tiles_co = ceil_div(Cout, BN);
     p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
     p.fd_co = make_fastdiv(p.tiles_co);
@@ -2249,7 +2475,6 @@ int halo_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStre
     p.fd_h = make_fastdiv(p.tiles_h);
     p.fd_tw = make_fastdiv(p.TW);
     p.fd_th = make_fastdiv(p.TH);
-    int rc;
     const uint64_t ktot = (uint64_t)ntaps * p.kchunks * 64;
     uint64_t dims[2] = {ktot, (uint64_t)Cout};
     uint64_t strides[1] = {ktot * 2};

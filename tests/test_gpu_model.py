@@ -215,18 +215,21 @@ def test_resnet_classifier_train_step_fp32(cuda, convert):
     print("resnet worst gradient rel err %.2e" % worst)
 
 
-def _denet_step(cuda, precision, tol):
+def _denet_step(cuda, precision, tol, centre=False):
     from denet_b200.layer import set_param, get_param
-    model = build(DENET_SMALL, (3, 128, 128), 4, 20, precision, convert=True)
+    desc = DENET_SMALL.replace("DNC[32,100]", "DNC.C[32,100]") if centre else DENET_SMALL
+    model = build(desc, (3, 128, 128), 4, 20, precision, convert=True)
     # a corner detector that fires: random corner rows, bias near the decision boundary
     dnc = [l for l in model.layers if l.type_name == "denet-corner"][0]
+    assert dnc.corner_num == (5 if centre else 4)
+    cn = dnc.corner_num
     conv = dnc.layers[1]
     rng = numpy.random.RandomState(4)
     w = get_param(conv.omega).copy()
-    w[:4] = rng.randn(*w[:4].shape) * 0.3
+    w[:cn] = rng.randn(*w[:cn].shape) * 0.3
     set_param(conv.omega, w)
     b = get_param(conv.beta).copy()
-    b[:4] = 2.0
+    b[:cn] = 2.0
     set_param(conv.beta, b)
     model.to_device(precision=precision)
     model.build_train_func("nesterov", [1.0, 0.5])
@@ -239,9 +242,11 @@ def _denet_step(cuda, precision, tol):
     return model, js, before, cap, x, cost, costs, bbox
 
 
-def test_denet_train_step_fp32(cuda):
-    """conv stack + skip + pool-inv + DNC/DNS/DND head, forward/backward/update vs the oracle on the same RoIs"""
-    model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "fp32", 1e-4)
+@pytest.mark.parametrize("centre", [False, True], ids=["DNC", "DNC.C"])
+def test_denet_train_step_fp32(cuda, centre):
+    """conv stack + skip + pool-inv + DNC/DNS/DND head, forward/backward/update vs the oracle on the same RoIs
+    (DNC.C: the v2 corner layer with a fifth, box-centre map feeding sampler, target and cost)"""
+    model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "fp32", 1e-4, centre)
     ref = RefModel(js, x.shape, 20, dtype=torch.float64)
     ref.relu_masks = relu_masks(model)
     ref.pool_argmax = pool_argmax(model)
@@ -259,7 +264,7 @@ def test_denet_train_step_fp32(cuda):
         if e >= 1e-4:
             over.append(name)
         assert e < max(1e-4, 3.0 * floor[name]), "gradient of %s: rel err %.3e (fp32 floor %.3e)" % (name, e, floor[name])
-    report("denet_small", worst_gradient_rel_err=worst, worst_fp32_floor=max(floor.values()), over_1e4=sorted(over),
+    report("denet_small" + ("_centre" if centre else ""), worst_gradient_rel_err=worst, worst_fp32_floor=max(floor.values()), over_1e4=sorted(over),
            tol=1e-4, cost=cost, oracle_cost=float(total))
     print("denet worst gradient rel err %.2e (fp32 floor %.2e)" % (worst, max(floor.values())))
 
