@@ -545,6 +545,15 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
         const long long pix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;
         const int co0 = ct * BN;
 
+        // residual of the first chunk: issued BEFORE the wait for the accumulator, so that the global-load latency
+        // (a full ~1 us per tile otherwise: more than the MMAs of a 64-channel tile) hides behind the MMAs
+        const bool res_fast = p.residual && row_ok && (p.Cout % 8 == 0);
+        const __nv_bfloat16* res_row = reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldy + co0;
+        uint4 rraw[4];
+        if (res_fast && co0 + half * 32 + 32 <= p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rraw[j] = __ldg(reinterpret_cast<const uint4*>(res_row + half * 32) + j);
+        }
         ptx::mbar_wait(&tfull_bar[as], aphase);
         ptx::tc_fence_after();
         // the staging tile is free once the previous tile's TMA stores have read it and every thread has finished
@@ -581,10 +590,27 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
                     }
                 }
                 if (p.residual) {
-                    float rres[32];
-                    load_row_chunk(p.residual, 0, pix * p.ldy + co, rres, nvalid);
+                    if (res_fast && nvalid == 32) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += rres[i];
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t wv[4] = {rraw[j].x, rraw[j].y, rraw[j].z, rraw[j].w};
+#pragma unroll
+                            for (int k2 = 0; k2 < 4; ++k2) {
+                                v[8 * j + 2 * k2] += __uint_as_float(wv[k2] << 16);
+                                v[8 * j + 2 * k2 + 1] += __uint_as_float(wv[k2] & 0xffff0000u);
+                            }
+                        }
+                        if (c0 + 64 < BN && co + 64 + 32 <= p.Cout) {      // next chunk of this warp: in flight during the stores
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                rraw[j] = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 64) + j);
+                        }
+                    } else {
+                        float rres[32];
+                        load_row_chunk(p.residual, 0, pix * p.ldy + co, rres, nvalid);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += rres[i];
+                    }
                 }
                 if (p.relu) {
 #pragma unroll
@@ -2131,7 +2157,8 @@ struct ReduceEntry {
     int splits, Cout, Cin, R, S, ldws, mode, Cp, accumulate, pad_;
 };
 constexpr int kReduceChunk = 1024;      // elementwise path: elements per block
-constexpr int kReduceItems = 4;         // tiled path: (co, 32-channel group) items per block
+constexpr int kReduceItems = 1;         // tiled path: (co, channel group) items per block
+constexpr int kReduceGroup = 128;       // tiled path: input channels per item
 
 __global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const ReduceEntry* __restrict__ entries,
                                                                   const int* __restrict__ block_entry,
@@ -2141,41 +2168,51 @@ __global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const ReduceEnt
     const int ntaps = R * S;
     if (e.mode == 0 && ntaps > 1) {
         // Tiled path (multi-tap filters): the workspace is [split][co][tap][ci], the reference gradient [co][ci][tap'].
-        // A block sums the splits of (co, 32 consecutive ci, all taps) with coalesced 128-byte reads per tap row,
-        // transposes through shared memory and writes the 32 * ntaps contiguous output floats coalesced (a
-        // per-element mapping writes 4 bytes out of every 4 * ntaps).
-        __shared__ float tile[32][65];
-        const int groups = (Cin + 31) / 32;
-        const long long units = static_cast<long long>(Cout) * groups;
-        const long long first = block_offset[blockIdx.x];
+        // A block owns (co, kReduceGroup = 128 consecutive ci, all taps): warp = tap, lane = 4 consecutive ci read as
+        // ONE 16-byte load per split (512 contiguous bytes per warp instruction, 8 splits in flight: the pass is pure
+        // streaming, the bytes in flight per SM and the contiguous run per request set its speed - 128-byte rows with
+        // 4 loads in flight ran at 1.9 TB/s), summed in split order, transposed through shared memory, and the
+        // 128 * ntaps contiguous output floats are written coalesced.
+        __shared__ float tile[kReduceGroup][65];
+        const int groups = (Cin + kReduceGroup - 1) / kReduceGroup;
+        const long long item = block_offset[blockIdx.x];
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const long long step = static_cast<long long>(Cout) * ntaps * e.ldws;
-        for (long long item = first; item < first + kReduceItems && item < units; ++item) {
-            const int co = static_cast<int>(item / groups);
-            const int ci0 = static_cast<int>(item % groups) * 32;
-            const int ci = ci0 + lane;
-            for (int t = warp; t < ntaps; t += 8) {
-                float acc = 0.f;
-                if (ci < Cin) {
-                    const float* src = e.ws + (static_cast<long long>(co) * ntaps + t) * e.ldws + ci;
-                    int sp = 0;
-                    for (; sp + 4 <= e.splits; sp += 4) {
-                        const float a0 = src[0], a1 = src[step], a2 = src[2 * step], a3 = src[3 * step];
-                        acc += a0; acc += a1; acc += a2; acc += a3;
-                        src += 4 * step;
+        const int co = static_cast<int>(item / groups);
+        const int ci0 = static_cast<int>(item % groups) * kReduceGroup;
+        const int ci = ci0 + lane * 4;
+        for (int t = warp; t < ntaps; t += 8) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ci < Cin) {         // ldws is a multiple of 4 and the pad columns of the workspace rows are never read back
+                const float* src = e.ws + (static_cast<long long>(co) * ntaps + t) * e.ldws + ci;
+                int sp = 0;
+                for (; sp + 8 <= e.splits; sp += 8) {
+                    float4 a[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = __ldcs(reinterpret_cast<const float4*>(src + j * step));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                                      // fixed (split) order
+                        acc.x += a[j].x; acc.y += a[j].y; acc.z += a[j].z; acc.w += a[j].w;
                     }
-                    for (; sp < e.splits; ++sp, src += step) acc += *src;
+                    src += 8 * step;
                 }
-                tile[lane][ntaps - 1 - t] = acc;       // tap (r, s) of the correlation = element (R-1-r, S-1-s)
+                for (; sp < e.splits; ++sp, src += step) {
+                    const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
+                    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+                }
             }
-            __syncthreads();
-            const int nci = Cin - ci0 < 32 ? Cin - ci0 : 32;
-            float* dst = e.dw + (static_cast<long long>(co) * Cin + ci0) * ntaps;
-            for (int i = threadIdx.x; i < nci * ntaps; i += blockDim.x) {
-                const float v = tile[i / ntaps][i % ntaps];
-                dst[i] = e.accumulate ? dst[i] + v : v;
-            }
-            __syncthreads();
+            const int tt = ntaps - 1 - t;           // tap (r, s) of the correlation = element (R-1-r, S-1-s)
+            tile[lane * 4 + 0][tt] = acc.x;
+            tile[lane * 4 + 1][tt] = acc.y;
+            tile[lane * 4 + 2][tt] = acc.z;
+            tile[lane * 4 + 3][tt] = acc.w;
+        }
+        __syncthreads();
+        const int nci = Cin - ci0 < kReduceGroup ? Cin - ci0 : kReduceGroup;
+        float* dst = e.dw + (static_cast<long long>(co) * Cin + ci0) * ntaps;
+        for (int i = threadIdx.x; i < nci * ntaps; i += blockDim.x) {
+            const float v = tile[i / ntaps][i % ntaps];
+            dst[i] = e.accumulate ? dst[i] + v : v;
         }
         return;
     }
@@ -2202,12 +2239,15 @@ __global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const ReduceEnt
         }
         float acc = 0.f;
         int sp = 0;
-        for (; sp + 4 <= e.splits; sp += 4) {
-            const float a0 = src[0], a1 = src[step], a2 = src[2 * step], a3 = src[3 * step];
-            acc += a0; acc += a1; acc += a2; acc += a3;
-            src += 4 * step;
+        for (; sp + 8 <= e.splits; sp += 8) {
+            float a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __ldcs(src + j * step);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += a[j];
+            src += 8 * step;
         }
-        for (; sp < e.splits; ++sp, src += step) acc += *src;
+        for (; sp < e.splits; ++sp, src += step) acc += __ldcs(src);
         e.dw[o] = e.accumulate ? e.dw[o] + acc : acc;
     }
 }
@@ -2567,6 +2607,7 @@ extern "C" int denet_conv_weight_prep_multi(const void* entries, const int* bloc
 extern "C" int denet_wgrad_reduce_entry_bytes(void) { return (int)sizeof(ReduceEntry); }
 extern "C" int denet_wgrad_reduce_chunk(void) { return kReduceChunk; }
 extern "C" int denet_wgrad_reduce_items(void) { return kReduceItems; }
+extern "C" int denet_wgrad_reduce_group(void) { return kReduceGroup; }
 
 extern "C" int denet_wgrad_reduce_multi(const void* entries, const int* block_entry, const long long* block_offset,
                                         int nblocks, cudaStream_t stream) {

@@ -358,6 +358,7 @@ def wgrad_reduce_pending(pending):
         assert L.denet_wgrad_reduce_entry_bytes() == 64
         chunk = L.denet_wgrad_reduce_chunk()
         items = L.denet_wgrad_reduce_items()
+        group = L.denet_wgrad_reduce_group()
         dev = pending[0].ws.device
         table = numpy.zeros((len(pending), 8), dtype=numpy.int64)
         ints = table.view(numpy.int32).reshape(len(pending), 16)
@@ -368,8 +369,8 @@ def wgrad_reduce_pending(pending):
             table[i, 1] = e.dw.data_ptr()
             table[i, 2] = total
             ints[i, 6:16] = [e.splits, e.cout, e.cin, e.R, e.S, e.ldws, e.mode, e.cp, int(e.accumulate), 0]
-            if e.mode == 0 and e.R * e.S > 1:      # tiled path: units of (co, 32-channel group)
-                units, per_block = e.cout * ((e.cin + 31) // 32), items
+            if e.mode == 0 and e.R * e.S > 1:      # tiled path: units of (co, channel group)
+                units, per_block = e.cout * ((e.cin + group - 1) // group), items
             else:
                 units, per_block = total, chunk
             for o in range(0, units, per_block):

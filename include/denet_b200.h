@@ -128,13 +128,15 @@ int denet_conv2d_wgrad(const void* dy_hi, const void* dy_lo, int N, int Ho, int 
  * long long total (= Cout*Cin*R*S); int splits, Cout, Cin, R, S, ldws, mode (0 generic, 1 row-folded), Cp,
  * accumulate, pad}.  Work of block i on entry block_entry[i]: for 1x1 filters and the row-folded stem, the elements
  * [block_offset[i], +denet_wgrad_reduce_chunk()); for multi-tap filters (mode 0, R*S > 1) the items
- * [block_offset[i], +denet_wgrad_reduce_items()) out of Cout * ceil(Cin/32), an item being one output channel times 32
- * consecutive input channels times all taps (transposed through shared memory so that both sides are coalesced). */
+ * [block_offset[i], +denet_wgrad_reduce_items()) out of Cout * ceil(Cin/G), G = denet_wgrad_reduce_group(), an item being
+ * one output channel times G consecutive input channels times all taps (transposed through shared memory so that both
+ * sides are coalesced; the 4-float pad columns of a workspace row may be read, never written out). */
 int denet_conv2d_wgrad_splits(int N, int Ho, int Wo, int Cout, int Cin, int R, int S, int stride_h, int stride_w);
 int denet_conv2d_rowfold_wgrad_splits(int N, int Ho, int Wo, int Cout, int R, int stride_h);
 int denet_wgrad_reduce_entry_bytes(void);
 int denet_wgrad_reduce_chunk(void);
 int denet_wgrad_reduce_items(void);
+int denet_wgrad_reduce_group(void);   /* input channels per work item of the tiled (multi-tap) path */
 int denet_wgrad_reduce_multi(const void* entries, const int* block_entry, const long long* block_offset, int nblocks,
                              cudaStream_t stream);
 
