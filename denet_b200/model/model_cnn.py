@@ -337,9 +337,17 @@ class ModelCNN:
         self._ready = True
         return self
 
-    def enable_data_parallel(self, bucket_bytes=32 << 20, average_bn_stats=True, group=None):
-        """gradient all-reduce across the ranks of torch.distributed (NCCL on GPUs), overlapped with backward"""
+    def enable_data_parallel(self, bucket_bytes=None, average_bn_stats=True, group=None):
+        """gradient all-reduce across the ranks of torch.distributed (NCCL on GPUs).  bucket_bytes > 0: buckets are
+        reduced on a side stream as the backward pass retires their layers; 0: ONE all-reduce of the whole flat
+        gradient after the backward pass (131 MB over NVLink/NVSwitch is ~0.35 ms on 8 GPUs - less than what the
+        overlapped variant loses when the collective's CTAs share the SMs with the persistent conv kernels).
+        Default from DENET_DDP_BUCKET_MB (32)."""
         from ..multi import GradientAllReduce
+        if bucket_bytes is None:
+            bucket_bytes = int(float(os.environ.get("DENET_DDP_BUCKET_MB", "32")) * (1 << 20))
+        if bucket_bytes <= 0:
+            bucket_bytes = 1 << 62
         if not self._ready:
             self.to_device()
         ranges = [(index, r[0], r[1]) for index, r in sorted(self.layer_grad_ranges.items())]
@@ -669,13 +677,23 @@ class ModelCNN:
         self.bn_stat_buffer.zero_()
         self._prep_version = -1                  # the operand preparation is part of the captured graph
         self.prepare_operands()
-        x = self.upload(layer_mod.slot_tensor("model/image" + self._slot_ns))
+        if self._image_outside_graph():
+            x = self._image              # filled by the eager conversion kernel that precedes this graph's replay
+        else:
+            x = self.upload(layer_mod.slot_tensor("model/image" + self._slot_ns))
         self.layers[0].output = x
         end = si if si is not None else len(self.layers)
         x = self.forward_layers(x, 1, end, train=True, with_targets=False)
         if si is not None:
             self.layers[si].enqueue_samples()
         return x
+
+    def _image_outside_graph(self):
+        """image stems keep the batch in a persistent zero-padded NHWC buffer (ops.PaddedImage): its fill kernel runs
+        eagerly right before graph A, so the fp32 staging tensor is free again after ONE kernel instead of after the
+        whole forward trunk - the next step's host->device upload gets (almost) the whole step to complete"""
+        first = self.layers[1] if len(self.layers) > 1 else None
+        return getattr(first, "rowfold", None) is not None and self._image is not None
 
     def _segment_b1(self, x, si):
         """sparse gather -> head -> costs (the end of the forward pass)"""
@@ -740,8 +758,13 @@ class ModelCNN:
         ga, gb1, gb2 = self._graphs
         if img_ready is not None:
             cur.wait_event(img_ready)
-        ga.replay()
-        self._img_consumed.record(cur)               # the staging tensor of the image may be overwritten from here on
+        if self._image_outside_graph():
+            self.upload(layer_mod.slot_tensor("model/image" + self._slot_ns))     # one kernel into the persistent buffer
+            self._img_consumed.record(cur)           # the staging tensor of the image may be overwritten from here on
+            ga.replay()
+        else:
+            ga.replay()
+            self._img_consumed.record(cur)
         self._img_consumed_valid = True
         if si is not None:
             sp = self.layers[si]

@@ -18,10 +18,56 @@ def init_process_group(backend=None):
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
         torch.cuda.set_device(local)
+        if os.environ.get("DENET_NUMA_BIND", "1") != "0":
+            bind_to_gpu_numa_node(local)
         dist.init_process_group(backend, device_id=torch.device("cuda", local))
     else:
         dist.init_process_group(backend)
     return dist.get_rank(), dist.get_world_size()
+
+
+def _pci_bus_id(local_rank):
+    """'0000:1b:00.0'-style PCI address of a CUDA device through the runtime API"""
+    import ctypes
+    for name in ("libcudart.so.12", "libcudart.so"):
+        try:
+            rt = ctypes.CDLL(name)
+            break
+        except OSError:
+            rt = None
+    if rt is None:
+        return None
+    buf = ctypes.create_string_buffer(32)
+    if rt.cudaDeviceGetPCIBusId(buf, 32, int(local_rank)) != 0:
+        return None
+    return buf.value.decode().lower()
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and therefore its pinned-host allocations, first touch) to the CPUs of the NUMA node its GPU
+    is attached to.  Round 1 ran all 8 ranks of a box on NUMA node 0: four GPUs pulled their 100 MB image batches
+    across the socket interconnect, and end-to-end scaling fell to 0.82 at N = 8.  Returns the node or None."""
+    try:
+        bus = _pci_bus_id(local_rank)
+        if bus is None:
+            return None
+        node_path = "/sys/bus/pci/devices/%s/numa_node" % bus
+        if not os.path.exists(node_path):
+            return None
+        node = int(open(node_path).read().strip())
+        if node < 0:
+            return None
+        cpulist = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or cpus          # the launcher may have restricted us to the other node: override
+        os.sched_setaffinity(0, use)
+        return node
+    except (OSError, ValueError):
+        return None
 
 
 def shard_batch(global_count, rank, world):

@@ -36,7 +36,7 @@ def test_host_side_queries_need_no_gpu():
     assert l.denet_solver_chunk() == 4096
     assert l.denet_loss_workspace_bytes() > 0
     assert l.denet_bn_workspace_bytes(1000, 64) > 0
-    assert l.denet_build_samples_workspace(2, 64, 64, 1024) == 2 * 4 * 1024 * 4 + 2 * 4 * 4
+    assert l.denet_build_samples_workspace(2, 64, 64, 1024) == 2 * 5 * 1024 * 4 + 2 * 5 * 4   # sized for 5 corner maps (DNC.C)
 
 
 def test_argument_errors_are_reported_not_thrown():
