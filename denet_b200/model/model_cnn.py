@@ -342,10 +342,11 @@ class ModelCNN:
         reduced on a side stream as the backward pass retires their layers; 0: ONE all-reduce of the whole flat
         gradient after the backward pass (131 MB over NVLink/NVSwitch is ~0.35 ms on 8 GPUs - less than what the
         overlapped variant loses when the collective's CTAs share the SMs with the persistent conv kernels).
-        Default from DENET_DDP_BUCKET_MB (32)."""
+        Default from DENET_DDP_BUCKET_MB, 0 = one all-reduce: measured on 8 B200 (profiles/r2_scaling.md) 22130 vs
+        21932 images/s device-resident and 22016 vs 18785 end to end against 32 MB overlapped buckets."""
         from ..multi import GradientAllReduce
         if bucket_bytes is None:
-            bucket_bytes = int(float(os.environ.get("DENET_DDP_BUCKET_MB", "32")) * (1 << 20))
+            bucket_bytes = int(float(os.environ.get("DENET_DDP_BUCKET_MB", "0")) * (1 << 20))
         if bucket_bytes <= 0:
             bucket_bytes = 1 << 62
         if not self._ready:
