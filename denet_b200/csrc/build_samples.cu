@@ -252,6 +252,43 @@ __device__ __forceinline__ bool pair_key(const PairCtx& c, long long idx, long l
     return true;
 }
 
+// corner lists of image b -> shared memory, position bitmaps (TL, BR; TR, BL for the centre phase); all threads
+__device__ __forceinline__ void setup_pair_ctx(PairCtx& c, const float* corner_pr, int CN, int H, int W, int max_corners,
+                                               const uint32_t* corners, const int* counts, int b, uint32_t* s_c,
+                                               uint32_t* s_bm, int bm_words) {
+    const int HW = H * W;
+    uint32_t* s_bm_tl = s_bm;
+    uint32_t* s_bm_br = s_bm + bm_words;
+    uint32_t* s_bm_tr = s_bm + 2 * bm_words;
+    uint32_t* s_bm_bl = s_bm + 3 * bm_words;
+    c.cp = corner_pr + (long long)b * 2 * CN * HW;
+    c.CN = CN; c.H = H; c.W = W; c.HW = HW;
+    c.n0 = counts[b * CN + 0]; c.n1 = counts[b * CN + 1]; c.n2 = counts[b * CN + 2]; c.n3 = counts[b * CN + 3];
+    c.n4 = CN == 5 ? counts[b * CN + 4] : 0;
+    c.c0 = s_c; c.c1 = s_c + max_corners; c.c2 = s_c + 2 * max_corners; c.c3 = s_c + 3 * max_corners;
+    c.c4 = s_c + 4 * max_corners;
+    c.bm_tl = s_bm_tl; c.bm_br = s_bm_br; c.bm_tr = s_bm_tr; c.bm_bl = s_bm_bl;
+    const uint32_t* gc = corners + (long long)b * CN * max_corners;
+    for (int i = threadIdx.x; i < CN * max_corners; i += kBsThreads) {
+        const int ci = i / max_corners, j = i % max_corners;
+        const int n = counts[b * CN + ci];
+        s_c[i] = j < n ? gc[i] : 0u;
+    }
+    for (int i = threadIdx.x; i < 4 * bm_words; i += kBsThreads) s_bm[i] = 0u;
+    __syncthreads();
+    for (int ci = 0; ci < 4; ++ci) {
+        if (CN != 5 && (ci == 1 || ci == 2)) continue;          // TR / BL bitmaps serve the centre phase only
+        const int n = ci == 0 ? c.n0 : (ci == 1 ? c.n1 : (ci == 2 ? c.n2 : c.n3));
+        uint32_t* bm = ci == 0 ? s_bm_tl : (ci == 1 ? s_bm_tr : (ci == 2 ? s_bm_bl : s_bm_br));
+        for (int i = threadIdx.x; i < n; i += kBsThreads) {
+            const uint32_t v = s_c[ci * max_corners + i];
+            const int p = (int)(v >> 16) * W + (int)(v & 0xffff);
+            atomicOr(&bm[p >> 5], 1u << (p & 31));
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __restrict__ corner_pr, int CN, int H,
                                                                   int W, int max_corners, int K,
                                                                   const uint32_t* __restrict__ corners,
@@ -277,33 +314,8 @@ __global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __
     __shared__ int s_need, s_below, s_done;
 
     PairCtx c;
-    c.cp = corner_pr + (long long)b * 2 * CN * HW;
-    c.CN = CN; c.H = H; c.W = W; c.HW = HW;
-    c.n0 = counts[b * CN + 0]; c.n1 = counts[b * CN + 1]; c.n2 = counts[b * CN + 2]; c.n3 = counts[b * CN + 3];
-    c.n4 = CN == 5 ? counts[b * CN + 4] : 0;
-    c.c0 = s_c; c.c1 = s_c + max_corners; c.c2 = s_c + 2 * max_corners; c.c3 = s_c + 3 * max_corners;
-    c.c4 = s_c + 4 * max_corners;
-    c.bm_tl = s_bm_tl; c.bm_br = s_bm_br; c.bm_tr = s_bm_tr; c.bm_bl = s_bm_bl;
-
-    const uint32_t* gc = corners + (long long)b * CN * max_corners;
-    for (int i = threadIdx.x; i < CN * max_corners; i += kBsThreads) {
-        const int ci = i / max_corners, j = i % max_corners;
-        const int n = counts[b * CN + ci];
-        s_c[i] = j < n ? gc[i] : 0u;
-    }
-    for (int i = threadIdx.x; i < 4 * bm_words; i += kBsThreads) s_bm_tl[i] = 0u;
+    setup_pair_ctx(c, corner_pr, CN, H, W, max_corners, corners, counts, b, s_c, s_bm_tl, bm_words);
     if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    for (int ci = 0; ci < 4; ++ci) {
-        if (CN != 5 && (ci == 1 || ci == 2)) continue;          // TR / BL bitmaps serve the centre phase only
-        const int n = ci == 0 ? c.n0 : (ci == 1 ? c.n1 : (ci == 2 ? c.n2 : c.n3));
-        uint32_t* bm = ci == 0 ? s_bm_tl : (ci == 1 ? s_bm_tr : (ci == 2 ? s_bm_bl : s_bm_br));
-        for (int i = threadIdx.x; i < n; i += kBsThreads) {
-            const uint32_t v = s_c[ci * max_corners + i];
-            const int p = (int)(v >> 16) * W + (int)(v & 0xffff);
-            atomicOr(&bm[p >> 5], 1u << (p & 31));
-        }
-    }
     __syncthreads();
 
     const long long nA = (long long)c.n0 * c.n3;
@@ -434,6 +446,397 @@ __global__ void __launch_bounds__(kBsThreads) pair_select_kernel(const float* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------ corner clustering
+// apply_cluster (denet_sparse.cc:165-242), run by the reference on images whose corner search found more than
+// sample_num^2 boxes when the sparse layer's nmsThreshold is < 1.  The reference processes the samples one by one on
+// the CPU: a sample joins the last cluster of a list that it overlaps (IoU > threshold with any member), the other
+// overlapping clusters are merged into that one.  What that sequential procedure computes is order-free except for the
+// list order, and both have closed forms that parallelise:
+//   * the clusters are the CONNECTED COMPONENTS of the graph "IoU(i, j) > threshold" over the input samples;
+//   * a merged cluster keeps the list position of the youngest cluster it absorbed, so the final list is ordered by
+//     the largest "creator" of each component - a creator being a sample with no edge to an earlier sample.
+// Three kernels: collect (CTA per image: the input set - all candidates in enumeration order, or the 10 K best by score
+// when there are more - with their scores / float boxes, in global memory), edges (grid over sample rows: IoU tests,
+// lock-free union-find with atomicCAS hooking, creator flags), finish (CTA per image: component sizes and list
+// positions, the clusters that survive the cap, 1 + floor(size * ratio) best samples of each, final ranking).
+// Sorts are bitonic over global memory (n <= 32768 per image).  Equal scores: see pair_select_kernel.
+struct ClusterWs {                   // per-image scratch, all arrays of capacity `cap` (power of two >= 10 * K)
+    unsigned long long* key;         // (d bits << 32 | box): ascending = descending score
+    unsigned long long* aux;         // sort scratch
+    float4* box;                     // normalised float box of the sample at processing position p
+    float* pr;                       // score
+    int* parent;                     // union-find
+    int* prank;                      // rank of position p in score order
+    int* flags;                      // bit0 creator
+    int* tmp;                        // sizes / list keys / selections
+    int* n;                          // [1] number of input samples (0: image not clustered)
+};
+
+__device__ __forceinline__ ClusterWs cluster_ws(void* base, int b, int cap) {
+    // layout per image: key, aux (u64) | box (float4) | pr, parent, prank, flags (4 B) | tmp (4 x cap ints) | n
+    const size_t per = (size_t)cap * (8 + 8 + 16 + 4 * 4 + 16) + 16;
+    uint8_t* p = reinterpret_cast<uint8_t*>(base) + per * (size_t)b;
+    ClusterWs w;
+    w.key = reinterpret_cast<unsigned long long*>(p); p += (size_t)cap * 8;
+    w.aux = reinterpret_cast<unsigned long long*>(p); p += (size_t)cap * 8;
+    w.box = reinterpret_cast<float4*>(p); p += (size_t)cap * 16;
+    w.pr = reinterpret_cast<float*>(p); p += (size_t)cap * 4;
+    w.parent = reinterpret_cast<int*>(p); p += (size_t)cap * 4;
+    w.prank = reinterpret_cast<int*>(p); p += (size_t)cap * 4;
+    w.flags = reinterpret_cast<int*>(p); p += (size_t)cap * 4;
+    w.tmp = reinterpret_cast<int*>(p); p += (size_t)cap * 16;
+    w.n = reinterpret_cast<int*>(p);
+    return w;
+}
+static size_t cluster_ws_bytes(int B, int cap) { return ((size_t)cap * (8 + 8 + 16 + 4 * 4 + 16) + 16) * (size_t)B; }
+
+// ascending bitonic sort of a[0..npow) (npow a power of two, padded by the caller), whole CTA
+__device__ __forceinline__ void bitonic_sort_global(unsigned long long* a, int npow) {
+    for (int k = 2; k <= npow; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow; i += kBsThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = a[i], y = a[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        a[i] = y;
+                        a[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ void key_to_sample(unsigned long long key, int H, int W, float* pr, float4* box) {
+    const float d = __uint_as_float((uint32_t)(key >> 32));
+    const uint32_t bx = (uint32_t)key;
+    const int x0 = bx >> 24, y0 = (bx >> 16) & 255, x1 = (bx >> 8) & 255, y1 = bx & 255;
+    *pr = (float)(1.0 / (1.0 + (double)expf_glibc(d)));
+    *box = make_float4((float)((double)x0 / (double)W), (float)((double)y0 / (double)H),
+                       (float)((double)(x1 + 1) / (double)W), (float)((double)(y1 + 1) / (double)H));
+}
+
+__global__ void __launch_bounds__(kBsThreads) cluster_collect_kernel(const float* __restrict__ corner_pr, int CN, int H,
+                                                                      int W, int max_corners, int K, int cap,
+                                                                      const uint32_t* __restrict__ corners,
+                                                                      const int* __restrict__ counts, void* ws_base) {
+    extern __shared__ __align__(16) uint8_t bs_smem[];
+    const int b = blockIdx.x;
+    const int bm_words = (H * W + 31) / 32;
+    uint32_t* s_c = reinterpret_cast<uint32_t*>(bs_smem);
+    uint32_t* s_bm = s_c + CN * max_corners;
+    int* s_hist = reinterpret_cast<int*>(s_bm + 4 * bm_words);
+    __shared__ int warp_sums[33];
+    __shared__ int s_cnt;
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need;
+    ClusterWs w = cluster_ws(ws_base, b, cap);
+    PairCtx c;
+    setup_pair_ctx(c, corner_pr, CN, H, W, max_corners, corners, counts, b, s_c, s_bm, bm_words);
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const long long nA = (long long)c.n0 * c.n3;
+    const long long nB = nA + (long long)c.n1 * c.n2;
+    const long long nP = nB + (long long)c.n4 * ((long long)c.n0 + c.n1 + c.n2 + c.n3);
+    {
+        int mine = 0;
+        for (long long idx = threadIdx.x; idx < nP; idx += kBsThreads) {
+            uint64_t key;
+            mine += pair_key(c, idx, nA, nB, &key) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+        __syncthreads();
+    }
+    const int total = s_cnt;
+    __syncthreads();
+    const int input_num = 10 * K;                       // cluster_snum (:497)
+    if (total <= K) {                                   // (:540) not over-full: pair_select_kernel's result stands
+        if (threadIdx.x == 0) *w.n = 0;
+        return;
+    }
+    const int n = total < input_num ? total : input_num;
+    if (total <= input_num) {
+        // all candidates, in the reference's enumeration order (= idx order): ordered compaction
+        int base = 0;
+        for (long long i0 = 0; i0 < nP; i0 += kBsThreads) {
+            const long long idx = i0 + threadIdx.x;
+            uint64_t key = 0;
+            const bool ok = idx < nP && pair_key(c, idx, nA, nB, &key);
+            int cnt;
+            const int rank = block_excl_scan(ok ? 1 : 0, warp_sums, &cnt);
+            if (ok) w.key[base + rank] = key;
+            base += cnt;
+        }
+    } else {
+        // the input_num best by score: MSB radix select of the input_num-th smallest (unique) key, then collect + sort
+        if (threadIdx.x == 0) {
+            s_prefix = 0;
+            s_need = input_num;
+        }
+        __syncthreads();
+        int shift = 64;
+        while (shift > 0) {
+            const int bits = shift >= kRadixBits ? kRadixBits : shift;
+            const int nshift = shift - bits;
+            for (int i = threadIdx.x; i < kRadixBins; i += kBsThreads) s_hist[i] = 0;
+            __syncthreads();
+            const unsigned long long pfx = s_prefix;
+            for (long long idx = threadIdx.x; idx < nP; idx += kBsThreads) {
+                uint64_t key;
+                if (pair_key(c, idx, nA, nB, &key)) {
+                    if (shift == 64 || (key >> shift) == pfx) atomicAdd(&s_hist[(key >> nshift) & ((1u << bits) - 1)], 1);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int need = s_need, bin = 0;
+                const int nb = 1 << bits;
+                for (; bin < nb - 1; ++bin) {
+                    if (s_hist[bin] >= need) break;
+                    need -= s_hist[bin];
+                }
+                s_prefix = (pfx << bits) | (unsigned long long)bin;
+                s_need = need;
+            }
+            __syncthreads();
+            shift = nshift;
+        }
+        const unsigned long long kth = s_prefix;        // keys are unique: exactly input_num keys are <= kth
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        for (long long idx = threadIdx.x; idx < nP; idx += kBsThreads) {
+            uint64_t key;
+            if (pair_key(c, idx, nA, nB, &key) && key <= kth) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot < cap) w.key[slot] = key;
+            }
+        }
+        __syncthreads();
+        int npow = 1;
+        while (npow < n) npow <<= 1;
+        for (int i = n + threadIdx.x; i < npow; i += kBsThreads) w.key[i] = ~0ull;
+        __syncthreads();
+        bitonic_sort_global(w.key, npow);               // ascending key = descending score (:170-173)
+    }
+    __syncthreads();
+    // scores, float boxes, union-find initial state; score rank of every processing position
+    for (int i = threadIdx.x; i < n; i += kBsThreads) {
+        key_to_sample(w.key[i], H, W, &w.pr[i], &w.box[i]);
+        w.parent[i] = i;
+        w.flags[i] = 1;                                 // creator until an edge to an earlier sample is found
+    }
+    if (total <= input_num) {
+        int npow = 1;
+        while (npow < n) npow <<= 1;
+        // (key with its low 32 box bits replaced by the position would lose uniqueness of equal d: sort (d, position))
+        for (int i = threadIdx.x; i < npow; i += kBsThreads)
+            w.aux[i] = i < n ? ((w.key[i] & 0xffffffff00000000ull) | (unsigned)i) : ~0ull;
+        __syncthreads();
+        bitonic_sort_global(w.aux, npow);
+        for (int r = threadIdx.x; r < n; r += kBsThreads) w.prank[(int)(w.aux[r] & 0xffffffffu)] = r;
+    } else {
+        for (int i = threadIdx.x; i < n; i += kBsThreads) w.prank[i] = i;
+    }
+    if (threadIdx.x == 0) *w.n = n;
+}
+
+__device__ __forceinline__ float sample_iou(const float4 a, const float4 b) {
+    // SampleType::overlap / overlap_iou (:90-101), fp32 operation for operation
+    const float dx = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    const float dy = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    const float ai = __fmul_rn(dx, dy);
+    const float aa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float ab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    return __fdiv_rn(ai, __fsub_rn(__fadd_rn(aa, ab), ai));
+}
+
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+    // loads bypass L1 (__ldcg): other SMs hook roots concurrently and L1 is not coherent - a stale root would make
+    // the hooking CAS below fail forever
+    while (true) {
+        const int p = __ldcg(parent + x);
+        if (p == x) return x;
+        const int g = __ldcg(parent + p);
+        if (g != p) atomicCAS(&parent[x], p, g);        // path halving (benign race: g is always an ancestor of x)
+        x = p;
+    }
+}
+
+// grid (row blocks, B): thread = sample i of the block's row range, tests every earlier sample j
+constexpr int kEdgeThreads = 256;
+__global__ void __launch_bounds__(kEdgeThreads) cluster_edges_kernel(void* ws_base, int cap, float threshold) {
+    const int b = blockIdx.y;
+    ClusterWs w = cluster_ws(ws_base, b, cap);
+    const int n = *w.n;
+    __shared__ float4 s_box[kEdgeThreads];
+    const int i = blockIdx.x * kEdgeThreads + threadIdx.x;
+    if (blockIdx.x * kEdgeThreads >= n) return;
+    const float4 bi = i < n ? w.box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    bool creator = true;
+    const int jmax = min(n, (blockIdx.x + 1) * kEdgeThreads);
+    for (int j0 = 0; j0 < jmax; j0 += kEdgeThreads) {
+        __syncthreads();
+        if (j0 + threadIdx.x < n) s_box[threadIdx.x] = w.box[j0 + threadIdx.x];
+        __syncthreads();
+        const int jend = min(kEdgeThreads, min(i, n) - j0);           // j < i only
+        for (int jj = 0; jj < jend; ++jj) {
+            if (sample_iou(bi, s_box[jj]) > threshold) {
+                creator = false;
+                // union(i, j0 + jj): hook the larger root under the smaller
+                int a = i, c2 = j0 + jj;
+                while (true) {
+                    a = uf_find(w.parent, a);
+                    c2 = uf_find(w.parent, c2);
+                    if (a == c2) break;
+                    const int hi = a > c2 ? a : c2, lo = a > c2 ? c2 : a;
+                    if (atomicCAS(&w.parent[hi], hi, lo) == hi) break;
+                }
+            }
+        }
+    }
+    if (i < n && !creator) w.flags[i] = 0;
+}
+
+__global__ void __launch_bounds__(kBsThreads) cluster_finish_kernel(void* ws_base, int cap, int K, int H, int W,
+                                                                     float* __restrict__ out_pr,
+                                                                     float* __restrict__ out_bbox,
+                                                                     int* __restrict__ out_ibox,
+                                                                     int* __restrict__ out_count) {
+    const int b = blockIdx.x;
+    ClusterWs w = cluster_ws(ws_base, b, cap);
+    const int n = *w.n;
+    if (n == 0) return;                                  // image not clustered: pair_select_kernel's output stands
+    __shared__ int warp_sums[33];
+    __shared__ int s_nsel;
+    int* size = w.tmp;                                   // [cap] members of the component rooted at r
+    int* lkey = w.tmp + cap;                             // [cap] list position key of the component rooted at r
+    int* keep = w.tmp + 2 * cap;                         // [cap] 1 if the component rooted at r survives the cap
+    int* take = w.tmp + 3 * cap;                         // [cap] samples the component rooted at r contributes
+    for (int i = threadIdx.x; i < n; i += kBsThreads) {
+        size[i] = 0;
+        lkey[i] = -1;
+        keep[i] = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kBsThreads) {  // flatten (the edges kernel has completed: no more hooks)
+        int r = i;
+        while (w.parent[r] != r) r = w.parent[r];
+        w.parent[i] = r;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kBsThreads) {
+        const int r = w.parent[i];
+        atomicAdd(&size[r], 1);
+        if (w.flags[i] & 1) atomicMax(&lkey[r], i);      // youngest creator = list position of the merged cluster
+    }
+    __syncthreads();
+    // clusters (roots) in list order; ncl of them
+    int ncl;
+    {
+        int base = 0;
+        for (int i0 = 0; i0 < n; i0 += kBsThreads) {
+            const int i = i0 + threadIdx.x;
+            int cnt;
+            block_excl_scan((i < n && w.parent[i] == i) ? 1 : 0, warp_sums, &cnt);
+            base += cnt;
+        }
+        ncl = base;
+    }
+    if (ncl > K) {
+        // :211-221 keep the K clusters with the most samples; std::list::sort is stable: ties keep list order.
+        // sort key: (n - size) << 32 | list key  (ascending)
+        int npow = 1;
+        while (npow < n) npow <<= 1;
+        for (int i = threadIdx.x; i < npow; i += kBsThreads)
+            w.aux[i] = (i < n && w.parent[i] == i)
+                           ? (((unsigned long long)(unsigned)(n - size[i]) << 32) | (unsigned)lkey[i]) : ~0ull;
+        __syncthreads();
+        bitonic_sort_global(w.aux, npow);
+        // the cluster with list key v is the one whose youngest creator is sample v: its root is parent[v]
+        for (int r = threadIdx.x; r < K; r += kBsThreads) keep[w.parent[(int)(w.aux[r] & 0xffffffffu)]] = 1;
+        ncl = K;
+    } else {
+        for (int i = threadIdx.x; i < n; i += kBsThreads)
+            if (w.parent[i] == i) keep[i] = 1;
+    }
+    __syncthreads();
+    // :225 cluster_ratio; every kept cluster contributes its 1 + floor(size * ratio) best samples (:230)
+    const double ratio = (double)(K - ncl) / (double)(n - ncl);
+    for (int i = threadIdx.x; i < n; i += kBsThreads) {
+        if (w.parent[i] == i && keep[i]) {
+            long long t = 1 + (long long)floor((double)size[i] * ratio);
+            take[i] = (int)(t < size[i] ? t : size[i]);
+        } else if (w.parent[i] == i) {
+            take[i] = 0;
+        }
+    }
+    __syncthreads();
+    // rank of every sample inside its cluster by score: sort (root, score rank), position inside the root's segment
+    int npow = 1;
+    while (npow < n) npow <<= 1;
+    for (int i = threadIdx.x; i < npow; i += kBsThreads)
+        w.aux[i] = i < n ? (((unsigned long long)(unsigned)w.parent[i] << 32) | (unsigned)w.prank[i]) : ~0ull;
+    __syncthreads();
+    bitonic_sort_global(w.aux, npow);
+    // segment starts: first sorted position of each root -> lkey (reused)
+    for (int r = threadIdx.x; r < n; r += kBsThreads) {
+        const int root = (int)(w.aux[r] >> 32);
+        if (r == 0 || (int)(w.aux[r - 1] >> 32) != root) lkey[root] = r;
+    }
+    __syncthreads();
+    // selected samples, keyed for the final ranking by their score key
+    if (threadIdx.x == 0) s_nsel = 0;
+    __syncthreads();
+    // prank -> processing position map in flags (score rank r belongs to position flags[r] >> 1)
+    for (int i = threadIdx.x; i < n; i += kBsThreads) atomicOr(&w.flags[w.prank[i]], i << 1);
+    __syncthreads();
+    // (size[] of a root is read before any slot of it is overwritten?  no: slots and roots share the array, so the
+    // selected positions go to the sort scratch of the SECOND half of aux, which the n <= cap/2 ... cap layout leaves
+    // free only when npow < cap; use prank[] instead - it is not needed any more once flags[] holds the inverse map)
+    __syncthreads();
+    int* selpos = w.prank;
+    for (int r = threadIdx.x; r < n; r += kBsThreads) {
+        const int root = (int)(w.aux[r] >> 32);
+        const int within = r - lkey[root];
+        if (keep[root] && within < take[root]) {
+            const int pos = w.flags[(int)(w.aux[r] & 0xffffffffu)] >> 1;     // processing position of that score rank
+            selpos[atomicAdd(&s_nsel, 1)] = pos;
+        }
+    }
+    __syncthreads();
+    const int nsel = s_nsel;                              // <= K by construction
+    int spow = 1;
+    while (spow < nsel) spow <<= 1;
+    for (int i = threadIdx.x; i < spow; i += kBsThreads) w.aux[i] = i < nsel ? w.key[selpos[i]] : ~0ull;
+    __syncthreads();
+    bitonic_sort_global(w.aux, spow);                    // :547 final ranking, descending score
+    const int nout = nsel < K ? nsel : K;
+    for (int i = threadIdx.x; i < K; i += kBsThreads) {
+        const long long o = (long long)b * K + i;
+        if (i < nout) {
+            const unsigned long long key = w.aux[i];
+            float pr;
+            float4 bx;
+            key_to_sample(key, H, W, &pr, &bx);
+            const uint32_t q = (uint32_t)key;
+            out_pr[o] = pr;
+            out_bbox[o * 4 + 0] = bx.x; out_bbox[o * 4 + 1] = bx.y; out_bbox[o * 4 + 2] = bx.z; out_bbox[o * 4 + 3] = bx.w;
+            out_ibox[o * 4 + 0] = q >> 24; out_ibox[o * 4 + 1] = (q >> 16) & 255;
+            out_ibox[o * 4 + 2] = (q >> 8) & 255; out_ibox[o * 4 + 3] = q & 255;
+        } else {
+            out_pr[o] = 0.f;
+            out_bbox[o * 4 + 0] = out_bbox[o * 4 + 1] = out_bbox[o * 4 + 2] = out_bbox[o * 4 + 3] = 0.f;
+            out_ibox[o * 4 + 0] = out_ibox[o * 4 + 1] = out_ibox[o * 4 + 2] = out_ibox[o * 4 + 3] = 0;
+        }
+    }
+    if (threadIdx.x == 0) out_count[b] = nout;
+}
+
 static size_t pair_smem_bytes(int CN, int H, int W, int max_corners) {
     const size_t bm_words = ((size_t)H * W + 31) / 32;
     return sizeof(uint64_t) * kSortCap + sizeof(uint32_t) * CN * max_corners + sizeof(uint32_t) * 4 * bm_words +
@@ -455,6 +858,48 @@ extern "C" int denet_build_samples(const float* corner_pr, int B, int H, int W, 
                                    cudaStream_t stream) {
     return denet_build_samples_cn(corner_pr, B, 4, H, W, corner_threshold, sample_num, max_corners, local_max, out_pr,
                                   out_bbox, out_ibox, out_count, out_ncand, workspace, workspace_bytes, stream);
+}
+
+static int cluster_cap(int sample_num) {
+    int cap = 1;
+    while (cap < 10 * sample_num * sample_num) cap <<= 1;
+    return cap;
+}
+
+extern "C" size_t denet_build_samples_cluster_workspace(int B, int H, int W, int max_corners, int sample_num) {
+    const size_t base = (denet_build_samples_workspace(B, H, W, max_corners) + 255) / 256 * 256;
+    return base + cluster_ws_bytes(B, cluster_cap(sample_num));
+}
+
+extern "C" int denet_build_samples_cluster(const float* corner_pr, int B, int corner_num, int H, int W,
+                                           float corner_threshold, int sample_num, int max_corners, int local_max,
+                                           float cluster_threshold, float* out_pr, float* out_bbox, int* out_ibox,
+                                           int* out_count, int* out_ncand, void* workspace, size_t workspace_bytes,
+                                           cudaStream_t stream) {
+    const bool cluster = cluster_threshold < 1.0f;
+    DN_REQUIRE(!cluster || workspace_bytes >= denet_build_samples_cluster_workspace(B, H, W, max_corners, sample_num),
+               "build_samples: workspace too small for clustering");
+    int rc = denet_build_samples_cn(corner_pr, B, corner_num, H, W, corner_threshold, sample_num, max_corners, local_max,
+                                    out_pr, out_bbox, out_ibox, out_count, out_ncand, workspace, workspace_bytes, stream);
+    if (rc || !cluster) return rc;
+    // images with more than sample_num^2 boxes are re-done through apply_cluster (denet_sparse.cc:540-541)
+    const int CN = corner_num, K = sample_num * sample_num, cap = cluster_cap(sample_num);
+    DN_REQUIRE(cap <= 65536, "build_samples: clustering supports sample_num <= 80");
+    uint32_t* corners = reinterpret_cast<uint32_t*>(workspace);
+    int* counts = reinterpret_cast<int*>(corners + (size_t)B * CN * max_corners);
+    void* cws = reinterpret_cast<uint8_t*>(workspace) + (denet_build_samples_workspace(B, H, W, max_corners) + 255) / 256 * 256;
+    const size_t bm_words = ((size_t)H * W + 31) / 32;
+    const size_t smem = sizeof(uint32_t) * CN * max_corners + sizeof(uint32_t) * 4 * bm_words + sizeof(int) * kRadixBins;
+    DN_CHECK_CUDA(cudaFuncSetAttribute(cluster_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cluster_collect_kernel<<<DN_G(B), kBsThreads, smem, stream>>>(corner_pr, CN, H, W, max_corners, K, cap, corners, counts,
+                                                                  cws);
+    DN_CHECK_LAUNCH();
+    cluster_edges_kernel<<<DN_G(dim3(ceil_div(10 * K, kEdgeThreads), B)), kEdgeThreads, 0, stream>>>(cws, cap,
+                                                                                                   cluster_threshold);
+    DN_CHECK_LAUNCH();
+    cluster_finish_kernel<<<DN_G(B), kBsThreads, 0, stream>>>(cws, cap, K, H, W, out_pr, out_bbox, out_ibox, out_count);
+    DN_CHECK_LAUNCH();
+    return 0;
 }
 
 extern "C" int denet_build_samples_cn(const float* corner_pr, int B, int corner_num, int H, int W,

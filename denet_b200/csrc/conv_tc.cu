@@ -482,6 +482,14 @@ template <int BN, bool PAIR>
 __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uint8_t* stage, float* stat_red,
                                                    uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                                    int warp, int lane) {
+    // Fused batch-norm backward (p.bnb_x, denet_conv2d_dgrad_bnbwd): this launch is the dgrad whose output dz is the
+    // gradient wrt the OUTPUT of a batch-norm(+ReLU) layer with input x.  The tile is masked with that layer's ReLU
+    // mask before it is staged (the mask inputs - x, or the layer's forward output when a residual was added - are
+    // prefetched per lane like the residual), and the two sums of the batch-norm backward's reduction pass are taken
+    // from the staged tile: sum(dz') and sum(dz' * xhat), x read column-wise (coalesced 128-byte rows, L2 hits: the
+    // lanes have just loaded the same lines).  The separate reduction pass over dz and x (2 x tensor bytes) is gone.
+    const bool bnb = p.bnb_x != nullptr;
+    float* bnb_tab = stat_red + 2 * 512;              // [mean | invstd | gamma*invstd | beta] x bnb_cpad, after stat_red (4 KB)
     const int ew = warp - 2;               // 0..7
     const int q = warp & 3;
     const int half = ew >> 2;
@@ -520,9 +528,22 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
         ptx::named_bar_sync(3, 256);
         s0 = s1 = q0 = q1 = 0.f;
     };
+    if (bnb) {
+        const int cp = p.bnb_cpad;
+        for (int c = et; c < cp; c += 256) {
+            const bool ok = c < p.Cout;
+            const float mu = ok ? p.bnb_mean[c] : 0.f, is = ok ? p.bnb_invstd[c] : 0.f;
+            bnb_tab[c] = mu;
+            bnb_tab[cp + c] = is;
+            bnb_tab[2 * cp + c] = ok ? p.bnb_gamma[c] * is : 0.f;
+            bnb_tab[3 * cp + c] = (ok && p.bnb_beta) ? p.bnb_beta[c] : 0.f;
+        }
+        ptx::named_bar_sync(3, 256);
+    }
     const uint32_t pair_rank = PAIR ? ptx::cluster_ctarank() : 0u;
     const int tile0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x, tile_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
     int it = 0;
+    float mu0 = 0.f, mu1 = 0.f, is0 = 0.f, is1 = 0.f;       // statistics threads, fused batch-norm backward: constants
     for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -533,6 +554,11 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
         if (ct != acc_ct) {
             flush_stats();
             acc_ct = ct;
+            if (bnb) {
+                const int c = ct * BN + 2 * cpair, cp = p.bnb_cpad;
+                mu0 = c < cp ? bnb_tab[c] : 0.f;          is0 = c < cp ? bnb_tab[cp + c] : 0.f;
+                mu1 = c + 1 < cp ? bnb_tab[c + 1] : 0.f;  is1 = c + 1 < cp ? bnb_tab[cp + c + 1] : 0.f;
+            }
         }
         p.fd_w.divmod(mt, mt, tw);
         p.fd_h.divmod(mt, tn, th);
@@ -553,6 +579,16 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
         if (res_fast && co0 + half * 32 + 32 <= p.Cout) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) rraw[j] = __ldg(reinterpret_cast<const uint4*>(res_row + half * 32) + j);
+        }
+        // fused batch-norm backward: mask input of the first chunk (x, or the layer's forward output)
+        const bool mask_on = bnb && p.bnb_relu;
+        const __nv_bfloat16* msk_row = reinterpret_cast<const __nv_bfloat16*>(p.bnb_yout ? p.bnb_yout : p.bnb_x) +
+                                       pix * p.ldy + co0;
+        const bool msk_fast = mask_on && row_ok && (p.Cout % 8 == 0);
+        uint4 mraw[4];
+        if (msk_fast && co0 + half * 32 + 32 <= p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mraw[j] = __ldg(reinterpret_cast<const uint4*>(msk_row + half * 32) + j);
         }
         ptx::mbar_wait(&tfull_bar[as], aphase);
         ptx::tc_fence_after();
@@ -616,6 +652,46 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
+                if (mask_on) {
+                    float mv[32];
+                    if (msk_fast && nvalid == 32) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t wv[4] = {mraw[j].x, mraw[j].y, mraw[j].z, mraw[j].w};
+#pragma unroll
+                            for (int k2 = 0; k2 < 4; ++k2) {
+                                mv[8 * j + 2 * k2] = __uint_as_float(wv[k2] << 16);
+                                mv[8 * j + 2 * k2 + 1] = __uint_as_float(wv[k2] & 0xffff0000u);
+                            }
+                        }
+                        if (c0 + 64 < BN && co + 64 + 32 <= p.Cout) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                mraw[j] = __ldg(reinterpret_cast<const uint4*>(msk_row + c0 + 64) + j);
+                        }
+                    } else {
+                        load_row_chunk(p.bnb_yout ? p.bnb_yout : p.bnb_x, 0, pix * p.ldy + co, mv, nvalid);
+                    }
+                    if (p.bnb_yout) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (!(mv[i] > 0.f)) v[i] = 0.f;
+                    } else {
+                        // the forward pass's exact expression (bn_apply_kernel): (x - mean) * (gamma*invstd) + beta > 0
+                        const int cp = p.bnb_cpad;
+                        const float4* t_mu = reinterpret_cast<const float4*>(bnb_tab + co);
+                        const float4* t_a = reinterpret_cast<const float4*>(bnb_tab + 2 * cp + co);
+                        const float4* t_b = reinterpret_cast<const float4*>(bnb_tab + 3 * cp + co);
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            const float4 mu = t_mu[g4], a = t_a[g4], b = t_b[g4];
+                            if (!((mv[4 * g4 + 0] - mu.x) * a.x + b.x > 0.f)) v[4 * g4 + 0] = 0.f;
+                            if (!((mv[4 * g4 + 1] - mu.y) * a.y + b.y > 0.f)) v[4 * g4 + 1] = 0.f;
+                            if (!((mv[4 * g4 + 2] - mu.z) * a.z + b.z > 0.f)) v[4 * g4 + 2] = 0.f;
+                            if (!((mv[4 * g4 + 3] - mu.w) * a.w + b.w > 0.f)) v[4 * g4 + 3] = 0.f;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     if (i >= nvalid) v[i] = 0.f;
@@ -654,7 +730,7 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
                 if (co0 + sb * 64 < p.Cout) ptx::tma_store_4d(&p.tmY, stage + sb * 16384, co0 + sb * 64, w0, h0, n0);
             ptx::bulk_commit_group();
         }
-        if (want_stats) {
+        if (want_stats && !bnb) {
 #pragma unroll 4
             for (int rr = 0; rr < kRowsPerGroup; ++rr) {
                 const uint32_t r2 = static_cast<uint32_t>(grp * kRowsPerGroup + rr);
@@ -662,6 +738,35 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
                 const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
                 s0 += f0; q0 = fmaf(f0, f0, q0);
                 s1 += f1; q1 = fmaf(f1, f1, q1);
+            }
+        } else if (want_stats) {
+            // sum(dz') and sum(dz' * xhat): dz' from the staged tile, x column-wise from global memory (8 rows in flight)
+            const int cx = co0 + 2 * cpair;
+            const bool col_ok = cx + 1 < p.Cout + 1 && cx < p.Cout;
+            const __nv_bfloat16* xcol = reinterpret_cast<const __nv_bfloat16*>(p.bnb_x) + cx;
+#pragma unroll 1
+            for (int r0 = 0; r0 < kRowsPerGroup; r0 += 8) {
+                uint32_t xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t r2 = static_cast<uint32_t>(grp * kRowsPerGroup + r0 + u);
+                    uint32_t q2, w2, n2, h2;
+                    p.fd_tw.divmod(r2, q2, w2);
+                    p.fd_th.divmod(q2, n2, h2);
+                    const int ww = w0 + static_cast<int>(w2), hh = h0 + static_cast<int>(h2), nn = n0 + static_cast<int>(n2);
+                    const bool ok = col_ok && ww < p.Wo && hh < p.Ho && nn < p.No;
+                    const long long px = (static_cast<long long>(nn) * p.Ho + hh) * p.Wo + ww;
+                    xv[u] = ok ? __ldg(reinterpret_cast<const uint32_t*>(xcol + px * p.ldy)) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t r2 = static_cast<uint32_t>(grp * kRowsPerGroup + r0 + u);
+                    const uint32_t wv = ptx::ld_shared_u32(stat_base + r2 * 128u + ((stat_chunk ^ (r2 & 7u)) << 4));
+                    const float d0 = __uint_as_float(wv << 16), d1 = __uint_as_float(wv & 0xffff0000u);
+                    const float x0 = __uint_as_float(xv[u] << 16), x1 = __uint_as_float(xv[u] & 0xffff0000u);
+                    s0 += d0; q0 = fmaf(d0, (x0 - mu0) * is0, q0);
+                    s1 += d1; q1 = fmaf(d1, (x1 - mu1) * is1, q1);
+                }
             }
         }
     }
@@ -2391,7 +2496,7 @@ static uint32_t staged_epilogue_bytes(ConvFpropParams& p, int BN, int* rc) {
     p.epi_tma = 0;
     // (the statistics are those of the conv output BEFORE a fused residual / ReLU: the staged tile holds the final
     // values, so that combination - which no layer of the model uses - keeps the register epilogue)
-    const bool ok = (g_fprop_mode & 8) && !p.y_fp32 && !p.bnb_x && p.osh == 1 && p.osw == 1 && p.ooh == 0 && p.oow == 0 &&
+    const bool ok = (g_fprop_mode & 8) && !p.y_fp32 && (!p.bnb_x || p.Cout % 2 == 0) && p.osh == 1 && p.osw == 1 && p.ooh == 0 && p.oow == 0 &&
                     p.Hf == p.Ho && p.Wf == p.Wo && p.TW <= 256 && p.TH <= 256 && p.TN <= 256 &&
                     !(p.stat_sum && (p.residual || p.relu));
     if (!ok) return 0;
@@ -2406,7 +2511,9 @@ static uint32_t staged_epilogue_bytes(ConvFpropParams& p, int BN, int* rc) {
 static size_t place_stage(ConvFpropParams& p, int BN, uint32_t stage_bytes) {
     const size_t front = (size_t)p.a_region_bytes + p.b_region_bytes + 512 + 8 * (size_t)BN * 8;
     if (!p.epi_tma) return 1024 + front + (p.bnb_x ? 16 * p.bnb_cpad : 0);
-    p.stage_off = (uint32_t)((front + 1023) / 1024 * 1024);
+    // staged epilogue: [.. | 512 barriers | stat_red 4 KB + batch-norm constant table 16 * cpad | -> 1024 | staging tile]
+    const size_t front2 = (size_t)p.a_region_bytes + p.b_region_bytes + 512 + 4096 + (p.bnb_x ? 16 * p.bnb_cpad : 0);
+    p.stage_off = (uint32_t)(((front2 > front ? front2 : front) + 1023) / 1024 * 1024);
     return 1024 + (size_t)p.stage_off + stage_bytes;
 }
 

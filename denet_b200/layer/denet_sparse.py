@@ -75,8 +75,6 @@ class DeNetSparseLayer(AbstractLayer):
         self.random_sample = json_param.get("randomSample", random_sample)
         self.local_max = json_param.get("localMax", local_max)
         self.version = json_param.get("version", version)
-        if self.nms_threshold < 1.0:
-            raise Exception("denet-sparse: corner clustering (nmsThreshold < 1) is not on the B200 hot path")
 
         self.corner_max = 1024
         self.thread_num = self.batch_size
@@ -118,7 +116,7 @@ class DeNetSparseLayer(AbstractLayer):
             corner_pr = self.corner_layer.corner_pr
         assert corner_pr is not None, "denet-sparse: the corner layer has not run a forward pass yet"
         pr, bbox, _, count, _ = ops.build_samples(corner_pr, self.corner_threshold, self.sample_num, self.corner_max,
-                                                  self.local_max)
+                                                  self.local_max, self.nms_threshold)
         b, k = self.batch_size, self.sample_count
         if self._packed_dev is None:
             self._packed_dev = torch.empty((5 * b * k + b,), dtype=torch.float32, device=corner_pr.device)
@@ -179,7 +177,7 @@ class DeNetSparseLayer(AbstractLayer):
         boxes (slots past the per-image count are zero boxes, like the reference's zero-initialised bbox array,
         denet_sparse.py:151-157); returns the per-image counts (B) int32 on the device"""
         pr, bbox, _, count, _ = ops.build_samples(self.corner_layer.corner_pr, self.corner_threshold, self.sample_num,
-                                                  self.corner_max, self.local_max)
+                                                  self.corner_max, self.local_max, self.nms_threshold)
         b, k = self.batch_size, self.sample_count
         valid = (torch.arange(k, device=bbox.device)[None, :] < count[:, None]).unsqueeze(-1)
         self.sample_bbox = torch.where(valid, bbox, torch.zeros_like(bbox)).reshape(b, self.sample_num, self.sample_num,

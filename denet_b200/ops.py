@@ -714,8 +714,6 @@ def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, loc
     Returns (pr (B,K), bbox (B,K,4), ibox (B,K,4) int32, count (B), ncand (B))"""
     assert corner_pr.dtype == torch.float32 and corner_pr.is_contiguous() and corner_pr.shape[1] == 2 and \
         corner_pr.shape[2] in (4, 5)
-    if cluster_threshold < 1.0:
-        raise NotImplementedError("build_samples: corner clustering (cluster_threshold < 1, denet_sparse.cc:165-242)")
     b, _, cn, h, w = corner_pr.shape
     k = sample_num * sample_num
     dev = corner_pr.device
@@ -724,11 +722,14 @@ def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, loc
     ibox = torch.empty((b, k, 4), dtype=torch.int32, device=dev)
     count = torch.empty((b,), dtype=torch.int32, device=dev)
     ncand = torch.empty((b,), dtype=torch.int32, device=dev)
-    nbytes = lib.load().denet_build_samples_workspace(b, h, w, max_corners)
+    if cluster_threshold < 1.0:
+        nbytes = lib.load().denet_build_samples_cluster_workspace(b, h, w, max_corners, sample_num)
+    else:
+        nbytes = lib.load().denet_build_samples_workspace(b, h, w, max_corners)
     ws = workspace(nbytes, dev, "samples")
-    call("denet_build_samples_cn", corner_pr.data_ptr(), b, cn, h, w, corner_threshold, sample_num, max_corners,
-         local_max, pr.data_ptr(), bbox.data_ptr(), ibox.data_ptr(), count.data_ptr(), ncand.data_ptr(), ws.data_ptr(),
-         ws.numel() * 4, _stream())
+    call("denet_build_samples_cluster", corner_pr.data_ptr(), b, cn, h, w, corner_threshold, sample_num, max_corners,
+         local_max, float(cluster_threshold), pr.data_ptr(), bbox.data_ptr(), ibox.data_ptr(), count.data_ptr(),
+         ncand.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream())
     return pr, bbox, ibox, count, ncand
 
 

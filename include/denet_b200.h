@@ -287,6 +287,16 @@ int denet_build_samples(const float* corner_pr, int B, int H, int W, float corne
  * (model token DNC.C, denet/layer/denet_corner.py:34-37): centres pair with every corner type
  * (denet_sparse.cc:377-468) and the centre probability joins every box score (:296-303).
  * corner_pr is (B, 2, corner_num, H, W). */
+/* the same followed by the reference's corner clustering (apply_cluster, denet_sparse.cc:165-242) for every image whose
+ * corner search found more than sample_num^2 boxes, when cluster_threshold < 1 (the sparse layer's nmsThreshold;
+ * constructor default 0.7, denet/layer/denet_sparse.py:29): the clusters are the connected components of
+ * "IoU > cluster_threshold" over the (at most 10 * sample_num^2 best) boxes; the largest sample_num^2 clusters survive
+ * and each contributes its 1 + floor(size * ratio) best boxes.  Needs the larger workspace. */
+size_t denet_build_samples_cluster_workspace(int B, int H, int W, int max_corners, int sample_num);
+int denet_build_samples_cluster(const float* corner_pr, int B, int corner_num, int H, int W, float corner_threshold,
+                                int sample_num, int max_corners, int local_max, float cluster_threshold, float* out_pr,
+                                float* out_bbox, int* out_ibox, int* out_count, int* out_ncand, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream);
 int denet_build_samples_cn(const float* corner_pr, int B, int corner_num, int H, int W, float corner_threshold,
                            int sample_num, int max_corners, int local_max, float* out_pr, float* out_bbox,
                            int* out_ibox, int* out_count, int* out_ncand, void* workspace, size_t workspace_bytes,

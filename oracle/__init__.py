@@ -100,8 +100,9 @@ def relu_inplace(x):
     return x
 
 
-def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, local_max=0):
-    """C restatement of denet_sparse.cc build_samples (4 corner types, or 5 with the centre map of DNC.C; no clustering).
+def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, local_max=0, cluster_threshold=1.0):
+    """C restatement of denet_sparse.cc build_samples (4 corner types, or 5 with the centre map of DNC.C;
+    cluster_threshold < 1 runs the reference's apply_cluster on over-full sample sets).
 
     corner_pr (B,2,4,H,W) fp32 log-probabilities.  Returns a list (per image) of structured arrays with fields
     pr,x0,y0,x1,y1 (normalised floats) and ix0,iy0,ix1,iy1 (integer corner positions), sorted by pr descending,
@@ -116,7 +117,7 @@ def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, loc
     lib = clib()
     lib.ref_build_samples.restype = ctypes.c_int
     rc = lib.ref_build_samples(_p(cp), B, C, H, W, ctypes.c_float(corner_threshold), sample_num, max_corners,
-                               local_max, _p(out), _p(counts), _p(ncand))
+                               local_max, ctypes.c_float(cluster_threshold), _p(out), _p(counts), _p(ncand))
     if rc != 0:
         raise ValueError("oracle.build_samples: unsupported arguments (corner_num must be 4 or 5)")
     return [out[b, :counts[b]].copy() for b in range(B)], ncand

@@ -524,21 +524,21 @@ def test_sparse_sample_matches_reference_cuda_kernels(cuda):
 
 
 # ------------------------------------------------------------------------------------------------ build_samples
-def _check_samples(cp, sample_num, max_corners=1024, local_max=0, thr=0.01):
+def _check_samples(cp, sample_num, max_corners=1024, local_max=0, thr=0.01, cluster_threshold=1.0):
     ops = _ops()
     B = cp.shape[0]
     K = sample_num * sample_num
     pr, bbox, ibox, count, ncand = [t.cpu().numpy() for t in
                                     ops.build_samples(torch.from_numpy(cp).cuda(), thr, sample_num, max_corners,
-                                                      local_max)]
-    ref, ref_ncand = oracle.build_samples(cp, thr, sample_num, max_corners, local_max)
+                                                      local_max, cluster_threshold)]
+    ref, ref_ncand = oracle.build_samples(cp, thr, sample_num, max_corners, local_max, cluster_threshold)
     for b in range(B):
         assert ncand[b] == ref_ncand[b], "number of unique candidate boxes differs"
         assert count[b] == len(ref[b])
         n = count[b]
         got = {tuple(int(v) for v in ibox[b, i]): i for i in range(n)}
         want = {(int(s["ix0"]), int(s["iy0"]), int(s["ix1"]), int(s["iy1"])): s for s in ref[b]}
-        if ref_ncand[b] > K:
+        if ref_ncand[b] > K and cluster_threshold >= 1.0:
             # std::partial_sort is unstable: boxes tied with the K-th score are interchangeable
             cut = ref[b][-1]["pr"]
             got_strict = {k for k, i in got.items() if pr[b, i] > cut}
@@ -582,6 +582,26 @@ def test_build_samples_centre_corners(cuda, k, H, sn):
             for i in range(cnt[b]):
                 if pr[b, i] > cut or nc[b] <= sn * sn:
                     assert want[tuple(bbox[b, i])] == pr[b, i]
+
+
+@pytest.mark.parametrize("k,H,sn,cthr,cn", [(12, 32, 4, 0.7, 4), (20, 48, 6, 0.5, 4), (30, 64, 8, 0.7, 4), (16, 32, 8, 0.3, 4),
+                                            (40, 64, 24, 0.7, 4), (14, 32, 5, 0.6, 5), (48, 128, 12, 0.7, 4)])
+def test_build_samples_clustering(cuda, k, H, sn, cthr, cn):
+    """nmsThreshold < 1: apply_cluster (denet_sparse.cc:165-242) as connected components on the device, against the C
+    restatement (which the CPU tests pin to the reference's compiled extension) and that extension itself"""
+    cp = busy_corner_map(3, H, H, k, seed=200 + k, corner_num=cn)
+    count, ncand = _check_samples(cp, sn, cluster_threshold=cthr)
+    assert (ncand > sn * sn).any(), "the case must exercise clustering"
+    ref_cc = oracle.reference_cc()
+    if ref_cc is not None:
+        ops = _ops()
+        pr, bbox, ibox, cnt, nc = [t.cpu().numpy() for t in
+                                   ops.build_samples(torch.from_numpy(cp).cuda(), 0.01, sn, 1024, 0, cthr)]
+        ref = ref_cc.build_samples(3, cp, 0.01, sn, 1024, 0, cthr)
+        for b in range(3):
+            assert cnt[b] == len(ref[b])
+            assert {(numpy.float32(p), tuple(numpy.float32(v) for v in bb)) for p, bb in ref[b]} == \
+                {(pr[b, i], tuple(bbox[b, i])) for i in range(cnt[b])}
 
 
 def test_build_samples_edge_cases(cuda):

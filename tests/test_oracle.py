@@ -85,6 +85,23 @@ def test_build_samples_restatement_vs_live_reference():
                 {(s["x0"], s["y0"], s["x1"], s["y1"]) for s in res[b]}
 
 
+@pytest.mark.parametrize("k,H,sn,cthr,cn", [(12, 32, 4, 0.7, 4), (30, 64, 8, 0.7, 4), (16, 32, 8, 0.3, 4), (14, 32, 5, 0.6, 5)])
+def test_clustering_and_centre_restatement_vs_live_reference(k, H, sn, cthr, cn):
+    """ref_kernels.c apply_cluster / centre-corner search == the reference's compiled extension (sequence for sequence)"""
+    ref = oracle.reference_cc()
+    if ref is None:
+        pytest.skip("oracle/_ref/denet_sparse*.so not built")
+    from util import busy_corner_map
+    cp = busy_corner_map(3, H, H, k, seed=200 + k, corner_num=cn)
+    want = ref.build_samples(3, cp, 0.01, sn, 1024, 0, cthr)
+    res, ncand = oracle.build_samples(cp, 0.01, sn, 1024, 0, cthr)
+    assert (ncand > sn * sn).any()
+    for b in range(3):
+        mine = [(s["pr"], (s["x0"], s["y0"], s["x1"], s["y1"])) for s in res[b]]
+        theirs = [(numpy.float32(p), tuple(numpy.float32(v) for v in bb)) for p, bb in want[b]]
+        assert mine == theirs
+
+
 def test_batchnorm_known_answer():
     """reference denet/layer/batch_norm.py:131-153: U(0,1) seed 1002, (64,128,32,32): after one training step the
     mean of the running inverse std is 1.24641 (momentum 0.9 from 1.0), |y.mean| < 1e-4, |y.std - 1| < 1e-4"""
