@@ -290,3 +290,30 @@ extern "C" int denet_softmax_nll(const void* o, int dtype, long long ld, int B, 
     DN_CHECK_LAUNCH();
     return 0;
 }
+
+
+// [total, cost_0, cost_1, ...] of the cost layers in one tiny launch (ModelCNN._pack_costs; the reference returns
+// `[cost] + costs` from its compiled train function, model/model_cnn.py:229-235,445): cost_i = sum of the lens[i] floats
+// at srcs[i] (a layer may keep its cost as several terms, e.g. detection + box cost), total = sum factors[i] * cost_i.
+namespace dn {
+__global__ void pack_costs_kernel(const float* const* __restrict__ srcs, const int* __restrict__ lens,
+                                  const float* __restrict__ factors, int n, float* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float total = 0.f;
+    for (int i = 0; i < n; ++i) {
+        float c = 0.f;
+        for (int j = 0; j < lens[i]; ++j) c += srcs[i][j];
+        out[1 + i] = c;
+        total += factors[i] * c;
+    }
+    out[0] = total;
+}
+}  // namespace dn
+
+extern "C" int denet_pack_costs(const void* srcs, const int* lens, const float* factors, int n, float* out,
+                                cudaStream_t stream) {
+    DN_REQUIRE(srcs && lens && factors && out && n > 0, "pack_costs: null pointer");
+    dn::pack_costs_kernel<<<DN_G(1), 32, 0, stream>>>(reinterpret_cast<const float* const*>(srcs), lens, factors, n, out);
+    DN_CHECK_LAUNCH();
+    return 0;
+}

@@ -48,6 +48,42 @@ def mt_import(mt, pos, version, gauss):
     random.setstate((version, tuple(mt.tolist()) + (int(pos.value),), gauss))
 
 
+class RandomAhead:
+    """python `random`'s Mersenne-Twister stepped ahead of time (denet_pyrandom_ahead): tempered words + the state after
+    every regeneration, generated while the GPU is busy, consumed by finish_target between the two graphs"""
+
+    def __init__(self, nwords_needed):
+        version, internal, gauss = random.getstate()
+        self.version, self.gauss = version, gauss
+        self.internal_head = internal[:8] + (internal[624],)
+        mt = numpy.array(internal[:624], dtype=numpy.uint32)
+        self.pos0 = int(internal[624])
+        self.mt0 = mt
+        nblocks = max(1, -(-max(0, nwords_needed - (624 - self.pos0)) // 624) + 1)
+        self.states = numpy.empty((nblocks, 624), dtype=numpy.uint32)
+        self.words = numpy.empty(((624 - self.pos0) + 624 * nblocks,), dtype=numpy.uint32)
+        n = ctypes.c_longlong(0)
+        call("denet_pyrandom_ahead", mt.ctypes.data, self.pos0, nblocks, self.states.ctypes.data,
+             self.words.ctypes.data, ctypes.addressof(n))
+        self.nwords = int(n.value)
+
+    def still_valid(self):
+        """nobody consumed python's `random` since the words were generated"""
+        internal = random.getstate()[1]
+        return internal[:8] + (internal[624],) == self.internal_head
+
+    def commit(self, used):
+        """advance the interpreter's generator by `used` words"""
+        first = 624 - self.pos0
+        if used <= first:
+            mt, pos = self.mt0, self.pos0 + used
+        else:
+            u = used - first
+            j = (u - 1) // 624
+            mt, pos = self.states[j], u - 624 * j
+        random.setstate((self.version, tuple(mt.tolist()) + (int(pos),), self.gauss))
+
+
 def py_random_sample(n, k):
     """random.sample(range(n), k), natively, consuming the interpreter's stream identically"""
     mt, pos, version, gauss = mt_export()
@@ -115,12 +151,13 @@ class DeNetSparseLayer(AbstractLayer):
         if corner_pr is None:
             corner_pr = self.corner_layer.corner_pr
         assert corner_pr is not None, "denet-sparse: the corner layer has not run a forward pass yet"
-        pr, bbox, _, count, _ = ops.build_samples(corner_pr, self.corner_threshold, self.sample_num, self.corner_max,
-                                                  self.local_max, self.nms_threshold)
         b, k = self.batch_size, self.sample_count
         if self._packed_dev is None:
             self._packed_dev = torch.empty((5 * b * k + b,), dtype=torch.float32, device=corner_pr.device)
-        torch.cat([pr.reshape(-1), bbox.reshape(-1), count.to(torch.float32)], out=self._packed_dev)
+        p = self._packed_dev        # the sampler writes straight into the packed buffer (counts as int32 bit patterns)
+        ops.build_samples(corner_pr, self.corner_threshold, self.sample_num, self.corner_max, self.local_max,
+                          self.nms_threshold, out=(p[:b * k].view(b, k), p[b * k:5 * b * k].view(b, k, 4),
+                                                   p[5 * b * k:].view(torch.int32)))
         return self._packed_dev
 
     def collect_samples(self):
@@ -129,7 +166,7 @@ class DeNetSparseLayer(AbstractLayer):
         packed = d2h(self._packed_dev, slot="denet-sparse/samples" + self._slot_ns)
         b, k = self.batch_size, self.sample_count
         return (packed[:b * k].reshape(b, k), packed[b * k:5 * b * k].reshape(b, k, 4),
-                packed[5 * b * k:].astype(numpy.int64))
+                packed[5 * b * k:].view(numpy.int32).astype(numpy.int64))
 
     def get_samples_arrays(self, corner_pr=None):
         self.enqueue_samples(corner_pr)
@@ -190,9 +227,15 @@ class DeNetSparseLayer(AbstractLayer):
         """denet_sparse.py:164-206, vectorised; consumes python's `random` stream exactly like the reference loops"""
         return self.finish_target(metas, *self.get_samples_arrays())
 
-    def finish_target(self, metas, pr32, bbox32, count):
+    def random_ahead(self):
+        """generate the random words one step can consume at most, ahead of time (call while the GPU is busy)"""
+        k = self.sample_count
+        return RandomAhead(self.batch_size * (8 * k + 4 * k) + 1248)
+
+    def finish_target(self, metas, pr32, bbox32, count, ahead=None):
         """host half of get_target: the reference's python-`random` post-processing of the ranked RoIs, then the
-        upload of the final (B,sn,sn,4) box tensor"""
+        upload of the final (B,sn,sn,4) box tensor.  ahead: a RandomAhead generated for this step (same stream, the
+        generator work already done)"""
         k = self.sample_count
         n_keep = k - math.floor(self.random_sample * k)
         pr = numpy.zeros((self.batch_size, k), dtype=numpy.float64)
@@ -204,10 +247,20 @@ class DeNetSparseLayer(AbstractLayer):
         # sub-sample / pad with python-`random` semantics for the whole batch in one native call
         # (csrc/pyrandom.cu: the interpreter's Mersenne-Twister state goes in and comes back advanced exactly as the
         # reference's loops over random.sample / random.uniform would have advanced it)
-        mt, pos, version, gauss = mt_export()
-        call("denet_sparse_postprocess", mt.ctypes.data, ctypes.addressof(pos), pr32.ctypes.data, bbox32.ctypes.data,
-             count.ctypes.data, nb, k, n_keep, pr.ctypes.data, bbox.ctypes.data)
-        mt_import(mt, pos, version, gauss)
+        done = False
+        if ahead is not None and ahead.still_valid():
+            used = ctypes.c_longlong(0)
+            rc = call("denet_sparse_postprocess_ahead", ahead.words.ctypes.data, ahead.nwords, ctypes.addressof(used),
+                      pr32.ctypes.data, bbox32.ctypes.data, count.ctypes.data, nb, k, n_keep, pr.ctypes.data,
+                      bbox.ctypes.data, allow=(1,))
+            if rc == 0:
+                ahead.commit(int(used.value))
+                done = True
+        if not done:
+            mt, pos, version, gauss = mt_export()
+            call("denet_sparse_postprocess", mt.ctypes.data, ctypes.addressof(pos), pr32.ctypes.data, bbox32.ctypes.data,
+                 count.ctypes.data, nb, k, n_keep, pr.ctypes.data, bbox.ctypes.data)
+            mt_import(mt, pos, version, gauss)
         if self.sample_gt:
             for b, meta in enumerate(metas):
                 if len(meta["bbox"]) > k:

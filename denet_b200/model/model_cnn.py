@@ -606,11 +606,20 @@ class ModelCNN:
         layer_mod.bump_param_version()
 
     def _pack_costs(self):
-        costs = torch.stack([l.cost().reshape(()) for l in self.cost_layers])
+        """[total, cost_0, ...] device tensor in ONE launch of our own (denet_pack_costs); every cost layer keeps its
+        terms in a persistent device tensor `cost_value` whose address is tabled once"""
         if self._cost_factor_t is None:
-            self._cost_factor_t = torch.tensor(self.cost_factors, dtype=torch.float32).to(costs.device)
-        total = (costs * self._cost_factor_t).sum().reshape(1)
-        return torch.cat([total, costs])
+            vals = [l.cost_value for l in self.cost_layers]
+            assert all(v is not None and v.is_cuda and v.dtype == torch.float32 for v in vals)
+            dev = vals[0].device
+            self._cost_table = (torch.tensor([v.data_ptr() for v in vals], dtype=torch.int64, device=dev),
+                                torch.tensor([v.numel() for v in vals], dtype=torch.int32, device=dev), vals)
+            self._cost_factor_t = torch.tensor(self.cost_factors, dtype=torch.float32, device=dev)
+            self._cost_out = torch.zeros((1 + len(vals),), dtype=torch.float32, device=dev)
+        ptrs, lens, vals = self._cost_table
+        lib.call("denet_pack_costs", ptrs.data_ptr(), lens.data_ptr(), self._cost_factor_t.data_ptr(), len(vals),
+                 self._cost_out.data_ptr(), ops._stream())
+        return self._cost_out
 
     def _train_step_device(self, data_x, data_m, epoch, it, learning_rate, momentum, decay):
         """forward + backward + update on the device; returns the device tensor [total, cost_0, cost_1, ...]"""
@@ -700,7 +709,7 @@ class ModelCNN:
         """sparse gather -> head -> costs (the end of the forward pass)"""
         if si is not None:
             x = self.forward_layers(x, si, len(self.layers), train=True, with_targets=False)
-        self._g_costs.copy_(self._pack_costs())
+        self._g_costs = self._pack_costs()          # persistent output tensor of denet_pack_costs
 
     def _segment_b2(self, hp_dev):
         """backward (+ gradient all-reduce) -> solver"""
@@ -769,7 +778,8 @@ class ModelCNN:
         self._img_consumed_valid = True
         if si is not None:
             sp = self.layers[si]
-            sp.finish_target(data_m, *sp.collect_samples())
+            ahead = sp.random_ahead()                # generator work while the GPU runs graph A
+            sp.finish_target(data_m, *sp.collect_samples(), ahead=ahead)
             gb1.replay()
         self._host_costs = None
         if host_image:

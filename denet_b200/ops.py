@@ -709,7 +709,8 @@ def sparse_sample_index(bbox, gs, H, W):
     return ys, xs
 
 
-def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, local_max=0, cluster_threshold=1.0):
+def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, local_max=0, cluster_threshold=1.0,
+                  out=None):
     """corner_pr (B,2,4|5,H,W) fp32 device (5 = with the centre map of DNC.C).
     Returns (pr (B,K), bbox (B,K,4), ibox (B,K,4) int32, count (B), ncand (B))"""
     assert corner_pr.dtype == torch.float32 and corner_pr.is_contiguous() and corner_pr.shape[1] == 2 and \
@@ -717,10 +718,14 @@ def build_samples(corner_pr, corner_threshold, sample_num, max_corners=1024, loc
     b, _, cn, h, w = corner_pr.shape
     k = sample_num * sample_num
     dev = corner_pr.device
-    pr = torch.empty((b, k), dtype=torch.float32, device=dev)
-    bbox = torch.empty((b, k, 4), dtype=torch.float32, device=dev)
+    if out is not None:
+        pr, bbox, count = out            # caller-owned (e.g. views of one packed buffer): pr (b,k) f32, bbox (b,k,4) f32, count (b) i32
+        assert pr.is_contiguous() and bbox.is_contiguous() and count.is_contiguous() and count.dtype == torch.int32
+    else:
+        pr = torch.empty((b, k), dtype=torch.float32, device=dev)
+        bbox = torch.empty((b, k, 4), dtype=torch.float32, device=dev)
+        count = torch.empty((b,), dtype=torch.int32, device=dev)
     ibox = torch.empty((b, k, 4), dtype=torch.int32, device=dev)
-    count = torch.empty((b,), dtype=torch.int32, device=dev)
     ncand = torch.empty((b,), dtype=torch.int32, device=dev)
     if cluster_threshold < 1.0:
         nbytes = lib.load().denet_build_samples_cluster_workspace(b, h, w, max_corners, sample_num)

@@ -333,6 +333,16 @@ int denet_softmax_nll(const void* o, int dtype, long long ld, int B, int classes
 int denet_sparse_postprocess(uint32_t* mt_state, int* mt_pos, const float* pr32, const float* bbox32,
                              const long long* count, int B, int K, int n_keep, double* pr, double* bbox);
 int denet_pyrandom_sample(uint32_t* mt_state, int* mt_pos, int n, int k, int* out_index);
+/* The same post-processing with the generator stepped AHEAD of time (while the GPU still runs the forward trunk):
+ * denet_pyrandom_ahead copies the state, produces the tempered words of the next nblocks regenerations
+ * (out_words, (624 - mt_pos) + 624 * nblocks of them, stream order) and the raw state after each regeneration
+ * (out_states [nblocks][624]); denet_sparse_postprocess_ahead consumes words from that buffer, reports how many it used
+ * and returns 1 if the buffer ran out (repeat on the live generator).  Host-only, no device work. */
+int denet_pyrandom_ahead(const uint32_t* mt_state, int mt_pos, int nblocks, uint32_t* out_states, uint32_t* out_words,
+                         long long* out_nwords);
+int denet_sparse_postprocess_ahead(const uint32_t* words, long long nwords, long long* used, const float* pr32,
+                                   const float* bbox32, const long long* count, int B, int K, int n_keep, double* pr,
+                                   double* bbox);
 int denet_pyrandom_random(uint32_t* mt_state, int* mt_pos, long long n, double* out);
 
 /* ------------------------------------------------------------------------------------------------ targets
@@ -364,6 +374,10 @@ int denet_solver_update(const void* entries, const int* block_tensor, const long
  * grad_scale} (6 floats), so that a CUDA graph captured once replays with the values of the current step. */
 int denet_solver_update_dev(const void* entries, const int* block_tensor, const long long* block_offset, int nblocks,
                             int solver, const float* hp, int bias_decay, cudaStream_t stream);
+
+/* [total, cost_0, ...]: cost_i = sum of the lens[i] floats at srcs[i] (device array of n device pointers), total =
+ * sum factors[i] * cost_i - what the reference's train function returns (`[cost] + costs`, model/model_cnn.py:229-235). */
+int denet_pack_costs(const void* srcs, const int* lens, const float* factors, int n, float* out, cudaStream_t stream);
 
 /* ---- inference tail: detect-layer outputs and per-class NMS --------------------------------------
  * detect_outputs: what DeNetDetectLayer.get_detections' compiled Theano function returns

@@ -210,3 +210,52 @@ def test_strided_dgrad_parity_classes_restate_the_data_gradient():
             assert tuple(out.shape[2:]) == (hc, wc)
             dx[:, :, a::s, b::s] = out
         assert float((dx - dx_ref).abs().max()) < 1e-10, (h, w, k, s, pad)
+
+
+@pytest.mark.parametrize("counts", [[0, 0, 0], [10, 300, 64], [64, 64, 64, 64], [700, 0, 33]])
+def test_random_ahead_equals_live_generator(counts):
+    """finish_target's generator work done AHEAD of time (denet_pyrandom_ahead + denet_sparse_postprocess_ahead) yields
+    the same boxes and leaves python's `random` in the same state as the live path - for any number of words consumed,
+    also across several 624-word regenerations and from any starting position inside a block"""
+    import ctypes
+    from denet_b200 import lib
+    from denet_b200.layer.denet_sparse import RandomAhead, mt_export, mt_import
+    B, K, n_keep = len(counts), 64, 58
+    rs = numpy.random.RandomState(5)
+    pr32 = rs.rand(B, K).astype(numpy.float32)
+    bbox32 = rs.rand(B, K, 4).astype(numpy.float32)
+    count = numpy.array(counts, dtype=numpy.int64)
+    for seed, burn in [(1, 0), (2, 311), (3, 623)]:
+        random.seed(seed)
+        for _ in range(burn):
+            random.getrandbits(32)
+        start = random.getstate()
+        # live
+        pr_a, bb_a = numpy.zeros((B, K)), numpy.zeros((B, K, 4))
+        mt, pos, version, gauss = mt_export()
+        lib.call("denet_sparse_postprocess", mt.ctypes.data, ctypes.addressof(pos), pr32.ctypes.data, bbox32.ctypes.data,
+                 count.ctypes.data, B, K, n_keep, pr_a.ctypes.data, bb_a.ctypes.data)
+        mt_import(mt, pos, version, gauss)
+        end_live = random.getstate()
+        # ahead
+        random.setstate(start)
+        ahead = RandomAhead(B * 12 * K + 1248)
+        assert ahead.still_valid()
+        pr_b, bb_b = numpy.zeros((B, K)), numpy.zeros((B, K, 4))
+        used = ctypes.c_longlong(0)
+        rc = lib.call("denet_sparse_postprocess_ahead", ahead.words.ctypes.data, ahead.nwords, ctypes.addressof(used),
+                      pr32.ctypes.data, bbox32.ctypes.data, count.ctypes.data, B, K, n_keep, pr_b.ctypes.data,
+                      bb_b.ctypes.data, allow=(1,))
+        assert rc == 0
+        ahead.commit(int(used.value))
+        assert numpy.array_equal(pr_a, pr_b) and numpy.array_equal(bb_a, bb_b)
+        assert random.getstate() == end_live
+        # a buffer that is too small reports it instead of returning garbage silently
+        random.setstate(start)
+        small = RandomAhead(0)
+        rc = lib.call("denet_sparse_postprocess_ahead", small.words.ctypes.data, min(small.nwords, 40),
+                      ctypes.addressof(used), pr32.ctypes.data, bbox32.ctypes.data, count.ctypes.data, B, K, n_keep,
+                      pr_b.ctypes.data, bb_b.ctypes.data, allow=(1,))
+        assert rc == (1 if sum(K - min(c, n_keep) for c in counts) > 0 else 0)
+        random.getrandbits(32)
+        assert not small.still_valid()
