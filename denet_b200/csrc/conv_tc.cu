@@ -955,7 +955,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_fprop_halo_kernel(const __g
     uint64_t* tfull_bar = b_empty + 16;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* bres_bar = tempty_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 2);    // its own 16-byte granule (racecheck pairs
+                                                                            // tcgen05.alloc's result slot with neighbouring barrier writes)
     float2* stat_smem = reinterpret_cast<float2*>(smem_b + p.b_region_bytes + 512);
 
     const int warp = threadIdx.x >> 5;
@@ -1233,7 +1234,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
     uint64_t* tfull_bar = b_empty + 16;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* bres_bar = tempty_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 2);    // its own 16-byte granule (racecheck pairs
+                                                                            // tcgen05.alloc's result slot with neighbouring barrier writes)
     float2* stat_smem = reinterpret_cast<float2*>(smem_b + p.b_region_bytes + 512);
 
     const int warp = threadIdx.x >> 5;
