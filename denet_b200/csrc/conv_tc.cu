@@ -1264,6 +1264,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
         ptx::tmem_relinquish_pair();
     }
     ptx::tc_fence_before();
+    __syncthreads();                              // (CTA-level ordering of the TMEM address slot; the cluster barrier below
+                                                  // implies it, but compute-sanitizer's racecheck only models bar.sync)
     ptx::cluster_sync_all();                      // barriers of BOTH CTAs initialised before any remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
