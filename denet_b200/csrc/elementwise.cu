@@ -173,6 +173,15 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
     const int cv = blockIdx.y * cvt + threadIdx.x % cvt;
     const int rl = threadIdx.x / cvt;
     __shared__ float s_mu[kBnThreads * (VEC == 8 ? 8 : 1)], s_is[kBnThreads * (VEC == 8 ? 8 : 1)];
+    // gamma / beta do not depend on the statistics: their loads overlap the prologue's
+    float a[VEC], b[VEC];
+    if (cv < CV) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            a[i] = gamma[cv * VEC + i];
+            b[i] = beta[cv * VEC + i];
+        }
+    }
     if (sums.sum) {
         const int c0 = blockIdx.y * cvt * VEC, nc = cvt * VEC;
         for (int j = threadIdx.x; j < nc; j += blockDim.x) {
@@ -199,14 +208,13 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
     if (cv >= CV || rl >= rlanes) return;
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
-    float mu[VEC], a[VEC], b[VEC];
+    float mu[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         const int c = cv * VEC + i;
         const int j = (threadIdx.x % cvt) * VEC + i;
         mu[i] = sums.sum ? s_mu[j] : mean[c];
-        a[i] = gamma[c] * (sums.sum ? s_is[j] : invstd[c]);
-        b[i] = beta[c];
+        a[i] = a[i] * (sums.sum ? s_is[j] : invstd[c]);
     }
     const long long coff = (long long)cv * VEC;
     for (long long r = r0 + rl; r < r1; r += (long long)rlanes * kBnUnroll) {
@@ -449,7 +457,7 @@ __global__ void __launch_bounds__(kBnThreads, 2)
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                         const float* __restrict__ beta, int relu, T* __restrict__ dx, T* __restrict__ dres,
                         float* __restrict__ partial, float* __restrict__ sums, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta, int accumulate, int sync_slot) {
+                        float* __restrict__ dbeta, int accumulate, int sync_slot, int wide_totals) {
     const int CV = C / VEC;
     const int cvt = CV < kBnThreads ? CV : kBnThreads;
     const int rlanes = kBnThreads / cvt;
@@ -463,6 +471,7 @@ __global__ void __launch_bounds__(kBnThreads, 2)
     unsigned int* sync = g_bn_sync[sync_slot];
     __shared__ float red[2 * kBnThreads * (VEC == 8 ? 8 : 1)];
     __shared__ double fin[2][8][33];
+    __shared__ double fin8[2][8][8];
     const bool active = (cv < CV) && (rl < rlanes);
     const bool mask_from_x = relu && (yout == nullptr);
     const long long coff = (long long)cv * VEC;
@@ -535,6 +544,55 @@ __global__ void __launch_bounds__(kBnThreads, 2)
     }
     grid_barrier(&sync[0], nblocks);
     // ---------------------------------------------------------------- slab totals (fixed order, double)
+    // wide form: a block totals 8 channels with 32 slab lanes, every lane's <= 10 loads issued before the first add
+    // (the 8-lane form below walks 37 slabs per thread: a chain of L2 latencies while every other block waits)
+    if (wide_totals) {
+        constexpr int KU = 5;
+        for (unsigned int cb = bid; cb * 8u < (unsigned int)C; cb += nblocks) {
+            const int cl = threadIdx.x & 7, sl = threadIdx.x >> 3;
+            const int c = cb * 8 + cl;
+            double a0 = 0.0, a1 = 0.0;
+            if (c < C) {
+                for (int sb0 = sl; sb0 < nslabs; sb0 += 32 * KU) {
+                    float v0[KU], v1[KU];
+#pragma unroll
+                    for (int k = 0; k < KU; ++k) {
+                        const int sb = sb0 + 32 * k;
+                        v0[k] = sb < nslabs ? __ldcg(partial + ((long long)sb * 2 + 0) * C + c) : 0.f;
+                        v1[k] = sb < nslabs ? __ldcg(partial + ((long long)sb * 2 + 1) * C + c) : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < KU; ++k) {
+                        a0 += (double)v0[k];
+                        a1 += (double)v1[k];
+                    }
+                }
+            }
+            // lanes of a warp: 4 slab lanes x 8 channels -> fixed tree over the slab lanes, then the 8 warps in order
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+            if ((threadIdx.x & 31) < 8) {
+                fin8[0][threadIdx.x >> 5][cl] = a0;
+                fin8[1][threadIdx.x >> 5][cl] = a1;
+            }
+            __syncthreads();
+            if (threadIdx.x < 8 && c < C) {
+                double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    t0 += fin8[0][j][cl];
+                    t1 += fin8[1][j][cl];
+                }
+                sums[c] = (float)t0;
+                sums[C + c] = (float)t1;
+                if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)t0 : (float)t0;
+                if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)t1 : (float)t1;
+            }
+            __syncthreads();
+        }
+    } else
     for (unsigned int cb = bid; cb * 32u < (unsigned int)C; cb += nblocks) {
         const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
         const int c = cb * 32 + cl;
@@ -1169,6 +1227,7 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int ns
 }
 
 static int g_bn_fused_bwd = 1;     // batch-norm backward as one launch with grid barriers (A/B: denet_bn_set_mode)
+static int g_bn_wave = 1;          // apply passes as ONE wave of blocks (3 per SM), wide slab totals in the fused backward
 
 // slabs for a grid of at most `max_blocks` co-resident blocks (rows split as evenly as the row-lane quantum allows)
 static int bn_slabs_for(long long M, int C, int vec, int max_blocks, int* rows_per_block, int* ychunks) {
@@ -1202,7 +1261,12 @@ static int ew_slabs(long long M, int C, int vec, int* rows_per_block, int* ychun
     const int cvt = CV < kBnThreads ? CV : kBnThreads;
     *ychunks = ceil_div(CV, cvt);
     const int rlanes = kBnThreads / cvt;
-    long long rpb = ceil_div_ll(M, (long long)num_sms() * 8);
+    // one wave (3 resident blocks of 256 threads x 80 registers per SM): every block pays its prologue - per-channel
+    // constants, statistics - once and in parallel; with 8 blocks per SM the small tensors (<= 34 MB: one 32-row
+    // iteration per block) ran 2.3 waves of prologue + one load latency each, ~17 us for 17 MB
+    const long long blocks = g_bn_wave ? std::max<long long>(1, (long long)num_sms() * 3 / *ychunks)
+                                       : (long long)num_sms() * 8;
+    long long rpb = ceil_div_ll(M, blocks);
     const long long quantum = (long long)rlanes * kBnUnroll;
     rpb = ceil_div_ll(rpb, quantum) * quantum;
     *rows_per_block = (int)std::min<long long>(rpb, 1 << 30);
@@ -1279,6 +1343,7 @@ extern "C" int denet_bn_apply_sums(const void* x, int dtype, long long M, int C,
 
 extern "C" int denet_bn_set_mode(int mode) {
     g_bn_fused_bwd = mode & 1;       // bit0: one-launch backward (grid barriers); 0 = partial / finalize / apply kernels
+    g_bn_wave = (mode >> 1) & 1;     // bit1: one-wave apply grids + wide slab totals (default on)
     return 0;
 }
 
@@ -1311,7 +1376,7 @@ extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x
                 constexpr int U = sizeof(T) == 4 ? 2 : 4;
                 bn_bwd_fused_kernel<T, VEC, U><<<DN_G(dim3(nsf, ycf)), kBnThreads, 0, stream>>>(
                     (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpbf, mean, invstd, gamma, beta, relu, (T*)dx,
-                    (T*)dres, workspace, sums, dgamma, dbeta, accumulate, slot);
+                    (T*)dres, workspace, sums, dgamma, dbeta, accumulate, slot, g_bn_wave);
             });
             DN_CHECK_LAUNCH();
             return 0;

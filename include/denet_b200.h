@@ -210,7 +210,9 @@ int denet_bn_apply_sums(const void* x, int dtype, long long M, int C, long long 
                         float momentum, cudaStream_t stream);
 int denet_bn_inference_invstd(const float* run_stdinv, float eps, float* out, int C, cudaStream_t stream);
 /* A/B switch for measurements: bit0 = denet_bn_backward as ONE launch (two grid-wide barriers between the reductions and
- * the apply pass; default) instead of three kernels.  Results are identical (same fixed summation order per mode). */
+ * the apply pass; default) instead of three kernels; bit1 = apply passes launched as ONE wave of blocks and the fused
+ * backward's slab totals taken 8 channels x 32 slab lanes per block (default).  Every mode sums in a fixed order
+ * (deterministic); the default is 3. */
 int denet_bn_set_mode(int mode);
 int denet_bn_backward(const void* dy, const void* yout, const void* x, int dtype, long long M, int C, long long ld,
                       const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
