@@ -20,6 +20,9 @@ int set_error(int code, const char* fmt, ...) {
 
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static int g_pdl = 0;     // measured: programmatic edges cost 2 % of the CUDA-graph step (tried and rejected)
+int pdl_enabled() { return g_pdl; }
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
@@ -91,5 +94,6 @@ extern "C" const char* denet_last_error(void) { return dn::last_error_buf(); }
 
 extern "C" int denet_abi_version(void) { return DENET_ABI_VERSION; }
 
-namespace dn { long long launch_count(); }
+namespace dn { long long launch_count(); void set_pdl(int on); }
+extern "C" int denet_set_pdl(int on) { dn::set_pdl(on); return 0; }
 extern "C" long long denet_launch_count(void) { return dn::launch_count(); }

@@ -35,6 +35,34 @@ int set_error(int code, const char* fmt, ...);
 void note_launch();
 #define DN_G(grid) (dn::note_launch(), (grid))
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched through launch_pdl() may be scheduled while its
+// predecessor in the stream is still draining; it runs its prologue (barrier init, TMEM allocation, descriptor
+// prefetch, loads of data no recent kernel writes) and blocks in ptx::griddep_wait() before it touches anything the
+// predecessor produces.  Every kernel launched this way MUST execute griddep_wait() on every path that reads or writes
+// global memory shared with earlier kernels (the guarantee is transitive only through kernels that wait).
+// denet_set_pdl(0) launches the same kernels fully serialised (the wait is then a no-op).
+int pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -1301,6 +1301,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
         const int tap_kstep = kchunks * kBK;
         int as = 0, bs = 0;
         uint32_t aphase = 0, bphase = 0;
+        griddep_wait();                      // the activations come from the previous kernel (the filters do not)
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             uint32_t ct, mt, tw, th, tn;
             p.fd_co.divmod(tile, mt, ct);
@@ -1355,6 +1356,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
                 }
             }
         }
+        griddep_launch();                         // all loads issued: the next kernel may take the SMs this grid leaves
     } else if (warp == 1 && rank == 0) {
         // ------------------------------------------------ MMA issuer (leader CTA only)
         constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 0, 0, 256);
@@ -1434,6 +1436,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
             __syncwarp();
         }
     } else if (warp >= 2) {
+        griddep_wait();                      // bias / residual reads, output and statistics writes
         if (p.epi_tma)
             fprop_epilogue_tma<BN, true>(p, smem + p.stage_off, reinterpret_cast<float*>(stat_smem), tmem_base, tfull_bar,
                                          tempty_bar, warp, lane);
@@ -2527,7 +2530,7 @@ static int launch_fprop_halo2(const ConvFpropParams& p, cudaStream_t stream) {
     auto kern = conv_fprop_halo2_kernel<BN, NT, RESIDENT, KM>;
     DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int pairs = p.num_tiles < num_sms() / 2 ? p.num_tiles : num_sms() / 2;
-    kern<<<DN_G(2 * pairs), kThreadsF, smem, stream>>>(p);
+    DN_CHECK_CUDA(launch_pdl(kern, dim3(DN_G(2 * pairs)), dim3(kThreadsF), smem, stream, p));
     DN_CHECK_LAUNCH();
     return 0;
 }

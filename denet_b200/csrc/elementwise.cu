@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
             b[i] = beta[cv * VEC + i];
         }
     }
+    griddep_wait();                    // x, the statistics and the residual come from the kernels just before
     if (sums.sum) {
         const int c0 = blockIdx.y * cvt * VEC, nc = cvt * VEC;
         for (int j = threadIdx.x; j < nc; j += blockDim.x) {
@@ -475,6 +476,7 @@ __global__ void __launch_bounds__(kBnThreads, 2)
     const bool active = (cv < CV) && (rl < rlanes);
     const bool mask_from_x = relu && (yout == nullptr);
     const long long coff = (long long)cv * VEC;
+    griddep_wait();
     float mu[VEC], is[VEC], k1[VEC], fb[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -1314,8 +1316,8 @@ extern "C" int denet_bn_apply(const void* x, int dtype, long long M, int C, long
     BnSums none;
     memset(&none, 0, sizeof(none));
     DN_DISPATCH(dtype, v, {
-        bn_apply_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>(
-            (const T*)x, M, C, ld, rpb, mean, invstd, gamma, beta, (const T*)residual, relu, (T*)y, none);
+        launch_pdl(bn_apply_kernel<T, VEC>, DN_G(dim3(nslabs, yc)), dim3(kBnThreads), 0, stream,
+                   (const T*)x, M, C, ld, rpb, mean, invstd, gamma, beta, (const T*)residual, relu, (T*)y, none);
     });
     DN_CHECK_LAUNCH();
     return 0;
@@ -1334,8 +1336,8 @@ extern "C" int denet_bn_apply_sums(const void* x, int dtype, long long M, int C,
     sm.sum = sum; sm.sqsum = sqsum; sm.M = M; sm.eps = eps; sm.mean_out = mean; sm.invstd_out = invstd;
     sm.run_mean = run_mean; sm.run_stdinv = run_stdinv; sm.momentum = momentum;
     DN_DISPATCH(dtype, v, {
-        bn_apply_kernel<T, VEC><<<DN_G(dim3(nslabs, yc)), kBnThreads, 0, stream>>>(
-            (const T*)x, M, C, ld, rpb, nullptr, nullptr, gamma, beta, (const T*)residual, relu, (T*)y, sm);
+        launch_pdl(bn_apply_kernel<T, VEC>, DN_G(dim3(nslabs, yc)), dim3(kBnThreads), 0, stream,
+                   (const T*)x, M, C, ld, rpb, nullptr, nullptr, gamma, beta, (const T*)residual, relu, (T*)y, sm);
     });
     DN_CHECK_LAUNCH();
     return 0;
@@ -1374,7 +1376,7 @@ extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x
             const int slot = (slot_counter++) % kBnSyncSlots;
             DN_DISPATCH(dtype, v, {
                 constexpr int U = sizeof(T) == 4 ? 2 : 4;
-                bn_bwd_fused_kernel<T, VEC, U><<<DN_G(dim3(nsf, ycf)), kBnThreads, 0, stream>>>(
+                launch_pdl(bn_bwd_fused_kernel<T, VEC, U>, DN_G(dim3(nsf, ycf)), dim3(kBnThreads), 0, stream,
                     (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpbf, mean, invstd, gamma, beta, relu, (T*)dx,
                     (T*)dres, workspace, sums, dgamma, dbeta, accumulate, slot, g_bn_wave);
             });

@@ -74,6 +74,10 @@ def load():
     # profiling / A-B switches (kernel variants only; every variant is a CUDA kernel of this library)
     if os.environ.get("DENET_FPROP_MODE"):
         lib.denet_conv2d_fprop_set_mode(int(os.environ["DENET_FPROP_MODE"]))
+    if os.environ.get("DENET_PDL"):
+        lib.denet_set_pdl(int(os.environ["DENET_PDL"]))
+    if os.environ.get("DENET_BN_MODE"):
+        lib.denet_bn_set_mode(int(os.environ["DENET_BN_MODE"]))
     if os.environ.get("DENET_WGRAD_MODE"):
         lib.denet_conv2d_wgrad_set_mode(int(os.environ["DENET_WGRAD_MODE"]))
     return lib

@@ -40,6 +40,10 @@ const char* denet_last_error(void);
 int denet_abi_version(void);
 /* number of CUDA kernels this library has enqueued in this process so far (all streams, all threads) */
 long long denet_launch_count(void);
+/* A/B switch: 1 launches the CTA-pair convolution and the batch-norm kernels with programmatic stream serialisation (a
+ * kernel's prologue overlaps its predecessor's tail; griddepcontrol.wait orders the data), 0 (default: measured faster
+ * inside CUDA graphs) fully serialised.  Results are identical. */
+int denet_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------ convolution
  * Replaces tensor.nnet.conv2d / its autodiff gradients, i.e. the cuDNN fprop / bwd-data / bwd-filter calls
