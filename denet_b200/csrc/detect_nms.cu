@@ -20,10 +20,16 @@
 namespace dn {
 
 // ------------------------------------------------------------------------------------------------ detect outputs
-// logits: rows = B*sn*sn RoIs in (b, j, i) order, `ld` floats apart, channels [0,s0) classes, [s0,s0+4) box regression
+// logits: rows = B*sn*sn RoIs in (b, j, i) order, `ld` floats apart, channels [0,s0) classes, [s0,s0+4) box regression,
+// then 6 independent-fitness logits (fit_mode bit1).  fit_mode bit0 (joint fitness, denet_detect.py:332-348): the s0 =
+// classNum*5+1 log-probabilities are folded into det_pr (B, classNum+1, sn, sn) = logsumexp over the 5 fitness bins of
+// a class (+ the null class) and fitness (B, classNum+1, sn, sn; null channel unused) = log(sum_f p(c,f) * val_f),
+// val_f = thr0 + f (1 - thr0) / 5.  bit1 (:392-397): fitness = det_pr + log(sum_f q_f * val'_f), q = softmax of the 6
+// fitness logits, val' = {0, thr0 + i (1 - thr0) / 5}.
 __global__ void detect_outputs_kernel(const float* __restrict__ logits, long long ld, int B, int sn, int s0, int use_bbox,
+                                      int class_num, int fit_mode, float thr0,
                                       const float* __restrict__ sample_bbox, float* __restrict__ det_pr,
-                                      float* __restrict__ bbox_out) {
+                                      float* __restrict__ fitness, float* __restrict__ bbox_out) {
     const int roi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one warp per RoI
     const int lane = threadIdx.x & 31;
     const int nroi = B * sn * sn;
@@ -39,8 +45,56 @@ __global__ void detect_outputs_kernel(const float* __restrict__ logits, long lon
     for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float ls = logf(s);
     const int b = roi / (sn * sn), ji = roi % (sn * sn);
-    // reference layout (B, s0, sn, sn); theano_util.log_softmax: (x - max) - log(sum(exp(x - max)))
-    for (int c = lane; c < s0; c += 32) det_pr[((long long)b * s0 + c) * sn * sn + ji] = (z[c] - m) - ls;
+    const long long plane = (long long)sn * sn;
+    float fit_add = 0.f;
+    if (fit_mode & 2) {
+        const int base = s0 + (use_bbox ? 4 : 0);
+        const bool in = lane < 6;
+        const float v = in ? z[base + lane] : -FLT_MAX;
+        float fm = v;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) fm = fmaxf(fm, __shfl_xor_sync(0xffffffffu, fm, o));
+        float fe = in ? expf(v - fm) : 0.f;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) fe += __shfl_xor_sync(0xffffffffu, fe, o);
+        const float q = in ? expf((v - fm) - logf(fe)) : 0.f;
+        // (the reference sums in float64 and rounds once; 6 terms in [0,1]: the double sum below does the same)
+        double term = (in && lane > 0) ? (double)q * ((double)thr0 + (lane - 1) * (1.0 - (double)thr0) / 5.0) : 0.0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+        fit_add = logf((float)term);
+    }
+    if (fit_mode & 1) {
+        const int s_out = class_num + 1;
+        for (int c = lane; c < class_num; c += 32) {
+            float lp[5], mm = -FLT_MAX;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                lp[f] = (z[c * 5 + f] - m) - ls;
+                mm = fmaxf(mm, lp[f]);
+            }
+            float se = 0.f, sv = 0.f;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                se += expf(lp[f] - mm);
+                sv += expf(lp[f]) * (thr0 + (float)f * (1.0f - thr0) / 5.0f);
+            }
+            det_pr[((long long)b * s_out + c) * plane + ji] = mm + logf(se);
+            fitness[((long long)b * s_out + c) * plane + ji] = logf(sv);
+        }
+        if (lane == 0) {
+            const float lp = (z[class_num * 5] - m) - ls;
+            det_pr[((long long)b * s_out + class_num) * plane + ji] = lp;
+            fitness[((long long)b * s_out + class_num) * plane + ji] = lp;
+        }
+    } else {
+        // reference layout (B, s0, sn, sn); theano_util.log_softmax: (x - max) - log(sum(exp(x - max)))
+        for (int c = lane; c < s0; c += 32) {
+            const float lp = (z[c] - m) - ls;
+            det_pr[((long long)b * s0 + c) * plane + ji] = lp;
+            if (fitness) fitness[((long long)b * s0 + c) * plane + ji] = lp + fit_add;
+        }
+    }
     if (lane == 0 && bbox_out) {
         const float* sb = sample_bbox + (long long)roi * 4;
         float x0 = sb[0], y0 = sb[1], x1 = sb[2], y1 = sb[3];
@@ -229,17 +283,27 @@ __global__ void __launch_bounds__(kNmsThreads) detections_nms_kernel(
 
 using namespace dn;
 
-extern "C" int denet_detect_outputs(const float* logits, long long ld, int B, int sn, int s0, int use_bbox,
-                                    const float* sample_bbox, float* det_pr, float* bbox_out, cudaStream_t stream) {
+extern "C" int denet_detect_outputs_v2(const float* logits, long long ld, int B, int sn, int s0, int use_bbox,
+                                       int class_num, int fit_mode, float thr0, const float* sample_bbox, float* det_pr,
+                                       float* fitness, float* bbox_out, cudaStream_t stream) {
     DN_REQUIRE(logits && det_pr, "detect_outputs: null pointer");
     DN_REQUIRE(!bbox_out || sample_bbox, "detect_outputs: the box output needs the sample boxes");
     DN_REQUIRE(B > 0 && sn > 0 && s0 > 0, "detect_outputs: empty tensor");
+    DN_REQUIRE((fit_mode & 3) != 3, "detect_outputs: joint and independent fitness exclude each other");
+    DN_REQUIRE(!fit_mode || fitness, "detect_outputs: the fitness modes need the fitness output");
+    DN_REQUIRE(!(fit_mode & 1) || s0 == class_num * 5 + 1, "detect_outputs: joint fitness expects classNum*5+1 channels");
     const int nroi = B * sn * sn;
     const int warps = 8;
-    detect_outputs_kernel<<<DN_G(ceil_div(nroi, warps)), warps * 32, 0, stream>>>(logits, ld, B, sn, s0, use_bbox,
-                                                                                 sample_bbox, det_pr, bbox_out);
+    detect_outputs_kernel<<<DN_G(ceil_div(nroi, warps)), warps * 32, 0, stream>>>(
+        logits, ld, B, sn, s0, use_bbox, class_num, fit_mode, thr0, sample_bbox, det_pr, fitness, bbox_out);
     DN_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int denet_detect_outputs(const float* logits, long long ld, int B, int sn, int s0, int use_bbox,
+                                    const float* sample_bbox, float* det_pr, float* bbox_out, cudaStream_t stream) {
+    return denet_detect_outputs_v2(logits, ld, B, sn, s0, use_bbox, s0 - 1, 0, 0.f, sample_bbox, det_pr, nullptr, bbox_out,
+                                   stream);
 }
 
 extern "C" int denet_detections_nms(const float* det_pr, const float* fitness, long long stride_b, long long stride_c,

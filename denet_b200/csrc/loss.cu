@@ -48,6 +48,14 @@ __global__ void sum_partials2_kernel(const float* __restrict__ partial, int n, f
     out[threadIdx.x] = (float)(a * (threadIdx.x == 0 ? scale0 : scale1));
 }
 
+__global__ void sum_partials3_kernel(const float* __restrict__ partial, int n, float scale0, float scale1, float scale2,
+                                     float* __restrict__ out) {
+    if (threadIdx.x >= 3) return;
+    double a = 0.0;
+    for (int i = 0; i < n; ++i) a += partial[(long long)i * 3 + threadIdx.x];
+    out[threadIdx.x] = (float)(a * (threadIdx.x == 0 ? scale0 : (threadIdx.x == 1 ? scale1 : scale2)));
+}
+
 // z: conv output rows = B*H*W pixels (NHWC), corner channels [0, cn).  corner_pr: (B, 2, cn, H, W) fp32.
 template <typename T>
 __global__ void corner_logprob_kernel(const T* __restrict__ z, long long ldz, int B, int cn, int H, int W,
@@ -104,22 +112,29 @@ __global__ void __launch_bounds__(kLossThreads) corner_cost_kernel(const T* __re
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-// One warp per RoI row. o: conv output rows (R, ld) with [0,s0) class logits and [s0,s0+4) box regression.
-// target_det (B,s0,sn,sn), target_valid (B,sn,sn), target_reg (B,8,sn,sn) in the reference's NCHW packing.
-// partial[blk] = {sum t*logp, sum smoothL1 term}; gradients written for channels [0, s0+4), zero for the padding.
+// One warp per RoI row. o: conv output rows (R, ld) with [0,s0) class logits (classNum+1, or classNum*5+1 with joint
+// fitness), [s0,s0+4) box regression when box_mode != 0, then nfit independent-fitness logits when nfit != 0.
+// target_det (B,s0,sn,sn), target_valid (B,sn,sn), target_reg (B,8,sn,sn), target_fit (B,nfit,sn,sn) in the reference's
+// NCHW packing.  box_mode 1: Fast R-CNN smooth-L1 on (tx,ty,tw,th) (denet_detect.py:288-295); 2: bounded IoU (:266-286)
+// on the decoded box (:80-97), sample_bbox (R,4) fp32.
+// partial[blk] = {sum t*logp, sum box term, sum t_fit*logp_fit}; gradients for channels [0, s0+4+nfit), zero beyond.
 template <typename T>
 __global__ void __launch_bounds__(kLossThreads) detect_cost_kernel(const T* __restrict__ o, long long ld, int R, int s0,
-                                                                    int sn2, int use_bbox,
+                                                                    int sn2, int box_mode, int nfit,
+                                                                    const float* __restrict__ sample_bbox,
                                                                     const float* __restrict__ target_det,
                                                                     const float* __restrict__ target_valid,
                                                                     const float* __restrict__ target_reg,
+                                                                    const float* __restrict__ target_fit,
                                                                     float det_grad_scale, float bbox_factor,
-                                                                    float bbox_grad_scale, T* __restrict__ dout,
-                                                                    int ncols_grad, float* __restrict__ partial) {
+                                                                    float bbox_grad_scale, float fit_grad_scale,
+                                                                    T* __restrict__ dout, int ncols_grad,
+                                                                    float* __restrict__ partial) {
     __shared__ float sh[kLossThreads / 32];
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
-    float acc_det = 0.f, acc_box = 0.f;
+    const int s1 = box_mode ? 4 : 0;
+    float acc_det = 0.f, acc_box = 0.f, acc_fit = 0.f;
     for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < R;
          row += (long long)gridDim.x * warps_per_block) {
         const int b = (int)(row / sn2);
@@ -149,29 +164,91 @@ __global__ void __launch_bounds__(kLossThreads) detect_cost_kernel(const T* __re
             const float p = expf(lp);
             grow[k] = from_f<T>(-(t - p * st) * det_grad_scale);
         }
-        if (use_bbox) {
-            if (lane < 4) {
-                const float valid = target_valid[(long long)b * sn2 + ji];
-                const float tg_c = target_reg[((long long)b * 8 + (lane & 1)) * sn2 + ji];          // target centre x|y
-                const float tg_s = target_reg[((long long)b * 8 + 2 + (lane & 1)) * sn2 + ji];      // target w|h
-                const float sm_c = target_reg[((long long)b * 8 + 4 + (lane & 1)) * sn2 + ji];      // sample centre
-                const float sm_s = target_reg[((long long)b * 8 + 6 + (lane & 1)) * sn2 + ji];      // sample w|h
+        if (box_mode && lane < 4) {
+            const int xy = lane & 1;
+            const float valid = target_valid[(long long)b * sn2 + ji];
+            const float tg_c = target_reg[((long long)b * 8 + xy) * sn2 + ji];              // target centre x|y
+            const float tg_s = target_reg[((long long)b * 8 + 2 + xy) * sn2 + ji];          // target w|h
+            float g;                                                                         // d(smooth-L1 term)/d(output)
+            float l;
+            if (box_mode == 1) {
+                const float sm_c = target_reg[((long long)b * 8 + 4 + xy) * sn2 + ji];      // sample centre
+                const float sm_s = target_reg[((long long)b * 8 + 6 + xy) * sn2 + ji];      // sample w|h
                 const float t = lane < 2 ? (tg_c - sm_c) / sm_s : logf(tg_s / sm_s);
                 const float d = t - to_f<T>(orow[s0 + lane]);
                 const float ad = fabsf(d);
-                const float l = ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-                acc_box += bbox_factor * valid * l;
-                const float dl = ad < 1.0f ? d : (d > 0.f ? 1.0f : -1.0f);
-                grow[s0 + lane] = from_f<T>(-bbox_factor * valid * dl * bbox_grad_scale);
+                l = ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+                g = -(ad < 1.0f ? d : (d > 0.f ? 1.0f : -1.0f));
+            } else {
+                const float* sb = sample_bbox + row * 4;
+                const float b0 = sb[xy], b1 = sb[2 + xy];
+                const float s_c = 0.5f * (b0 + b1), s_s = b1 - b0;                           // :84-87
+                const float pc = to_f<T>(orow[s0 + xy]) * s_s + s_c;                         // :89-92
+                const float ps = expf(to_f<T>(orow[s0 + 2 + xy])) * s_s;
+                const float p0 = pc - ps * 0.5f, p1 = pc + ps * 0.5f;                        // :93-96
+                const float predict_c = 0.5f * (p0 + p1), predict_s = p1 - p0;               // :271-274
+                const float eps = 0.001f;
+                float c, dc;                                                                 // cost and d cost / d output
+                if (lane < 2) {
+                    const float d = tg_c - predict_c;                                        // :276-283
+                    if (d >= 0.0f) {
+                        const float den = tg_s + d + eps;
+                        c = 2.0f * d / den;
+                        dc = 2.0f * (tg_s + eps) / (den * den);
+                    } else {
+                        const float den = tg_s - d + eps;
+                        c = -2.0f * d / den;
+                        dc = -2.0f * (tg_s + eps) / (den * den);
+                    }
+                    dc *= -s_s;                                                              // d(d)/d(output) = -sample size
+                } else {
+                    const float q0 = tg_s / (predict_s + eps), q1 = predict_s / (tg_s + eps);   // :284-285
+                    if (q0 < q1) {
+                        c = 1.0f - q0;
+                        dc = tg_s / ((predict_s + eps) * (predict_s + eps));
+                    } else {
+                        c = 1.0f - q1;
+                        dc = -1.0f / (tg_s + eps);
+                    }
+                    dc *= ps;                                                                // d(size)/d(output) = size
+                }
+                const float ac = fabsf(c);
+                l = ac < 1.0f ? 0.5f * c * c : ac - 0.5f;
+                g = (ac < 1.0f ? c : (c > 0.f ? 1.0f : -1.0f)) * dc;
+            }
+            acc_box += bbox_factor * valid * l;
+            grow[s0 + lane] = from_f<T>(bbox_factor * valid * g * bbox_grad_scale);
+        }
+        if (nfit) {                                                                          // :100-104, 297-299
+            const int base = s0 + s1;
+            const bool in = lane < nfit;
+            const float v = in ? to_f<T>(orow[base + lane]) : -INFINITY;
+            float fm = v;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) fm = fmaxf(fm, __shfl_xor_sync(0xffffffffu, fm, off));
+            float fe = in ? expf(v - fm) : 0.f;
+            float ft = in ? target_fit[((long long)b * nfit + lane) * sn2 + ji] : 0.f;
+            const float t = ft;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                fe += __shfl_xor_sync(0xffffffffu, fe, off);
+                ft += __shfl_xor_sync(0xffffffffu, ft, off);
+            }
+            if (in) {
+                const float lp = (v - fm) - logf(fe);
+                acc_fit += t * lp;
+                grow[base + lane] = from_f<T>(-(t - expf(lp) * ft) * fit_grad_scale);
             }
         }
-        for (int k = s0 + (use_bbox ? 4 : 0) + lane; k < ncols_grad; k += 32) grow[k] = from_f<T>(0.f);
+        for (int k = s0 + s1 + nfit + lane; k < ncols_grad; k += 32) grow[k] = from_f<T>(0.f);
     }
     const float s_det = block_sum(acc_det, sh);
     const float s_box = block_sum(acc_box, sh);
+    const float s_fit = block_sum(acc_fit, sh);
     if (threadIdx.x == 0) {
-        partial[blockIdx.x * 2 + 0] = s_det;
-        partial[blockIdx.x * 2 + 1] = s_box;
+        partial[blockIdx.x * 3 + 0] = s_det;
+        partial[blockIdx.x * 3 + 1] = s_box;
+        partial[blockIdx.x * 3 + 2] = s_fit;
     }
 }
 
@@ -216,7 +293,7 @@ using namespace dn;
 
 static const int kLossBlocks = 148;
 
-extern "C" size_t denet_loss_workspace_bytes(void) { return sizeof(float) * 2 * kLossBlocks; }
+extern "C" size_t denet_loss_workspace_bytes(void) { return sizeof(float) * (3 * kLossBlocks + 4); }
 
 extern "C" int denet_corner_logprob(const void* z, int dtype, long long ldz, int B, int cn, int H, int W,
                                     float* corner_pr, cudaStream_t stream) {
@@ -249,27 +326,51 @@ extern "C" int denet_corner_cost(const void* z, int dtype, long long ldz, int B,
     return 0;
 }
 
-extern "C" int denet_detect_cost(const void* o, int dtype, long long ld, int B, int sn, int s0, int use_bbox,
-                                 const float* target_det, const float* target_valid, const float* target_reg,
-                                 float cost_factor, float bbox_factor, float grad_factor, void* dout, int ncols_grad,
-                                 float* cost2, float* workspace, cudaStream_t stream) {
-    DN_REQUIRE(o && target_det && dout && cost2 && workspace, "detect_cost: null pointer");
-    DN_REQUIRE(!use_bbox || (target_valid && target_reg), "detect_cost: bbox targets missing");
+extern "C" int denet_detect_cost_v2(const void* o, int dtype, long long ld, int B, int sn, int s0, int box_mode, int nfit,
+                                    const float* sample_bbox, const float* target_det, const float* target_valid,
+                                    const float* target_reg, const float* target_fit, float cost_factor,
+                                    float bbox_factor, float fit_factor, float grad_factor, void* dout, int ncols_grad,
+                                    float* cost3, float* workspace, cudaStream_t stream) {
+    DN_REQUIRE(o && target_det && dout && cost3 && workspace, "detect_cost: null pointer");
+    DN_REQUIRE(box_mode >= 0 && box_mode <= 2, "detect_cost: box_mode must be 0 (none), 1 (Fast R-CNN) or 2 (bounded IoU)");
+    DN_REQUIRE(!box_mode || (target_valid && target_reg), "detect_cost: bbox targets missing");
+    DN_REQUIRE(box_mode != 2 || sample_bbox, "detect_cost: bounded IoU needs the sample boxes");
+    DN_REQUIRE(nfit >= 0 && nfit <= 32 && (!nfit || target_fit), "detect_cost: fitness target missing (or nfit > 32)");
+    DN_REQUIRE(s0 + (box_mode ? 4 : 0) + nfit <= ncols_grad, "detect_cost: gradient row narrower than the outputs");
     const int sn2 = sn * sn;
     const int R = B * sn2;
     const float det_scale = cost_factor / ((float)B * logf((float)s0));
     const float box_scale = bbox_factor / (float)B;
+    const float fit_scale = nfit ? fit_factor / ((float)B * logf((float)nfit)) : 0.f;
     if (dtype == DENET_F32)
         detect_cost_kernel<float><<<DN_G(kLossBlocks), kLossThreads, 0, stream>>>(
-            (const float*)o, ld, R, s0, sn2, use_bbox, target_det, target_valid, target_reg, det_scale * grad_factor,
-            bbox_factor, box_scale * grad_factor, (float*)dout, ncols_grad, workspace);
+            (const float*)o, ld, R, s0, sn2, box_mode, nfit, sample_bbox, target_det, target_valid, target_reg, target_fit,
+            det_scale * grad_factor, bbox_factor, box_scale * grad_factor, fit_scale * grad_factor, (float*)dout,
+            ncols_grad, workspace);
     else
         detect_cost_kernel<__nv_bfloat16><<<DN_G(kLossBlocks), kLossThreads, 0, stream>>>(
-            (const __nv_bfloat16*)o, ld, R, s0, sn2, use_bbox, target_det, target_valid, target_reg,
-            det_scale * grad_factor, bbox_factor, box_scale * grad_factor, (__nv_bfloat16*)dout, ncols_grad, workspace);
-    // cost2[0] = detection cost, cost2[1] = box cost, each including its factors (reference :308-310)
-    sum_partials2_kernel<<<DN_G(1), 32, 0, stream>>>(workspace, kLossBlocks, -det_scale, box_scale, cost2);
+            (const __nv_bfloat16*)o, ld, R, s0, sn2, box_mode, nfit, sample_bbox, target_det, target_valid, target_reg,
+            target_fit, det_scale * grad_factor, bbox_factor, box_scale * grad_factor, fit_scale * grad_factor,
+            (__nv_bfloat16*)dout, ncols_grad, workspace);
+    // cost3 = {detection, box, independent fitness} cost, each including its factors (reference :308-312)
+    sum_partials3_kernel<<<DN_G(1), 32, 0, stream>>>(workspace, kLossBlocks, -det_scale, box_scale, -fit_scale, cost3);
     DN_CHECK_LAUNCH();
+    return 0;
+}
+
+// the round-1 entry point: Fast R-CNN box loss, no fitness head; cost2 = {detection, box}
+extern "C" int denet_detect_cost(const void* o, int dtype, long long ld, int B, int sn, int s0, int use_bbox,
+                                 const float* target_det, const float* target_valid, const float* target_reg,
+                                 float cost_factor, float bbox_factor, float grad_factor, void* dout, int ncols_grad,
+                                 float* cost2, float* workspace, cudaStream_t stream) {
+    DN_REQUIRE(cost2 && workspace, "detect_cost: null pointer");
+    // the third sum lands in the workspace tail (the kernel's partials use 3 * kLossBlocks floats of 3 * kLossBlocks + 4)
+    float* cost3 = workspace + 3 * kLossBlocks;
+    const int rc = denet_detect_cost_v2(o, dtype, ld, B, sn, s0, use_bbox ? 1 : 0, 0, nullptr, target_det, target_valid,
+                                        target_reg, nullptr, cost_factor, bbox_factor, 0.f, grad_factor, dout, ncols_grad,
+                                        cost3, workspace, stream);
+    if (rc) return rc;
+    DN_CHECK_CUDA(cudaMemcpyAsync(cost2, cost3, 2 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     return 0;
 }
 

@@ -63,22 +63,28 @@ __global__ void corner_target_scatter_kernel(const double* __restrict__ gt, cons
 
 constexpr int kMaxGt = 64;   // ground-truth boxes per image handled on the device
 
-// one thread per RoI
+// one thread per RoI.  fit_mode bit0: joint fitness (denet_detect.py:58-61,179-182: classNum x 5 fitness bins + null),
+// bit1: independent fitness (:100-104,187-191: a second 6-way target, bin 0 = "no object").
 __global__ void detect_target_kernel(const double* __restrict__ gt, const int* __restrict__ gt_class,
                                      const int* __restrict__ gt_count, const double* __restrict__ samples, int B, int G,
-                                     int sn, int class_num, float thr0, float thr1, int use_bbox,
-                                     float* __restrict__ det, float* __restrict__ valid, float* __restrict__ reg) {
+                                     int sn, int class_num, float thr0, float thr1, int use_bbox, int fit_mode,
+                                     double thr0_d, float* __restrict__ det, float* __restrict__ valid,
+                                     float* __restrict__ reg, float* __restrict__ fit) {
     const int K = sn * sn;
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= (long long)B * K) return;
     const int b = (int)(idx / K), k = (int)(idx % K);
-    const int s0 = class_num + 1;
+    const bool joint = (fit_mode & 1) != 0, indfit = (fit_mode & 2) != 0;
+    const int fitness_num = joint ? 5 : 6;
+    const int null_class = joint ? class_num * fitness_num : class_num;
+    const int s0 = null_class + 1;
     const float nfactor = (float)K;
     const double* sb = samples + idx * 4;
     const float y0 = (float)sb[0], y1 = (float)sb[1], y2 = (float)sb[2], y3 = (float)sb[3];
     const float y_area = __fmul_rn(__fsub_rn(y2, y0), __fsub_rn(y3, y1));
     int pos_cls[kMaxGt];
     int npos = 0;
+    unsigned int fit_bins = 0;
     float best = 0.f;
     int best_g = -1;
     const int ng = gt_count[b];
@@ -93,7 +99,21 @@ __global__ void detect_target_kernel(const double* __restrict__ gt, const int* _
         const float uni = __fsub_rn(__fadd_rn(x_area, y_area), inter);
         const float iou = __fdiv_rn(inter, uni);
         if (iou > thr0) {                       // :172-177 positives (NaN compares false like numpy)
-            const int c = gt_class[b * G + g];
+            int c = gt_class[b * G + g];
+            if (fit_mode) {
+                // :177 sample_f in double (numpy float32 scalar with python floats under numpy 1.x promotion)
+                const double sample_f = __ddiv_rn(__dsub_rn((double)iou, thr0_d), __dsub_rn(1.0, thr0_d));
+                if (joint) {                    // :180 int() truncates toward zero
+                    int f = (int)__dmul_rn((double)fitness_num, sample_f);
+                    f = f < 0 ? 0 : (f > fitness_num - 1 ? fitness_num - 1 : f);
+                    c = c * fitness_num + f;
+                }
+                if (indfit) {                   // :188-189
+                    int f = 1 + (int)floor(__dmul_rn((double)(fitness_num - 1), sample_f));
+                    f = f < 1 ? 1 : (f > fitness_num - 1 ? fitness_num - 1 : f);
+                    fit_bins |= 1u << f;
+                }
+            }
             bool seen = false;
             for (int i = 0; i < npos; ++i) seen |= (pos_cls[i] == c);
             if (!seen) pos_cls[npos++] = c;
@@ -109,10 +129,17 @@ __global__ void detect_target_kernel(const double* __restrict__ gt, const int* _
     const float v_null = __fdiv_rn(__fdiv_rn(1.f, 1.f), nfactor);
     for (int c = 0; c < s0; ++c) d[(long long)c * plane] = 0.f;
     if (npos == 0) {
-        d[(long long)class_num * plane] = v_null;
+        d[(long long)null_class * plane] = v_null;
     } else {
         const float v = __fdiv_rn(__fdiv_rn(1.f, (float)npos), nfactor);
         for (int i = 0; i < npos; ++i) d[(long long)pos_cls[i] * plane] = v;
+    }
+    if (indfit) {
+        float* f = fit + (long long)b * fitness_num * plane + k;
+        const int nb = __popc(fit_bins);
+        const float v = __fdiv_rn(__fdiv_rn(1.f, (float)(nb ? nb : 1)), nfactor);
+        f[0] = nb ? 0.f : v;
+        for (int i = 1; i < fitness_num; ++i) f[(long long)i * plane] = ((fit_bins >> i) & 1u) ? v : 0.f;
     }
     if (use_bbox) {
         float r[8] = {0.f, 0.f, 1.f, 1.f, 0.f, 0.f, 1.f, 1.f};
@@ -156,17 +183,27 @@ extern "C" int denet_corner_target(const double* gt_bbox, const int* gt_count, i
     return 0;
 }
 
+extern "C" int denet_detect_target_v2(const double* gt_bbox, const int* gt_class, const int* gt_count,
+                                      const double* sample_bbox, int B, int G, int sn, int class_num, double thr0,
+                                      double thr1, int use_bbox, int fit_mode, float* target_det, float* target_valid,
+                                      float* target_reg, float* target_fit, cudaStream_t stream) {
+    DN_REQUIRE(gt_bbox && gt_class && gt_count && sample_bbox && target_det, "detect_target: null pointer");
+    DN_REQUIRE(!use_bbox || (target_valid && target_reg), "detect_target: box targets requested without buffers");
+    DN_REQUIRE(!(fit_mode & 2) || target_fit, "detect_target: fitness target requested without a buffer");
+    DN_REQUIRE((fit_mode & 3) != 3, "detect_target: joint and independent fitness exclude each other");
+    DN_REQUIRE(G > 0 && G <= kMaxGt, "detect_target: at most %d ground-truth boxes per image (got %d)", kMaxGt, G);
+    const long long total = (long long)B * sn * sn;
+    detect_target_kernel<<<DN_G((int)ceil_div_ll(total, 128)), 128, 0, stream>>>(
+        gt_bbox, gt_class, gt_count, sample_bbox, B, G, sn, class_num, (float)thr0, (float)thr1, use_bbox, fit_mode, thr0,
+        target_det, target_valid, target_reg, target_fit);
+    DN_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int denet_detect_target(const double* gt_bbox, const int* gt_class, const int* gt_count,
                                    const double* sample_bbox, int B, int G, int sn, int class_num, float thr0,
                                    float thr1, int use_bbox, float* target_det, float* target_valid, float* target_reg,
                                    cudaStream_t stream) {
-    DN_REQUIRE(gt_bbox && gt_class && gt_count && sample_bbox && target_det, "detect_target: null pointer");
-    DN_REQUIRE(!use_bbox || (target_valid && target_reg), "detect_target: box targets requested without buffers");
-    DN_REQUIRE(G > 0 && G <= kMaxGt, "detect_target: at most %d ground-truth boxes per image (got %d)", kMaxGt, G);
-    const long long total = (long long)B * sn * sn;
-    detect_target_kernel<<<DN_G((int)ceil_div_ll(total, 128)), 128, 0, stream>>>(
-        gt_bbox, gt_class, gt_count, sample_bbox, B, G, sn, class_num, thr0, thr1, use_bbox, target_det, target_valid,
-        target_reg);
-    DN_CHECK_LAUNCH();
-    return 0;
+    return denet_detect_target_v2(gt_bbox, gt_class, gt_count, sample_bbox, B, G, sn, class_num, thr0, thr1, use_bbox, 0,
+                                  target_det, target_valid, target_reg, nullptr, stream);
 }

@@ -6,6 +6,10 @@ outputs when bbox_factor > 0).  get_target assigns classes / box targets by IoU 
 (:147-235); the cost is -sum(t*logp)/ln(s0) per RoI summed / batch * cost_factor, plus the Fast R-CNN smooth-L1 box
 loss (:238-313, bbox_factor applied in :295 and again in :310).  get_detections (:316-424) is the inference tail:
 one test-mode forward, device sampler, head, per-class NMS on the GPU (csrc/detect_nms.cu).
+
+v2 variants (the "J" / "B" tags and the fourth parameter of DND): joint fitness (:58-61, 179-182, 332-348) - every
+class splits into 5 IoU-fitness bins, classNum*5+1 outputs; independent fitness (:100-104, 187-191, 297-299,
+392-397) - a second 6-way softmax head; bounded-IoU box loss (:266-286) on the decoded box.
 """
 import numpy
 import torch
@@ -48,8 +52,7 @@ class DeNetDetectLayer(AbstractLayer):
         self.use_bounded_iou = json_param.get("useBoundedIoU", use_bounded_iou)
         self.indfit_factor = json_param.get("fitnessFactor", indfit_factor)
         self.use_indfit = self.indfit_factor > 0.0
-        if self.use_jointfit or self.use_indfit or self.use_bounded_iou:
-            raise Exception("denet-detect: joint / independent fitness and bounded IoU are not on the B200 hot path")
+        assert not (self.use_indfit and self.use_jointfit), "Cannot enable both fitness methods at once!"
 
         sparse_layer = common.find_layers(layers, "denet-sparse", False)
         assert sparse_layer is not None, "Error: Requires denet-sparse layer to be specified before denet-detect layer!"
@@ -58,18 +61,28 @@ class DeNetDetectLayer(AbstractLayer):
         self.use_bbox_reg = self.bbox_factor > 0.0
         self.batch_size = sparse_layer.batch_size
         self.sample_num = sparse_layer.sample_num
-        self.null_class = self.class_num
-        s0 = self.class_num + 1
+        if self.use_jointfit:                   # :58-66
+            self.fitness_num = 5
+            self.null_class = self.class_num * self.fitness_num
+        else:
+            self.fitness_num = 6
+            self.null_class = self.class_num
+        s0 = self.null_class + 1
         s1 = 4 if self.use_bbox_reg else 0
-        conv = ConvLayer([InitialLayer(None, self.input_shape)], (s0 + s1, self.input_shape[1], 1, 1), (1, 1), True,
+        s2 = self.fitness_num if self.use_indfit else 0
+        conv = ConvLayer([InitialLayer(None, self.input_shape)], (s0 + s1 + s2, self.input_shape[1], 1, 1), (1, 1), True,
                          "valid", 0.0)
         conv.out_fp32 = True
         self.layers.append(conv)
         self.det_shape = (self.batch_size, s0, self.sample_num, self.sample_num)
         if self.use_bbox_reg:
             self.bbox_shape = (self.batch_size, s1, self.sample_num, self.sample_num)
+        if self.use_indfit:
+            self.indfit_shape = (self.batch_size, s2, self.sample_num, self.sample_num)
+        self.fit_mode = (1 if self.use_jointfit else 0) | (2 if self.use_indfit else 0)
+        self.box_mode = 0 if not self.use_bbox_reg else (2 if self.use_bounded_iou else 1)
         self.grad_factor = 1.0
-        self.cost_value = None     # device tensor [detection cost, box cost] of the last training forward
+        self.cost_value = None     # device tensor [detection, box, fitness cost] of the last training forward
         self._targets = None
         self._targets_dev = None    # persistent target buffers filled by denet_detect_target
         self._dout = None
@@ -119,6 +132,9 @@ class DeNetDetectLayer(AbstractLayer):
             bbox_valid = numpy.zeros((self.batch_size, sn, sn), dtype=numpy.float32)
             bbox_reg = numpy.zeros((self.batch_size, 8, sn, sn), dtype=numpy.float32)
             bbox_reg[:, [2, 3, 6, 7]] = 1.0
+        if self.use_indfit:
+            indfit_pr = numpy.zeros(self.indfit_shape, dtype=numpy.float32)
+            indfit_pr[:, 0] = 1.0
         all_samples = self.sparse_layer.sample_bbox_host            # (B,K,4) float64
         for b, meta in enumerate(metas):
             samples = all_samples[b]
@@ -128,8 +144,20 @@ class DeNetDetectLayer(AbstractLayer):
             bbox_indexs, sample_indexs = numpy.where(overlap > thr0)
             if len(bbox_indexs) > 0:
                 cls = numpy.asarray(meta["class"], dtype=numpy.int64)[bbox_indexs]
+                if self.fit_mode:
+                    # :177 in float64: the reference mixes a numpy float32 scalar with python floats (numpy 1.x promotes
+                    # that to float64)
+                    sample_f = (overlap[bbox_indexs, sample_indexs].astype(numpy.float64) - thr0) / (1.0 - thr0)
+                if self.use_jointfit:               # :179-182 (int() truncates toward zero)
+                    f = numpy.clip(numpy.trunc(self.fitness_num * sample_f).astype(numpy.int64), 0, self.fitness_num - 1)
+                    cls = cls * self.fitness_num + f
                 det_pr[b, cls, sample_indexs // sn, sample_indexs % sn] = 1.0
                 det_pr[b, self.null_class, sample_indexs // sn, sample_indexs % sn] = 0.0
+                if self.use_indfit:                 # :187-191
+                    f = 1 + numpy.floor((self.fitness_num - 1) * sample_f).astype(numpy.int64)
+                    f = numpy.clip(f, 1, self.fitness_num - 1)
+                    indfit_pr[b, 0, sample_indexs // sn, sample_indexs % sn] = 0.0
+                    indfit_pr[b, f, sample_indexs // sn, sample_indexs % sn] = 1.0
             if self.use_bbox_reg:
                 overlap_max = overlap.argmax(axis=0)
                 index = numpy.arange(len(samples))
@@ -154,23 +182,31 @@ class DeNetDetectLayer(AbstractLayer):
         if self.use_bbox_reg:
             bbox_valid /= nfactor
             yt_value = numpy.concatenate((yt_value, bbox_valid.flatten(), bbox_reg.flatten()))
+        if self.use_indfit:
+            indfit_pr /= indfit_pr.sum(axis=1)[:, None]
+            indfit_pr /= nfactor
+            yt_value = numpy.concatenate((yt_value, indfit_pr.flatten()))
         return numpy.array([], dtype=numpy.int64), yt_value
 
     def set_target(self, yt_index, yt_value):
         v = h2d(numpy.ascontiguousarray(yt_value, dtype=numpy.float32))
         n0 = int(numpy.prod(self.det_shape))
         n1 = self.batch_size * self.sample_num * self.sample_num
+        off = n0
+        t_valid = t_reg = t_fit = None
         if self.use_bbox_reg:
-            self._targets = (v[:n0], v[n0:n0 + n1], v[n0 + n1:n0 + 9 * n1])
-        else:
-            self._targets = (v[:n0], None, None)
+            t_valid, t_reg = v[n0:n0 + n1], v[n0 + n1:n0 + 9 * n1]
+            off += 9 * n1
+        if self.use_indfit:
+            t_fit = v[off:off + self.fitness_num * n1]
+        self._targets = (v[:n0], t_valid, t_reg, t_fit)
 
     def forward(self, x):
         self.input = self.output = x
         o = self.layers[0].forward(x)            # (B,sn,sn,s0+s1) fp32
         self.logits = o
         if self.cost_value is None:
-            self.cost_value = torch.zeros((2,), dtype=torch.float32, device=x.device)
+            self.cost_value = torch.zeros((3,), dtype=torch.float32, device=x.device)
         if get_train():
             if device_targets():
                 if self._targets_dev is None:
@@ -180,17 +216,21 @@ class DeNetDetectLayer(AbstractLayer):
                         torch.empty((self.batch_size, sn, sn), dtype=torch.float32, device=dev) if self.use_bbox_reg
                         else None,
                         torch.empty((self.batch_size, 8, sn, sn), dtype=torch.float32, device=dev) if self.use_bbox_reg
-                        else None)
+                        else None,
+                        torch.empty(self.indfit_shape, dtype=torch.float32, device=dev) if self.use_indfit else None)
                 thr0, thr1 = self._thresholds()
+                t_det, t_valid, t_reg, t_fit = self._targets_dev
                 ops.detect_target(get_ground_truth(), self.sparse_layer.sample_bbox64, self.sample_num, self.class_num,
-                                  thr0, thr1, self.use_bbox_reg, *self._targets_dev)
+                                  thr0, thr1, self.use_bbox_reg, t_det, t_valid, t_reg, fit_mode=self.fit_mode, fit=t_fit)
                 self._targets = self._targets_dev
             assert self._targets is not None, "denet-detect: get_target/set_target must precede a training forward"
             self._dout = ops.alloc_like(o)
-            t_det, t_valid, t_reg = self._targets
-            ops.detect_cost(o, self.sample_num, self.det_shape[1], self.use_bbox_reg, t_det, t_valid, t_reg,
+            t_det, t_valid, t_reg, t_fit = self._targets
+            ops.detect_cost(o, self.sample_num, self.det_shape[1], self.box_mode, t_det, t_valid, t_reg,
                             float(self.cost_factor), float(self.bbox_factor), self.grad_factor, self._dout,
-                            self.cost_value)
+                            self.cost_value, nfit=self.fitness_num if self.use_indfit else 0, target_fit=t_fit,
+                            fit_factor=float(self.indfit_factor),
+                            sample_bbox=self.sparse_layer.sample_bbox if self.box_mode == 2 else None)
         return x
 
     def cost(self, yt_index=None, yt_value=None):
@@ -231,8 +271,10 @@ class DeNetDetectLayer(AbstractLayer):
         return [{"detections": detlist, "meta": data_m[i]} for i, detlist in enumerate(detlists)]
 
     def detect_outputs(self):
-        """(det_pr (B,s0,sn,sn), fitness, bbox (B,sn,sn,4)) device tensors of the last test-mode forward
-        (the outputs of the reference's detect_func, denet_detect.py:330-362; fitness = det_pr without joint fitness)"""
-        det_pr, bbox = ops.detect_outputs(self.logits, self.sample_num, self.det_shape[1], self.use_bbox_reg,
-                                          self.sparse_layer.sample_bbox)
-        return det_pr, det_pr, bbox
+        """(det_pr (B,classNum+1,sn,sn), fitness, bbox (B,sn,sn,4)) device tensors of the last test-mode forward
+        (the outputs of the reference's detect_func, denet_detect.py:330-362, with the host arithmetic of :378-397 folded
+        in; fitness = det_pr without a fitness head)"""
+        thr0, _ = self._thresholds()
+        return ops.detect_outputs(self.logits, self.sample_num, self.det_shape[1], self.use_bbox_reg,
+                                  self.sparse_layer.sample_bbox, class_num=self.class_num, fit_mode=self.fit_mode,
+                                  thr0=thr0)

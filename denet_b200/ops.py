@@ -750,13 +750,14 @@ def corner_target(gt, cn, H, W, out):
     return out
 
 
-def detect_target(gt, sample_bbox64, sn, class_num, thr0, thr1, use_bbox, det, valid, reg):
+def detect_target(gt, sample_bbox64, sn, class_num, thr0, thr1, use_bbox, det, valid, reg, fit_mode=0, fit=None):
+    """fit_mode bit0 joint fitness (det has classNum*5+1 channels), bit1 independent fitness (fit (B,6,sn,sn))"""
     gt_bbox, gt_class, gt_count = gt
     b, g = gt_bbox.shape[:2]
     assert sample_bbox64.dtype == torch.float64 and sample_bbox64.is_contiguous()
-    call("denet_detect_target", gt_bbox.data_ptr(), gt_class.data_ptr(), gt_count.data_ptr(),
-         sample_bbox64.data_ptr(), b, g, sn, class_num, float(thr0), float(thr1), int(use_bbox), det.data_ptr(),
-         _ptr(valid), _ptr(reg), _stream())
+    call("denet_detect_target_v2", gt_bbox.data_ptr(), gt_class.data_ptr(), gt_count.data_ptr(),
+         sample_bbox64.data_ptr(), b, g, sn, class_num, float(thr0), float(thr1), int(use_bbox), int(fit_mode),
+         det.data_ptr(), _ptr(valid), _ptr(reg), _ptr(fit), _stream())
 
 
 # ---------------------------------------------------------------------------------------------- costs
@@ -780,14 +781,18 @@ def corner_cost(z, cn, target, cost_factor, grad_factor, dz, cost):
          grad_factor, dz.data_ptr(), cost.data_ptr(), ws.data_ptr(), _stream())
 
 
-def detect_cost(o, sn, s0, use_bbox, target_det, target_valid, target_reg, cost_factor, bbox_factor, grad_factor, dout,
-                cost2):
+def detect_cost(o, sn, s0, box_mode, target_det, target_valid, target_reg, cost_factor, bbox_factor, grad_factor, dout,
+                cost3, nfit=0, target_fit=None, fit_factor=0.0, sample_bbox=None):
+    """box_mode 0 none / 1 Fast R-CNN / 2 bounded IoU (needs sample_bbox (B,sn,sn,4) fp32); nfit independent-fitness
+    logits after the box outputs; cost3 (3) fp32 = {detection, box, fitness} cost"""
     b = o.shape[0]
-    assert _pitch(dout) == _pitch(o) and dout.dtype == o.dtype
+    assert _pitch(dout) == _pitch(o) and dout.dtype == o.dtype and cost3.numel() >= 3
+    assert sample_bbox is None or (sample_bbox.dtype == torch.float32 and sample_bbox.is_contiguous())
     ws = _loss_ws(o.device)
-    call("denet_detect_cost", o.data_ptr(), _dtype_code(o), _pitch(o), b, sn, s0, int(use_bbox), target_det.data_ptr(),
-         _ptr(target_valid), _ptr(target_reg), cost_factor, bbox_factor, grad_factor, dout.data_ptr(), dout.shape[-1],
-         cost2.data_ptr(), ws.data_ptr(), _stream())
+    call("denet_detect_cost_v2", o.data_ptr(), _dtype_code(o), _pitch(o), b, sn, s0, int(box_mode), int(nfit),
+         _ptr(sample_bbox), target_det.data_ptr(), _ptr(target_valid), _ptr(target_reg), _ptr(target_fit), cost_factor,
+         bbox_factor, fit_factor, grad_factor, dout.data_ptr(), dout.shape[-1], cost3.data_ptr(), ws.data_ptr(),
+         _stream())
 
 
 def softmax_nll(o, classes, label, grad_factor, dout, logp, cost):
@@ -799,15 +804,19 @@ def softmax_nll(o, classes, label, grad_factor, dout, logp, cost):
 
 
 # ---------------------------------------------------------------------------------------------- inference tail
-def detect_outputs(logits, sn, s0, use_bbox, sample_bbox):
-    """detect-layer logits (B,sn,sn,>=s0[+4]) fp32 -> (det_pr (B,s0,sn,sn) log-probabilities, bbox (B,sn,sn,4))"""
+def detect_outputs(logits, sn, s0, use_bbox, sample_bbox, class_num=None, fit_mode=0, thr0=0.5):
+    """detect-layer logits (B,sn,sn,>=s0[+4][+6]) fp32 -> (det_pr (B,classNum+1,sn,sn) log-probabilities,
+    fitness (same shape; det_pr itself without a fitness head), bbox (B,sn,sn,4)).
+    fit_mode bit0: joint fitness (s0 = classNum*5+1), bit1: independent fitness"""
     assert logits.dtype == torch.float32
     b = logits.shape[0]
-    det_pr = torch.empty((b, s0, sn, sn), dtype=torch.float32, device=logits.device)
+    class_num = s0 - 1 if class_num is None else class_num
+    det_pr = torch.empty((b, class_num + 1, sn, sn), dtype=torch.float32, device=logits.device)
+    fitness = torch.empty_like(det_pr) if fit_mode else None
     bbox = torch.empty((b, sn, sn, 4), dtype=torch.float32, device=logits.device)
-    call("denet_detect_outputs", logits.data_ptr(), _pitch(logits), b, sn, s0, int(use_bbox), sample_bbox.data_ptr(),
-         det_pr.data_ptr(), bbox.data_ptr(), _stream())
-    return det_pr, bbox
+    call("denet_detect_outputs_v2", logits.data_ptr(), _pitch(logits), b, sn, s0, int(use_bbox), class_num,
+         int(fit_mode), float(thr0), sample_bbox.data_ptr(), det_pr.data_ptr(), _ptr(fitness), bbox.data_ptr(), _stream())
+    return det_pr, (fitness if fit_mode else det_pr), bbox
 
 
 def detections_nms(det_pr, fitness, bbox, bbox_num, pr_threshold, nms_threshold, use_soft_nms):

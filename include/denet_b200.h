@@ -326,6 +326,15 @@ int denet_detect_cost(const void* o, int dtype, long long ld, int B, int sn, int
                       const float* target_det, const float* target_valid, const float* target_reg, float cost_factor,
                       float bbox_factor, float grad_factor, void* dout, int ncols_grad, float* cost2, float* workspace,
                       cudaStream_t stream);
+/* detect_cost_v2: the same with the v2 variants of the layer: box_mode 0 none / 1 Fast R-CNN (:288-295) / 2 bounded IoU
+ *   (:266-286, on the box decoded against sample_bbox (B*sn*sn, 4) fp32 as :80-97), nfit = 6 independent-fitness logits
+ *   after the box outputs (:100-104, 297-299) with target_fit (B, nfit, sn, sn); joint fitness (:58-61) only changes s0
+ *   to classNum*5+1.  cost3 = {detection, box, fitness} cost, factors included (:308-312). */
+int denet_detect_cost_v2(const void* o, int dtype, long long ld, int B, int sn, int s0, int box_mode, int nfit,
+                         const float* sample_bbox, const float* target_det, const float* target_valid,
+                         const float* target_reg, const float* target_fit, float cost_factor, float bbox_factor,
+                         float fit_factor, float grad_factor, void* dout, int ncols_grad, float* cost3, float* workspace,
+                         cudaStream_t stream);
 int denet_softmax_nll(const void* o, int dtype, long long ld, int B, int classes, const int* label, float grad_factor,
                       void* dout, float* logp_out, float* cost, float* workspace, cudaStream_t stream);
 
@@ -364,6 +373,14 @@ int denet_corner_target(const double* gt_bbox, const int* gt_count, int B, int G
 int denet_detect_target(const double* gt_bbox, const int* gt_class, const int* gt_count, const double* sample_bbox,
                         int B, int G, int sn, int class_num, float thr0, float thr1, int use_bbox, float* target_det,
                         float* target_valid, float* target_reg, cudaStream_t stream);
+/* detect_target_v2: fit_mode bit0 = joint fitness (:58-61,179-182: target_det (B, classNum*5+1, sn, sn), a positive RoI
+ *   marks class*5 + fitness bin), bit1 = independent fitness (:187-191: target_fit (B, 6, sn, sn)); thr0 / thr1 as
+ *   doubles: the IoU comparison uses them rounded to fp32 like the reference's array comparison, the fitness bin
+ *   (:177) is computed in double as numpy 1.x promotes the reference's scalar arithmetic. */
+int denet_detect_target_v2(const double* gt_bbox, const int* gt_class, const int* gt_count, const double* sample_bbox,
+                           int B, int G, int sn, int class_num, double thr0, double thr1, int use_bbox, int fit_mode,
+                           float* target_det, float* target_valid, float* target_reg, float* target_fit,
+                           cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ solver
  * ModelCNN.build_train_func update rules (model/model_cnn.py:282-305, 320-324) for ALL parameter
@@ -400,6 +417,12 @@ int denet_pack_costs(const void* srcs, const int* lens, const float* factors, in
  *   expf's bits, out_index = sample index k; out_count (B, class_num).  Results are bit-identical to the reference. */
 int denet_detect_outputs(const float* logits, long long ld, int B, int sn, int s0, int use_bbox,
                          const float* sample_bbox, float* det_pr, float* bbox_out, cudaStream_t stream);
+/* detect_outputs_v2: fit_mode bit0 = joint fitness (s0 = classNum*5+1 channels folded to det_pr (B, classNum+1, sn, sn)
+ *   and fitness (B, classNum+1, sn, sn), :332-348), bit1 = independent fitness (fitness = det_pr + log E[fitness],
+ *   :392-397); fit_mode 0 with fitness != NULL copies det_pr (:386).  thr0 = overlapThreshold[0]. */
+int denet_detect_outputs_v2(const float* logits, long long ld, int B, int sn, int s0, int use_bbox, int class_num,
+                            int fit_mode, float thr0, const float* sample_bbox, float* det_pr, float* fitness,
+                            float* bbox_out, cudaStream_t stream);
 int denet_detections_nms(const float* det_pr, const float* fitness, long long stride_b, long long stride_c,
                          long long stride_k, const float* bbox, const int* bbox_num, int B, int class_num, int K,
                          float pr_threshold, float nms_threshold, int use_soft_nms, float* out_score, int* out_index,

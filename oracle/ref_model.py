@@ -203,10 +203,16 @@ class RefModel:
             elif k == "denet-detect":
                 conv = [c for c in node.children if c.kind == "conv"][0]
                 o = self._conv(conv, h)
-                s0 = js["classNum"] + 1
-                out["det_pr"] = R.log_softmax(o[:, :s0], 1)          # denet_detect.py:76-78
+                joint = js.get("useJointFitness", False)              # denet_detect.py:58-66
+                nf = 5 if joint else 6
+                s0 = js["classNum"] * nf + 1 if joint else js["classNum"] + 1
+                out["det_pr"] = R.log_softmax(o[:, :s0], 1)          # :76-78
+                s1 = 0
                 if js.get("bboxFactor", 0.0) > 0.0:
                     out["bbox_reg"] = o[:, s0:s0 + 4]
+                    s1 = 4
+                if js.get("fitnessFactor", 0.0) > 0.0:               # :100-104
+                    out["indfit_pr"] = R.log_softmax(o[:, s0 + s1:s0 + s1 + nf], 1)
                 out["detect_js"] = js
             elif k == "regression":
                 if js.get("valid"):
@@ -240,26 +246,17 @@ class RefModel:
             elif k == "denet-detect":
                 v = _t(targets[ti][1], self.dtype)
                 ti += 1
-                det_shape = out["det_pr"].shape
-                B, s0, sn, _ = det_shape
-                n0 = int(np.prod(det_shape))
-                det_t = v[:n0].reshape(det_shape)
-                det_err = -(det_t * out["det_pr"]).sum(dim=1) / math.log(s0)               # denet_detect.py:257
-                cost = js.get("costFactor", 1.0) * det_err.sum() / B                        # :308
+                B = out["det_pr"].shape[0]
                 bf = js.get("bboxFactor", 0.0)
-                if bf > 0.0:
-                    n1 = B * sn * sn
-                    valid = v[n0:n0 + n1].reshape(B, sn, sn)
-                    reg = v[n0 + n1:n0 + n1 + 8 * n1].reshape(B, 8, sn, sn)
-                    tgt, smp = reg[:, 0:4], reg[:, 4:8]
-                    assert not js.get("useBoundedIoU", False)
-                    tx = (tgt[:, 0] - smp[:, 0]) / smp[:, 2]                                 # :289-292
-                    ty = (tgt[:, 1] - smp[:, 1]) / smp[:, 3]
-                    tw = torch.log(tgt[:, 2] / smp[:, 2])
-                    th = torch.log(tgt[:, 3] / smp[:, 3])
-                    dt = torch.stack([tx, ty, tw, th], dim=1) - out["bbox_reg"]
-                    bbox_err = bf * valid * R.smooth_l1(dt).sum(dim=1)                       # :295
+                ff = js.get("fitnessFactor", 0.0)
+                det_err, bbox_err, fit_err = R.detect_errors(
+                    out["det_pr"], out.get("bbox_reg") if bf > 0.0 else None, out.get("indfit_pr") if ff > 0.0 else None,
+                    _t(out["sample_bbox"], self.dtype), v, bf, js.get("useBoundedIoU", False))
+                cost = js.get("costFactor", 1.0) * det_err.sum() / B                        # denet_detect.py:308
+                if bbox_err is not None:
                     cost = cost + bf * bbox_err.sum() / B                                    # :310 (factor twice)
+                if fit_err is not None:
+                    cost = cost + ff * fit_err.sum() / B                                     # :312
                 costs.append(cost)
             elif k == "regression":
                 idx = torch.as_tensor(np.asarray(targets[ti][0]), dtype=torch.long)

@@ -248,19 +248,26 @@ def overlap_iou_matrix(obj_bboxs, sample_bboxs):
     return inter / union
 
 
-def detect_target(metas, sample_bbox_list, batch_size, sample_num, class_num, overlap_threshold, use_bbox_reg):
-    """DeNetDetectLayer.get_target, denet_detect.py:147-235 (no joint / independent fitness).
-    overlap_threshold: scalar or pair (the reference indexes [0]/[1] although parse_desc passes a scalar)."""
+def detect_target(metas, sample_bbox_list, batch_size, sample_num, class_num, overlap_threshold, use_bbox_reg,
+                  use_jointfit=False, use_indfit=False):
+    """DeNetDetectLayer.get_target, denet_detect.py:147-235, incl. the joint-fitness (:179-182) and independent-fitness
+    (:187-191) targets.  overlap_threshold: scalar or pair (the reference indexes [0]/[1] although parse_desc passes a
+    scalar).  sample_f (:177) mixes a numpy float32 scalar with python floats: under the numpy the reference ran on
+    (1.x, value-based scalar promotion) that arithmetic is float64, which is what float(...) restates here."""
     thr = overlap_threshold if isinstance(overlap_threshold, (tuple, list)) else (overlap_threshold,
                                                                                   overlap_threshold)
-    null_class = class_num
-    det_shape = (batch_size, class_num + 1, sample_num, sample_num)
+    fitness_num = 5 if use_jointfit else 6                                              # :58-66
+    null_class = class_num * fitness_num if use_jointfit else class_num
+    det_shape = (batch_size, null_class + 1, sample_num, sample_num)
     det_pr = np.zeros(det_shape, dtype=np.float32)
     det_pr[:, null_class] = 1.0
     if use_bbox_reg:
         bbox_valid = np.zeros((batch_size, sample_num, sample_num), dtype=np.float32)
         bbox_reg = np.zeros((batch_size, 8, sample_num, sample_num), dtype=np.float32)
         bbox_reg[:, [2, 3, 6, 7]] = 1.0
+    if use_indfit:
+        indfit_pr = np.zeros((batch_size, fitness_num, sample_num, sample_num), dtype=np.float32)
+        indfit_pr[:, 0] = 1.0
     for b, meta in enumerate(metas):
         samples = [bbox for _, bbox in sample_bbox_list[b]]
         if len(meta["bbox"]) > 0 and len(samples) > 0:
@@ -268,8 +275,19 @@ def detect_target(metas, sample_bbox_list, batch_size, sample_num, class_num, ov
             bbox_indexs, sample_indexs = np.where(overlap > thr[0])
             for obj, index in zip(bbox_indexs.tolist(), sample_indexs.tolist()):
                 si, sj = index % sample_num, index // sample_num
-                det_pr[b, meta["class"][obj], sj, si] = 1.0
+                sample_cls = meta["class"][obj]
+                sample_f = (float(overlap[obj, index]) - thr[0]) / (1.0 - thr[0])        # :177
+                if use_jointfit:
+                    f = max(0, min(int(fitness_num * sample_f), fitness_num - 1))
+                    det_pr[b, sample_cls * fitness_num + f, sj, si] = 1.0
+                else:
+                    det_pr[b, sample_cls, sj, si] = 1.0
                 det_pr[b, null_class, sj, si] = 0.0
+                if use_indfit:
+                    f = 1 + int(math.floor((fitness_num - 1) * sample_f))
+                    f = max(1, min(f, fitness_num - 1))
+                    indfit_pr[b, 0, sj, si] = 0.0
+                    indfit_pr[b, f, sj, si] = 1.0
             if use_bbox_reg:
                 overlap_max = overlap.argmax(axis=0)
                 for index in range(len(samples)):
@@ -288,13 +306,105 @@ def detect_target(metas, sample_bbox_list, batch_size, sample_num, class_num, ov
                     bbox_reg[b, 6, sj, si] = sample[2] - sample[0]
                     bbox_reg[b, 7, sj, si] = sample[3] - sample[1]
     det_pr /= det_pr.sum(axis=1)[:, None]
+    if use_indfit:
+        indfit_pr /= indfit_pr.sum(axis=1)[:, None]
     nfactor = sample_num * sample_num
     det_pr /= nfactor
     yt_value = det_pr.flatten()
     if use_bbox_reg:
         bbox_valid /= nfactor
         yt_value = np.concatenate((yt_value, bbox_valid.flatten(), bbox_reg.flatten()))
+    if use_indfit:
+        indfit_pr /= nfactor
+        yt_value = np.concatenate((yt_value, indfit_pr.flatten()))
     return np.array([], dtype=np.int64), yt_value
+
+
+def detect_errors(det_pr, bbox_reg, indfit_pr, sample_bbox, yt_value, bbox_factor, use_bounded_iou):
+    """DeNetDetectLayer.get_errors, denet_detect.py:238-301, on torch tensors (differentiable).
+    det_pr (B,s0,sn,sn) log-softmax, bbox_reg (B,4,sn,sn) or None, indfit_pr (B,nf,sn,sn) log-softmax or None,
+    sample_bbox (B,sn,sn,4); returns (det_errors, bbox_errors | None, indfit_errors | None), each (B,sn,sn)."""
+    B, s0, sn, _ = det_pr.shape
+    n0, n1 = B * s0 * sn * sn, B * sn * sn
+    v = yt_value
+    det_t = v[:n0].reshape(det_pr.shape)
+    det_errors = -(det_t * det_pr).sum(dim=1) / math.log(s0)                              # :257
+    off = n0
+    bbox_errors = None
+    if bbox_reg is not None:
+        valid = v[off:off + n1].reshape(B, sn, sn)
+        reg = v[off + n1:off + 9 * n1].reshape(B, 8, sn, sn)
+        off += 9 * n1
+        tgt, smp = reg[:, 0:4], reg[:, 4:8]
+        if use_bounded_iou:                                                                # :266-286
+            sb = sample_bbox
+            sample_cx, sample_cy = 0.5 * (sb[..., 0] + sb[..., 2]), 0.5 * (sb[..., 1] + sb[..., 3])     # :84-87
+            sample_w, sample_h = sb[..., 2] - sb[..., 0], sb[..., 3] - sb[..., 1]
+            pcx, pcy = bbox_reg[:, 0] * sample_w + sample_cx, bbox_reg[:, 1] * sample_h + sample_cy     # :89-92
+            pw, ph = torch.exp(bbox_reg[:, 2]) * sample_w, torch.exp(bbox_reg[:, 3]) * sample_h
+            x0, y0, x1, y1 = pcx - pw * 0.5, pcy - ph * 0.5, pcx + pw * 0.5, pcy + ph * 0.5             # :93-96
+            predict_x, predict_y, predict_w, predict_h = 0.5 * (x0 + x1), 0.5 * (y0 + y1), x1 - x0, y1 - y0
+            dx, dy = tgt[:, 0] - predict_x, tgt[:, 1] - predict_y
+            eps = 0.001
+            cost_x = torch.where(dx >= 0.0, 2 * dx / (tgt[:, 2] + dx + eps), -2 * dx / (tgt[:, 2] - dx + eps))
+            cost_y = torch.where(dy >= 0.0, 2 * dy / (tgt[:, 3] + dy + eps), -2 * dy / (tgt[:, 3] - dy + eps))
+            cost_w = 1.0 - torch.minimum(tgt[:, 2] / (predict_w + eps), predict_w / (tgt[:, 2] + eps))
+            cost_h = 1.0 - torch.minimum(tgt[:, 3] / (predict_h + eps), predict_h / (tgt[:, 3] + eps))
+            cost = torch.stack([cost_x, cost_y, cost_w, cost_h], dim=1)
+            bbox_errors = bbox_factor * valid * smooth_l1(cost).sum(dim=1)
+        else:
+            tx = (tgt[:, 0] - smp[:, 0]) / smp[:, 2]                                      # :289-292
+            ty = (tgt[:, 1] - smp[:, 1]) / smp[:, 3]
+            tw = torch.log(tgt[:, 2] / smp[:, 2])
+            th = torch.log(tgt[:, 3] / smp[:, 3])
+            dt = torch.stack([tx, ty, tw, th], dim=1) - bbox_reg
+            bbox_errors = bbox_factor * valid * smooth_l1(dt).sum(dim=1)                   # :295
+    indfit_errors = None
+    if indfit_pr is not None:
+        nf = indfit_pr.shape[1]
+        fit_t = v[off:off + nf * n1].reshape(indfit_pr.shape)
+        indfit_errors = -(fit_t * indfit_pr).sum(dim=1) / math.log(nf)                    # :299
+    return det_errors, bbox_errors, indfit_errors
+
+
+def detect_outputs(logits, sample_bbox, class_num, overlap_threshold, use_bbox_reg, use_jointfit, use_indfit):
+    """What get_detections hands to build_detections_nms (denet_detect.py:330-399), numpy float32:
+    logits (B, s0+s1+s2, sn, sn), sample_bbox (B,sn,sn,4) -> det_pr (B,classNum+1,sn,sn), fitness (B,classNum[+1],sn,sn),
+    bboxs (B,sn,sn,4)."""
+    thr0 = overlap_threshold[0] if isinstance(overlap_threshold, (tuple, list)) else overlap_threshold
+    o = torch.from_numpy(np.asarray(logits, np.float32))
+    fitness_num = 5 if use_jointfit else 6
+    s0 = class_num * fitness_num + 1 if use_jointfit else class_num + 1
+    s1 = 4 if use_bbox_reg else 0
+    lp = log_softmax(o[:, :s0], 1)
+    B, _, sn, _ = o.shape
+    if use_jointfit:                                                                       # :332-348
+        det_fit = lp[:, :class_num * fitness_num].reshape(B, class_num, fitness_num, sn, sn)
+        m = det_fit.max(dim=2)[0]
+        det_pr = m + torch.log(torch.sum(torch.exp(det_fit - m[:, :, None]), dim=2))
+        det_pr = torch.cat([det_pr, lp[:, class_num * fitness_num][:, None]], dim=1)
+        val = torch.tensor([thr0 + i * (1.0 - thr0) / fitness_num for i in range(fitness_num)], dtype=torch.float32)
+        fitness = torch.log(torch.sum(torch.exp(det_fit) * val[None, None, :, None, None], dim=2))
+    else:
+        det_pr = lp
+        fitness = lp.clone()
+    sb = torch.from_numpy(np.asarray(sample_bbox, np.float32))
+    if use_bbox_reg:                                                                       # :80-97
+        r = o[:, s0:s0 + 4]
+        scx, scy = 0.5 * (sb[..., 0] + sb[..., 2]), 0.5 * (sb[..., 1] + sb[..., 3])
+        sw, sh = sb[..., 2] - sb[..., 0], sb[..., 3] - sb[..., 1]
+        pcx, pcy = r[:, 0] * sw + scx, r[:, 1] * sh + scy
+        pw, ph = torch.exp(r[:, 2]) * sw, torch.exp(r[:, 3]) * sh
+        bboxs = torch.stack([pcx - pw * 0.5, pcy - ph * 0.5, pcx + pw * 0.5, pcy + ph * 0.5], dim=-1)
+    else:
+        bboxs = sb
+    det_pr, fitness, bboxs = det_pr.numpy(), fitness.numpy(), bboxs.numpy()
+    if use_indfit:                                                                         # :392-397
+        indfit_pr = torch.exp(log_softmax(o[:, s0 + s1:s0 + s1 + fitness_num], 1)).numpy()
+        fitness_val = np.array([0.0] + [thr0 + i * (1.0 - thr0) / (fitness_num - 1) for i in range(fitness_num - 1)])
+        fitness_exp = np.sum(indfit_pr * fitness_val[None, :, None, None], axis=1).astype(np.float32)
+        fitness = fitness + np.log(fitness_exp)[:, None, :, :]
+    return det_pr, fitness, bboxs
 
 
 def sparse_postprocess(sample_bboxs, metas, sample_count, random_sample, sample_gt, rng):

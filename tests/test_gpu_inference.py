@@ -54,7 +54,8 @@ def test_detect_outputs_vs_restatement(cuda):
     sb[..., 2:] += sb[..., :2] + 0.05
     lg = ops.alloc_nhwc(B, sn, sn, s0 + 4, torch.float32, cuda)
     lg.copy_(logits)
-    det_pr, bbox = ops.detect_outputs(lg, sn, s0, True, sb.to(cuda))
+    det_pr, fitness, bbox = ops.detect_outputs(lg, sn, s0, True, sb.to(cuda))
+    assert fitness is det_pr
     z = logits.double().permute(0, 3, 1, 2)
     want = R.log_softmax(z[:, :s0], 1)
     assert (det_pr.cpu().double() - want).abs().max() < 1e-5
@@ -65,8 +66,37 @@ def test_detect_outputs_vs_restatement(cuda):
     pw, ph = torch.exp(reg[:, 2]) * w, torch.exp(reg[:, 3]) * h
     wantb = torch.stack([pcx - pw * 0.5, pcy - ph * 0.5, pcx + pw * 0.5, pcy + ph * 0.5], dim=-1)
     assert (bbox.cpu().double() - wantb).abs().max() < 1e-5
-    _, plain = ops.detect_outputs(lg, sn, s0, False, sb.to(cuda))
+    _, _, plain = ops.detect_outputs(lg, sn, s0, False, sb.to(cuda))
     assert torch.equal(plain.cpu(), sb)
+
+
+@pytest.mark.parametrize("joint,indfit,use_bbox", [(True, False, False), (True, False, True), (False, True, True),
+                                                   (False, True, False)])
+def test_detect_outputs_fitness_heads(cuda, joint, indfit, use_bbox):
+    """the v2 heads of get_detections (denet_detect.py:332-348 joint fitness, :392-397 independent fitness) against the
+    oracle's numpy / torch-CPU float32 restatement (the reference evaluates these in Theano + numpy float32: 1e-5)"""
+    from denet_b200 import ops
+    B, sn, classes, thr0 = 3, 7, 20, 0.6
+    s0 = classes * 5 + 1 if joint else classes + 1
+    nout = s0 + (4 if use_bbox else 0) + (6 if indfit else 0)
+    g = torch.Generator().manual_seed(9)
+    logits = torch.randn(B, sn, sn, nout, generator=g) * 2
+    if use_bbox:
+        logits[..., s0:s0 + 4] *= 0.2
+    sb = torch.rand(B, sn, sn, 4, generator=g) * 0.5
+    sb[..., 2:] += sb[..., :2] + 0.05
+    lg = ops.alloc_nhwc(B, sn, sn, nout, torch.float32, cuda)
+    lg.copy_(logits)
+    det_pr, fitness, bbox = ops.detect_outputs(lg, sn, s0, use_bbox, sb.to(cuda), class_num=classes,
+                                               fit_mode=(1 if joint else 0) | (2 if indfit else 0), thr0=thr0)
+    want_pr, want_fit, want_box = R.detect_outputs(logits.permute(0, 3, 1, 2).numpy(), sb.numpy(), classes, thr0, use_bbox,
+                                                   joint, indfit)
+    assert det_pr.shape == (B, classes + 1, sn, sn) and fitness.shape == det_pr.shape
+    assert numpy.abs(det_pr.cpu().numpy() - want_pr).max() < 1e-5
+    nf = want_fit.shape[1]
+    assert numpy.abs(fitness.cpu().numpy()[:, :nf] - want_fit).max() < 1e-5
+    assert numpy.abs(bbox.cpu().numpy() - want_box).max() < 1e-5
+    assert numpy.abs(fitness.cpu().numpy()[:, :classes] - det_pr.cpu().numpy()[:, :classes]).max() > 1e-3
 
 
 def test_get_detections_end_to_end(cuda):

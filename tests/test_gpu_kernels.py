@@ -697,6 +697,20 @@ def test_device_targets_bit_exact(cuda, B, H, sn, classes, use_bbox):
     assert numpy.array_equal(got[:n0], ref[:n0]), "class targets"
     assert (ref[:n0].reshape(B, classes + 1, -1)[:, :classes] > 0).sum() > 0, "the case must contain positives"
     assert numpy.array_equal(got, ref)
+    # v2 targets: joint fitness (classNum*5+1 channels, denet_detect.py:179-182) and independent fitness (:187-191)
+    for thr in (0.5, 0.7):
+        detj = torch.empty((B, classes * 5 + 1, sn, sn), device="cuda")
+        ops.detect_target(gt, s64, sn, classes, thr, thr, use_bbox, detj, valid, reg, fit_mode=1)
+        ref = R.detect_target(metas, samples, B, sn, classes, thr, use_bbox, use_jointfit=True)[1]
+        got = torch.cat([t.reshape(-1) for t in (detj, valid, reg) if t is not None]).cpu().numpy()
+        assert numpy.array_equal(got, ref), "joint fitness targets"
+        bins = ref[:detj.numel()].reshape(B, classes * 5 + 1, -1)[:, :classes * 5].reshape(B, classes, 5, -1)
+        assert ((bins > 0).sum(axis=(0, 1, 3)) > 0).sum() >= 3, "several fitness bins must occur"
+        fit = torch.empty((B, 6, sn, sn), device="cuda")
+        ops.detect_target(gt, s64, sn, classes, thr, thr, use_bbox, det, valid, reg, fit_mode=2, fit=fit)
+        ref = R.detect_target(metas, samples, B, sn, classes, thr, use_bbox, use_indfit=True)[1]
+        got = torch.cat([t.reshape(-1) for t in (det, valid, reg, fit) if t is not None]).cpu().numpy()
+        assert numpy.array_equal(got, ref), "independent fitness targets"
 
 
 # ------------------------------------------------------------------------------------------------ costs
@@ -722,39 +736,63 @@ def test_corner_logprob_and_cost(cuda):
     assert relerr(nchw(dz)[:, :cn], dref[:, :cn]) < 1e-5
 
 
-@pytest.mark.parametrize("use_bbox", [False, True])
-def test_detect_cost(cuda, use_bbox):
+@pytest.mark.parametrize("box_mode,nfit,joint", [(0, 0, False), (1, 0, False), (2, 0, False), (1, 6, False),
+                                                 (2, 0, True), (0, 6, False)])
+def test_detect_cost(cuda, box_mode, nfit, joint):
+    """denet_detect_cost_v2 == autograd through the oracle's restatement of get_errors / cost (denet_detect.py:238-313):
+    Fast R-CNN and bounded-IoU box losses, the independent-fitness head, joint-fitness channel count"""
     ops = _ops()
-    g = torch.Generator().manual_seed(4)
-    B, sn, s0 = 3, 6, 21
-    nout = s0 + (4 if use_bbox else 0)
-    o = torch.randn(B, nout, sn, sn, generator=g)
+    g = torch.Generator().manual_seed(4 + box_mode + nfit)
+    B, sn = 3, 6
+    s0 = 20 * 5 + 1 if joint else 21
+    s1 = 4 if box_mode else 0
+    o = torch.randn(B, s0 + s1 + nfit, sn, sn, generator=g)
+    if box_mode:
+        o[:, s0:s0 + 4] *= 0.3
     od = nhwc(o, torch.float32, cuda)
     t_det = torch.rand(B, s0, sn, sn, generator=g)
     t_det = t_det / t_det.sum(dim=1, keepdim=True) / (sn * sn)
     valid = (torch.rand(B, sn, sn, generator=g) > 0.5).float() / (sn * sn)
-    reg = torch.rand(B, 8, sn, sn, generator=g) + 0.1
+    sb = torch.rand(B, sn, sn, 4, generator=g) * 0.5
+    sb[..., 2:] += sb[..., :2] + 0.05
+    reg = torch.rand(B, 8, sn, sn, generator=g) * 0.5 + 0.1
+    if box_mode == 2:      # targets near the samples so that both branches of every switch / minimum occur
+        reg[:, 0] = 0.5 * (sb[..., 0] + sb[..., 2]) + (torch.rand(B, sn, sn, generator=g) - 0.5) * 0.2
+        reg[:, 1] = 0.5 * (sb[..., 1] + sb[..., 3]) + (torch.rand(B, sn, sn, generator=g) - 0.5) * 0.2
+        reg[:, 2] = (sb[..., 2] - sb[..., 0]) * (0.5 + torch.rand(B, sn, sn, generator=g))
+        reg[:, 3] = (sb[..., 3] - sb[..., 1]) * (0.5 + torch.rand(B, sn, sn, generator=g))
+    t_fit = torch.rand(B, max(nfit, 1), sn, sn, generator=g)
+    t_fit = t_fit / t_fit.sum(dim=1, keepdim=True) / (sn * sn)
+    parts = [t_det.reshape(-1)]
+    if box_mode:
+        parts += [valid.reshape(-1), reg.reshape(-1)]
+    if nfit:
+        parts += [t_fit.reshape(-1)]
+    yt = torch.cat(parts).double()
     og = o.double().requires_grad_(True)
-    logp = R.log_softmax(og[:, :s0], 1)
-    det = 1.5 * (-(t_det.double() * logp).sum(dim=1) / math.log(s0)).sum() / B
-    total = det
-    box = torch.zeros(())
-    if use_bbox:
-        tgt, smp = reg[:, :4].double(), reg[:, 4:].double()
-        tt = torch.stack([(tgt[:, 0] - smp[:, 0]) / smp[:, 2], (tgt[:, 1] - smp[:, 1]) / smp[:, 3],
-                          torch.log(tgt[:, 2] / smp[:, 2]), torch.log(tgt[:, 3] / smp[:, 3])], dim=1)
-        berr = 2.0 * valid.double() * R.smooth_l1(tt - og[:, s0:s0 + 4]).sum(dim=1)
-        box = 2.0 * berr.sum() / B
-        total = det + box
-    dref, = torch.autograd.grad(total * 0.7, og)
+    det_pr = R.log_softmax(og[:, :s0], 1)
+    fit_pr = R.log_softmax(og[:, s0 + s1:], 1) if nfit else None
+    cf, bf, ff = 1.5, 2.0 if box_mode else 0.0, 0.8 if nfit else 0.0
+    e_det, e_box, e_fit = R.detect_errors(det_pr, og[:, s0:s0 + 4] if box_mode else None, fit_pr, sb.double(), yt, bf,
+                                          box_mode == 2)
+    det = cf * e_det.sum() / B
+    box = bf * e_box.sum() / B if box_mode else torch.zeros((), dtype=torch.float64)
+    fitc = ff * e_fit.sum() / B if nfit else torch.zeros((), dtype=torch.float64)
+    dref, = torch.autograd.grad((det + box + fitc) * 0.7, og)
     dout = ops.alloc_like(od)
-    cost2 = torch.zeros(2, device=cuda)
-    ops.detect_cost(od, sn, s0, use_bbox, t_det.to(cuda).contiguous(), valid.to(cuda).contiguous() if use_bbox else None,
-                    reg.to(cuda).contiguous() if use_bbox else None, 1.5, 2.0 if use_bbox else 0.0, 0.7, dout, cost2)
-    assert abs(cost2[0].item() - det.item()) < 1e-4 * abs(det.item())
-    if use_bbox:
-        assert abs(cost2[1].item() - box.item()) < 1e-4 * abs(box.item())
+    cost3 = torch.zeros(3, device=cuda)
+    ops.detect_cost(od, sn, s0, box_mode, t_det.to(cuda).contiguous(), valid.to(cuda).contiguous() if box_mode else None,
+                    reg.to(cuda).contiguous() if box_mode else None, cf, bf, 0.7, dout, cost3, nfit=nfit,
+                    target_fit=t_fit.to(cuda).contiguous() if nfit else None, fit_factor=ff,
+                    sample_bbox=sb.to(cuda).contiguous() if box_mode == 2 else None)
+    assert abs(cost3[0].item() - det.item()) < 1e-4 * abs(det.item())
+    if box_mode:
+        assert box.item() > 0 and abs(cost3[1].item() - box.item()) < 1e-4 * abs(box.item())
+    if nfit:
+        assert abs(cost3[2].item() - fitc.item()) < 1e-4 * abs(fitc.item())
     assert relerr(nchw(dout), dref) < 1e-5
+    if box_mode:
+        assert relerr(nchw(dout)[:, s0:s0 + 4], dref[:, s0:s0 + 4]) < 1e-4
 
 
 def test_softmax_nll(cuda):

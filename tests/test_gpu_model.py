@@ -91,7 +91,8 @@ def oracle_targets(model, metas):
             t = R.corner_target(metas, l.corner_shape, l.use_center)
         elif l.type_name == "denet-detect":
             t = R.detect_target(metas, dns[0].sample_bbox_list, l.batch_size, l.sample_num, l.class_num,
-                                l.overlap_threshold, l.use_bbox_reg)
+                                l.overlap_threshold, l.use_bbox_reg, use_jointfit=l.use_jointfit,
+                                use_indfit=l.use_indfit)
         elif l.type_name == "regression":
             classes = l.output_shape[1]
             t = (numpy.array([b * classes + int(m["image_class"]) for b, m in enumerate(metas)], dtype=numpy.int64),
@@ -215,10 +216,18 @@ def test_resnet_classifier_train_step_fp32(cuda, convert):
     print("resnet worst gradient rel err %.2e" % worst)
 
 
-def _denet_step(cuda, precision, tol, centre=False):
+def _denet_step(cuda, precision, tol, centre=False, dnd=None):
     from denet_b200.layer import set_param, get_param
     desc = DENET_SMALL.replace("DNC[32,100]", "DNC.C[32,100]") if centre else DENET_SMALL
+    if dnd:
+        desc = desc.replace("DND[0.5,1,1]", dnd)
     model = build(desc, (3, 128, 128), 4, 20, precision, convert=True)
+    if dnd:
+        # the detect head starts at zero (denet_detect.py:71): give the v2 losses something to differentiate
+        head = [l for l in model.layers if l.type_name == "denet-detect"][0].layers[0]
+        rs = numpy.random.RandomState(11)
+        set_param(head.omega, (rs.randn(*get_param(head.omega).shape) * 0.05).astype(numpy.float32))
+        set_param(head.beta, (rs.randn(*get_param(head.beta).shape) * 0.1).astype(numpy.float32))
     # a corner detector that fires: random corner rows, bias near the decision boundary
     dnc = [l for l in model.layers if l.type_name == "denet-corner"][0]
     assert dnc.corner_num == (5 if centre else 4)
@@ -242,11 +251,14 @@ def _denet_step(cuda, precision, tol, centre=False):
     return model, js, before, cap, x, cost, costs, bbox
 
 
-@pytest.mark.parametrize("centre", [False, True], ids=["DNC", "DNC.C"])
-def test_denet_train_step_fp32(cuda, centre):
+@pytest.mark.parametrize("centre,dnd", [(False, None), (True, None), (False, "DND.J[0.5,1,1]"),
+                                        (False, "DND.B[0.5,1,1,0.5]")],
+                         ids=["DNC", "DNC.C", "DND.J", "DND.B+fitness"])
+def test_denet_train_step_fp32(cuda, centre, dnd):
     """conv stack + skip + pool-inv + DNC/DNS/DND head, forward/backward/update vs the oracle on the same RoIs
-    (DNC.C: the v2 corner layer with a fifth, box-centre map feeding sampler, target and cost)"""
-    model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "fp32", 1e-4, centre)
+    (DNC.C: the v2 corner layer with a fifth, box-centre map feeding sampler, target and cost; DND.J: joint-fitness
+    classes; DND.B + fitness factor: bounded-IoU box loss and the independent-fitness head)"""
+    model, js, before, cap, x, cost, costs, bbox = _denet_step(cuda, "fp32", 1e-4, centre, dnd)
     ref = RefModel(js, x.shape, 20, dtype=torch.float64)
     ref.relu_masks = relu_masks(model)
     ref.pool_argmax = pool_argmax(model)
@@ -264,7 +276,7 @@ def test_denet_train_step_fp32(cuda, centre):
         if e >= 1e-4:
             over.append(name)
         assert e < max(1e-4, 3.0 * floor[name]), "gradient of %s: rel err %.3e (fp32 floor %.3e)" % (name, e, floor[name])
-    report("denet_small" + ("_centre" if centre else ""), worst_gradient_rel_err=worst, worst_fp32_floor=max(floor.values()), over_1e4=sorted(over),
+    report("denet_small" + ("_centre" if centre else "") + ("_" + dnd.split("[")[0] if dnd else ""), worst_gradient_rel_err=worst, worst_fp32_floor=max(floor.values()), over_1e4=sorted(over),
            tol=1e-4, cost=cost, oracle_cost=float(total))
     print("denet worst gradient rel err %.2e (fp32 floor %.2e)" % (worst, max(floor.values())))
 

@@ -72,9 +72,9 @@ def test_json_roundtrip_on_host():
     assert numpy.array_equal(w1, numpy.asarray(js2["layers"][0]["weight"])) and w1.shape == (8, 3, 7, 7)
 
 
-def _denet(batch=3, classes=6):
+def _denet(batch=3, classes=6, dnd="DND[0.5,1,1]"):
     desc = ("C.B[8,7,2] BN A P[3,2,1] nRSN.O[1,8,3] SKIPSRC[0] nRSN.O[1,16,3,2] PI[2] C[8,3] SKIP[0] BNA DNC[8,100] "
-            "DNS[3,4,0.01,0.25] C[16,1] BNA DND[0.5,1,1]")
+            "DNS[3,4,0.01,0.25] C[16,1] BNA " + dnd)
     return build(desc, (3, 64, 64), batch, classes, True)
 
 
@@ -104,6 +104,46 @@ def test_host_target_builders_match_oracle():
     got = dnd.get_target_host(metas)[1]
     assert numpy.array_equal(got, want)
     assert (want[:3 * 7 * k].reshape(3, 7, k)[:, :6] > 0).any()
+
+
+@pytest.mark.parametrize("dnd,joint,indfit", [("DND.J[0.5,1,1]", True, False), ("DND.JB[0.6,1,1]", True, False),
+                                              ("DND[0.5,1,1,0.5]", False, True), ("DND.B[0.5,1,0,2]", False, True)])
+def test_host_detect_target_v2_matches_oracle(dnd, joint, indfit):
+    """joint-fitness / independent-fitness targets (denet_detect.py:58-66,177-191) of the host builder, the head's
+    channel count, and the export keys the reference writes (:131-139)"""
+    m = _denet(dnd=dnd)
+    l = [x for x in m.layers if x.type_name == "denet-detect"][0]
+    dns = [x for x in m.layers if x.type_name == "denet-sparse"][0]
+    use_bbox = l.bbox_factor > 0
+    s0 = 6 * 5 + 1 if joint else 7
+    assert l.layers[0].filter_shape[0] == s0 + (4 if use_bbox else 0) + (6 if indfit else 0)
+    assert l.use_jointfit == joint and l.use_indfit == indfit and l.use_bounded_iou == ("B" in dnd.split("[")[0])
+    js = l.export_json()
+    assert js["useJointFitness"] == joint and js["useBoundedIoU"] == l.use_bounded_iou
+    assert js["fitnessFactor"] == l.indfit_factor
+    metas = synthetic_metas(3, 6, seed=7, max_boxes=5)
+    rnd = random.Random(3)
+    k = dns.sample_count
+    bbox = numpy.zeros((3, k, 4))
+    for b in range(3):
+        for i in range(k):
+            if metas[b]["bbox"] and i % 3 != 2:
+                g = metas[b]["bbox"][i % len(metas[b]["bbox"])]
+                j = 0.06 * (i % 5) / 4.0                    # IoU spread over the fitness bins
+                bbox[b, i] = [g[0] + rnd.uniform(-j, j), g[1] + rnd.uniform(-j, j), g[2], g[3] + rnd.uniform(-j, j)]
+            else:
+                x0, y0 = rnd.uniform(0, 1), rnd.uniform(0, 1)
+                bbox[b, i] = [x0, y0, rnd.uniform(x0, 1), rnd.uniform(y0, 1)]
+    dns.sample_pr_host, dns.sample_bbox_host = numpy.zeros((3, k)), bbox
+    samples = [[(0.0, tuple(bbox[b, i])) for i in range(k)] for b in range(3)]
+    thr = l.overlap_threshold
+    want = R.detect_target(metas, samples, 3, dns.sample_num, 6, thr, use_bbox, use_jointfit=joint, use_indfit=indfit)[1]
+    got = l.get_target_host(metas)[1]
+    assert got.shape == want.shape and numpy.array_equal(got, want)
+    det = want[:3 * s0 * k].reshape(3, s0, k)
+    assert (det[:, :s0 - 1] > 0).any()
+    if joint:
+        assert len(set(numpy.nonzero(det[:, :s0 - 1])[1] % 5)) >= 3, "several fitness bins must occur"
 
 
 @pytest.mark.parametrize("counts", [[0, 3, 16], [16, 16, 16], [2, 14, 5], [13, 16, 1]])
