@@ -2272,7 +2272,51 @@ constexpr int kReduceChunk = 1024;      // elementwise path: elements per block
 constexpr int kReduceItems = 1;         // tiled path: (co, channel group) items per block
 constexpr int kReduceGroup = 128;       // tiled path: input channels per item
 
-__global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const ReduceEntry* __restrict__ entries,
+// 1x1 filters, vector form: workspace [split][co][ci] and gradient [co][ci] enumerate alike; a thread owns V consecutive
+// ci (start, Cin and ldws are multiples of V) with 8 splits in flight, summed in split order.
+template <typename VT, int V>
+__device__ __forceinline__ void reduce_1x1_vec(const ReduceEntry& e, long long start, long long end) {
+    const long long step = static_cast<long long>(e.Cout) * e.ldws;
+    for (long long idx = start + V * threadIdx.x; idx < end; idx += V * blockDim.x) {
+        const int ci = static_cast<int>(idx % e.Cin);
+        const int co = static_cast<int>(idx / e.Cin);
+        const float* src = e.ws + static_cast<long long>(co) * e.ldws + ci;
+        VT accv;
+        float* acc = reinterpret_cast<float*>(&accv);
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = 0.f;
+        int sp = 0;
+        for (; sp + 8 <= e.splits; sp += 8) {
+            VT a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __ldcs(reinterpret_cast<const VT*>(src + j * step));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float* f = reinterpret_cast<const float*>(&a[j]);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] += f[v];
+            }
+            src += 8 * step;
+        }
+        for (; sp < e.splits; ++sp, src += step) {
+            const VT a = __ldcs(reinterpret_cast<const VT*>(src));
+            const float* f = reinterpret_cast<const float*>(&a);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] += f[v];
+        }
+        VT* dst = reinterpret_cast<VT*>(e.dw + idx);
+        if (e.accumulate) {
+            const VT o = *dst;
+            const float* f = reinterpret_cast<const float*>(&o);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] += f[v];
+        }
+        *dst = accv;
+    }
+}
+
+constexpr int kReduceThreads = 288;     // 9 warps: one per tap of a 3x3 filter (a second, one-warp round cost a full latency)
+__global__ void __launch_bounds__(kReduceThreads) wgrad_reduce_multi_kernel(const ReduceEntry* __restrict__ entries,
                                                                   const int* __restrict__ block_entry,
                                                                   const long long* __restrict__ block_offset) {
     const ReduceEntry e = entries[block_entry[blockIdx.x]];
@@ -2293,7 +2337,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const ReduceEnt
         const int co = static_cast<int>(item / groups);
         const int ci0 = static_cast<int>(item % groups) * kReduceGroup;
         const int ci = ci0 + lane * 4;
-        for (int t = warp; t < ntaps; t += 8) {
+        for (int t = warp; t < ntaps; t += kReduceThreads / 32) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ci < Cin) {         // ldws is a multiple of 4 and the pad columns of the workspace rows are never read back
                 const float* src = e.ws + (static_cast<long long>(co) * ntaps + t) * e.ldws + ci;
@@ -2330,6 +2374,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const ReduceEnt
     }
     const long long start = block_offset[blockIdx.x];
     const long long end = start + kReduceChunk < e.total ? start + kReduceChunk : e.total;
+    if (e.mode == 0 && (Cin & 1) == 0) {
+        if ((Cin & 3) == 0)
+            reduce_1x1_vec<float4, 4>(e, start, end);
+        else
+            reduce_1x1_vec<float2, 2>(e, start, end);
+        return;
+    }
     for (long long idx = start + threadIdx.x; idx < end; idx += blockDim.x) {
         const float* src;
         long long step, o;
@@ -2727,7 +2778,7 @@ extern "C" int denet_wgrad_reduce_multi(const void* entries, const int* block_en
                                         int nblocks, cudaStream_t stream) {
     DN_REQUIRE(entries && block_entry && block_offset, "wgrad_reduce_multi: null pointer");
     if (nblocks == 0) return 0;
-    wgrad_reduce_multi_kernel<<<DN_G(nblocks), 256, 0, stream>>>((const ReduceEntry*)entries, block_entry, block_offset);
+    wgrad_reduce_multi_kernel<<<DN_G(nblocks), kReduceThreads, 0, stream>>>((const ReduceEntry*)entries, block_entry, block_offset);
     DN_CHECK_LAUNCH();
     return 0;
 }
