@@ -48,12 +48,23 @@ __global__ void sum_partials2_kernel(const float* __restrict__ partial, int n, f
     out[threadIdx.x] = (float)(a * (threadIdx.x == 0 ? scale0 : scale1));
 }
 
+// one warp: lane l adds partials l, l+32, ... in order (double), then the 32 lane sums are added in lane order
 __global__ void sum_partials3_kernel(const float* __restrict__ partial, int n, float scale0, float scale1, float scale2,
                                      float* __restrict__ out) {
-    if (threadIdx.x >= 3) return;
-    double a = 0.0;
-    for (int i = 0; i < n; ++i) a += partial[(long long)i * 3 + threadIdx.x];
-    out[threadIdx.x] = (float)(a * (threadIdx.x == 0 ? scale0 : (threadIdx.x == 1 ? scale1 : scale2)));
+    const int lane = threadIdx.x;
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int i = lane; i < n; i += 32)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) a[q] += partial[(long long)i * 3 + q];
+    __shared__ double sh[3][32];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) sh[q][lane] = a[q];
+    __syncwarp();
+    if (lane < 3) {
+        double t = 0.0;
+        for (int l = 0; l < 32; ++l) t += sh[lane][l];
+        out[lane] = (float)(t * (lane == 0 ? scale0 : (lane == 1 ? scale1 : scale2)));
+    }
 }
 
 // z: conv output rows = B*H*W pixels (NHWC), corner channels [0, cn).  corner_pr: (B, 2, cn, H, W) fp32.
@@ -292,8 +303,10 @@ __global__ void __launch_bounds__(kLossThreads) softmax_nll_kernel(const T* __re
 using namespace dn;
 
 static const int kLossBlocks = 148;
+static const int kDetectBlocks = 148 * 8;   // detect_cost: one or two RoIs per warp (each RoI is a chain of dependent,
+                                            // strided target reads: 16 RoIs per warp in sequence took 78 us for 13 MB)
 
-extern "C" size_t denet_loss_workspace_bytes(void) { return sizeof(float) * (3 * kLossBlocks + 4); }
+extern "C" size_t denet_loss_workspace_bytes(void) { return sizeof(float) * (3 * kDetectBlocks + 4); }
 
 extern "C" int denet_corner_logprob(const void* z, int dtype, long long ldz, int B, int cn, int H, int W,
                                     float* corner_pr, cudaStream_t stream) {
@@ -342,18 +355,19 @@ extern "C" int denet_detect_cost_v2(const void* o, int dtype, long long ld, int 
     const float det_scale = cost_factor / ((float)B * logf((float)s0));
     const float box_scale = bbox_factor / (float)B;
     const float fit_scale = nfit ? fit_factor / ((float)B * logf((float)nfit)) : 0.f;
+    const int grid = std::min(kDetectBlocks, ceil_div(R, kLossThreads / 32));
     if (dtype == DENET_F32)
-        detect_cost_kernel<float><<<DN_G(kLossBlocks), kLossThreads, 0, stream>>>(
+        detect_cost_kernel<float><<<DN_G(grid), kLossThreads, 0, stream>>>(
             (const float*)o, ld, R, s0, sn2, box_mode, nfit, sample_bbox, target_det, target_valid, target_reg, target_fit,
             det_scale * grad_factor, bbox_factor, box_scale * grad_factor, fit_scale * grad_factor, (float*)dout,
             ncols_grad, workspace);
     else
-        detect_cost_kernel<__nv_bfloat16><<<DN_G(kLossBlocks), kLossThreads, 0, stream>>>(
+        detect_cost_kernel<__nv_bfloat16><<<DN_G(grid), kLossThreads, 0, stream>>>(
             (const __nv_bfloat16*)o, ld, R, s0, sn2, box_mode, nfit, sample_bbox, target_det, target_valid, target_reg,
             target_fit, det_scale * grad_factor, bbox_factor, box_scale * grad_factor, fit_scale * grad_factor,
             (__nv_bfloat16*)dout, ncols_grad, workspace);
     // cost3 = {detection, box, independent fitness} cost, each including its factors (reference :308-312)
-    sum_partials3_kernel<<<DN_G(1), 32, 0, stream>>>(workspace, kLossBlocks, -det_scale, box_scale, -fit_scale, cost3);
+    sum_partials3_kernel<<<DN_G(1), 32, 0, stream>>>(workspace, grid, -det_scale, box_scale, -fit_scale, cost3);
     DN_CHECK_LAUNCH();
     return 0;
 }
@@ -364,8 +378,8 @@ extern "C" int denet_detect_cost(const void* o, int dtype, long long ld, int B, 
                                  float cost_factor, float bbox_factor, float grad_factor, void* dout, int ncols_grad,
                                  float* cost2, float* workspace, cudaStream_t stream) {
     DN_REQUIRE(cost2 && workspace, "detect_cost: null pointer");
-    // the third sum lands in the workspace tail (the kernel's partials use 3 * kLossBlocks floats of 3 * kLossBlocks + 4)
-    float* cost3 = workspace + 3 * kLossBlocks;
+    // the third sum lands in the workspace tail (the kernel's partials use 3 * kDetectBlocks floats of 3 * kDetectBlocks + 4)
+    float* cost3 = workspace + 3 * kDetectBlocks;
     const int rc = denet_detect_cost_v2(o, dtype, ld, B, sn, s0, use_bbox ? 1 : 0, 0, nullptr, target_det, target_valid,
                                         target_reg, nullptr, cost_factor, bbox_factor, 0.f, grad_factor, dout, ncols_grad,
                                         cost3, workspace, stream);
