@@ -95,24 +95,10 @@ __device__ __forceinline__ bool reduce_slabs(const float* __restrict__ partial, 
     double acc[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
-    if (c < C) {
-        // 6 slabs' loads in flight before the first add (the slab loop is a chain of L2 latencies otherwise); same order
-        constexpr int KU = 6;
-        for (int s0 = sl; s0 < nslabs; s0 += 32 * KU) {
-            float v[KU][NQ];
+    if (c < C)
+        for (int s = sl; s < nslabs; s += 32)
 #pragma unroll
-            for (int k = 0; k < KU; ++k)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    const int s = s0 + 32 * k;
-                    v[k][q] = s < nslabs ? partial[((long long)s * NQ + q) * C + c] : 0.f;
-                }
-#pragma unroll
-            for (int k = 0; k < KU; ++k)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) acc[q] += (double)v[k][q];
-        }
-    }
+            for (int q = 0; q < NQ; ++q) acc[q] += (double)partial[((long long)s * NQ + q) * C + c];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) red[q][sl][cl] = acc[q];
     __syncthreads();
