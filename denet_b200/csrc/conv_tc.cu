@@ -568,7 +568,8 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
         const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
         const int w = w0 + rw, h = h0 + rh, n = n0 + rn;
         const bool row_ok = (w < p.Wo) && (h < p.Ho) && (n < p.No);
-        const long long pix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;
+        // (scatter-aware: pixel (n, h, w) of a parity-class launch lives at (n, h*osh + ooh, w*osw + oow) of the full tensor)
+        const long long pix = (static_cast<long long>(n) * p.Hf + (h * p.osh + p.ooh)) * p.Wf + (w * p.osw + p.oow);
         const int co0 = ct * BN;
 
         // residual of the first chunk: issued BEFORE the wait for the accumulator, so that the global-load latency
@@ -755,7 +756,7 @@ __device__ __forceinline__ void fprop_epilogue_tma(const ConvFpropParams& p, uin
                     p.fd_th.divmod(q2, n2, h2);
                     const int ww = w0 + static_cast<int>(w2), hh = h0 + static_cast<int>(h2), nn = n0 + static_cast<int>(n2);
                     const bool ok = col_ok && ww < p.Wo && hh < p.Ho && nn < p.No;
-                    const long long px = (static_cast<long long>(nn) * p.Ho + hh) * p.Wo + ww;
+                    const long long px = (static_cast<long long>(nn) * p.Hf + (hh * p.osh + p.ooh)) * p.Wf + (ww * p.osw + p.oow);
                     xv[u] = ok ? __ldg(reinterpret_cast<const uint32_t*>(xcol + px * p.ldy)) : 0u;
                 }
 #pragma unroll
@@ -912,6 +913,9 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_fprop_kernel(const __grid_c
                 __syncwarp();
             }
         }
+    } else if (p.epi_tma) {
+        fprop_epilogue_tma<BN, false>(p, smem + p.stage_off, reinterpret_cast<float*>(smem + L::kStatOffset), tmem_base,
+                                      tfull_bar, tempty_bar, warp, lane);
     } else {
         fprop_epilogue<BN>(p, reinterpret_cast<float2*>(smem + L::kStatOffset), tmem_base, tfull_bar, tempty_bar, warp,
                            lane);
@@ -2442,7 +2446,8 @@ template <int BN, int STAGES>
 static int launch_fprop(const ConvFpropParams& p, cudaStream_t stream) {
     using L = SmemLayout<BN, STAGES>;
     auto kern = conv_fprop_kernel<BN, STAGES>;
-    const int smem = L::kTotal + (p.bnb_x ? 16 * p.bnb_cpad : 0);     // + batch-norm constant table [4][cpad] fp32
+    // + batch-norm constant table [4][cpad] fp32, or (staged epilogue) the 1024-aligned staging tile after the ring
+    const int smem = p.epi_tma ? (int)p.smem_total : L::kTotal + (p.bnb_x ? 16 * p.bnb_cpad : 0);
     DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     kern<<<DN_G(grid), kThreadsF, smem, stream>>>(p);
@@ -2485,6 +2490,8 @@ static int make_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, 
 }
 
 
+static uint32_t staged_epilogue_bytes(ConvFpropParams& p, int BN, int* rc);
+
 // weight tensor map(s) + kernel dispatch, shared by the generic and the row-folded entry points.  p must hold the
 // A map(s), the tiling and the epilogue fields; p.tiles_co / p.num_tiles are filled here.
 int fprop_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStream_t stream) {
@@ -2504,6 +2511,21 @@ int fprop_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStr
     uint32_t box[2] = {64, (uint32_t)BN};
     if ((rc = encode_tmap_bf16(&p.tmB[0], b_hi, 2, dims, strides, box, nullptr))) return rc;
     if (b_lo && (rc = encode_tmap_bf16(&p.tmB[1], b_lo, 2, dims, strides, box, nullptr))) return rc;
+    // staged epilogue for the narrow tiles (the parity-class launches of the strided data gradients, the 1x1 / strided
+    // layers with <= 128 output channels: K loops of 1-4 taps, where the register epilogue's ~2500 cycles per 128 x 64
+    // tile are exposed); the 256-wide tiles keep four stages and the register epilogue (long K loops hide it)
+    p.epi_tma = 0;
+    if (BN <= 128 && !p.bnb_x) {
+        const uint32_t stage_bytes = staged_epilogue_bytes(p, BN, &rc);
+        if (rc) return rc;
+        if (stage_bytes) {
+            const uint32_t front = BN == 64 ? SmemLayout<64, 8>::kStatOffset + 8 * 64 * 8
+                                            : SmemLayout<128, 5>::kStatOffset + 8 * 128 * 8;
+            p.stage_off = (front + 1023) / 1024 * 1024;
+            p.smem_total = 1024 + p.stage_off + stage_bytes;
+            return BN == 64 ? launch_fprop<64, 8>(p, stream) : launch_fprop<128, 5>(p, stream);
+        }
+    }
     switch (BN) {
         case 64: return launch_fprop<64, 8>(p, stream);
         case 128: return launch_fprop<128, 6>(p, stream);
@@ -2554,14 +2576,17 @@ static uint32_t staged_epilogue_bytes(ConvFpropParams& p, int BN, int* rc) {
     p.epi_tma = 0;
     // (the statistics are those of the conv output BEFORE a fused residual / ReLU: the staged tile holds the final
     // values, so that combination - which no layer of the model uses - keeps the register epilogue)
-    const bool ok = (g_fprop_mode & 8) && !p.y_fp32 && (!p.bnb_x || p.Cout % 2 == 0) && p.osh == 1 && p.osw == 1 && p.ooh == 0 && p.oow == 0 &&
-                    p.Hf == p.Ho && p.Wf == p.Wo && p.TW <= 256 && p.TH <= 256 && p.TN <= 256 &&
-                    !(p.stat_sum && (p.residual || p.relu));
+    const bool ok = (g_fprop_mode & 8) && !p.y_fp32 && (!p.bnb_x || p.Cout % 2 == 0) && p.TW <= 256 && p.TH <= 256 &&
+                    p.TN <= 256 && !(p.stat_sum && (p.residual || p.relu));
     if (!ok) return 0;
+    // The store map describes the pixels of THIS launch: all of them, or - for a parity class of a strided data gradient
+    // - every osw-th / osh-th pixel from (ooh, oow) of the Hf x Wf tensor, as a strided view (plain byte strides, no
+    // element strides), so that the scatter costs nothing.
     uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.No};
-    uint64_t strides[3] = {(uint64_t)p.ldy * 2, (uint64_t)p.ldy * 2 * p.Wo, (uint64_t)p.ldy * 2 * p.Wo * p.Ho};
+    uint64_t strides[3] = {(uint64_t)p.ldy * 2 * p.osw, (uint64_t)p.ldy * 2 * p.Wf * p.osh, (uint64_t)p.ldy * 2 * p.Wf * p.Hf};
     uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-    if ((*rc = encode_tmap_bf16(&p.tmY, p.y, 4, dims, strides, box, nullptr))) return 0;
+    const uint8_t* ybase = reinterpret_cast<const uint8_t*>(p.y) + ((size_t)p.ooh * p.Wf + p.oow) * p.ldy * 2;
+    if ((*rc = encode_tmap_bf16(&p.tmY, ybase, 4, dims, strides, box, nullptr))) return 0;
     p.epi_tma = 1;
     return (uint32_t)(128 * BN * 2);
 }
