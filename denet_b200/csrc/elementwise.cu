@@ -1122,7 +1122,7 @@ __global__ void pool_inv_bwd_kernel(const T* __restrict__ dy, int N, int H, int 
 // One thread per OUTPUT pack so every byte of `out` is written exactly once (no separate memset pass).
 template <typename T, int VEC>
 __global__ void dilate_kernel(const T* __restrict__ x, int N, int H, int W, int C, long long ldx, int sh, int sw, int Hd,
-                              int Wd, long long ldy, T* __restrict__ y) {
+                              int Wd, long long ldy, T* __restrict__ y, const T* __restrict__ add) {
     const int CV = C / VEC;
     const long long total = (long long)N * Hd * Wd * CV;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -1141,7 +1141,14 @@ __global__ void dilate_kernel(const T* __restrict__ x, int N, int H, int W, int 
 #pragma unroll
             for (int i = 0; i < VEC; ++i) p.v[i] = 0.f;
         }
-        p.store(y + (((long long)n * Hd + hd) * Wd + wd) * ldy + (long long)cv * VEC);
+        const long long o = (((long long)n * Hd + hd) * Wd + wd) * ldy + (long long)cv * VEC;
+        if (add) {      // (the other branch's gradient: saves the separate add pass over the full tensor)
+            Pack<T, VEC> q;
+            q.load(add + o);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) p.v[i] += q.v[i];
+        }
+        p.store(y + o);
     }
 }
 
@@ -1550,17 +1557,22 @@ extern "C" int denet_pool_inv_bwd(const void* dy, int dtype, int N, int H, int W
     return 0;
 }
 
-extern "C" int denet_dilate(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sh, int sw, void* y,
-                            int Hd, int Wd, long long ldy, cudaStream_t stream) {
+extern "C" int denet_dilate_add(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sh, int sw,
+                                const void* add, void* y, int Hd, int Wd, long long ldy, cudaStream_t stream) {
     DN_REQUIRE(x && y, "dilate: null pointer");
     DN_REQUIRE(sh >= 1 && sw >= 1, "dilate: bad stride");
-    const bool v = vec8_ok(C, ldx, x) && vec8_ok(C, ldy, y);
+    const bool v = vec8_ok(C, ldx, x) && vec8_ok(C, ldy, y, add);
     DN_DISPATCH(dtype, v, {
         dilate_kernel<T, VEC><<<DN_G(ew_grid((long long)N * Hd * Wd * (C / VEC), 256)), 256, 0, stream>>>(
-            (const T*)x, N, H, W, C, ldx, sh, sw, Hd, Wd, ldy, (T*)y);
+            (const T*)x, N, H, W, C, ldx, sh, sw, Hd, Wd, ldy, (T*)y, (const T*)add);
     });
     DN_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int denet_dilate(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sh, int sw, void* y,
+                            int Hd, int Wd, long long ldy, cudaStream_t stream) {
+    return denet_dilate_add(x, dtype, N, H, W, C, ldx, sh, sw, nullptr, y, Hd, Wd, ldy, stream);
 }
 
 extern "C" int denet_bn_finalize_sums(const float* sum, const float* sqsum, long long M, int C, float eps, float* mean,

@@ -323,9 +323,7 @@ class ConvLayer(AbstractLayer):
                 elif (R, S) == (1, 1) and self.pad == (0, 0):
                     # a 1x1 convolution commutes with the zero insertion: GEMM at the small resolution, then scatter
                     dxc = ops.conv2d_fprop(dyop, wop_d, (0, 0), dy.shape[1:3], gdt)
-                    dx = ops.dilate(dxc, self.stride, (h, w))
-                    if add_to is not None:
-                        dx = ops.add(dx, add_to, out=dx)
+                    dx = ops.dilate(dxc, self.stride, (h, w), add=add_to)
                 elif self.dgrad_classes() is not None and self._wop_dc is not None:
                     # strided conv: one stride-1 correlation per parity class of the input pixel, on the undilated dy,
                     # each scattering its pixels (and adding add_to there) into dx

@@ -463,12 +463,13 @@ def conv2d_rowfold_wgrad(dyop, img, R, S, stride, dw, accumulate=False, defer=No
     return dw
 
 
-def dilate(x, stride, out_hw):
-    """zero-insertion upsampling (strided dgrad helper): y[:, h*sh, w*sw] = x[:, h, w]"""
+def dilate(x, stride, out_hw, add=None):
+    """zero-insertion upsampling (strided dgrad helper): y[:, h*sh, w*sw] = x[:, h, w] (+ add, a tensor like y)"""
     n, h, w, c = x.shape
     y = alloc_nhwc(n, out_hw[0], out_hw[1], c, x.dtype, x.device)
-    call("denet_dilate", x.data_ptr(), _dtype_code(x), n, h, w, c, _pitch(x), stride[0], stride[1], y.data_ptr(),
-         out_hw[0], out_hw[1], _pitch(y), _stream())
+    assert add is None or (add.shape == y.shape and add.dtype == y.dtype and _pitch(add) == _pitch(y))
+    call("denet_dilate_add", x.data_ptr(), _dtype_code(x), n, h, w, c, _pitch(x), stride[0], stride[1], _ptr(add),
+         y.data_ptr(), out_hw[0], out_hw[1], _pitch(y), _stream())
     return y
 
 

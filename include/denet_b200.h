@@ -152,6 +152,10 @@ int denet_conv2d_wgrad_set_mode(int row_shared);
  * data gradient of a strided convolution into a stride-1 correlation (cuDNN bwd-data of convolution.py:83). */
 int denet_dilate(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sh, int sw, void* y, int Hd,
                  int Wd, long long ldy, cudaStream_t stream);
+/* the same plus `add` (a tensor shaped and pitched like y, or NULL): y = dilate(x) + add in one pass - the data gradient
+ * of a strided 1x1 projection meeting the gradient of the block's other branch (denet/layer/resnet.py:96-113). */
+int denet_dilate_add(const void* x, int dtype, int N, int H, int W, int C, long long ldx, int sh, int sw,
+                     const void* add, void* y, int Hd, int Wd, long long ldy, cudaStream_t stream);
 
 /* Explicit im2col / col2im (column order k = (r*S+s)*C + c) for the 3-channel stem, whose 147-element patch rows
  * are too ragged for the TMA implicit-GEMM path; the GEMM then runs as a 1x1 convolution over the column matrix.
