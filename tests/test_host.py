@@ -121,6 +121,10 @@ def test_host_detect_target_v2_matches_oracle(dnd, joint, indfit):
     js = l.export_json()
     assert js["useJointFitness"] == joint and js["useBoundedIoU"] == l.use_bounded_iou
     assert js["fitnessFactor"] == l.indfit_factor
+    from denet_b200.model import model_cnn
+    l2 = [x for x in model_cnn.load_from_json(m.export_json(), batch_size=3).layers if x.type_name == "denet-detect"][0]
+    assert (l2.use_jointfit, l2.use_indfit, l2.use_bounded_iou) == (l.use_jointfit, l.use_indfit, l.use_bounded_iou)
+    assert l2.layers[0].filter_shape == l.layers[0].filter_shape and l2.det_shape == l.det_shape
     metas = synthetic_metas(3, 6, seed=7, max_boxes=5)
     rnd = random.Random(3)
     k = dns.sample_count
