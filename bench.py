@@ -302,25 +302,44 @@ def run_b200(args):
         it += 1
         return c
 
-    # ---- conv kernel timing (roofline): eager launches of the same steps, every conv entry point bracketed by CUDA
-    # events on its stream (events cannot be recorded inside a replayed graph)
+    # ---- conv kernel timing (roofline): every conv entry point bracketed by CUDA events on its stream.  With CUDA graphs
+    # the events are EXTERNAL event-record nodes captured into the step's graphs and re-recorded by every replay, i.e. the
+    # kernels are timed where they run in the timed regions below (an eager launch of a kernel shorter than the host's
+    # ~20 us launch cost measures the host: the parity-class launches of the strided data gradients read 24 us eager,
+    # 13 us as graph nodes); --eager times the eager launches.
     timed_names = ["denet_conv2d_fprop", "denet_conv2d_fprop_scatter", "denet_conv2d_dgrad_bnbwd", "denet_conv2d_wgrad",
                    "denet_conv2d_rowfold_fprop",
                    "denet_conv2d_rowfold_wgrad", "denet_wgrad_reduce_multi"]
+    graphs = not args.eager
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    lib.start_timing(timed_names)
+    if not graphs:
+        lib.start_timing(timed_names)
     le0 = clib.denet_launch_count()
     t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0e.record()
-    for _ in range(args.steps):
+    eager_steps = args.steps if not graphs else min(args.steps, 5)
+    for _ in range(eager_steps):
         step_device()
     t1e.record()
     barrier()
-    ms_eager = max_over_ranks(t0e.elapsed_time(t1e))
-    launches = (clib.denet_launch_count() - le0) / args.steps     # kernels per step (graph mode replays the same nodes)
-    timings = lib.stop_timing()
+    ms_eager = max_over_ranks(t0e.elapsed_time(t1e)) * args.steps / eager_steps
+    launches = (clib.denet_launch_count() - le0) / eager_steps    # kernels per step (graph mode replays the same nodes)
+    if not graphs:
+        timings = lib.stop_timing()
+    else:
+        lib.start_timing(timed_names, in_graph=True)
+        model.enable_cuda_graphs(True)
+        for _ in range(6):                    # eager warm-up step, capture (events become graph nodes), first replays
+            step_device()
+        timings = {n: [] for n in timed_names}
+        for _ in range(args.steps):
+            step_device()
+            for n, evs in lib.read_timing().items():
+                timings[n].extend(evs)
+        lib.stop_timing()
+        barrier()
 
     graphs = not args.eager
     if graphs:
@@ -455,8 +474,10 @@ def run_b200(args):
                 "launches_per_step": n_conv_launch / args.steps,
                 "conv_ms_per_step": conv_ms / args.steps,
                 "conv_share_of_step": (conv_ms / args.steps) / (ms_a / args.steps),
-                "timed_in": "eager launches of the same steps (%.2f ms/step eager); value/e2e are %s" % (
-                    ms_eager / args.steps, "CUDA-graph replays" if graphs else "eager too"),
+                "timed_in": ("external event-record nodes inside the step's CUDA graphs, read after each of %d replays "
+                             "(eager launches: %.2f ms/step)" % (args.steps, ms_eager / args.steps)) if graphs else
+                            "eager launches of the same steps (%.2f ms/step); value/e2e are eager too" % (
+                                ms_eager / args.steps),
                 "families": {k: {"tflops": (v[1] / (v[0] / 1000.0) / 1e12 if v[0] > 0 else None),
                                  "ms_per_step": v[0] / args.steps} for k, v in fam.items()},
                 "algorithmic_gflop_per_image": train_flops / batch / 1e9}

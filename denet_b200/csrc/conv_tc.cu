@@ -2558,12 +2558,18 @@ template <int BN>
 static int dispatch_fprop_halo(const ConvFpropParams& p, cudaStream_t stream) {
     const int ntaps = p.R * p.S;
     constexpr int BR = BN <= 128 ? BN : 128;      // resident filters exist for BN <= 128 only
+    // (2 and 4 taps: the parity classes of a 3x3 / stride-2 data gradient - 8-32 MMAs per tile, where the run-time-count
+    // instance's ~100 cycles per issued MMA, 220 per (chunk, tap) iteration even without MMAs, are the whole tile time)
     if (p.b_resident) {
         if (BN == 64 && ntaps == 9 && p.kmmas == 4) return launch_fprop_halo<64, 9, true, 4>(p, stream);
         if (BN == 64 && ntaps == 7 && p.kmmas == 2) return launch_fprop_halo<64, 7, true, 2>(p, stream);
+        if (BN == 64 && ntaps == 4 && p.kmmas == 4) return launch_fprop_halo<64, 4, true, 4>(p, stream);
+        if (BN == 64 && ntaps == 2 && p.kmmas == 4) return launch_fprop_halo<64, 2, true, 4>(p, stream);
         return launch_fprop_halo<BR, 0, true, 0>(p, stream);
     }
     if (ntaps == 9 && p.kmmas == 4) return launch_fprop_halo<BN, 9, false, 4>(p, stream);
+    if (BN <= 128 && ntaps == 4 && p.kmmas == 4) return launch_fprop_halo<BR, 4, false, 4>(p, stream);
+    if (BN <= 128 && ntaps == 2 && p.kmmas == 4) return launch_fprop_halo<BR, 2, false, 4>(p, stream);
     if (BN == 64 && ntaps == 7 && p.kmmas == 2) return launch_fprop_halo<64, 7, false, 2>(p, stream);
     return launch_fprop_halo<BN, 0, false, 0>(p, stream);
 }
@@ -2616,7 +2622,8 @@ static int halo2_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, 
     const int Cout = p.Cout;
     const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
     const int ntaps = p.R * p.S;
-    if (ntaps != 9 || p.kmmas != 4 || p.a_loads != 1) return 1;
+    if ((ntaps != 9 && ntaps != 4 && ntaps != 2) || p.kmmas != 4 || p.a_loads != 1) return 1;
+    if (ntaps != 9 && BN == 256) return 1;        // (2 / 4 taps = parity classes of a strided data gradient: <= 128 wide)
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     if (m_tiles < 2) return 1;
     const uint32_t bh_bytes = (BN / 2) * 128;
@@ -2654,6 +2661,16 @@ static int halo2_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, 
     uint32_t box[2] = {64, (uint32_t)(BN / 2)};
     if ((rc = encode_tmap_bf16(&p.tmB[0], b_hi, 2, dims, strides, box, nullptr))) return rc;
     if (b_lo && (rc = encode_tmap_bf16(&p.tmB[1], b_lo, 2, dims, strides, box, nullptr))) return rc;
+    if (ntaps == 4) {
+        if (BN == 64) return p.b_resident ? launch_fprop_halo2<64, 4, true, 4>(p, stream)
+                                          : launch_fprop_halo2<64, 4, false, 4>(p, stream);
+        return launch_fprop_halo2<128, 4, false, 4>(p, stream);
+    }
+    if (ntaps == 2) {
+        if (BN == 64) return p.b_resident ? launch_fprop_halo2<64, 2, true, 4>(p, stream)
+                                          : launch_fprop_halo2<64, 2, false, 4>(p, stream);
+        return launch_fprop_halo2<128, 2, false, 4>(p, stream);
+    }
     switch (BN) {
         case 64:
             return p.b_resident ? launch_fprop_halo2<64, 9, true, 4>(p, stream)

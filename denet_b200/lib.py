@@ -101,19 +101,31 @@ def launch_count():
 # bench.py brackets selected entry points with CUDA events on the stream they are enqueued on (the roofline figure
 # needs the device duration of the conv kernels measured live inside the timed region).
 _timed = None     # {entry point name: [(start_event, end_event, tag)]} while timing is on
+_timed_in_graph = False
 
 
-def start_timing(names):
-    global _timed
+def start_timing(names, in_graph=False):
+    """in_graph: bracket only the calls made while the stream is being CAPTURED, with external events (event-record
+    nodes of the CUDA graph): every replay of that graph re-records them, read_timing() after a replay returns the
+    device durations inside the graph - eager launches of kernels shorter than the host's launch cost (~20 us through
+    ctypes + tensor-map encoding) measure the host instead."""
+    global _timed, _timed_in_graph
     _timed = {n: [] for n in names}
+    _timed_in_graph = bool(in_graph)
+
+
+def read_timing():
+    """-> {name: [(milliseconds, tag)]} of the event pairs recorded so far (last replay for in-graph events);
+    synchronises the device, keeps timing on"""
+    import torch
+    torch.cuda.synchronize()
+    return {n: [(a.elapsed_time(b), tag) for a, b, tag in evs] for n, evs in (_timed or {}).items()}
 
 
 def stop_timing():
     """-> {name: [(milliseconds, tag)]}; synchronises the device"""
     global _timed
-    import torch
-    torch.cuda.synchronize()
-    out = {n: [(a.elapsed_time(b), tag) for a, b, tag in evs] for n, evs in (_timed or {}).items()}
+    out = read_timing()
     _timed = None
     return out
 
@@ -144,7 +156,12 @@ def call(name, *args, allow=()):
         return rc
     if _timed is not None and name in _timed:
         import torch
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if _timed_in_graph and not capturing:
+            check(fn(*args), name)
+            return 0
+        a = torch.cuda.Event(enable_timing=True, external=capturing)
+        b = torch.cuda.Event(enable_timing=True, external=capturing)
         a.record()
         rc = fn(*args)
         b.record()

@@ -6,7 +6,10 @@ from denet_b200 import ops, lib
 L = lib.load()
 cuda = torch.device("cuda:0")
 buf = torch.zeros(3 * 64 * 4, dtype=torch.int64, device=cuda)
-for (n, h, w, cin, cout, k) in [(32, 128, 128, 64, 64, 3), (32, 64, 64, 128, 128, 3)]:
+cases = [(32, 128, 128, 64, 64, 3), (32, 64, 64, 128, 128, 3)]
+if len(sys.argv) > 1:
+    cases = [tuple(int(v) for v in a.split(',')) for a in sys.argv[1:]]
+for (n, h, w, cin, cout, k) in cases:
     x = ops.ActOperand(torch.randn(n, h, w, cin, device=cuda).bfloat16())
     wt = torch.randn(cout, cin, k, k, device=cuda) * 0.05
     wop = ops.conv_weight_prep(wt, 0, False)
@@ -15,10 +18,10 @@ for (n, h, w, cin, cout, k) in [(32, 128, 128, 64, 64, 3), (32, 64, 64, 128, 128
         L.denet_conv2d_fprop_set_mode(mode)
         L.denet_conv2d_fprop_set_timeline(None)
         for _ in range(2):
-            ops.conv2d_fprop(x, wop, (1, 1), (h, w), torch.bfloat16, out=out)
+            ops.conv2d_fprop(x, wop, ((k - 1) // 2, (k - 1) // 2), (h, w), torch.bfloat16, out=out)
         buf.zero_()
         L.denet_conv2d_fprop_set_timeline(buf.data_ptr())
-        ops.conv2d_fprop(x, wop, (1, 1), (h, w), torch.bfloat16, out=out)
+        ops.conv2d_fprop(x, wop, ((k - 1) // 2, (k - 1) // 2), (h, w), torch.bfloat16, out=out)
         torch.cuda.synchronize()
         L.denet_conv2d_fprop_set_timeline(None)
         t = buf.cpu().view(3, 64, 4)
