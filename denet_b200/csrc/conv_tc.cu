@@ -1228,6 +1228,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
     conv_fprop_halo2_kernel(const __grid_constant__ ConvFpropParams p) {
     constexpr int kBHalfBytes = (BN / 2) * kBK * 2;          // this CTA's half of a B tile
     constexpr uint32_t kB16 = kBHalfBytes >> 4;
+    // taps per filter stage (halo2_taps_per_stage on the host): with N <= 128 the per-stage handshake of the issuing
+    // thread (wait, fence, elect, commit, ~150 cycles) plus four ~50-cycle MMA issues exceeds the 4 x 64 cycles the MMAs
+    // occupy the tensor pipe - one stage per filter ROW (12 MMAs per handshake) makes those layers MMA-bound again
+    constexpr int TG = (!RESIDENT && NT == 9 && BN <= 128) ? 3 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_b = smem + p.a_region_bytes;
@@ -1339,15 +1343,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
                     if (!RESIDENT) {
                         int kcol = kc * kBK;
 #pragma unroll 1
-                        for (int t = 0; t < NT; ++t, kcol += tap_kstep) {
+                        for (int t = 0; t < NT; t += TG, kcol += TG * tap_kstep) {
                             ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
                             if (ptx::elect_one()) {
                                 const uint32_t bar = b_full0 + bs * 8;
                                 if (debug & 8) {
                                     ptx::mbar_arrive_cluster(bar);
                                 } else {
-                                    ptx::mbar_expect_tx_cluster(bar, kBHalfBytes);
-                                    ptx::tma_load_2d_pair(smem_b + bs * kBHalfBytes, mapB, bar, kcol, co0);
+                                    ptx::mbar_expect_tx_cluster(bar, TG * kBHalfBytes);
+#pragma unroll
+                                    for (int u = 0; u < TG; ++u)
+                                        ptx::tma_load_2d_pair(smem_b + (bs * TG + u) * kBHalfBytes, mapB, bar,
+                                                              kcol + u * tap_kstep, co0);
                                 }
                             }
                             __syncwarp();
@@ -1408,19 +1415,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
                         __syncwarp();
                     } else {
 #pragma unroll
-                        for (int t = 0; t < NT; ++t) {
+                        for (int t = 0; t < NT; t += TG) {
                             ptx::mbar_wait(&b_full[bs], bphase);
                             ptx::tc_fence_after();
-                            const uint64_t bd = bdesc0 + static_cast<uint64_t>(bs * kB16);
+                            const uint64_t bd = bdesc0 + static_cast<uint64_t>(bs * (TG * kB16));
                             if (ptx::elect_one()) {
                                 if (do_mma) {
 #pragma unroll
-                                    for (int j = 0; j < KM; ++j)
-                                        ptx::umma_f16_pair(d_tmem, ad + toff[t] + 2 * j, bd + 2 * j, idesc,
-                                                           (t | j) != 0 ? 1u : accflag);
+                                    for (int u = 0; u < TG; ++u)
+#pragma unroll
+                                        for (int j = 0; j < KM; ++j)
+                                            ptx::umma_f16_pair(d_tmem, ad + toff[t + u] + 2 * j, bd + u * kB16 + 2 * j, idesc,
+                                                               (t | u | j) != 0 ? 1u : accflag);
                                 }
                                 ptx::umma_commit_pair(&b_empty[bs]);
-                                if (t == NT - 1) ptx::umma_commit_pair(&a_empty[as]);
+                                if (t + TG >= NT) ptx::umma_commit_pair(&a_empty[as]);
                             }
                             __syncwarp();
                             if (++bs == b_stages) {
@@ -2640,8 +2649,10 @@ static int halo2_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, 
         p.a_stages = (int)((budget - p.b_region_bytes) / p.a_stage_bytes);
         if (p.a_stages > 6) p.a_stages = 6;
     } else {
-        p.b_stages = BN == 256 ? (stage_bytes ? 4 : 8) : 12;
-        p.b_region_bytes = p.b_stages * bh_bytes;
+        // (stages of TG taps each: one filter row per stage for the 9-tap, <= 128-wide instances - see the kernel)
+        const int TG = (ntaps == 9 && BN <= 128) ? 3 : 1;
+        p.b_stages = BN == 256 ? (stage_bytes ? 4 : 8) : 12 / TG;
+        p.b_region_bytes = p.b_stages * TG * bh_bytes;
         p.a_stages = (int)((budget - p.b_region_bytes) / p.a_stage_bytes);
         if (p.a_stages > 4) p.a_stages = 4;
     }
