@@ -1467,9 +1467,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
-template <int BN, int STAGES>
+// KS = k-blocks (64 pixels each) per pipeline stage: one full / empty handshake of the issuing thread (~150 cycles) per
+// 4 * KS MMAs.  With BN <= 128 four MMAs occupy the tensor pipe for <= 256 cycles, less than the handshake plus four
+// ~50-cycle issues: two k-blocks per stage make those instances MMA-bound (STAGES counts stages of KS k-blocks).
+template <int BN, int STAGES, int KS>
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_constant__ ConvWgradParams p) {
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES * KS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
@@ -1547,19 +1550,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                 p.fd_w.divmod(kb0, t2, tw);
                 p.fd_h.divmod(t2, tn, th);
 #pragma unroll 1
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    const int w0 = tw * TW, h0 = th * TH, n0 = tn * TN;
-                    {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sA = smem + stage * L::kStageBytes;
-                        uint8_t* sB = sA + L::kABytes;
-                        if (ptx::elect_one()) {
-                            if (debug & 2) {
-                                ptx::mbar_arrive(&full_bar[stage]);
-                            } else {
+                for (int kb = kb0; kb < kb1; kb += KS) {
+                    const int nsub = kb1 - kb < KS ? kb1 - kb : KS;
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (ptx::elect_one()) {
+                        if (debug & 2)
+                            ptx::mbar_arrive(&full_bar[stage]);
+                        else
+                            ptx::mbar_expect_tx(&full_bar[stage], nsub * stage_tx);
+                    }
+#pragma unroll
+                    for (int u = 0; u < KS; ++u) {
+                        if (u < nsub) {
+                            const int w0 = tw * TW, h0 = th * TH, n0 = tn * TN;
+                            uint8_t* sA = smem + (stage * KS + u) * L::kStageBytes;
+                            uint8_t* sB = sA + L::kABytes;
+                            if (!(debug & 2) && ptx::elect_one()) {
                                 // Cout <= 64: the second 64-channel dY box would be all TMA zero fill; skip it (its
                                 // accumulator rows are never read)
-                                ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
                                 ptx::tma_load_4d(sA, &p.tmDY[ai], &full_bar[stage], cA, w0, h0, n0);
                                 if (a_boxes > 1)
                                     ptx::tma_load_4d(sA + kBoxBytes, &p.tmDY[ai], &full_bar[stage], cA + 64, w0, h0, n0);
@@ -1568,19 +1576,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                                     ptx::tma_load_4d(sB + i * kBoxBytes, &p.tmX[bi], &full_bar[stage],
                                                      cB + i * 64, w0 * stride_w + dw, h0 * stride_h + dh, n0);
                             }
-                        }
-                        __syncwarp();
-                        if (++stage == STAGES) {
-                            stage = 0;
-                            phase ^= 1;
+                            if (++tw == tiles_w) {
+                                tw = 0;
+                                if (++th == tiles_h) {
+                                    th = 0;
+                                    ++tn;
+                                }
+                            }
                         }
                     }
-                    if (++tw == tiles_w) {
-                        tw = 0;
-                        if (++th == tiles_h) {
-                            th = 0;
-                            ++tn;
-                        }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
                 }
@@ -1602,28 +1610,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
-                const int nk = (kb1 - kb0) * nterms;
+                uint32_t accflag = 0;                       // 0 only for the first MMA of the tile
+                for (int term = 0; term < nterms; ++term) {
 #pragma unroll 1
-                for (int kb = 0; kb < nk; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    // MN-major: LBO = next 64-channel box, SBO = next group of 8 pixel rows
-                    const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (L::kStageBytes >> 4));
-                    const uint64_t bdesc = adesc + (L::kABytes >> 4);
-                    if (ptx::elect_one()) {
-                        if (do_mma) {
+                    for (int kb = kb0; kb < kb1; kb += KS) {
+                        const int nsub = kb1 - kb < KS ? kb1 - kb : KS;
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        // MN-major: LBO = next 64-channel box, SBO = next group of 8 pixel rows
+                        const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * KS * (L::kStageBytes >> 4));
+                        const uint64_t bdesc = adesc + (L::kABytes >> 4);
+                        if (ptx::elect_one()) {
+                            if (do_mma) {
 #pragma unroll
-                            for (int j = 0; j < kBK / 16; ++j) {
-                                // advance 16 pixel rows = 2048 B
-                                ptx::umma_f16(d_tmem, adesc + 128 * j, bdesc + 128 * j, idesc, (kb | j) != 0);
+                                for (int u = 0; u < KS; ++u) {
+                                    if (u < nsub) {
+#pragma unroll
+                                        for (int j = 0; j < kBK / 16; ++j) {
+                                            // advance 16 pixel rows = 2048 B; next k-block of the stage = kStageBytes on
+                                            ptx::umma_f16(d_tmem, adesc + u * (L::kStageBytes >> 4) + 128 * j,
+                                                          bdesc + u * (L::kStageBytes >> 4) + 128 * j, idesc,
+                                                          (u | j) != 0 ? 1u : accflag);
+                                        }
+                                    }
+                                }
                             }
+                            ptx::umma_commit(&empty_bar[stage]);
                         }
-                        ptx::umma_commit(&empty_bar[stage]);
-                    }
-                    __syncwarp();
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
+                        __syncwarp();
+                        accflag = 1;
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
                 if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[as]);
@@ -2464,10 +2483,10 @@ static int launch_fprop(const ConvFpropParams& p, cudaStream_t stream) {
     return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int KS>
 static int launch_wgrad(const ConvWgradParams& p, cudaStream_t stream) {
-    using L = SmemLayout<BN, STAGES>;
-    auto kern = conv_wgrad_kernel<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES * KS>;
+    auto kern = conv_wgrad_kernel<BN, STAGES, KS>;
     DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     kern<<<DN_G(grid), kThreads, L::kTotal, stream>>>(p);
@@ -2786,9 +2805,11 @@ int wgrad_splits(int total_kblocks, int base_tiles, int bn_cols, int stage_bytes
 int wgrad_launch(ConvWgradParams& p, cudaStream_t stream) {
     const int BN = p.Cin <= 64 ? 64 : (p.Cin <= 128 ? 128 : 256);
     switch (BN) {
-        case 64: return launch_wgrad<64, 8>(p, stream);
-        case 128: return launch_wgrad<128, 6>(p, stream);
-        default: return launch_wgrad<256, 4>(p, stream);
+        // (KS = 2 measured: the 128-wide instance issues faster - 43 -> 37 us with the loads switched off - but three
+        // 64 KB stages expose the L2 -> shared-memory fill, 590 MB per launch, which is the floor: 43 -> 45 us)
+        case 64: return launch_wgrad<64, 8, 1>(p, stream);
+        case 128: return launch_wgrad<128, 6, 1>(p, stream);
+        default: return launch_wgrad<256, 4, 1>(p, stream);
     }
 }
 
