@@ -1695,6 +1695,223 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, CTA pairs
+// conv_wgrad_kernel<256> on CTA PAIRS (tcgen05 cta_group::2): the two CTAs of a cluster take two adjacent Cout tiles
+// (rank r: rows [(2 cp + r) * 128, +128) of the filter gradient - its own dY boxes, its own accumulator lanes, its own
+// epilogue) of the SAME (Cin tile, tap, split), so they share the X operand: one MMA of M = 256 reads N / 2 = 128 input
+// channels of the X box from each CTA's shared memory.  Per k-block a CTA fetches 16 KB of dY + 16 KB of X instead of
+// 16 + 32 KB: the one-CTA kernel needs 148 x 48 KB per 512 tensor cycles = ~21 TB/s of L2 -> shared-memory fill to keep
+// the tensor pipe busy, the L2 delivers ~14 (measured: 958 TFLOP/s = 0.68 of the MMA rate on the 256-channel layers).
+// Barrier protocol as in conv_fprop_halo2_kernel: "full" barriers in the leader (2 arrive.expect_tx + the bytes of both
+// CTAs' loads), multicast commits to the "empty" / "accumulator full" barriers of both CTAs, both epilogues release
+// the accumulator on the leader's barrier.
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    conv_wgrad2_kernel(const __grid_constant__ ConvWgradParams p) {
+    constexpr int BN = 256;
+    constexpr int kBoxBytes = kBK * 128;                  // one [64 pixels][64 channels] bf16 box
+    constexpr int kABytes = 2 * kBoxBytes;                // dY: this CTA's 128 output channels
+    constexpr int kBBytes = (BN / 128) * kBoxBytes;       // X: this CTA's half (128 input channels)
+    constexpr int kStageBytes = kABytes + kBBytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    constexpr uint32_t kTmemCols = 2 * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 2);              // one arrive.expect_tx per CTA of the pair
+            ptx::mbar_init(&empty_bar[s], 1);             // multicast commit of the leader's MMA thread
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 2 * 4);        // the epilogue warps of both CTAs
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc_pair(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish_pair();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();                              // barriers of BOTH CTAs initialised before any remote arrive
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ntaps = p.R * p.S;
+    const int nterms = p.nterms, debug = p.debug, num_tiles = p.num_tiles;
+    const int tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+    // pair tile -> (co tile PAIR, ci tile, tap, split): p.fd_cot divides by the number of pairs
+    auto decode = [&](int tile, int& cop, int& cit, int& tap, int& split, int& kb0, int& kb1) {
+        uint32_t t, a, b, c;
+        p.fd_cot.divmod(tile, t, a);
+        p.fd_cit.divmod(t, t, b);
+        p.fd_taps.divmod(t, t, c);
+        cop = a; cit = b; tap = c;
+        split = t;
+        kb0 = static_cast<int>(static_cast<long long>(p.total_kblocks) * split / p.splits);
+        kb1 = static_cast<int>(static_cast<long long>(p.total_kblocks) * (split + 1) / p.splits);
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer (both CTAs: own dY boxes, own half of X)
+        if (ptx::elect_one()) {
+            ptx::tma_prefetch_desc(&p.tmDY[0]);
+            ptx::tma_prefetch_desc(&p.tmX[0]);
+        }
+        const uint32_t full0 = ptx::mapa_u32(ptx::smem_u32(full_bar), 0);      // the leader's barriers
+        int stage = 0;
+        uint32_t phase = 0;
+        const int TW = p.TW, TH = p.TH, TN = p.TN, stride_w = p.stride_w, stride_h = p.stride_h;
+        const uint32_t tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            int cop, cit, tap, split, kb0, kb1;
+            decode(tile, cop, cit, tap, split, kb0, kb1);
+            const int dh = tap / p.S - p.pad_h;
+            const int dw = tap % p.S - p.pad_w;
+            const int cA = (2 * cop + static_cast<int>(rank)) * kBM;
+            const int cB = cit * BN + static_cast<int>(rank) * (BN / 2);
+            for (int term = 0; term < nterms; ++term) {
+                // terms of the fp32-parity split, corrections first (see conv_wgrad_kernel)
+                const int ai = (nterms == 3 && term == 0) ? 1 : 0;
+                const int bi = (nterms == 3 && term == 1) ? 1 : 0;
+                uint32_t tw, th, tn, t2;
+                p.fd_w.divmod(kb0, t2, tw);
+                p.fd_h.divmod(t2, tn, th);
+#pragma unroll 1
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int w0 = tw * TW, h0 = th * TH, n0 = tn * TN;
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * kStageBytes;
+                    uint8_t* sB = sA + kABytes;
+                    if (ptx::elect_one()) {
+                        const uint32_t bar = full0 + stage * 8;
+                        if (debug & 2) {
+                            ptx::mbar_arrive_cluster(bar);
+                        } else {
+                            ptx::mbar_expect_tx_cluster(bar, kStageBytes);
+                            ptx::tma_load_4d_pair(sA, &p.tmDY[ai], bar, cA, w0, h0, n0);
+                            ptx::tma_load_4d_pair(sA + kBoxBytes, &p.tmDY[ai], bar, cA + 64, w0, h0, n0);
+#pragma unroll
+                            for (int i = 0; i < BN / 128; ++i)
+                                ptx::tma_load_4d_pair(sB + i * kBoxBytes, &p.tmX[bi], bar, cB + i * 64,
+                                                      w0 * stride_w + dw, h0 * stride_h + dh, n0);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    if (++tw == tiles_w) {
+                        tw = 0;
+                        if (++th == tiles_h) {
+                            th = 0;
+                            ++tn;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ------------------------------------------------ MMA issuer (leader CTA only)
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BN, 1, 1, 256);
+        const uint64_t adesc0 = ptx::make_smem_desc(ptx::smem_u32(smem), kBoxBytes, 1024);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        const bool do_mma = !(debug & 1);
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+            int cop, cit, tap, split, kb0, kb1;
+            decode(tile, cop, cit, tap, split, kb0, kb1);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            const int nk = (kb1 - kb0) * nterms;
+#pragma unroll 1
+            for (int kb = 0; kb < nk; ++kb) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                // MN-major: LBO = next 64-channel box, SBO = next group of 8 pixel rows
+                const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (kStageBytes >> 4));
+                const uint64_t bdesc = adesc + (kABytes >> 4);
+                if (ptx::elect_one()) {
+                    if (do_mma) {
+#pragma unroll
+                        for (int j = 0; j < kBK / 16; ++j)      // advance 16 pixel rows = 2048 B
+                            ptx::umma_f16_pair(d_tmem, adesc + 128 * j, bdesc + 128 * j, idesc, (kb | j) != 0);
+                    }
+                    ptx::umma_commit_pair(&empty_bar[stage]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (ptx::elect_one()) ptx::umma_commit_pair(&tfull_bar[as]);
+            __syncwarp();
+        }
+    } else if (warp >= 2) {
+        // ------------------------------------------------ epilogue (both CTAs: own 128 rows x 256 columns)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t tempty0 = ptx::mapa_u32(ptx::smem_u32(tempty_bar), 0);
+        int it = 0;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+            int cop, cit, tap, split, kb0, kb1;
+            decode(tile, cop, cit, tap, split, kb0, kb1);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int co = (2 * cop + static_cast<int>(rank)) * kBM + row;
+            const bool row_ok = co < p.Cout;
+            float* dst_row =
+                p.ws + ((static_cast<long long>(split) * p.Cout + co) * ntaps + tap) * static_cast<long long>(p.ldws);
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0;
+                ptx::tmem_ld_32x32b_x32(taddr, r);
+                ptx::tmem_ld_wait();
+                const int ci = cit * BN + c0;
+                int nvalid = p.Cin - ci;
+                nvalid = nvalid > 32 ? 32 : nvalid;
+                if (row_ok && nvalid > 0 && !(p.debug & 4)) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    store_row_chunk(dst_row, 1, ci, v, nvalid);
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tempty0 + as * 8);
+        }
+    }
+
+    // the peer's shared memory and barriers must outlive every MMA read / remote arrive of the pair
+    ptx::tc_fence_before();
+    ptx::cluster_sync_all();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad, row-shared
 // Stride-1 filter gradient with the S taps of one filter row computed from ONE pair of TMA loads per k-block: the X
 // box is fetched with an (S-1)-pixel halo along W and tap s reads it through a descriptor that starts s rows (s*128 B)
@@ -2542,16 +2759,21 @@ int fprop_finish(ConvFpropParams& p, const void* b_hi, const void* b_lo, cudaStr
     // staged epilogue for the narrow tiles (the parity-class launches of the strided data gradients, the 1x1 / strided
     // layers with <= 128 output channels: K loops of 1-4 taps, where the register epilogue's ~2500 cycles per 128 x 64
     // tile are exposed); the 256-wide tiles keep four stages and the register epilogue (long K loops hide it)
+    // 256-wide tiles with K <= 1536 (the head's 1x1 layers after the first): the register epilogue with statistics takes
+    // ~10k cycles per 128 x 256 tile, more than the tile's <= 96 MMAs - staged epilogue on a three-stage ring
     p.epi_tma = 0;
-    if (BN <= 128 && !p.bnb_x) {
+    const int num_kb = p.nterms * p.R * p.S * p.kchunks;
+    if (!p.bnb_x && (BN <= 128 || num_kb <= 24)) {
         const uint32_t stage_bytes = staged_epilogue_bytes(p, BN, &rc);
         if (rc) return rc;
         if (stage_bytes) {
-            const uint32_t front = BN == 64 ? SmemLayout<64, 8>::kStatOffset + 8 * 64 * 8
-                                            : SmemLayout<128, 5>::kStatOffset + 8 * 128 * 8;
+            const uint32_t front = BN == 64    ? SmemLayout<64, 8>::kStatOffset + 8 * 64 * 8
+                                   : BN == 128 ? SmemLayout<128, 5>::kStatOffset + 8 * 128 * 8
+                                               : SmemLayout<256, 3>::kStatOffset + 8 * 256 * 8;
             p.stage_off = (front + 1023) / 1024 * 1024;
             p.smem_total = 1024 + p.stage_off + stage_bytes;
-            return BN == 64 ? launch_fprop<64, 8>(p, stream) : launch_fprop<128, 5>(p, stream);
+            return BN == 64 ? launch_fprop<64, 8>(p, stream)
+                            : (BN == 128 ? launch_fprop<128, 5>(p, stream) : launch_fprop<256, 3>(p, stream));
         }
     }
     switch (BN) {
@@ -2801,9 +3023,24 @@ int wgrad_splits(int total_kblocks, int base_tiles, int bn_cols, int stage_bytes
     return best;
 }
 
+static int g_wgrad_pairs = 1;        // CTA-pair kernel for the 256-wide tiles (A/B: denet_conv2d_wgrad_set_mode bit 7 = off)
+
 // dispatch of the wgrad GEMM; p holds the maps, the k-block tiling, Cout/Cin (GEMM N extent), R, S and the workspace
 int wgrad_launch(ConvWgradParams& p, cudaStream_t stream) {
     const int BN = p.Cin <= 64 ? 64 : (p.Cin <= 128 ? 128 : 256);
+    if (BN == 256 && g_wgrad_pairs && p.co_tiles % 2 == 0 && p.a_boxes == 2) {
+        constexpr int kStages = 6;                              // 6 x (16 KB dY + 16 KB X half)
+        ConvWgradParams q = p;
+        q.fd_cot = make_fastdiv(p.co_tiles / 2);
+        q.num_tiles = p.num_tiles / 2;                          // PAIR tiles
+        const int smem = kStages * 32768 + 256 + 1024;
+        auto kern = conv_wgrad2_kernel<kStages>;
+        DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int pairs = q.num_tiles < num_sms() / 2 ? q.num_tiles : num_sms() / 2;
+        kern<<<DN_G(2 * pairs), kThreads, smem, stream>>>(q);
+        DN_CHECK_LAUNCH();
+        return 0;
+    }
     switch (BN) {
         // (KS = 2 measured: the 128-wide instance issues faster - 43 -> 37 us with the loads switched off - but three
         // 64 KB stages expose the L2 -> shared-memory fill, 590 MB per launch, which is the floor: 43 -> 45 us)
@@ -3059,6 +3296,7 @@ extern "C" int denet_conv2d_wgrad_set_mode(int row_shared) {
                                                   // MMA, bit2: no TMA, bit3: no store; bit5: per-tap MMAs in the rows kernel)
     g_wgrad_legacy_splits = (row_shared >> 4) & 1;   // bit4: the former split-K rule (A/B measurements)
     g_wgrad_rows_max_cin = ((row_shared >> 6) & 1) ? 4096 : 64;   // bit6: row-shared kernel for every channel count
+    g_wgrad_pairs = ((row_shared >> 7) & 1) ? 0 : 1;              // bit7: no CTA pairs for the 256-wide tiles
     return 0;
 }
 
