@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(kBnThreads, 2)
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                         const float* __restrict__ beta, int relu, T* __restrict__ dx, T* __restrict__ dres,
                         float* __restrict__ partial, float* __restrict__ sums, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta, int accumulate, int sync_slot, int wide_totals) {
+                        float* __restrict__ dbeta, int accumulate, int sync_slot, int wide_totals, int debug) {
     const int CV = C / VEC;
     const int cvt = CV < kBnThreads ? CV : kBnThreads;
     const int rlanes = kBnThreads / cvt;
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(kBnThreads, 2)
             }
         }
     }
-    grid_barrier(&sync[0], nblocks);
+    if (!(debug & 1)) grid_barrier(&sync[0], nblocks);
     // ---------------------------------------------------------------- slab totals (fixed order, double)
     // wide form: a block totals 8 channels with 32 slab lanes, every lane's <= 10 loads issued before the first add
     // (the 8-lane form below walks 37 slabs per thread: a chain of L2 latencies while every other block waits)
@@ -620,9 +620,9 @@ __global__ void __launch_bounds__(kBnThreads, 2)
         }
         __syncthreads();
     }
-    grid_barrier(&sync[1], nblocks);
+    if (!(debug & 1)) grid_barrier(&sync[1], nblocks);
     // ---------------------------------------------------------------- phase 2
-    if (active) {
+    if (active && !(debug & 2)) {
         const float inv_m = 1.0f / (float)M;
         float c1[VEC], c2[VEC];
 #pragma unroll
@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(kBnThreads, 2)
     }
     // the last block out re-arms the slot
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !(debug & 1)) {
         const unsigned int ticket = atomicAdd(&sync[2], 1u);
         if (ticket == nblocks - 1) {
             sync[0] = 0;
@@ -1236,6 +1236,7 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int ns
 }
 
 static int g_bn_fused_bwd = 1;     // batch-norm backward as one launch with grid barriers (A/B: denet_bn_set_mode)
+static int g_bn_debug = 0;         // profiling knobs of the fused backward (results are garbage): 1 no grid barriers, 2 no phase 2
 static int g_bn_wave = 1;          // apply passes as ONE wave of blocks (3 per SM), wide slab totals in the fused backward
 
 // slabs for a grid of at most `max_blocks` co-resident blocks (rows split as evenly as the row-lane quantum allows)
@@ -1353,6 +1354,7 @@ extern "C" int denet_bn_apply_sums(const void* x, int dtype, long long M, int C,
 extern "C" int denet_bn_set_mode(int mode) {
     g_bn_fused_bwd = mode & 1;       // bit0: one-launch backward (grid barriers); 0 = partial / finalize / apply kernels
     g_bn_wave = (mode >> 1) & 1;     // bit1: one-wave apply grids + wide slab totals (default on)
+    g_bn_debug = (mode >> 2) & 3;    // undocumented profiling knobs (scripts/bench_bn.py)
     return 0;
 }
 
@@ -1385,7 +1387,7 @@ extern "C" int denet_bn_backward(const void* dy, const void* yout, const void* x
                 constexpr int U = sizeof(T) == 4 ? 2 : 4;
                 launch_pdl(bn_bwd_fused_kernel<T, VEC, U>, DN_G(dim3(nsf, ycf)), dim3(kBnThreads), 0, stream,
                     (const T*)dy, (const T*)yout, (const T*)x, M, C, ld, rpbf, mean, invstd, gamma, beta, relu, (T*)dx,
-                    (T*)dres, workspace, sums, dgamma, dbeta, accumulate, slot, g_bn_wave);
+                    (T*)dres, workspace, sums, dgamma, dbeta, accumulate, slot, g_bn_wave, g_bn_debug);
             });
             DN_CHECK_LAUNCH();
             return 0;
