@@ -440,13 +440,17 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
 constexpr int kBnSyncSlots = 64;
 __device__ unsigned int g_bn_sync[kBnSyncSlots][4];
 
+// Release / acquire at GPU scope around a relaxed counter (the block's writes reach thread 0 through bar.sync; the data the
+// other blocks publish - slab partials, totals - is read with L1-bypassing loads).  __threadfence() + a volatile poll
+// compiled to MEMBAR.SC.GPU + CGAERRBAR + CCTL.IVALL twice per barrier and system-scope polling loads: ~4 us per barrier.
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*reinterpret_cast<volatile unsigned int*>(counter) < expected) __nanosleep(32);
-        __threadfence();
+        unsigned int v;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < expected);
     }
     __syncthreads();
 }
