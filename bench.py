@@ -458,7 +458,7 @@ def run_b200(args):
     # launch list of this same command committed under profiles/ (newest round first) and is labelled with its source;
     # null when no such file exists.
     traffic, traffic_src = None, None
-    for name in ("r2_conv_traffic.json", "r1_conv_traffic_final.json"):
+    for name in ("r2_conv_traffic_final.json", "r2_conv_traffic.json", "r1_conv_traffic_final.json"):
         try:
             traffic = float(json.load(open(os.path.join(ROOT, "profiles", name)))["conv_dram_bytes_per_launch"])
             traffic_src = "profiles/" + name
